@@ -1,0 +1,30 @@
+# Builds libphare_b200.so (hand-written sm_100a kernels behind the C ABI of include/phare_b200.h)
+# and the test-only CPU oracle.  nvcc cross-compiles without a GPU.
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: products and sums are rounded separately, like the reference's default CPU build;
+# the few deliberate fusions are explicit fma() calls.
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+SRC       := $(wildcard phare_b200/csrc/*.cu)
+OBJ       := $(patsubst phare_b200/csrc/%.cu,build/%.o,$(SRC))
+LIB       := phare_b200/lib/libphare_b200.so
+
+all: lib oracle
+
+lib: $(LIB)
+
+build/%.o: phare_b200/csrc/%.cu phare_b200/csrc/common.cuh phare_b200/csrc/particle_math.cuh include/phare_b200.h
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+
+$(LIB): $(OBJ)
+	@mkdir -p phare_b200/lib
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -lcudart
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf build $(LIB)
+	$(MAKE) -C oracle clean
+.PHONY: all lib oracle clean

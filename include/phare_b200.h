@@ -1,0 +1,208 @@
+/* phare_b200.h — C ABI of libphare_b200.so: the B200 (sm_100a) implementation of PHARE's per-patch
+ * hybrid-PIC hot path (SolverPPC's particle sweeps and field solvers).
+ *
+ * Every entry point cites the reference interface it replaces (paths relative to the PHARE tree).
+ * Conventions
+ *   - plain C types only; every array pointer is a DEVICE pointer unless its name starts with h_
+ *   - every function returns 0 on success, a phb_status otherwise; text via phb_last_error(ctx)
+ *   - kernels are enqueued on the context's stream and return without synchronising, except the
+ *     functions documented as "host-returning" (they copy a few counters back)
+ *   - arrays are C-ordered (last index fastest) with the reference's allocation shapes
+ *     (GridLayout::allocSize, src/core/data/grid/gridlayout.hpp:849-864) -> phb_field_shape()
+ *   - there is NO CPU fallback: without a CUDA device phb_create fails.
+ */
+#ifndef PHARE_B200_H
+#define PHARE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PHB_OK                = 0,
+    PHB_ERR_INVALID       = 1, /* bad argument (dim, interp, null pointer, capacity)            */
+    PHB_ERR_CUDA          = 2, /* CUDA runtime error                                            */
+    PHB_ERR_MOVE_TWO_CELL = 3, /* a particle moved more than 2 cells in a half push
+                                  (boris.hpp:164-165 MoveTwoCellException)                       */
+    PHB_ERR_OUTSIDE_GHOST = 4, /* a particle left the ghost box (ion_updater.hpp:256-271, debug)   */
+    PHB_ERR_CAPACITY      = 5, /* destination particle array too small                           */
+    PHB_ERR_NO_DEVICE     = 6
+} phb_status;
+
+/* HybridQuantity::Scalar subset used on the path (models/quantities/hybrid_quantities.hpp:16-40);
+ * centerings follow gridlayout_hybrid_yee.hpp:54-85 */
+typedef enum {
+    PHB_BX = 0, PHB_BY, PHB_BZ, PHB_EX, PHB_EY, PHB_EZ, PHB_JX, PHB_JY, PHB_JZ,
+    PHB_RHO, PHB_VX, PHB_VY, PHB_VZ, PHB_P, PHB_NQTY
+} phb_qty;
+
+/* == GridLayout constructor arguments (gridlayout.hpp:122-139) */
+typedef struct {
+    int      dim;          /* 1,2,3 */
+    int      interp;       /* 1,2,3 -> field ghosts {2,4,4}, particle ghosts {1,2,2}
+                              (models/options/hybrid_options.hpp:24-25) */
+    int      level;        /* AMR level number (used by Ohm spatial hyper-resistivity) */
+    int      amr_lower[3]; /* AMR index of the first cell of the patch */
+    uint32_t ncells[3];    /* physical cells per direction */
+    double   dx[3];
+    double   origin[3];
+} phb_layout;
+
+typedef struct { double* comp[3]; } phb_vecfield; /* x,y,z components, each allocSize(qty) */
+
+typedef struct { int lower[3], upper[3]; } phb_box; /* inclusive AMR cell box (utilities/box/box.hpp:28) */
+
+/* device-resident SoA particle store; replaces ParticleArray<dim> (particle_array.hpp:21-238)
+ * Particle members: particle.hpp:55-61 */
+typedef struct {
+    int*    icell[3];
+    double* delta[3];
+    double* v[3];
+    double* weight;
+    double* charge;
+    size_t  n;        /* live particles */
+    size_t  capacity; /* allocated slots per column */
+} phb_particles;
+
+typedef struct phb_ctx phb_ctx;
+
+/* ---- context / memory ------------------------------------------------------------------- */
+int         phb_create(int device, int dim, int interp, phb_ctx** out);
+void        phb_destroy(phb_ctx*);
+const char* phb_last_error(phb_ctx*);
+const char* phb_version(void);
+int         phb_set_stream(phb_ctx*, void* cuda_stream); /* cudaStream_t; default: own stream */
+void*       phb_get_stream(phb_ctx*);
+int         phb_sync(phb_ctx*);
+/* 1: products unfused exactly as the reference build (no -march -> no FMA); 0: allow FMA
+ * contraction in the gather/Boris arithmetic (positions stay unfused). Default 1. */
+int         phb_set_exact(phb_ctx*, int exact);
+/* host-returning: synchronises, returns PHB_ERR_MOVE_TWO_CELL / PHB_ERR_OUTSIDE_GHOST raised by a
+ * kernel since the last poll, with the offending delta/velocity in phb_last_error; mirrors
+ * mpi::any_errors() after moveIons (solver_ppc.hpp:562) */
+int         phb_poll_error(phb_ctx*);
+/* number of kernels launched by this context so far (bench bookkeeping) */
+uint64_t    phb_launch_count(phb_ctx*);
+
+int phb_malloc(phb_ctx*, size_t bytes, void** d_out);
+int phb_free(phb_ctx*, void* d);
+int phb_memset(phb_ctx*, void* d, int byte, size_t bytes);
+int phb_h2d(phb_ctx*, void* d_dst, const void* h_src, size_t bytes);
+int phb_d2h(phb_ctx*, void* h_dst, const void* d_src, size_t bytes);
+int phb_d2d(phb_ctx*, void* d_dst, const void* d_src, size_t bytes);
+int phb_host_alloc(size_t bytes, void** h_out); /* pinned */
+int phb_host_free(void* h);
+
+/* ---- geometry (pure host arithmetic) ----------------------------------------------------- */
+/* GridLayout::allocSize(qty), gridlayout.hpp:849-864 ; returns element count, fills shape[dim] */
+size_t phb_field_shape(const phb_layout*, int qty, uint32_t shape[3]);
+int    phb_field_ghosts(int interp);    /* {2,4,4} */
+int    phb_particle_ghosts(int interp); /* {1,2,2} */
+
+/* ---- particle store ---------------------------------------------------------------------- */
+int phb_particles_alloc(phb_ctx*, size_t capacity, phb_particles* out);
+int phb_particles_free(phb_ctx*, phb_particles*);
+/* host AoS interop with reference Particle<dim> records (sizeof 56/64/80, particle.hpp:38-73) */
+size_t phb_aos_stride(int dim);
+int phb_particles_from_aos(phb_ctx*, const void* h_aos, size_t n, phb_particles* dst);
+int phb_particles_to_aos(phb_ctx*, const phb_particles* src, void* h_aos);
+/* host SoA interop (ContiguousParticles layout, particle_array.hpp:250-354: iCell[n*dim],
+ * delta[n*dim], weight[n], charge[n], v[n*3]) */
+int phb_particles_from_soa(phb_ctx*, const int* h_icell, const double* h_delta, const double* h_weight,
+                           const double* h_charge, const double* h_v, size_t n, phb_particles* dst);
+int phb_particles_to_soa(phb_ctx*, const phb_particles* src, int* h_icell, double* h_delta,
+                         double* h_weight, double* h_charge, double* h_v);
+/* dst[dst_first .. dst_first+count) = src[src_first ..) column by column (device to device);
+ * ParticleArray copy / append (ion_updater.hpp:181, std::copy+back_inserter :253) */
+int phb_particles_copy(phb_ctx*, const phb_particles* src, size_t src_first, size_t count,
+                       phb_particles* dst, size_t dst_first);
+
+/* ---- K1 fused interpolate + Boris push ---------------------------------------------------
+ * BorisPusher::move (pusher/boris.hpp:93-138) = prePushStep_ (:180-216), firstSelector,
+ * Interpolator::operator()(particle, em, layout) (interpolator.hpp:420-456), accelerate_
+ * (:240-300), postPushStep_ (:218-234).  `in` and `out` may be the same store (in-place).
+ * first_selector: NULL = noop; else particles whose pre-pushed cell is outside that box keep the
+ * pre-pushed position and the old velocity (they are "not selected", ion_updater.hpp:137-140).
+ * The second selector is phb_bin / the box predicates of phb_deposit.
+ * Pusher::setMeshAndTimeStep (boris.hpp:143-148) is folded in through layout->dx and dt. */
+int phb_push(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,
+             const phb_particles* in, phb_particles* out, double mass, double dt,
+             const phb_box* first_selector);
+
+/* ---- K2 cell binning / counting sort -------------------------------------------------------
+ * Replaces CellMap maintenance + partition selectors + erase (cellmap.hpp:411-470,
+ * ion_updater.hpp:119-163,245-273).  Key space over `domain` (the patch cell box), G = domain
+ * grown by the particle ghost width, and the union `keep[nkeep]` (nonLevelGhostBox,
+ * amr_utils.hpp:233-253):
+ *    cell in domain                     -> key = rowmajor(cell - domain.lower)        in [0,Nd)
+ *    cell in G, in some keep box        -> key = Nd + rowmajor(cell - G.lower)        in [Nd,Nd+Ng)
+ *    anything else (level-ghost leavers, or outside G) -> key = Nd+Ng (dropped)
+ * `out` receives the particles sorted by key; d_cell_start[k] (Nd+Ng+2 entries) is the index of
+ * the first particle of key k.  host-returning: h_counts = {#domain, #patch-ghost, #dropped}.
+ * out->n is set to #domain + #patch-ghost. in and out must be distinct stores. */
+size_t phb_bin_nkeys(const phb_layout*, const phb_box* domain);
+int phb_bin(phb_ctx*, const phb_layout*, const phb_particles* in, phb_particles* out,
+            const phb_box* domain, const phb_box* keep, int nkeep, uint32_t* d_cell_start,
+            size_t h_counts[3]);
+/* append to `dst` every particle of src[first,last) whose cell lies in `box` (minus `minus` when
+ * not NULL), adding `shift` to its cell: ParticleArray::export_particles (particle_array.hpp
+ * :135-160) and ParticlesData pack/unpack with periodic shift (particles_data.hpp:702-784).
+ * host-returning: *h_appended. Order of the appended particles = source order. */
+int phb_export(phb_ctx*, const phb_layout*, const phb_particles* src, size_t first, size_t last,
+               const phb_box* box, const phb_box* minus, const int shift[3], phb_particles* dst,
+               size_t* h_appended);
+
+/* ---- K3 moment deposit ----------------------------------------------------------------------
+ * Interpolator::operator()(range, particleDensity, chargeDensity, flux, layout, coef)
+ * (interpolator.hpp:468-504) restricted to particles [first,last) whose cell is in one of
+ * `sel[nsel]` (nsel = 0: all particles; this is the `allowed` range the second selector of
+ * move() returns, ion_updater.hpp:186-189).
+ * d_cell_start != NULL selects the cell-ordered kernel: particles are expected to be (mostly)
+ * grouped by the keys of phb_bin for `domain`; particles whose current cell differs from their
+ * group's cell are still deposited correctly (through the atomic path). */
+int phb_deposit(phb_ctx*, const phb_layout*, const phb_particles*, size_t first, size_t last,
+                double* rho_n, double* rho_q, const phb_vecfield* flux, double coef,
+                const phb_box* sel, int nsel, const phb_box* domain, const uint32_t* d_cell_start);
+
+/* ---- K4-K7 field solvers and pointwise ops -------------------------------------------------- */
+/* Faraday::operator()(B,E,Bnew,dt)  faraday/faraday.hpp:28-97 */
+int phb_faraday(phb_ctx*, const phb_layout*, const phb_vecfield* B, const phb_vecfield* E,
+                phb_vecfield* Bnew, double dt);
+/* Ampere::operator()(B,J)           ampere/ampere.hpp:26-95 */
+int phb_ampere(phb_ctx*, const phb_layout*, const phb_vecfield* B, phb_vecfield* J);
+/* Ohm::operator()(n,Ve,Pe,B,J,Enew) ohm/ohm.hpp:48-270 ; hyper_mode 0 = constant, 1 = spatial */
+int phb_ohm(phb_ctx*, const phb_layout*, const double* n, const phb_vecfield* Ve, const double* Pe,
+            const phb_vecfield* B, const phb_vecfield* J, phb_vecfield* Enew, double eta, double nu,
+            int hyper_mode);
+/* Electrons::update: Ve = Vi - project(J)/Ne on the physical primal box; Pe = Ne*Te everywhere
+ * (data/electrons/electrons.hpp:102-128,202-212,304-314) */
+int phb_electrons_update(phb_ctx*, const phb_layout*, const double* Ne, const phb_vecfield* Vi,
+                         const phb_vecfield* J, double Te, phb_vecfield* Ve, double* Pe);
+/* Ions::computeChargeDensity / computeMassDensity / computeBulkVelocity (data/ions/ions.hpp:75-145)
+ * h_* arrays of npop device pointers / masses live on the host */
+int phb_ions_totals(phb_ctx*, size_t nnodes, int npop, const double* const* h_rho_n,
+                    const double* const* h_rho_q, const phb_vecfield* h_flux, const double* h_mass,
+                    double* rho_q_tot, double* rho_m_tot, phb_vecfield* V);
+/* core::average (utilities/algorithm.hpp:68-77): avg = (a+b)*0.5 over n doubles */
+int phb_average(phb_ctx*, size_t n, const double* a, const double* b, double* avg);
+
+/* ---- K8 same-level periodic halo on one device ----------------------------------------------
+ * dst region = box `dst_box` (local array indices, inclusive) of array `dst` with shape
+ * dst_shape; src likewise; op 0 = copy (ghost fill, field_data.hpp:212-290), 1 = += (border sum,
+ * field_operate_transaction.hpp:33 PlusEquals), 2 = max (SetMax, types.hpp:577-581) */
+int phb_box_op(phb_ctx*, int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3],
+               const double* src, const uint32_t src_shape[3], const uint32_t src_lo[3],
+               const uint32_t extent[3], int op);
+/* pack / unpack a box to / from a contiguous buffer (NCCL send / recv staging) */
+int phb_box_pack(phb_ctx*, int dim, const double* src, const uint32_t src_shape[3],
+                 const uint32_t src_lo[3], const uint32_t extent[3], double* buf);
+int phb_box_unpack(phb_ctx*, int dim, double* dst, const uint32_t dst_shape[3],
+                   const uint32_t dst_lo[3], const uint32_t extent[3], const double* buf, int op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,152 @@
+"""ctypes view of the C ABI declared in include/phare_b200.h.
+
+The structs here are shared by three libraries that take the same argument types:
+  * phare_b200/lib/libphare_b200.so  (phb_*)  the product: CUDA kernels, DEVICE pointers
+  * oracle/liboracle.so              (pho_*)  test-only CPU restatement, HOST pointers
+  * oracle/_ref/libphare_ref.so      (phr_*)  test-only: the reference itself, HOST pointers
+This module only loads the product library; tests/ and bench.py load the other two through
+phare_b200.testing (never imported by the product path).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "lib", "libphare_b200.so")
+
+PHB_OK, PHB_ERR_INVALID, PHB_ERR_CUDA, PHB_ERR_MOVE_TWO_CELL = 0, 1, 2, 3
+PHB_ERR_OUTSIDE_GHOST, PHB_ERR_CAPACITY, PHB_ERR_NO_DEVICE = 4, 5, 6
+
+# phb_qty
+BX, BY, BZ, EX, EY, EZ, JX, JY, JZ, RHO, VX, VY, VZ, P = range(14)
+
+c_double_p = C.POINTER(C.c_double)
+c_int_p = C.POINTER(C.c_int)
+c_u32_p = C.POINTER(C.c_uint32)
+
+
+class Layout(C.Structure):
+    _fields_ = [("dim", C.c_int), ("interp", C.c_int), ("level", C.c_int), ("amr_lower", C.c_int * 3),
+                ("ncells", C.c_uint32 * 3), ("dx", C.c_double * 3), ("origin", C.c_double * 3)]
+
+
+class VecField(C.Structure):
+    _fields_ = [("comp", C.c_void_p * 3)]
+
+
+class Box(C.Structure):
+    _fields_ = [("lower", C.c_int * 3), ("upper", C.c_int * 3)]
+
+
+class Particles(C.Structure):
+    _fields_ = [("icell", C.c_void_p * 3), ("delta", C.c_void_p * 3), ("v", C.c_void_p * 3),
+                ("weight", C.c_void_p), ("charge", C.c_void_p), ("n", C.c_size_t), ("capacity", C.c_size_t)]
+
+
+def make_layout(dim, interp, ncells, dx, amr_lower=None, origin=None, level=0):
+    L = Layout()
+    L.dim, L.interp, L.level = dim, interp, level
+    for d in range(3):
+        L.ncells[d] = int(ncells[d]) if d < dim else 0
+        L.dx[d] = float(dx[d]) if d < dim else 0.0
+        L.amr_lower[d] = int(amr_lower[d]) if (amr_lower is not None and d < dim) else 0
+        L.origin[d] = float(origin[d]) if (origin is not None and d < dim) else 0.0
+    return L
+
+
+def make_box(lower, upper):
+    b = Box()
+    for d in range(3):
+        b.lower[d] = int(lower[d]) if d < len(lower) else 0
+        b.upper[d] = int(upper[d]) if d < len(upper) else 0
+    return b
+
+
+def box_array(boxes):
+    arr = (Box * max(len(boxes), 1))()
+    for i, b in enumerate(boxes):
+        arr[i] = b
+    return arr
+
+
+_PROTOS = {
+    # name: (restype, argtypes)
+    "phb_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "phb_destroy": (None, [C.c_void_p]),
+    "phb_last_error": (C.c_char_p, [C.c_void_p]),
+    "phb_version": (C.c_char_p, []),
+    "phb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phb_get_stream": (C.c_void_p, [C.c_void_p]),
+    "phb_sync": (C.c_int, [C.c_void_p]),
+    "phb_set_exact": (C.c_int, [C.c_void_p, C.c_int]),
+    "phb_poll_error": (C.c_int, [C.c_void_p]),
+    "phb_launch_count": (C.c_uint64, [C.c_void_p]),
+    "phb_malloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "phb_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phb_memset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "phb_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "phb_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "phb_d2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "phb_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "phb_host_free": (C.c_int, [C.c_void_p]),
+    "phb_field_shape": (C.c_size_t, [C.POINTER(Layout), C.c_int, c_u32_p]),
+    "phb_field_ghosts": (C.c_int, [C.c_int]),
+    "phb_particle_ghosts": (C.c_int, [C.c_int]),
+    "phb_particles_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(Particles)]),
+    "phb_particles_free": (C.c_int, [C.c_void_p, C.POINTER(Particles)]),
+    "phb_aos_stride": (C.c_size_t, [C.c_int]),
+    "phb_particles_from_aos": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Particles)]),
+    "phb_particles_to_aos": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_void_p]),
+    "phb_particles_from_soa": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_size_t, C.POINTER(Particles)]),
+    "phb_particles_to_soa": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "phb_particles_copy": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t,
+                                     C.POINTER(Particles), C.c_size_t]),
+    "phb_push": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                           C.POINTER(Particles), C.POINTER(Particles), C.c_double, C.c_double, C.POINTER(Box)]),
+    "phb_bin_nkeys": (C.c_size_t, [C.POINTER(Layout), C.POINTER(Box)]),
+    "phb_bin": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.POINTER(Particles),
+                          C.POINTER(Box), C.POINTER(Box), C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "phb_export": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t,
+                             C.POINTER(Box), C.POINTER(Box), c_int_p, C.POINTER(Particles),
+                             C.POINTER(C.c_size_t)]),
+    "phb_deposit": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t,
+                              C.c_void_p, C.c_void_p, C.POINTER(VecField), C.c_double, C.POINTER(Box), C.c_int,
+                              C.POINTER(Box), C.c_void_p]),
+    "phb_faraday": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                              C.POINTER(VecField), C.c_double]),
+    "phb_ampere": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField)]),
+    "phb_ohm": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_void_p, C.POINTER(VecField), C.c_void_p,
+                          C.POINTER(VecField), C.POINTER(VecField), C.POINTER(VecField), C.c_double, C.c_double,
+                          C.c_int]),
+    "phb_electrons_update": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_void_p, C.POINTER(VecField),
+                                       C.POINTER(VecField), C.c_double, C.POINTER(VecField), C.c_void_p]),
+    "phb_ions_totals": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                  C.POINTER(VecField), c_double_p, C.c_void_p, C.c_void_p, C.POINTER(VecField)]),
+    "phb_average": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "phb_box_op": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, C.c_void_p, c_u32_p, c_u32_p,
+                             c_u32_p, C.c_int]),
+    "phb_box_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p]),
+    "phb_box_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p,
+                                 C.c_int]),
+}
+
+EXPORTED = sorted(_PROTOS)
+
+_lib = None
+
+
+def load():
+    """Load libphare_b200.so (built in-tree by `make lib` / __graft_entry__.build()).
+    There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `make lib` (or __graft_entry__.build())")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib

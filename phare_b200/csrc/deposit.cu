@@ -1,0 +1,404 @@
+// K3 — moment deposit (density, charge density, flux).  Replaces
+// Interpolator::operator()(range, particleDensity, chargeDensity, flux, layout, coef)
+// (src/core/numerics/interpolator/interpolator.hpp:468-504) with ParticleToMesh<dim> (:278-363).
+//
+// Two kernels:
+//  * deposit_cells_kernel — for the cell-ordered store (phb_bin).  A group of GS lanes owns one
+//    cell: the lanes stride over the cell's particles (coalesced column reads), every lane keeps
+//    the cell's S^d x 5 node sums in registers, the group folds them with a shuffle
+//    reduce-scatter, and each lane commits its node(s) with ONE FP64 reduction per node and
+//    field (RED.E.ADD.F64).  A particle whose cell differs from its group's cell (it moved since
+//    the store was ordered) takes the per-particle atomic path, so the result is the same for
+//    any order.  HBM traffic per particle: iCell 4d + delta 8d + v 24 + weight 8 + charge 8
+//    = 52 / 64 / 76 B.
+//  * deposit_atomic_kernel — any order, one thread per particle, one FP64 atomic per node and
+//    field; used for small unsorted arrays (patch-ghost, level-ghost) and for (3-D, order 2/3).
+//
+// Each contribution is computed exactly as the reference does: ((q*weight)*coef)*wx*wy*wz; only
+// the order in which contributions are summed into a node differs (FP64 addition is not
+// associative: agreement with the sequential reference is ~1e-16*sqrt(N) relative).
+#include "particle_math.cuh"
+
+namespace phb
+{
+struct MomentViews
+{
+    double* f[5]; // rho_n, rho_q, Fx, Fy, Fz : all primal, same shape
+    int n[3];
+    __device__ __forceinline__ size_t at(int i, int j, int k) const
+    {
+        return (size_t(i) * n[1] + j) * n[2] + k;
+    }
+};
+
+template<int DIM>
+struct DepositParams
+{
+    DevLayout L;
+    PartView P;
+    MomentViews M;
+    size_t first, last;
+    double coef;
+    BoxList sel;               // n == 0: everything selected
+    DevBox keybox;             // cell-ordered kernel: key -> cell
+    const uint32_t* cell_start;
+    unsigned nkeys;
+};
+
+template<int DIM>
+__device__ __forceinline__ bool selected(const BoxList& sel, const int* c)
+{
+    if (sel.n == 0)
+        return true;
+    for (int b = 0; b < sel.n; ++b)
+        if (in_box<DIM>(c, sel.b[b]))
+            return true;
+    return false;
+}
+
+// per-particle atomic scatter (ParticleToMesh<DIM>, interpolator.hpp:278-363)
+template<int DIM, int ORDER>
+__device__ __forceinline__ void scatter_atomic(const DevLayout& L, const MomentViews& M, const int* icell,
+                                               const double* delta, const double (&dep)[5])
+{
+    int start[DIM];
+    double w[DIM][ORDER + 1];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+        start[d] = index_and_weights<ORDER, PRIMAL>(icell[d] - (L.amr_lower[d] - L.g), delta[d], w[d]);
+#pragma unroll
+    for (int f = 0; f < 5; ++f)
+    {
+        if constexpr (DIM == 1)
+        {
+#pragma unroll
+            for (int ix = 0; ix <= ORDER; ++ix)
+                atomicAdd(M.f[f] + M.at(start[0] + ix, 0, 0), dep[f] * w[0][ix]);
+        }
+        else if constexpr (DIM == 2)
+        {
+#pragma unroll
+            for (int ix = 0; ix <= ORDER; ++ix)
+#pragma unroll
+                for (int iy = 0; iy <= ORDER; ++iy)
+                    atomicAdd(M.f[f] + M.at(start[0] + ix, start[1] + iy, 0), dep[f] * w[0][ix] * w[1][iy]);
+        }
+        else
+        {
+#pragma unroll
+            for (int ix = 0; ix <= ORDER; ++ix)
+#pragma unroll
+                for (int iy = 0; iy <= ORDER; ++iy)
+#pragma unroll
+                    for (int iz = 0; iz <= ORDER; ++iz)
+                        atomicAdd(M.f[f] + M.at(start[0] + ix, start[1] + iy, start[2] + iz),
+                                  dep[f] * w[0][ix] * w[1][iy] * w[2][iz]);
+        }
+    }
+}
+
+template<int DIM, int ORDER>
+__global__ void __launch_bounds__(256) deposit_atomic_kernel(const __grid_constant__ DepositParams<DIM> A)
+{
+    size_t const i = A.first + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= A.last)
+        return;
+    int icell[DIM];
+    double delta[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+    {
+        icell[d] = __ldcs(A.P.icell[d] + i);
+        delta[d] = __ldcs(A.P.delta[d] + i);
+    }
+    if (!selected<DIM>(A.sel, icell))
+        return;
+    double const weight = __ldcs(A.P.weight + i);
+    double const dep[5] = {1. * weight * A.coef, __ldcs(A.P.charge + i) * weight * A.coef,
+                           __ldcs(A.P.v[0] + i) * weight * A.coef, __ldcs(A.P.v[1] + i) * weight * A.coef,
+                           __ldcs(A.P.v[2] + i) * weight * A.coef};
+    scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+}
+
+// union of the primal supports of all particles of one cell, per direction:
+// order 1: {l, l+1}; order 2: {l-1 .. l+2} (start = l-1 or l); order 3: {l-1 .. l+2}
+template<int ORDER> constexpr int cell_support() { return ORDER == 1 ? 2 : 4; }
+template<int ORDER> constexpr int cell_base_shift() { return ORDER == 1 ? 0 : 1; }
+constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
+
+template<int NV, int GS, int NCHUNK, int MASK>
+struct GroupReduce
+{
+    // a[0 .. NCHUNK*5) valid on entry; after all steps the lane owns chunks [base, base+nleft)
+    __device__ static __forceinline__ void run(double (&a)[NV], int lane, int& base, int& nleft)
+    {
+        if constexpr (MASK < GS)
+        {
+            if constexpr (NCHUNK > 1)
+            {
+                constexpr int half = NCHUNK / 2;
+                bool const upper   = (lane & MASK) != 0;
+#pragma unroll
+                for (int i = 0; i < half * 5; ++i)
+                {
+                    double const send = upper ? a[i] : a[i + half * 5];
+                    double const keep = upper ? a[i + half * 5] : a[i];
+                    a[i]              = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
+                }
+                base += upper ? half : 0;
+                GroupReduce<NV, GS, half, MASK * 2>::run(a, lane, base, nleft);
+            }
+            else
+            {
+#pragma unroll
+                for (int i = 0; i < 5; ++i)
+                    a[i] += __shfl_xor_sync(0xffffffffu, a[i], MASK);
+                GroupReduce<NV, GS, 1, MASK * 2>::run(a, lane, base, nleft);
+            }
+        }
+        else
+            nleft = NCHUNK;
+    }
+};
+
+template<int DIM, int ORDER, int GS>
+__global__ void __launch_bounds__(256) deposit_cells_kernel(const __grid_constant__ DepositParams<DIM> A)
+{
+    constexpr int S     = cell_support<ORDER>();
+    constexpr int NODES = ipow(S, DIM);
+    constexpr int NV    = NODES * 5;
+
+    unsigned const gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned const key  = gtid / GS;
+    int const sub       = int(gtid % GS);
+    bool const live     = key < A.nkeys;
+
+    // key -> cell (row-major over keybox), and the cell's first node
+    int cell[DIM], base[DIM];
+    {
+        unsigned k = live ? key : 0;
+#pragma unroll
+        for (int d = DIM - 1; d >= 0; --d)
+        {
+            unsigned const ext = unsigned(A.keybox.hi[d] - A.keybox.lo[d] + 1);
+            cell[d]            = A.keybox.lo[d] + int(k % ext);
+            k /= ext;
+            base[d] = cell[d] - (A.L.amr_lower[d] - A.L.g) - cell_base_shift<ORDER>();
+        }
+    }
+
+    double acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+        acc[i] = 0.;
+
+    if (live)
+    {
+        size_t begin = A.cell_start[key], end = A.cell_start[key + 1];
+        begin = begin > A.first ? begin : A.first;
+        end   = end < A.last ? end : A.last;
+        bool const cell_selected = selected<DIM>(A.sel, cell);
+        for (size_t p = begin + sub; p < end; p += GS)
+        {
+            int icell[DIM];
+            double delta[DIM];
+            bool same = true;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                icell[d] = __ldcs(A.P.icell[d] + p);
+                delta[d] = __ldcs(A.P.delta[d] + p);
+                same     = same && icell[d] == cell[d];
+            }
+            double const weight = __ldcs(A.P.weight + p);
+            double const dep[5] = {1. * weight * A.coef, __ldcs(A.P.charge + p) * weight * A.coef,
+                                   __ldcs(A.P.v[0] + p) * weight * A.coef,
+                                   __ldcs(A.P.v[1] + p) * weight * A.coef,
+                                   __ldcs(A.P.v[2] + p) * weight * A.coef};
+            if (same)
+            {
+                if (!cell_selected)
+                    continue;
+                // weights placed on the cell's union support
+                double wf[DIM][S];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                {
+                    double w[ORDER + 1];
+                    int const start = index_and_weights<ORDER, PRIMAL>(cell[d] - (A.L.amr_lower[d] - A.L.g),
+                                                                       delta[d], w);
+                    if constexpr (ORDER == 2)
+                    {
+                        bool const hi = (start - base[d]) != 0; // support {l..l+2} instead of {l-1..l+1}
+                        wf[d][0]      = hi ? 0. : w[0];
+                        wf[d][1]      = hi ? w[0] : w[1];
+                        wf[d][2]      = hi ? w[1] : w[2];
+                        wf[d][3]      = hi ? w[2] : 0.;
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+                            wf[d][s] = w[s];
+                    }
+                }
+#pragma unroll
+                for (int f = 0; f < 5; ++f)
+                {
+                    if constexpr (DIM == 1)
+                    {
+#pragma unroll
+                        for (int ix = 0; ix < S; ++ix)
+                            acc[ix * 5 + f] += dep[f] * wf[0][ix];
+                    }
+                    else if constexpr (DIM == 2)
+                    {
+#pragma unroll
+                        for (int ix = 0; ix < S; ++ix)
+#pragma unroll
+                            for (int iy = 0; iy < S; ++iy)
+                                acc[(ix * S + iy) * 5 + f] += dep[f] * wf[0][ix] * wf[1][iy];
+                    }
+                    else
+                    {
+#pragma unroll
+                        for (int ix = 0; ix < S; ++ix)
+#pragma unroll
+                            for (int iy = 0; iy < S; ++iy)
+#pragma unroll
+                                for (int iz = 0; iz < S; ++iz)
+                                    acc[((ix * S + iy) * S + iz) * 5 + f]
+                                        += dep[f] * wf[0][ix] * wf[1][iy] * wf[2][iz];
+                    }
+                }
+            }
+            else if (selected<DIM>(A.sel, icell))
+                scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+        }
+    }
+
+    // fold the GS lanes of the group; afterwards this lane owns nodes [node0, node0 + nleft)
+    int node0 = 0, nleft = NODES;
+    GroupReduce<NV, GS, NODES, 1>::run(acc, sub, node0, nleft);
+    // when GS > NODES the trailing butterfly steps leave duplicates on lanes whose high bits differ
+    bool const owner = (GS <= NODES) || (sub / NODES) == 0;
+    if (!live || !owner)
+        return;
+#pragma unroll
+    for (int c = 0; c < (GS >= NODES ? 1 : NODES / GS); ++c)
+    {
+        int node = node0 + c;
+        int o[3] = {0, 0, 0};
+#pragma unroll
+        for (int d = DIM - 1; d >= 0; --d)
+        {
+            o[d] = base[d] + node % S;
+            node /= S;
+        }
+        size_t const idx = A.M.at(o[0], o[1], o[2]);
+#pragma unroll
+        for (int f = 0; f < 5; ++f)
+        {
+            double const v = acc[c * 5 + f];
+            if (v != 0.)
+                atomicAdd(A.M.f[f] + idx, v);
+        }
+    }
+}
+
+template<int DIM, int ORDER, int GS>
+void launch_cells(phb_ctx* ctx, const DepositParams<DIM>& A)
+{
+    constexpr int BS     = 256;
+    size_t const threads = size_t(A.nkeys) * GS;
+    unsigned const grid  = unsigned((threads + BS - 1) / BS);
+    deposit_cells_kernel<DIM, ORDER, GS><<<grid, BS, 0, ctx->stream>>>(A);
+}
+
+template<int DIM, int ORDER>
+int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
+{
+    if (A.last <= A.first)
+        return PHB_OK;
+    // register-resident node sums exist for supports up to 16 nodes (and 3-D order 1)
+    constexpr bool cell_kernel_ok = ipow(cell_support<ORDER>(), DIM) <= 16;
+    if constexpr (cell_kernel_ok)
+    {
+        if (cells && A.nkeys > 0)
+        {
+            size_t const ppc = (A.last - A.first) / A.nkeys;
+            if (ppc >= 96)
+                launch_cells<DIM, ORDER, 16>(ctx, A);
+            else if (ppc >= 24)
+                launch_cells<DIM, ORDER, 8>(ctx, A);
+            else if (ppc >= 6)
+                launch_cells<DIM, ORDER, 4>(ctx, A);
+            else
+                launch_cells<DIM, ORDER, 2>(ctx, A);
+            PHB_LAUNCH_CHECK(ctx);
+            return PHB_OK;
+        }
+    }
+    constexpr int BS    = 256;
+    unsigned const grid = unsigned((A.last - A.first + BS - 1) / BS);
+    deposit_atomic_kernel<DIM, ORDER><<<grid, BS, 0, ctx->stream>>>(A);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+
+template<int DIM>
+int deposit_dim(phb_ctx* ctx, const phb_layout* L, const phb_particles* P, size_t first, size_t last,
+                double* rho_n, double* rho_q, const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
+                const phb_box* domain, const uint32_t* cell_start)
+{
+    DepositParams<DIM> A;
+    A.L      = make_dev_layout(*L);
+    A.P      = make_part(*P);
+    A.M.f[0] = rho_n;
+    A.M.f[1] = rho_q;
+    for (int c = 0; c < 3; ++c)
+        A.M.f[2 + c] = flux->comp[c];
+    for (int d = 0; d < 3; ++d)
+        A.M.n[d] = alloc_extent(A.L, PHB_RHO, d);
+    A.first = first;
+    A.last  = last;
+    A.coef  = coef;
+    A.sel.n = nsel;
+    for (int b = 0; b < nsel; ++b)
+        A.sel.b[b] = make_box(sel[b], DIM);
+    A.cell_start = cell_start;
+    A.nkeys      = 0;
+    bool const cells = cell_start != nullptr && domain != nullptr;
+    if (cells)
+    {
+        A.keybox   = make_box(*domain, DIM);
+        size_t vol = 1;
+        for (int d = 0; d < DIM; ++d)
+            vol *= size_t(domain->upper[d] - domain->lower[d] + 1);
+        A.nkeys = unsigned(vol);
+    }
+    switch (L->interp)
+    {
+        case 1: return deposit_order<DIM, 1>(ctx, A, cells);
+        case 2: return deposit_order<DIM, 2>(ctx, A, cells);
+        default: return deposit_order<DIM, 3>(ctx, A, cells);
+    }
+}
+} // namespace phb
+
+extern "C" int phb_deposit(phb_ctx* ctx, const phb_layout* L, const phb_particles* P, size_t first, size_t last,
+                           double* rho_n, double* rho_q, const phb_vecfield* flux, double coef,
+                           const phb_box* sel, int nsel, const phb_box* domain, const uint32_t* d_cell_start)
+{
+    if (!phb::valid_layout(ctx, L) || !P || !rho_n || !rho_q || !flux || nsel < 0 || nsel > phb::MAX_BOXES
+        || (nsel > 0 && !sel))
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_deposit: invalid argument");
+    if (last > P->n)
+        last = P->n;
+    switch (L->dim)
+    {
+        case 1: return phb::deposit_dim<1>(ctx, L, P, first, last, rho_n, rho_q, flux, coef, sel, nsel, domain, d_cell_start);
+        case 2: return phb::deposit_dim<2>(ctx, L, P, first, last, rho_n, rho_q, flux, coef, sel, nsel, domain, d_cell_start);
+        default: return phb::deposit_dim<3>(ctx, L, P, first, last, rho_n, rho_q, flux, coef, sel, nsel, domain, d_cell_start);
+    }
+}

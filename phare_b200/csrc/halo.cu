@@ -1,0 +1,92 @@
+// K8 — box copy / += / max between field arrays, and pack / unpack of a box to a contiguous
+// buffer (NCCL staging).  These are the data movers behind the same-level messenger semantics:
+//   ghost fill  : FieldData::copy / packStream / unpackStream  (src/amr/data/field/field_data.hpp:212-290)
+//   border sum  : FieldBorderOp with PlusEquals               (src/amr/data/field/field_data.hpp:446-462,
+//                                                              src/core/utilities/types.hpp:570-575)
+//   border max  : SetMax                                       (src/core/utilities/types.hpp:577-581)
+// Which boxes are exchanged is decided on the host (phare_b200/halo.py restates
+// field_geometry.hpp:139-304 and field_variable_fill_pattern.hpp:30-313).
+#include "common.cuh"
+
+namespace phb
+{
+struct BoxOpParams
+{
+    double* dst;
+    const double* src;
+    int dn[3], dlo[3], sn[3], slo[3], ext[3];
+    int op;
+};
+
+__device__ __forceinline__ double apply_op(int op, double d, double s)
+{
+    return op == 0 ? s : op == 1 ? d + s : (d > s ? d : s); // copy / PlusEquals / std::max(d, s)
+}
+
+__global__ void __launch_bounds__(256) box_op_kernel(const __grid_constant__ BoxOpParams A)
+{
+    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(A.ext[0]) * A.ext[1] * A.ext[2])
+        return;
+    int const k = int(t % A.ext[2]);
+    t /= A.ext[2];
+    int const j = int(t % A.ext[1]);
+    int const i = int(t / A.ext[1]);
+    size_t const pd = (size_t(A.dlo[0] + i) * A.dn[1] + (A.dlo[1] + j)) * A.dn[2] + (A.dlo[2] + k);
+    size_t const ps = (size_t(A.slo[0] + i) * A.sn[1] + (A.slo[1] + j)) * A.sn[2] + (A.slo[2] + k);
+    A.dst[pd]       = apply_op(A.op, A.dst[pd], A.src[ps]);
+}
+
+inline void fill3(int dim, const uint32_t* src, int* dst, int dflt)
+{
+    for (int d = 0; d < 3; ++d)
+        dst[d] = d < dim ? int(src[d]) : dflt;
+}
+
+int box_op(phb_ctx* ctx, int dim, double* dst, const uint32_t* ds, const uint32_t* dlo, const double* src,
+           const uint32_t* ss, const uint32_t* slo, const uint32_t* ext, int op)
+{
+    BoxOpParams A;
+    A.dst = dst;
+    A.src = src;
+    fill3(dim, ds, A.dn, 1);
+    fill3(dim, dlo, A.dlo, 0);
+    fill3(dim, ss, A.sn, 1);
+    fill3(dim, slo, A.slo, 0);
+    fill3(dim, ext, A.ext, 1);
+    A.op           = op;
+    size_t const n = size_t(A.ext[0]) * A.ext[1] * A.ext[2];
+    if (n == 0)
+        return PHB_OK;
+    box_op_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(A);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+} // namespace phb
+
+extern "C" {
+int phb_box_op(phb_ctx* ctx, int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3],
+               const double* src, const uint32_t src_shape[3], const uint32_t src_lo[3], const uint32_t extent[3],
+               int op)
+{
+    if (!ctx || dim < 1 || dim > 3 || !dst || !src || op < 0 || op > 2)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_box_op: invalid argument");
+    return phb::box_op(ctx, dim, dst, dst_shape, dst_lo, src, src_shape, src_lo, extent, op);
+}
+int phb_box_pack(phb_ctx* ctx, int dim, const double* src, const uint32_t src_shape[3], const uint32_t src_lo[3],
+                 const uint32_t extent[3], double* buf)
+{
+    if (!ctx || dim < 1 || dim > 3 || !buf || !src)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_box_pack: invalid argument");
+    uint32_t const zero[3] = {0, 0, 0};
+    return phb::box_op(ctx, dim, buf, extent, zero, src, src_shape, src_lo, extent, 0);
+}
+int phb_box_unpack(phb_ctx* ctx, int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3],
+                   const uint32_t extent[3], const double* buf, int op)
+{
+    if (!ctx || dim < 1 || dim > 3 || !buf || !dst || op < 0 || op > 2)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_box_unpack: invalid argument");
+    uint32_t const zero[3] = {0, 0, 0};
+    return phb::box_op(ctx, dim, dst, dst_shape, dst_lo, buf, extent, zero, extent, op);
+}
+}

@@ -1,0 +1,255 @@
+"""Thin Python handle on the C ABI (include/phare_b200.h): a context, device arrays and the
+device-resident particle store.  Every compute call goes straight to libphare_b200.so; there is no
+numpy/torch implementation of any operator here, and nothing imports the oracle.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+
+class PhbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[phb status {code}] {msg}")
+        self.code = code
+
+
+class DeviceArray:
+    """A device allocation owned through phb_malloc."""
+
+    def __init__(self, ctx, shape, dtype=np.float64, zero=True):
+        self.ctx = ctx
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        self.size = int(np.prod(self.shape))
+        self.nbytes = self.size * self.dtype.itemsize
+        p = C.c_void_p()
+        ctx._check(ctx.lib.phb_malloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+        if zero:
+            self.zero()
+
+    def zero(self):
+        self.ctx._check(self.ctx.lib.phb_memset(self.ctx.h, self.ptr, 0, self.nbytes))
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.size == self.size, (host.shape, self.shape)
+        self.ctx._check(self.ctx.lib.phb_h2d(self.ctx.h, self.ptr, host.ctypes.data, self.nbytes))
+        self.ctx.sync()  # `host` may be a temporary
+        return self
+
+    def download(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        self.ctx._check(self.ctx.lib.phb_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.phb_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class DeviceVec:
+    """Three components of a vector quantity (VecField)."""
+
+    def __init__(self, ctx, layout, qty0, host=None):
+        self.comps = []
+        for c in range(3):
+            a = DeviceArray(ctx, ctx.field_shape(layout, qty0 + c))
+            if host is not None:
+                a.upload(host[c])
+            self.comps.append(a)
+        self.c = abi.VecField()
+        for c in range(3):
+            self.c.comp[c] = self.comps[c].ptr
+
+    def download(self):
+        return [a.download() for a in self.comps]
+
+    def __getitem__(self, i):
+        return self.comps[i]
+
+
+class DeviceParticles:
+    """Device-resident SoA particle store (replaces ParticleArray<dim>)."""
+
+    def __init__(self, ctx, capacity):
+        self.ctx = ctx
+        self.c = abi.Particles()
+        ctx._check(ctx.lib.phb_particles_alloc(ctx.h, int(capacity), C.byref(self.c)))
+
+    @property
+    def n(self):
+        return self.c.n
+
+    @n.setter
+    def n(self, v):
+        self.c.n = int(v)
+
+    @property
+    def capacity(self):
+        return self.c.capacity
+
+    def upload_soa(self, icell, delta, weight, charge, v):
+        """ContiguousParticles layout: icell (n,dim) int32, delta (n,dim), weight (n,), charge (n,), v (n,3)."""
+        n = len(weight)
+        icell = np.ascontiguousarray(icell, dtype=np.int32).reshape(n, self.ctx.dim)
+        delta = np.ascontiguousarray(delta, dtype=np.float64).reshape(n, self.ctx.dim)
+        weight = np.ascontiguousarray(weight, dtype=np.float64)
+        charge = np.ascontiguousarray(charge, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64).reshape(n, 3)
+        self.ctx._check(self.ctx.lib.phb_particles_from_soa(
+            self.ctx.h, icell.ctypes.data, delta.ctypes.data, weight.ctypes.data, charge.ctypes.data,
+            v.ctypes.data, n, C.byref(self.c)))
+        self.ctx.sync()
+        return self
+
+    def download_soa(self):
+        n, dim = self.c.n, self.ctx.dim
+        icell = np.empty((n, dim), np.int32)
+        delta = np.empty((n, dim))
+        weight = np.empty(n)
+        charge = np.empty(n)
+        v = np.empty((n, 3))
+        self.ctx._check(self.ctx.lib.phb_particles_to_soa(
+            self.ctx.h, C.byref(self.c), icell.ctypes.data, delta.ctypes.data, weight.ctypes.data,
+            charge.ctypes.data, v.ctypes.data))
+        return icell, delta, weight, charge, v
+
+    def upload_aos(self, raw):
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        stride = self.ctx.lib.phb_aos_stride(self.ctx.dim)
+        n = raw.size // stride
+        self.ctx._check(self.ctx.lib.phb_particles_from_aos(self.ctx.h, raw.ctypes.data, n, C.byref(self.c)))
+        self.ctx.sync()
+        return self
+
+    def download_aos(self):
+        stride = self.ctx.lib.phb_aos_stride(self.ctx.dim)
+        raw = np.zeros(self.c.n * stride, np.uint8)
+        self.ctx._check(self.ctx.lib.phb_particles_to_aos(self.ctx.h, C.byref(self.c), raw.ctypes.data))
+        return raw
+
+    def free(self):
+        if self.c.weight:
+            self.ctx.lib.phb_particles_free(self.ctx.h, C.byref(self.c))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """phb_ctx: one per (device, dim, interp_order)."""
+
+    def __init__(self, dim, interp, device=0, stream=None):
+        self.lib = abi.load()
+        self.dim, self.interp = dim, interp
+        h = C.c_void_p()
+        rc = self.lib.phb_create(device, dim, interp, C.byref(h))
+        if rc != abi.PHB_OK:
+            raise PhbError(rc, self.lib.phb_last_error(None).decode())
+        self.h = h
+        if stream is not None:
+            self._check(self.lib.phb_set_stream(self.h, C.c_void_p(stream)))
+
+    def _check(self, rc):
+        if rc != abi.PHB_OK:
+            raise PhbError(rc, self.lib.phb_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.phb_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._check(self.lib.phb_sync(self.h))
+
+    def set_exact(self, exact):
+        self._check(self.lib.phb_set_exact(self.h, 1 if exact else 0))
+
+    def poll_error(self):
+        self._check(self.lib.phb_poll_error(self.h))
+
+    @property
+    def launches(self):
+        return int(self.lib.phb_launch_count(self.h))
+
+    def field_shape(self, layout, qty):
+        s = (C.c_uint32 * 3)()
+        self.lib.phb_field_shape(C.byref(layout), qty, s)
+        return tuple(int(s[d]) for d in range(layout.dim))
+
+    # ---- operators (argument meaning == the reference functors, see include/phare_b200.h) ----
+    def push(self, layout, E, B, pin, pout, mass, dt, first_selector=None):
+        fs = C.byref(first_selector) if first_selector is not None else None
+        self._check(self.lib.phb_push(self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(pin.c),
+                                      C.byref(pout.c), mass, dt, fs))
+
+    def bin(self, layout, pin, pout, domain, keep, cell_start):
+        counts = (C.c_size_t * 3)()
+        self._check(self.lib.phb_bin(self.h, C.byref(layout), C.byref(pin.c), C.byref(pout.c), C.byref(domain),
+                                     abi.box_array(keep), len(keep), cell_start.ptr, counts))
+        return tuple(int(c) for c in counts)
+
+    def bin_nkeys(self, layout, domain):
+        return int(self.lib.phb_bin_nkeys(C.byref(layout), C.byref(domain)))
+
+    def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
+        n = C.c_size_t()
+        sh = (C.c_int * 3)(*([int(s) for s in shift] + [0] * (3 - len(shift)))) if shift is not None else None
+        self._check(self.lib.phb_export(self.h, C.byref(layout), C.byref(src.c), first, last, C.byref(box),
+                                        C.byref(minus) if minus is not None else None, sh, C.byref(dst.c),
+                                        C.byref(n)))
+        return int(n.value)
+
+    def deposit(self, layout, parts, rho_n, rho_q, flux, coef=1.0, first=0, last=None, sel=(), domain=None,
+                cell_start=None):
+        last = parts.n if last is None else last
+        self._check(self.lib.phb_deposit(
+            self.h, C.byref(layout), C.byref(parts.c), first, last, rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef,
+            abi.box_array(list(sel)), len(sel), C.byref(domain) if domain is not None else None,
+            cell_start.ptr if cell_start is not None else None))
+
+    def faraday(self, layout, B, E, Bnew, dt):
+        self._check(self.lib.phb_faraday(self.h, C.byref(layout), C.byref(B.c), C.byref(E.c), C.byref(Bnew.c), dt))
+
+    def ampere(self, layout, B, J):
+        self._check(self.lib.phb_ampere(self.h, C.byref(layout), C.byref(B.c), C.byref(J.c)))
+
+    def ohm(self, layout, n, Ve, Pe, B, J, Enew, eta, nu, hyper_mode=0):
+        self._check(self.lib.phb_ohm(self.h, C.byref(layout), n.ptr, C.byref(Ve.c), Pe.ptr, C.byref(B.c),
+                                     C.byref(J.c), C.byref(Enew.c), eta, nu, hyper_mode))
+
+    def electrons_update(self, layout, Ne, Vi, J, Te, Ve, Pe):
+        self._check(self.lib.phb_electrons_update(self.h, C.byref(layout), Ne.ptr, C.byref(Vi.c), C.byref(J.c), Te,
+                                                  C.byref(Ve.c), Pe.ptr))
+
+    def ions_totals(self, rho_n, rho_q, flux, mass, rho_q_tot, rho_m_tot, V):
+        npop = len(mass)
+        pn = (C.c_void_p * npop)(*[a.ptr for a in rho_n])
+        pq = (C.c_void_p * npop)(*[a.ptr for a in rho_q])
+        fl = (abi.VecField * npop)(*[f.c for f in flux])
+        ms = (C.c_double * npop)(*mass)
+        self._check(self.lib.phb_ions_totals(self.h, rho_q_tot.size, npop, pn, pq, fl, ms, rho_q_tot.ptr,
+                                             rho_m_tot.ptr, C.byref(V.c)))
+
+    def average(self, a, b, avg):
+        self._check(self.lib.phb_average(self.h, a.size, a.ptr, b.ptr, avg.ptr))
+
+    def box_op(self, dim, dst, dst_shape, dst_lo, src, src_shape, src_lo, extent, op):
+        u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))
+        dptr = dst.ptr if hasattr(dst, "ptr") else dst
+        sptr = src.ptr if hasattr(src, "ptr") else src
+        self._check(self.lib.phb_box_op(self.h, dim, dptr, u3(dst_shape), u3(dst_lo), sptr, u3(src_shape),
+                                        u3(src_lo), u3(extent), op))
