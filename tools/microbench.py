@@ -1,0 +1,110 @@
+"""Kernel micro-benchmarks on one B200 (CUDA events on the stream the kernels are launched on).
+Not the contract bench (that is bench.py); used to steer optimisation.  usage: python tools/microbench.py [cfg]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from phare_b200 import abi
+from phare_b200.device import Context
+from phare_b200.torch_interop import (TorchParticles, TorchArray, TorchVec, current_stream_ptr,
+                                      uniform_sorted_particles)
+
+HBM = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] \
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+
+CFGS = {
+    "c1": dict(dim=1, interp=1, ncells=[16384 * 64], ppc=100, dx=[0.2]),
+    "c2": dict(dim=1, interp=2, ncells=[500 * 2048], ppc=100, dx=[1.0]),
+    "c3": dict(dim=2, interp=1, ncells=[1024, 1024], ppc=100, dx=[0.4, 0.4]),
+    "c4": dict(dim=2, interp=3, ncells=[1024, 512], ppc=100, dx=[0.2, 0.2]),
+    "c5": dict(dim=3, interp=1, ncells=[128, 128, 128], ppc=64, dx=[0.2, 0.2, 0.2]),
+    "c5s": dict(dim=3, interp=1, ncells=[64, 64, 64], ppc=64, dx=[0.2, 0.2, 0.2]),
+}
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return min(ts), sum(ts) / len(ts)
+
+
+def run(name, cfg):
+    dim, interp = cfg["dim"], cfg["interp"]
+    dev = torch.device("cuda:0")
+    ctx = Context(dim, interp, device=0, stream=current_stream_ptr())
+    L = abi.make_layout(dim, interp, cfg["ncells"], cfg["dx"])
+    P = uniform_sorted_particles(ctx, L, cfg["ppc"], 0.3, dev)
+    n = P.n
+    Q = TorchParticles(dim, P.capacity, dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    E = TorchVec(ctx, L, abi.EX, dev)
+    B = TorchVec(ctx, L, abi.BX, dev)
+    for c in range(3):
+        E[c].t.normal_(0, 0.01, generator=g)
+        B[c].t.normal_(0, 0.01, generator=g)
+    B[0].t += 1.0
+    rn, rq = TorchArray(ctx.field_shape(L, abi.RHO), dev), TorchArray(ctx.field_shape(L, abi.RHO), dev)
+    F = TorchVec(ctx, L, abi.VX, dev)
+    lo = [0] * dim
+    hi = [cfg["ncells"][d] - 1 for d in range(dim)]
+    dom = abi.make_box(lo, hi)
+    pg = 1 if interp == 1 else 2
+    keep = [abi.make_box([l - pg for l in lo], [h + pg for h in hi])]
+    cs = TorchArray((ctx.bin_nkeys(L, dom) + 1,), dev, dtype=torch.int32)
+    bpp_push = {1: 80, 2: 104, 3: 128}[dim]
+    bpp_dep = {1: 52, 2: 64, 3: 76}[dim]
+    dt = 1e-3 * min(cfg["dx"]) / 0.2
+    out = {}
+
+    def report(label, ms, bytes_pp):
+        gbs = n * bytes_pp / ms / 1e6
+        out[label] = dict(ms=round(ms, 3), gparts_s=round(n / ms / 1e6, 2), gbs=round(gbs, 1), frac=round(gbs / HBM, 3))
+        print(f"{name:4s} {label:22s} {ms:9.3f} ms  {n / ms / 1e6:8.2f} Gp/s  {gbs:8.1f} GB/s  {gbs / HBM:6.3f} of HBM peak",
+              flush=True)
+
+    for exact in (True, False):
+        ctx.set_exact(exact)
+        ms, _ = timeit(lambda: ctx.push(L, E, B, P, Q, 1.0, dt))
+        report(f"push[{'exact' if exact else 'fma'}] oop", ms, bpp_push + 16)
+    ctx.set_exact(True)
+    # bin first so that cell_start is valid (P is sorted already, Q pushed)
+    counts = ctx.bin(L, Q, P, dom, keep, cs)
+    ms, _ = timeit(lambda: ctx.bin(L, Q, P, dom, keep, cs))
+    report("bin (count+scan+scatter)", ms, 2 * bpp_dep)
+    print("   counts", counts, flush=True)
+
+    def dep_cells():
+        ctx.deposit(L, P, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=counts[0])
+    ms, _ = timeit(dep_cells)
+    report("deposit[cells]", ms, bpp_dep)
+    if n <= 40_000_000:
+        ms, _ = timeit(lambda: ctx.deposit(L, P, rn, rq, F, sel=keep), iters=2, warm=1)
+        report("deposit[atomic]", ms, bpp_dep)
+    ms, _ = timeit(lambda: ctx.push(L, E, B, P, P, 1.0, 0.0))  # dt = 0: in place, store stays sorted
+    report("push[exact] in place", ms, bpp_push)
+    ctx.poll_error()
+    ctx.close()
+    return out
+
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or ["c5s", "c5", "c3", "c4", "c1", "c2"]
+    res = {}
+    for nm in names:
+        res[nm] = run(nm, CFGS[nm])
+        torch.cuda.empty_cache()
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
