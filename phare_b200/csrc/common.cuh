@@ -155,6 +155,7 @@ struct phb_ctx
 {
     int device = 0, dim = 0, interp = 0;
     bool exact            = true;
+    bool no_tma           = false; // PHB_NO_TMA=1: force the plain (non bulk-copy) kernels
     cudaStream_t stream   = nullptr;
     bool own_stream       = false;
     phb::DevError* d_err  = nullptr;

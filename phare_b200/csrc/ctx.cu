@@ -3,6 +3,7 @@
 
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace phb
 {
@@ -70,6 +71,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
         return PHB_ERR_CUDA;
     }
     ctx->own_stream = true;
+    if (const char* e = getenv("PHB_NO_TMA"))
+        ctx->no_tma = e[0] == '1';
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return PHB_OK;

@@ -29,22 +29,27 @@ __device__ __forceinline__ int start_shift(double delta)
 }
 
 // Weighter<ORDER>::computeWeight (interpolator.hpp:54-125) + indexAndWeights_ (:381-406).
-// l = local (ghost-offset) cell index; returns start index, fills w[ORDER+1]
+// l = local (ghost-offset) cell index, dl = double(l) (the reference converts its uint32 iCell);
+// returns the start index, fills w[ORDER+1].  double(start) is formed as dl - double(shift): both are
+// small integers, so the subtraction is exact and equals the reference's int -> double conversion
+// (saves the slow I2F.F64 per centering and direction).
 template<int ORDER, int CENTER>
-__device__ __forceinline__ int index_and_weights(int l, double delta, double (&w)[ORDER + 1])
+__device__ __forceinline__ int index_and_weights(int l, double dl, double delta, double (&w)[ORDER + 1])
 {
-    int const start = l - start_shift<ORDER, CENTER>(delta);
-    double x        = double(unsigned(l)) + delta; // iCell is uint32 in the reference
+    int const shift    = start_shift<ORDER, CENTER>(delta);
+    int const start    = l - shift;
+    double const dstart = dl - double(shift); // shift in {0,1,2}: a select of constants, no conversion
+    double x           = dl + delta;
     if constexpr (CENTER == DUAL)
         x -= .5;
     if constexpr (ORDER == 1)
     {
-        w[1] = x - double(start);
+        w[1] = x - dstart;
         w[0] = 1. - w[1];
     }
     else if constexpr (ORDER == 2)
     {
-        double const d     = double(start + 1) - x;
+        double const d     = (dstart + 1.) - x; // double(start + 1), exact
         double const coef1 = 0.5 + d, coef2 = d, coef3 = 0.5 - d;
         w[0] = 0.5 * coef1 * coef1;
         w[1] = 0.75 - coef2 * coef2;
@@ -53,7 +58,7 @@ __device__ __forceinline__ int index_and_weights(int l, double delta, double (&w
     else
     {
         constexpr double _4_over_3 = 4. / 3., _2_over_3 = 2. / 3.;
-        double const index = double(start) - x;
+        double const index = dstart - x;
         double const coef1 = 1. + 0.5 * index, coef2 = index + 1, coef3 = index + 2;
         double const coef4 = 1. - 0.5 * (index + 3);
         double const coef2_sq = coef2 * coef2, coef2_cub = coef2_sq * coef2;
@@ -64,6 +69,11 @@ __device__ __forceinline__ int index_and_weights(int l, double delta, double (&w
         w[3] = _4_over_3 * coef4 * coef4 * coef4;
     }
     return start;
+}
+template<int ORDER, int CENTER>
+__device__ __forceinline__ int index_and_weights(int l, double delta, double (&w)[ORDER + 1])
+{
+    return index_and_weights<ORDER, CENTER>(l, double(unsigned(l)), delta, w);
 }
 
 template<int DIM, int ORDER>
@@ -80,38 +90,45 @@ __device__ __forceinline__ void both_centerings(const DevLayout& L, const int* i
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
     {
-        int const l       = icell[d] - (L.amr_lower[d] - L.g); // AMRToLocal, gridlayout.hpp:746-763
-        iw.start[DUAL][d]   = index_and_weights<ORDER, DUAL>(l, delta[d], iw.w[DUAL][d]);
-        iw.start[PRIMAL][d] = index_and_weights<ORDER, PRIMAL>(l, delta[d], iw.w[PRIMAL][d]);
+        int const l     = icell[d] - (L.amr_lower[d] - L.g); // AMRToLocal, gridlayout.hpp:746-763
+        double const dl = double(unsigned(l));
+        iw.start[DUAL][d]   = index_and_weights<ORDER, DUAL>(l, dl, delta[d], iw.w[DUAL][d]);
+        iw.start[PRIMAL][d] = index_and_weights<ORDER, PRIMAL>(l, dl, delta[d], iw.w[PRIMAL][d]);
     }
 }
 
-// MeshToParticle<DIM>::operator(), interpolator.hpp:152-264: nested z -> y -> x accumulation
-template<int DIM, int ORDER, int QTY, bool EXACT, typename Load>
-__device__ __forceinline__ double gather(const IndexWeights<DIM, ORDER>& iw, Load&& load)
+// MeshToParticle<DIM>::operator(), interpolator.hpp:152-264: nested z -> y -> x accumulation.
+// One base pointer per component, one row pointer per (ix,iy), immediate offsets along the row.
+template<int DIM, int ORDER, int QTY, bool EXACT>
+__device__ __forceinline__ double gather(const IndexWeights<DIM, ORDER>& iw, const FieldView& f)
 {
     constexpr int cx = centering(QTY, 0), cy = centering(QTY, 1), cz = centering(QTY, 2);
     double F = 0.;
     if constexpr (DIM == 1)
     {
+        const double* row = f.p + iw.start[cx][0];
 #pragma unroll
         for (int ix = 0; ix <= ORDER; ++ix)
-            F = mad<EXACT>(load(iw.start[cx][0] + ix, 0, 0), iw.w[cx][0][ix], F);
+            F = mad<EXACT>(__ldg(row + ix), iw.w[cx][0][ix], F);
     }
     else if constexpr (DIM == 2)
     {
+        const double* base = f.p + (iw.start[cx][0] * f.n[1] + iw.start[cy][1]);
 #pragma unroll
         for (int ix = 0; ix <= ORDER; ++ix)
         {
-            double Y = 0.;
+            const double* row = base + ix * f.n[1];
+            double Y          = 0.;
 #pragma unroll
             for (int iy = 0; iy <= ORDER; ++iy)
-                Y = mad<EXACT>(load(iw.start[cx][0] + ix, iw.start[cy][1] + iy, 0), iw.w[cy][1][iy], Y);
+                Y = mad<EXACT>(__ldg(row + iy), iw.w[cy][1][iy], Y);
             F = mad<EXACT>(Y, iw.w[cx][0][ix], F);
         }
     }
     else
     {
+        int const s1 = f.n[2], s0 = f.n[1] * f.n[2];
+        const double* base = f.p + (iw.start[cx][0] * s0 + iw.start[cy][1] * s1 + iw.start[cz][2]);
 #pragma unroll
         for (int ix = 0; ix <= ORDER; ++ix)
         {
@@ -119,11 +136,11 @@ __device__ __forceinline__ double gather(const IndexWeights<DIM, ORDER>& iw, Loa
 #pragma unroll
             for (int iy = 0; iy <= ORDER; ++iy)
             {
-                double Z = 0.;
+                const double* row = base + (ix * s0 + iy * s1);
+                double Z          = 0.;
 #pragma unroll
                 for (int iz = 0; iz <= ORDER; ++iz)
-                    Z = mad<EXACT>(load(iw.start[cx][0] + ix, iw.start[cy][1] + iy, iw.start[cz][2] + iz),
-                                   iw.w[cz][2][iz], Z);
+                    Z = mad<EXACT>(__ldg(row + iz), iw.w[cz][2][iz], Z);
                 Y = mad<EXACT>(Z, iw.w[cy][1][iy], Y);
             }
             F = mad<EXACT>(Y, iw.w[cx][0][ix], F);
@@ -174,26 +191,23 @@ __device__ __forceinline__ void boris(double (&v)[3], double charge, double dto2
 
 // BorisPusher::advancePosition_, boris.hpp:156-172 (always unfused: it decides the cell index)
 template<int DIM>
-__device__ __forceinline__ bool advance_position(const double* h, int* icell, double* delta, const double* v,
-                                                 double& bad_delta, double& bad_vel)
+__device__ __forceinline__ void advance_position(const double* h, int* icell, double* delta, const double* v,
+                                                 bool& ok, double& bad_delta, double& bad_vel)
 {
-    bool ok = true;
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
     {
         double const t = __dadd_rn(delta[d], __dmul_rn(h[d], v[d]));
-        if (fabs(t) > 2)
+        if (fabs(t) > 2 && ok) // the reference throws at the first offending direction
         {
             ok        = false;
             bad_delta = t;
             bad_vel   = v[d];
         }
-        double const fl = floor(t);
-        int const s     = int(fl);
-        delta[d]        = t - double(s);
+        int const s = int(floor(t));
+        delta[d]    = t - double(s);
         icell[d] += s;
     }
-    return ok;
 }
 
 } // namespace phb

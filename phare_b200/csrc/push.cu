@@ -11,6 +11,9 @@
 // two-address broadcast that hits L1/L2; field arrays are (o+1)^d-fold reused and never the
 // HBM bound.
 #include "particle_math.cuh"
+#include "pipeline.cuh"
+
+#include <algorithm>
 
 namespace phb
 {
@@ -28,33 +31,14 @@ struct PushParams
     bool copy_weight_charge;
 };
 
+// the per-particle work shared by both kernels: pre-push, (first selector), gather, Boris, post-push
 template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
-__global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushParams<DIM> P)
+__device__ __forceinline__ void push_particle(const PushParams<DIM>& P, size_t i, int (&icell)[DIM],
+                                              double (&delta)[DIM], double (&v)[3], double charge)
 {
-    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= P.n)
-        return;
-
-    int icell[DIM];
-    double delta[DIM], v[3];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d)
-    {
-        icell[d] = __ldcs(P.in.icell[d] + i);
-        delta[d] = __ldcs(P.in.delta[d] + i);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        v[c] = __ldcs(P.in.v[c] + i);
-    double const charge = __ldcs(P.in.charge + i);
-    if (P.copy_weight_charge)
-    {
-        __stcs(P.out.charge + i, charge);
-        __stcs(P.out.weight + i, __ldcs(P.in.weight + i));
-    }
-
     double bad_delta = 0, bad_vel = 0;
-    bool ok = advance_position<DIM>(P.h, icell, delta, v, bad_delta, bad_vel);
+    bool ok = true;
+    advance_position<DIM>(P.h, icell, delta, v, ok, bad_delta, bad_vel);
 
     bool selected = true;
     if constexpr (HAS_FIRST)
@@ -65,17 +49,14 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushP
         IndexWeights<DIM, ORDER> iw;
         both_centerings<DIM, ORDER>(P.L, icell, delta, iw);
         double E[3], B[3];
-        auto ld = [](const FieldView& f) {
-            return [&f](int a, int b, int c) { return __ldg(f.p + f.at(a, b, c)); };
-        };
-        E[0] = gather<DIM, ORDER, PHB_EX, EXACT>(iw, ld(P.E[0]));
-        E[1] = gather<DIM, ORDER, PHB_EY, EXACT>(iw, ld(P.E[1]));
-        E[2] = gather<DIM, ORDER, PHB_EZ, EXACT>(iw, ld(P.E[2]));
-        B[0] = gather<DIM, ORDER, PHB_BX, EXACT>(iw, ld(P.B[0]));
-        B[1] = gather<DIM, ORDER, PHB_BY, EXACT>(iw, ld(P.B[1]));
-        B[2] = gather<DIM, ORDER, PHB_BZ, EXACT>(iw, ld(P.B[2]));
+        E[0] = gather<DIM, ORDER, PHB_EX, EXACT>(iw, P.E[0]);
+        E[1] = gather<DIM, ORDER, PHB_EY, EXACT>(iw, P.E[1]);
+        E[2] = gather<DIM, ORDER, PHB_EZ, EXACT>(iw, P.E[2]);
+        B[0] = gather<DIM, ORDER, PHB_BX, EXACT>(iw, P.B[0]);
+        B[1] = gather<DIM, ORDER, PHB_BY, EXACT>(iw, P.B[1]);
+        B[2] = gather<DIM, ORDER, PHB_BZ, EXACT>(iw, P.B[2]);
         boris<EXACT>(v, charge, P.dto2m, E, B);
-        ok = advance_position<DIM>(P.h, icell, delta, v, bad_delta, bad_vel) && ok;
+        advance_position<DIM>(P.h, icell, delta, v, ok, bad_delta, bad_vel);
     }
 
 #pragma unroll
@@ -96,29 +77,181 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushP
     }
 }
 
+// plain kernel: any alignment, any count; used for the ragged tail and for foreign (unaligned) stores
+template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
+__global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushParams<DIM> P, size_t first)
+{
+    size_t const i = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P.n)
+        return;
+    int icell[DIM];
+    double delta[DIM], v[3];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+    {
+        icell[d] = __ldcs(P.in.icell[d] + i);
+        delta[d] = __ldcs(P.in.delta[d] + i);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        v[c] = __ldcs(P.in.v[c] + i);
+    double const charge = __ldcs(P.in.charge + i);
+    if (P.copy_weight_charge)
+    {
+        __stcs(P.out.charge + i, charge);
+        __stcs(P.out.weight + i, __ldcs(P.in.weight + i));
+    }
+    push_particle<DIM, ORDER, EXACT, HAS_FIRST>(P, i, icell, delta, v, charge);
+}
+
+// TMA kernel: 256-particle tiles of every needed column are streamed into a ring of shared-memory
+// stages with cp.async.bulk (completion on an mbarrier).  The 8 warps of the CTA pick their
+// particle out of the stage, release it at once, and do gather + Boris + stores while the next
+// PUSH_STAGES-1 tiles are already in flight (thread 0 issues the copies; no warp is set aside, so
+// three CTAs stay resident per SM).  Persistent CTAs, tiles handed out round-robin.
+constexpr int PUSH_TILE   = 256;
+constexpr int PUSH_STAGES = 3;
+template<int DIM> __host__ __device__ constexpr int push_ncol8(bool copy_wq) { return DIM + 3 + 1 + (copy_wq ? 1 : 0); }
+template<int DIM> __host__ __device__ constexpr int push_stage_bytes(bool copy_wq)
+{
+    return PUSH_TILE * (8 * push_ncol8<DIM>(copy_wq) + 4 * DIM);
+}
+
+template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool COPY_WQ>
+__global__ void __launch_bounds__(PUSH_TILE, 3)
+    push_tma_kernel(const __grid_constant__ PushParams<DIM> P, unsigned ntiles)
+{
+    constexpr int NC8   = push_ncol8<DIM>(COPY_WQ);
+    constexpr int BYTES = push_stage_bytes<DIM>(COPY_WQ);
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full  = reinterpret_cast<uint64_t*>(smem + PUSH_STAGES * BYTES);
+    uint64_t* empty = full + PUSH_STAGES;
+
+    // number of tiles this CTA processes: blockIdx.x, blockIdx.x + gridDim.x, ...
+    unsigned const my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    uint64_t pol = 0;
+    // producer step j: fill stage j % STAGES with this CTA's j-th tile (thread 0 only)
+    auto issue = [&](unsigned j) {
+        int const s = j % PUSH_STAGES;
+        mbar_wait(empty + s, ((j / PUSH_STAGES) & 1) ^ 1);
+        mbar_expect_tx(full + s, BYTES);
+        unsigned char* st = smem + s * BYTES;
+        size_t const i0   = (size_t(blockIdx.x) + size_t(j) * gridDim.x) * PUSH_TILE;
+        int c8            = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+            bulk_g2s(st + (c8++) * PUSH_TILE * 8, P.in.delta[d] + i0, PUSH_TILE * 8, full + s, pol);
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            bulk_g2s(st + (c8++) * PUSH_TILE * 8, P.in.v[c] + i0, PUSH_TILE * 8, full + s, pol);
+        bulk_g2s(st + (c8++) * PUSH_TILE * 8, P.in.charge + i0, PUSH_TILE * 8, full + s, pol);
+        if constexpr (COPY_WQ)
+            bulk_g2s(st + (c8++) * PUSH_TILE * 8, P.in.weight + i0, PUSH_TILE * 8, full + s, pol);
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+            bulk_g2s(st + NC8 * PUSH_TILE * 8 + d * PUSH_TILE * 4, P.in.icell[d] + i0, PUSH_TILE * 4, full + s, pol);
+    };
+
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < PUSH_STAGES; ++s)
+        {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, PUSH_TILE / 32);
+        }
+        mbar_fence_init();
+        pol = policy_evict_first();
+        for (unsigned j = 0; j < PUSH_STAGES - 1 && j < my_tiles; ++j)
+            issue(j);
+    }
+    __syncthreads();
+
+    for (unsigned it = 0; it < my_tiles; ++it)
+    {
+        if (threadIdx.x == 0 && it + PUSH_STAGES - 1 < my_tiles)
+            issue(it + PUSH_STAGES - 1);
+        int const s = it % PUSH_STAGES;
+        mbar_wait(full + s, (it / PUSH_STAGES) & 1);
+        const double* c8 = reinterpret_cast<const double*>(smem + s * BYTES);
+        const int* c4    = reinterpret_cast<const int*>(smem + s * BYTES + NC8 * PUSH_TILE * 8);
+        int icell[DIM];
+        double delta[DIM], v[3];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+        {
+            delta[d] = c8[d * PUSH_TILE + threadIdx.x];
+            icell[d] = c4[d * PUSH_TILE + threadIdx.x];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            v[c] = c8[(DIM + c) * PUSH_TILE + threadIdx.x];
+        double const charge = c8[(DIM + 3) * PUSH_TILE + threadIdx.x];
+        double weight       = 0;
+        if constexpr (COPY_WQ)
+            weight = c8[(DIM + 4) * PUSH_TILE + threadIdx.x];
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0)
+            mbar_arrive(empty + s); // the stage can be refilled while we compute
+        size_t const i = (size_t(blockIdx.x) + size_t(it) * gridDim.x) * PUSH_TILE + threadIdx.x;
+        if constexpr (COPY_WQ)
+        {
+            __stcs(P.out.charge + i, charge);
+            __stcs(P.out.weight + i, weight);
+        }
+        push_particle<DIM, ORDER, EXACT, HAS_FIRST>(P, i, icell, delta, v, charge);
+    }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
+int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P)
+{
+    // full tiles through the TMA kernel when every input column is 16-byte aligned
+    bool tma_ok = aligned16(P.in.charge) && aligned16(P.in.weight);
+    for (int d = 0; d < DIM; ++d)
+        tma_ok = tma_ok && aligned16(P.in.icell[d]) && aligned16(P.in.delta[d]);
+    for (int c = 0; c < 3; ++c)
+        tma_ok = tma_ok && aligned16(P.in.v[c]);
+    size_t const ntiles = tma_ok && !ctx->no_tma ? P.n / PUSH_TILE : 0;
+    if (ntiles)
+    {
+        bool const wq      = P.copy_weight_charge;
+        size_t const smem  = size_t(PUSH_STAGES) * push_stage_bytes<DIM>(wq) + 2 * PUSH_STAGES * sizeof(uint64_t);
+        unsigned const grid = unsigned(std::min<size_t>(ntiles, size_t(ctx->sm_count) * 3));
+        auto launch = [&](auto kernel) -> int {
+            PHB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            kernel<<<grid, PUSH_TILE, smem, ctx->stream>>>(P, unsigned(ntiles));
+            PHB_LAUNCH_CHECK(ctx);
+            return PHB_OK;
+        };
+        int const rc = wq ? launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, true>)
+                          : launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, false>);
+        if (rc)
+            return rc;
+    }
+    size_t const first = ntiles * PUSH_TILE;
+    if (first < P.n)
+    {
+        constexpr int BS = 256;
+        push_kernel<DIM, ORDER, EXACT, HAS_FIRST><<<unsigned((P.n - first + BS - 1) / BS), BS, 0, ctx->stream>>>(P, first);
+        PHB_LAUNCH_CHECK(ctx);
+    }
+    return PHB_OK;
+}
+
 template<int DIM, int ORDER>
 int launch_push(phb_ctx* ctx, const PushParams<DIM>& P, bool has_first)
 {
     if (P.n == 0)
         return PHB_OK;
-    constexpr int BS = 256;
-    unsigned const grid = unsigned((P.n + BS - 1) / BS);
     if (ctx->exact)
-    {
-        if (has_first)
-            push_kernel<DIM, ORDER, true, true><<<grid, BS, 0, ctx->stream>>>(P);
-        else
-            push_kernel<DIM, ORDER, true, false><<<grid, BS, 0, ctx->stream>>>(P);
-    }
-    else
-    {
-        if (has_first)
-            push_kernel<DIM, ORDER, false, true><<<grid, BS, 0, ctx->stream>>>(P);
-        else
-            push_kernel<DIM, ORDER, false, false><<<grid, BS, 0, ctx->stream>>>(P);
-    }
-    PHB_LAUNCH_CHECK(ctx);
-    return PHB_OK;
+        return has_first ? launch_push_variant<DIM, ORDER, true, true>(ctx, P)
+                         : launch_push_variant<DIM, ORDER, true, false>(ctx, P);
+    return has_first ? launch_push_variant<DIM, ORDER, false, true>(ctx, P)
+                     : launch_push_variant<DIM, ORDER, false, false>(ctx, P);
 }
 
 template<int DIM>

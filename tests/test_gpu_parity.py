@@ -85,7 +85,9 @@ def test_push_fma_mode_within_1e12(ctxs, cpu_oracle, dim, interp):
     gi, gd, _, _, gv = pin.download_soa()
     wi, wd, _, _, wv = want.soa()
     assert np.array_equal(gi, wi)  # cells still bit-exact on this input
-    assert np.max(np.abs(gv - wv) / (np.abs(wv) + 1e-300)) <= 1e-12
+    # <= 1e-12 relative to the particle's speed (a component that nearly cancels has no relative meaning)
+    speed = np.linalg.norm(wv, axis=1, keepdims=True)
+    assert np.max(np.abs(gv - wv) / speed) <= 1e-12
     assert np.max(np.abs(gd - wd)) <= 1e-12
 
 
