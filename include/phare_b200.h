@@ -202,6 +202,19 @@ int phb_box_pack(phb_ctx*, int dim, const double* src, const uint32_t src_shape[
 int phb_box_unpack(phb_ctx*, int dim, double* dst, const uint32_t dst_shape[3],
                    const uint32_t dst_lo[3], const uint32_t extent[3], const double* buf, int op);
 
+/* batched form: one launch executes `nops` box operations (a whole exchange phase).  Descriptors are
+ * in DEVICE memory; shapes/lows/extents are padded with 1/0/1 in unused trailing directions;
+ * `first` = running sum of the element counts of the preceding descriptors. Overlapping
+ * destinations inside one batch are only allowed for op 0 with identical values and op 2. */
+typedef struct {
+    double*       dst;
+    const double* src;
+    uint32_t      dst_shape[3], dst_lo[3], src_shape[3], src_lo[3], ext[3];
+    int32_t       op;
+    uint64_t      first;
+} phb_box_desc;
+int phb_box_op_batch(phb_ctx*, const phb_box_desc* d_ops, int nops, uint64_t total_elements);
+
 #ifdef __cplusplus
 }
 #endif

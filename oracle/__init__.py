@@ -338,7 +338,9 @@ class Cpu:
             raise RuntimeError(self.lib.phr_last_error().decode())
         for i in range(npop):  # sizes were updated in the struct copies
             domain[i].n, patch_ghost[i].n, level_ghost[i].n = dom[i].n, pg[i].n, lg[i].n
-        return dict(rho_n=rho_n, rho_q=rho_q, flux=flux, rho_q_tot=q, rho_m_tot=m, V=V)
+        self.lib.phr_last_seconds.restype = C.c_double
+        return dict(rho_n=rho_n, rho_q=rho_q, flux=flux, rho_q_tot=q, rho_m_tot=m, V=V,
+                    seconds=float(self.lib.phr_last_seconds()))
 
     def maxwellian(self, layout, n, V, Vth, charge, ppc, seed):
         """MaxwellianParticleInitializer::loadParticles with per-cell profile arrays (row-major over the patch)."""

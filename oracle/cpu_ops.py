@@ -1,0 +1,235 @@
+"""TEST INFRASTRUCTURE — CPU back end for phare_b200.solver (same `ops` interface as GpuOps) built on the
+oracle (phare_oracle.c).  Injected by tests to cross-check the step orchestration and the messenger
+plans against the CUDA path, and by bench.py's cpu_baseline / --impl reference legs.  Never imported
+by the product package."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from phare_b200 import abi
+from . import Cpu, HostParticles, host_vec
+
+
+class Arr:
+    def __init__(self, a):
+        self.a = a
+        self.shape = tuple(a.shape)
+        self.size = a.size
+
+    @property
+    def ptr(self):
+        return self.a.ctypes.data
+
+
+class Vec:
+    def __init__(self, comps):
+        self.comps = comps
+        self.c = abi.VecField()
+        for k in range(3):
+            self.c.comp[k] = comps[k].a.ctypes.data
+
+    def __getitem__(self, i):
+        return self.comps[i]
+
+
+class CpuOps:
+    def __init__(self, dim, interp, impl="oracle"):
+        self.cpu = Cpu(impl) if impl != "oracle" else Cpu("oracle")
+        self.orc = Cpu("oracle")
+        self.lib = self.orc.lib
+        self.dim, self.interp = dim, interp
+        self.err = 0
+        self.last_error = ""
+
+    # ---- memory
+    def field(self, layout, qty):
+        return Arr(np.zeros(self.orc.field_shape(layout, qty)))
+
+    def vec(self, layout, qty0):
+        return Vec([self.field(layout, qty0 + c) for c in range(3)])
+
+    def zero(self, h):
+        h.a[...] = 0.
+
+    def copy(self, dst, src):
+        dst.a[...] = src.a
+
+    def set_field(self, h, host):
+        h.a[...] = host
+
+    def get_field(self, h):
+        return h.a.copy()
+
+    def particles(self, capacity):
+        return HostParticles(self.dim, capacity)
+
+    def set_particles(self, store, icell, delta, weight, charge, v):
+        n = len(weight)
+        for d in range(self.dim):
+            store.icell[d][:n] = icell[:, d]
+            store.delta[d][:n] = delta[:, d]
+        for k in range(3):
+            store.v[k][:n] = v[:, k]
+        store.weight[:n] = weight
+        store.charge[:n] = charge
+        store.n = n
+
+    def get_particles(self, store, first=0, last=None):
+        last = store.n if last is None else last
+        ic, de, w, q, v = store.soa()
+        return ic[first:last], de[first:last], w[first:last], q[first:last], v[first:last]
+
+    def count(self, store):
+        return store.n
+
+    def set_count(self, store, n):
+        store.n = n
+
+    def capacity(self, store):
+        return int(store.c.capacity)
+
+    def alias_weight_charge(self, store, other):
+        return store  # the CPU push copies weight and charge like the reference
+
+    def particles_copy(self, src, first, count, dst, dst_first):
+        for d in range(self.dim):
+            dst.icell[d][dst_first:dst_first + count] = src.icell[d][first:first + count]
+            dst.delta[d][dst_first:dst_first + count] = src.delta[d][first:first + count]
+        for k in range(3):
+            dst.v[k][dst_first:dst_first + count] = src.v[k][first:first + count]
+        dst.weight[dst_first:dst_first + count] = src.weight[first:first + count]
+        dst.charge[dst_first:dst_first + count] = src.charge[first:first + count]
+        dst.n = max(dst.n, dst_first + count)
+
+    def cell_start(self, nkeys):
+        return Arr(np.zeros(nkeys + 1, np.uint32))
+
+    def bin_nkeys(self, layout, domain):
+        self.lib.pho_bin_nkeys.restype = C.c_size_t
+        return int(self.lib.pho_bin_nkeys(C.byref(layout), C.byref(domain)))
+
+    # ---- operators
+    def push(self, layout, E, B, pin, pout, mass, dt, first_selector=None):
+        ed, ev = C.c_double(), C.c_double()
+        fs = C.byref(first_selector) if first_selector is not None else None
+        rc = self.lib.pho_push(C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(pin.c), C.byref(pout.c),
+                               C.c_double(mass), C.c_double(dt), fs, C.byref(ed), C.byref(ev))
+        if rc and not self.err:
+            self.err, self.last_error = rc, f"Particle moved 2 cells with delta/vel: {ed.value:g}/{ev.value:g}"
+
+    def deposit(self, layout, parts, rho_n, rho_q, F, coef=1.0, first=0, last=None, sel=(), domain=None,
+                cell_start=None):
+        last = parts.n if last is None else last
+        rc = self.lib.pho_deposit(C.byref(layout), C.byref(parts.c), C.c_size_t(first), C.c_size_t(last),
+                                  C.c_void_p(rho_n.ptr), C.c_void_p(rho_q.ptr), C.byref(F.c), C.c_double(coef),
+                                  abi.box_array(list(sel)), C.c_int(len(sel)))
+        assert rc == 0
+
+    def bin(self, layout, pin, pout, domain, keep, cell_start):
+        counts = (C.c_size_t * 3)()
+        rc = self.lib.pho_bin(C.byref(layout), C.byref(pin.c), C.byref(pout.c), C.byref(domain),
+                              abi.box_array(list(keep)), C.c_int(len(keep)), C.c_void_p(cell_start.ptr), counts)
+        assert rc == 0, rc
+        return tuple(int(c) for c in counts)
+
+    def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
+        if not isinstance(box, abi.Box):
+            box = abi.make_box(box.lo, box.hi)
+        n = C.c_size_t()
+        sh = (C.c_int * 3)(*([int(s) for s in shift] + [0] * (3 - len(shift)))) if shift is not None else None
+        rc = self.lib.pho_export(C.byref(layout), C.byref(src.c), C.c_size_t(first), C.c_size_t(last), C.byref(box),
+                                 C.byref(minus) if minus is not None else None, sh, C.byref(dst.c), C.byref(n))
+        assert rc == 0, rc
+        return int(n.value)
+
+    def faraday(self, layout, B, E, Bnew, dt):
+        assert self.lib.pho_faraday(C.byref(layout), C.byref(B.c), C.byref(E.c), C.byref(Bnew.c), C.c_double(dt)) == 0
+
+    def ampere(self, layout, B, J):
+        assert self.lib.pho_ampere(C.byref(layout), C.byref(B.c), C.byref(J.c)) == 0
+
+    def ohm(self, layout, n, Ve, Pe, B, J, Enew, eta, nu, hyper_mode):
+        assert self.lib.pho_ohm(C.byref(layout), C.c_void_p(n.ptr), C.byref(Ve.c), C.c_void_p(Pe.ptr), C.byref(B.c),
+                                C.byref(J.c), C.byref(Enew.c), C.c_double(eta), C.c_double(nu), C.c_int(hyper_mode)) == 0
+
+    def electrons_update(self, layout, Ne, Vi, J, Te, Ve, Pe):
+        assert self.lib.pho_electrons_update(C.byref(layout), C.c_void_p(Ne.ptr), C.byref(Vi.c), C.byref(J.c),
+                                             C.c_double(Te), C.byref(Ve.c), C.c_void_p(Pe.ptr)) == 0
+
+    def ions_totals(self, rho_n, rho_q, flux, mass, rho_q_tot, rho_m_tot, V):
+        npop = len(mass)
+        pn = (C.c_void_p * npop)(*[a.ptr for a in rho_n])
+        pq = (C.c_void_p * npop)(*[a.ptr for a in rho_q])
+        fl = (abi.VecField * npop)(*[f.c for f in flux])
+        ms = (C.c_double * npop)(*mass)
+        assert self.lib.pho_ions_totals(C.c_size_t(rho_q_tot.size), C.c_int(npop), pn, pq, fl, ms,
+                                        C.c_void_p(rho_q_tot.ptr), C.c_void_p(rho_m_tot.ptr), C.byref(V.c)) == 0
+
+    def average(self, a, b, avg):
+        assert self.lib.pho_average(C.c_size_t(a.size), C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(avg.ptr)) == 0
+
+    def poll_error(self):
+        rc, self.err = self.err, 0
+        return rc
+
+    def sync(self):
+        pass
+
+    # ---- box ops
+    def compile_box_ops(self, entries):
+        return entries or None
+
+    def run_box_ops(self, compiled):
+        if not compiled:
+            return
+        u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))
+        for (dst, dlo, src, slo, ext, op) in compiled:
+            rc = self.lib.pho_box_op(C.c_int(len(ext)), C.c_void_p(dst.ptr), u3(dst.shape), u3(dlo),
+                                     C.c_void_p(src.ptr), u3(src.shape), u3(slo), u3(ext), C.c_int(op))
+            assert rc == 0
+
+    def new_buffer(self, n):
+        return Arr(np.zeros(max(int(n), 0)))
+
+    def buffer_slice(self, buf, off, ext):
+        n = int(np.prod(ext))
+        return Arr(buf.a[off:off + n].reshape([int(e) for e in ext]))
+
+    def as_tensor(self, buf):
+        return torch.from_numpy(buf.a if isinstance(buf, Arr) else buf)
+
+    def size(self, buf):
+        return (buf.a if isinstance(buf, Arr) else buf).size
+
+    # ---- particle staging
+    def staging_particles(self, layout, capacity):
+        return HostParticles(self.dim, capacity)
+
+    def grow_particles(self, layout, store, capacity):
+        return store.copy(capacity=int(capacity * 1.5) + 16)
+
+    def _columns(self, s):
+        return list(s.icell) + list(s.delta) + list(s.v) + [s.weight, s.charge]
+
+    def particle_bytes(self):
+        return 4 * self.dim + 8 * self.dim + 24 + 16
+
+    def pack_particles(self, layout, stores):
+        chunks = []
+        for ci in range(len(self._columns(stores[0]))):
+            for s in stores:
+                chunks.append(self._columns(s)[ci][:s.n].view(np.uint8))
+        return np.concatenate(chunks) if chunks else np.zeros(0, np.uint8)
+
+    def new_particle_buffer(self, layout, total):
+        return np.zeros(total * self.particle_bytes(), np.uint8)
+
+    def unpack_particles(self, layout, buf, off, n, total, dst):
+        base = 0
+        for col in self._columns(dst):
+            esz = col.itemsize
+            raw = buf[base + off * esz: base + (off + n) * esz]
+            col[dst.n:dst.n + n] = raw.view(col.dtype)
+            base += total * esz
+        dst.n = dst.n + n

@@ -845,7 +845,7 @@ int pho_box_op(int dim, double* dst, const uint32_t ds[3], const uint32_t dlo[3]
                 else if (op == 1)
                     dst[pd] += src[ps];
                 else
-                    dst[pd] = dst[pd] > src[ps] ? dst[pd] : src[ps]; /* std::max(d, d0) */
+                    dst[pd] = (dst[pd] < src[ps]) ? src[ps] : dst[pd]; /* std::max(d, d0): NaN d stays, NaN d0 ignored */
             }
     return 0;
 }

@@ -26,6 +26,7 @@
 
 #include "../../include/phare_b200.h"
 
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -37,6 +38,7 @@ using namespace PHARE::core;
 namespace
 {
 thread_local std::string g_err;
+thread_local double g_seconds = 0; // time spent inside the reference calls of the last phr_* (excludes AoS staging)
 
 template<std::size_t dim, std::size_t interp>
 struct Ref
@@ -401,10 +403,12 @@ struct Ref
         initializer::PHAREDict ud;
         ud["pusher"]["name"] = std::string{"modified_boris"};
         Updater_t updater{ud};
+        auto const t0 = std::chrono::steady_clock::now();
         updater.updatePopulations(*h.ions, em, boxing, dt,
                                   mode == 1 ? UpdaterMode::domain_only : UpdaterMode::all);
         if (do_update_ions)
             updater.updateIons(*h.ions);
+        g_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         for (int i = 0; i < npop; ++i)
         {
             if (int rc = store(*h.domain[i], domain[i]))
@@ -479,6 +483,7 @@ int dispatch(int dim, int interp, Fn&& fn)
 extern "C" {
 
 const char* phr_last_error() { return g_err.c_str(); }
+double phr_last_seconds() { return g_seconds; }
 
 size_t phr_aos_stride(int dim)
 {

@@ -43,6 +43,12 @@ class Particles(C.Structure):
                 ("weight", C.c_void_p), ("charge", C.c_void_p), ("n", C.c_size_t), ("capacity", C.c_size_t)]
 
 
+class BoxDesc(C.Structure):
+    _fields_ = [("dst", C.c_void_p), ("src", C.c_void_p), ("dst_shape", C.c_uint32 * 3), ("dst_lo", C.c_uint32 * 3),
+                ("src_shape", C.c_uint32 * 3), ("src_lo", C.c_uint32 * 3), ("ext", C.c_uint32 * 3),
+                ("op", C.c_int32), ("first", C.c_uint64)]
+
+
 def make_layout(dim, interp, ncells, dx, amr_lower=None, origin=None, level=0):
     L = Layout()
     L.dim, L.interp, L.level = dim, interp, level
@@ -128,6 +134,7 @@ _PROTOS = {
     "phb_box_op": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, C.c_void_p, c_u32_p, c_u32_p,
                              c_u32_p, C.c_int]),
     "phb_box_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p]),
+    "phb_box_op_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64]),
     "phb_box_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p,
                                  C.c_int]),
 }

@@ -20,7 +20,9 @@ struct BoxOpParams
 
 __device__ __forceinline__ double apply_op(int op, double d, double s)
 {
-    return op == 0 ? s : op == 1 ? d + s : (d > s ? d : s); // copy / PlusEquals / std::max(d, s)
+    // copy / PlusEquals / SetMax: d = std::max(d, s) = (d < s) ? s : d  (a NaN destination stays NaN, a NaN
+    // source is ignored: utilities/types.hpp:577-581)
+    return op == 0 ? s : op == 1 ? d + s : ((d < s) ? s : d);
 }
 
 __global__ void __launch_bounds__(256) box_op_kernel(const __grid_constant__ BoxOpParams A)
@@ -62,6 +64,56 @@ int box_op(phb_ctx* ctx, int dim, double* dst, const uint32_t* ds, const uint32_
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
+
+// ---- batched variant: one launch runs a whole exchange phase (every face/edge/corner box of every
+// component of every patch pair).  Descriptors live in device memory and are built once per plan.
+__global__ void __launch_bounds__(256)
+    box_op_batch_kernel(const phb_box_desc* __restrict__ ops, int nops, unsigned long long total)
+{
+    unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total)
+        return;
+    // binary search: last op whose first element index is <= t
+    int lo = 0, hi = nops - 1;
+    while (lo < hi)
+    {
+        int const mid = (lo + hi + 1) >> 1;
+        if (ops[mid].first <= t)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    const phb_box_desc& A = ops[lo];
+    unsigned long long r  = t - A.first;
+    unsigned const k      = unsigned(r % A.ext[2]);
+    r /= A.ext[2];
+    unsigned const j = unsigned(r % A.ext[1]);
+    unsigned const i = unsigned(r / A.ext[1]);
+    size_t const pd  = (size_t(A.dst_lo[0] + i) * A.dst_shape[1] + (A.dst_lo[1] + j)) * A.dst_shape[2] + (A.dst_lo[2] + k);
+    size_t const ps  = (size_t(A.src_lo[0] + i) * A.src_shape[1] + (A.src_lo[1] + j)) * A.src_shape[2] + (A.src_lo[2] + k);
+    // several overlaps of one phase may cover the same destination node (faces, edges and corners of the
+    // ghost box): += and max must therefore be atomic; copies never overlap (the plan deduplicates them)
+    double const sv = A.src[ps];
+    if (A.op == 0)
+        A.dst[pd] = sv;
+    else if (A.op == 1)
+        atomicAdd(A.dst + pd, sv);
+    else
+    {
+        auto* addr                 = reinterpret_cast<unsigned long long*>(A.dst + pd);
+        unsigned long long old     = *addr;
+        while (true)
+        {
+            double const d = __longlong_as_double((long long)old);
+            if (!(d < sv))
+                break;
+            unsigned long long const seen = atomicCAS(addr, old, (unsigned long long)__double_as_longlong(sv));
+            if (seen == old)
+                break;
+            old = seen;
+        }
+    }
+}
 } // namespace phb
 
 extern "C" {
@@ -88,5 +140,16 @@ int phb_box_unpack(phb_ctx* ctx, int dim, double* dst, const uint32_t dst_shape[
         return phb::set_error(ctx, PHB_ERR_INVALID, "phb_box_unpack: invalid argument");
     uint32_t const zero[3] = {0, 0, 0};
     return phb::box_op(ctx, dim, dst, dst_shape, dst_lo, buf, extent, zero, extent, op);
+}
+int phb_box_op_batch(phb_ctx* ctx, const phb_box_desc* d_ops, int nops, uint64_t total_elements)
+{
+    if (!ctx || (nops > 0 && !d_ops))
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_box_op_batch: invalid argument");
+    if (nops <= 0 || total_elements == 0)
+        return PHB_OK;
+    phb::box_op_batch_kernel<<<unsigned((total_elements + 255) / 256), 256, 0, ctx->stream>>>(d_ops, nops,
+                                                                                             total_elements);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
 }
 }

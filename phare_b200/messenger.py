@@ -1,0 +1,324 @@
+"""Same-level periodic messenger: what SAMRAI RefineSchedules + PHARE's fill patterns do between
+every sub-step of SolverPPC, restated as explicit box transfer plans executed by the batched box
+kernel (K8) and, across GPUs, by torch.distributed point-to-point (NCCL over NVLink).
+
+Semantics restated (file:line relative to the PHARE tree):
+  field ghost fill   HybridHybridMessengerStrategy::fill{Magnetic,Electric,Current}Ghosts
+                     (src/amr/messengers/hybrid_hybrid_messenger_strategy.hpp:376-400); overlap =
+                     dst ghost field box ^ shifted src interior field box, minus dst interior field box
+                     (src/amr/data/field/field_geometry.hpp:139-304, field_variable_fill_pattern.hpp:30-211)
+  moment border sum  fillFluxBorders / fillDensityBorders (:423-485): dst += src over the full
+                     ghost-box intersection, through a scratch copy (field_variable_fill_pattern.hpp:219-313)
+  border max         fillIonBorders (:488-497): dst = max(dst, src) over the same overlaps
+  particle migration fillIonGhostParticles (:410-419) with ParticleDomainFromGhostFillPattern
+                     (src/amr/data/particles/particles_variable_fill_pattern.hpp:66-107) and the periodic
+                     iCell shift of ParticlesData::pack (src/amr/data/particles/particles_data.hpp:702-784)
+The level is periodic in every direction (src/amr/wrappers/hierarchy.hpp:347-349).
+"""
+import numpy as np
+
+from . import abi
+from .boxes import Box, periodic_shifts
+
+PRIMAL, DUAL = 0, 1
+
+
+def centering(qty, d):
+    if qty <= abi.BZ:
+        return PRIMAL if (qty - abi.BX) == d else DUAL
+    if qty <= abi.JZ:
+        base = abi.EX if qty <= abi.EZ else abi.JX
+        return DUAL if (qty - base) == d else PRIMAL
+    return PRIMAL
+
+
+class PatchGeom:
+    """cell box + owner of one patch of the level (what every rank knows about every patch)"""
+
+    def __init__(self, pid, box, owner):
+        self.id, self.box, self.owner = pid, box, owner
+
+    def interior_field_box(self, qty):
+        hi = self.box.hi.copy()
+        for d in range(self.box.dim):
+            if centering(qty, d) == PRIMAL:
+                hi[d] += 1  # field_geometry.hpp:139-181
+        return Box(self.box.lo, hi)
+
+    def ghost_field_box(self, qty, g):
+        return self.interior_field_box(qty).grow(g)
+
+    def local(self, node_lo, g):
+        """array index of an AMR node/cell index (GridLayout::AMRToLocal, gridlayout.hpp:746-763)"""
+        return node_lo - (self.box.lo - g)
+
+
+class LevelGeom:
+    def __init__(self, domain_shape, patches, interp):
+        self.domain_shape = tuple(int(s) for s in domain_shape)
+        self.dim = len(self.domain_shape)
+        self.patches = patches
+        self.g = 2 if interp == 1 else 4
+        self.pg = 1 if interp == 1 else 2
+        self.shifts = periodic_shifts(self.domain_shape)
+        self._nb = {}
+
+    def neighbours(self, p):
+        """(src patch, shift) pairs whose shifted cell box touches p's ghost region; excludes (p, 0)"""
+        if p.id not in self._nb:
+            out = []
+            reach = p.box.grow(self.g)
+            for q in self.patches:
+                for t in self.shifts:
+                    if q.id == p.id and not t.any():
+                        continue
+                    if reach * q.box.shift(t) is not None:
+                        out.append((q, t))
+            self._nb[p.id] = out
+        return self._nb[p.id]
+
+    # ---- transfer plans: lists of (dst patch, src patch, dst_lo, src_lo, extent) in local indices
+    def ghost_fill_plan(self, qty):
+        plan = []
+        for p in self.patches:
+            gbox, ibox = p.ghost_field_box(qty, self.g), p.interior_field_box(qty)
+            covered = []
+            for q, t in self.neighbours(p):
+                ov = gbox * q.interior_field_box(qty).shift(t)
+                if ov is None:
+                    continue
+                pieces = ov.minus(ibox)
+                for c in covered:  # a ghost node is written once (first provider wins)
+                    pieces = [r for b in pieces for r in b.minus(c)]
+                for b in pieces:
+                    covered.append(b)
+                    plan.append((p, q, p.local(b.lo, self.g), q.local(b.lo - t, self.g), b.shape()))
+        return plan
+
+    def border_plan(self):
+        """full ghost-box intersections of primal quantities (moments)"""
+        plan = []
+        for p in self.patches:
+            gbox = p.ghost_field_box(abi.RHO, self.g)
+            for q, t in self.neighbours(p):
+                ov = gbox * q.ghost_field_box(abi.RHO, self.g).shift(t)
+                if ov is not None:
+                    plan.append((p, q, p.local(ov.lo, self.g), q.local(ov.lo - t, self.g), ov.shape()))
+        return plan
+
+    def migration_plan(self):
+        """(src patch S, dst patch D, box in S's frame, shift): patch-ghost particles of S lying in the
+        image of D's cell box move to D with iCell += shift"""
+        plan = []
+        for s in self.patches:
+            ghost = s.box.grow(self.pg)
+            for d, t in self.neighbours(s):
+                # D + t is the image of D seen from S; particles are shifted by -t into D's frame
+                img = ghost * d.box.shift(t)
+                if img is not None:
+                    plan.append((s, d, abi.make_box(img.lo, img.hi), [int(-x) for x in t]))
+        return plan
+
+
+class LocalComm:
+    """single process: every patch is local"""
+    rank, size = 0, 1
+
+    def exchange(self, sends, recvs):
+        assert not sends and not recvs
+
+    def allreduce_max(self, v):
+        return v
+
+    def alltoall_counts(self, counts):
+        return counts
+
+
+class TorchComm:
+    """one process per GPU, torch.distributed (NCCL on GPU tensors, gloo on CPU tensors)"""
+
+    def __init__(self, device):
+        import torch.distributed as dist
+        self.dist, self.device = dist, device
+        self.rank, self.size = dist.get_rank(), dist.get_world_size()
+
+    def exchange(self, sends, recvs):
+        """sends/recvs: {peer: 1-D tensor}; one grouped point-to-point phase"""
+        ops = []
+        for peer in sorted(recvs):
+            ops.append(self.dist.P2POp(self.dist.irecv, recvs[peer], peer))
+        for peer in sorted(sends):
+            ops.append(self.dist.P2POp(self.dist.isend, sends[peer], peer))
+        if ops:
+            for r in self.dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def allreduce_max(self, v):
+        import torch
+        t = torch.tensor([int(v)], dtype=torch.int64, device=self.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return int(t.item())
+
+    def alltoall_counts(self, counts):
+        """counts[peer] = ints I send to peer (list of equal length per peer); returns what they send me"""
+        import torch
+        k = len(counts[0])
+        src = torch.tensor(counts, dtype=torch.int64, device=self.device).reshape(self.size, k)
+        dst = torch.empty_like(src)
+        self.dist.all_to_all_single(dst, src)
+        return dst.cpu().tolist()
+
+
+class HybridMessenger:
+    """Executes the plans of a LevelGeom on the patches owned by this rank.
+    `ops` is the compute back end (phare_b200.solver.GpuOps in production)."""
+
+    def __init__(self, geom, ops, comm):
+        self.geom, self.ops, self.comm = geom, ops, comm
+        self.me = comm.rank
+        self._plans = {}
+        self._compiled = {}
+        self._migration = geom.migration_plan()
+
+    def _plan(self, kind, qty):
+        key = (kind, qty)
+        if key not in self._plans:
+            self._plans[key] = self.geom.ghost_fill_plan(qty) if kind == "fill" else self.geom.border_plan()
+        return self._plans[key]
+
+    def _compile(self, key, kind, qtys, arrays, op):
+        """arrays: {patch id: [array handle per qty]} for local patches. Returns the compiled phase:
+        local box ops, and per peer (pack ops, send buffer, recv buffer, unpack ops)."""
+        if key not in self._compiled:
+            me = self.me
+            local, send_items, recv_items = [], {}, {}
+            for ci, qty in enumerate(qtys):
+                for (p, q, dlo, slo, ext) in self._plan(kind, qty):
+                    if p.owner == me and q.owner == me:
+                        local.append((arrays[p.id][ci], dlo, arrays[q.id][ci], slo, ext, op))
+                    elif p.owner == me:
+                        recv_items.setdefault(q.owner, []).append((arrays[p.id][ci], dlo, ext))
+                    elif q.owner == me:
+                        send_items.setdefault(p.owner, []).append((arrays[q.id][ci], slo, ext))
+            self._compiled[key] = self._finish(local, send_items, recv_items, op)
+        return self._compiled[key]
+
+    def _run(self, phase):
+        ops = self.ops
+        for peer, ph in phase["peers"].items():
+            ops.run_box_ops(ph["pack"])
+        ops.run_box_ops(phase["local"])
+        if phase["peers"]:
+            self.comm.exchange({p: ops.as_tensor(ph["sbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["sbuf"])},
+                               {p: ops.as_tensor(ph["rbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["rbuf"])})
+            for peer, ph in phase["peers"].items():
+                ops.run_box_ops(ph["unpack"])
+
+    # ---- public API, named after the reference messenger --------------------------------------
+    def fill_ghosts(self, name, qty0, vecs):
+        """vecs: {patch id: vector field}; fillMagneticGhosts (qty0=BX), fillElectricGhosts (EX),
+        fillCurrentGhosts (JX)"""
+        arrays = {pid: [v[c] for c in range(3)] for pid, v in vecs.items()}
+        self._run(self._compile(("fill", name), "fill", [qty0, qty0 + 1, qty0 + 2], arrays, 0))
+
+    def sum_borders(self, name, arrays, scratch):
+        """arrays/scratch: {patch id: [primal arrays]}: a += neighbours' ORIGINAL values on the ghost-box
+        overlaps (fillFluxBorders + fillDensityBorders)"""
+        ops = self.ops
+        for pid, lst in arrays.items():
+            for a, s in zip(lst, scratch[pid]):
+                ops.copy(s, a)
+        n = len(next(iter(arrays.values())))
+        key = ("sum", name)
+        if key not in self._compiled:
+            # destination = arrays, source = scratch copies (local) / packed from scratch (remote)
+            me, local, send_items, recv_items = self.me, [], {}, {}
+            for ci in range(n):
+                for (p, q, dlo, slo, ext) in self._plan("border", abi.RHO):
+                    if p.owner == me and q.owner == me:
+                        local.append((arrays[p.id][ci], dlo, scratch[q.id][ci], slo, ext, 1))
+                    elif p.owner == me:
+                        recv_items.setdefault(q.owner, []).append((arrays[p.id][ci], dlo, ext))
+                    elif q.owner == me:
+                        send_items.setdefault(p.owner, []).append((scratch[q.id][ci], slo, ext))
+            self._compiled[key] = self._finish(local, send_items, recv_items, 1)
+        self._run(self._compiled[key])
+
+    def max_borders(self, name, arrays):
+        """fillIonBorders: a = max(a, neighbour) on the ghost-box overlaps"""
+        n = len(next(iter(arrays.values())))
+        self._run(self._compile(("max", name), "border", [abi.RHO] * n, arrays, 2))
+
+    def _finish(self, local, send_items, recv_items, op):
+        ops = self.ops
+        phase = dict(local=ops.compile_box_ops(local), peers={})
+        for peer in sorted(set(send_items) | set(recv_items)):
+            s_items, r_items = send_items.get(peer, []), recv_items.get(peer, [])
+            sbuf = ops.new_buffer(sum(int(np.prod(e)) for _, _, e in s_items))
+            rbuf = ops.new_buffer(sum(int(np.prod(e)) for _, _, e in r_items))
+            pack, unpack, off = [], [], 0
+            for (arr, lo, ext) in s_items:
+                pack.append((ops.buffer_slice(sbuf, off, ext), [0] * len(ext), arr, lo, ext, 0))
+                off += int(np.prod(ext))
+            off = 0
+            for (arr, lo, ext) in r_items:
+                unpack.append((arr, lo, ops.buffer_slice(rbuf, off, ext), [0] * len(ext), ext, op))
+                off += int(np.prod(ext))
+            phase["peers"][peer] = dict(pack=ops.compile_box_ops(pack), unpack=ops.compile_box_ops(unpack),
+                                        sbuf=sbuf, rbuf=rbuf)
+        return phase
+
+    def migrate_particles(self, layouts, patch_ghost, domain):
+        """fillIonGhostParticles for one population.
+        patch_ghost: {pid: (store, first, last)} the new patch-ghost particles of my patches;
+        domain: {pid: store} destination stores of my patches.  Returns the number received per patch."""
+        ops, me = self.ops, self.me
+        received = {pid: 0 for pid in domain}
+        remote = {}  # (dst owner, dst pid) -> staging store
+        for (s, d, box, shift) in self._migration:
+            if s.owner != me:
+                continue
+            store, first, last = patch_ghost[s.id]
+            if last <= first:
+                continue
+            if d.owner == me:
+                received[d.id] += ops.export(layouts[s.id], store, first, last, box, domain[d.id], shift=shift)
+            else:
+                key = (d.owner, d.id)
+                if key not in remote:
+                    remote[key] = ops.staging_particles(layouts[s.id], max(last - first, 1))
+                st = remote[key]
+                if ops.capacity(st) < ops.count(st) + (last - first):
+                    st = remote[key] = ops.grow_particles(layouts[s.id], st, ops.count(st) + (last - first))
+                ops.export(layouts[s.id], store, first, last, box, st, shift=shift)
+        if self.comm.size > 1:
+            self._exchange_particles(layouts, remote, domain, received)
+        return received
+
+    def _exchange_particles(self, layouts, remote, domain, received):
+        ops, comm, geom = self.ops, self.comm, self.geom
+        # every rank announces, per destination patch, how many particles it ships
+        npatch = len(geom.patches)
+        counts = [[0] * npatch for _ in range(comm.size)]
+        for (owner, pid), st in remote.items():
+            counts[owner][pid] = ops.count(st)
+        incoming = comm.alltoall_counts(counts)  # incoming[src rank][pid]
+        any_layout = next(iter(layouts.values()))
+        sends, recvs, recv_meta = {}, {}, {}
+        for peer in range(comm.size):
+            if peer == self.me:
+                continue
+            out = [(pid, remote[(peer, pid)]) for pid in range(npatch) if counts[peer][pid]]
+            if out:
+                sends[peer] = ops.pack_particles(any_layout, [st for _, st in out])
+            inc = [(pid, incoming[peer][pid]) for pid in range(npatch) if incoming[peer][pid]]
+            if inc:
+                recvs[peer] = ops.new_particle_buffer(any_layout, sum(n for _, n in inc))
+                recv_meta[peer] = inc
+        comm.exchange({p: ops.as_tensor(b) for p, b in sends.items()}, {p: ops.as_tensor(b) for p, b in recvs.items()})
+        for peer, inc in recv_meta.items():
+            off = 0
+            for pid, n in inc:
+                ops.unpack_particles(layouts[pid], recvs[peer], off, n, sum(m for _, m in inc), domain[pid])
+                received[pid] += n
+                off += n

@@ -1,0 +1,496 @@
+"""Host-side restatement of the reference's step sequencing for ONE level of same-size or arbitrary
+patches on a periodic domain, driving the C ABI (libphare_b200.so) kernel by kernel.
+
+Mirrors, with the reference's names (file:line relative to the PHARE tree):
+  SolverPPC::advanceLevel / predictor1_ / predictor2_ / corrector_ / average_ / moveIons_
+                                   src/amr/solvers/solver_ppc.hpp:315-598
+  SolverPPC::prepareStep           src/amr/solvers/solver_ppc.hpp:242-259
+  IonUpdater::updatePopulations / updateIons      src/core/numerics/ion_updater/ion_updater.hpp:90-295
+  HybridLevelInitializer::initialize (root level) src/amr/level_initializer/hybrid_level_initializer.hpp:100-182
+  level transformers (per-patch dispatch, n/Ve/Pe wiring)  src/amr/solvers/solver_field_evolvers.hpp:33-77,
+                                   src/amr/solvers/solver_hybrid_field_evolvers.hpp:29-41
+
+The compute back end is injected (`ops`): GpuOps below (CUDA through the C ABI; the only one the
+product ships) — the parity tests inject a CPU back end built on the oracle to cross-check the
+orchestration.  There is no fallback: GpuOps raises if the CUDA library or a device is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .boxes import Box
+from .messenger import HybridMessenger, LevelGeom, LocalComm, PatchGeom
+
+DOMAIN_ONLY, ALL = 1, 2  # UpdaterMode, ion_updater.hpp:22
+
+
+# ---------------------------------------------------------------------------------------------------
+class GpuOps:
+    """libphare_b200.so back end; device memory is torch CUDA tensors (plumbing only)."""
+
+    def __init__(self, dim, interp, device):
+        import torch
+        from .device import Context
+        from . import torch_interop as ti
+        self.torch, self.ti = torch, ti
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.ctx = Context(dim, interp, device=self.device.index or 0, stream=ti.current_stream_ptr())
+        self.dim, self.interp = dim, interp
+        self.kernel_timing = False  # bench.py: CUDA-event pairs around the particle kernels
+        self.timed = {}
+
+    def _timed(self, name, fn):
+        if not self.kernel_timing:
+            return fn()
+        a, b = self.torch.cuda.Event(enable_timing=True), self.torch.cuda.Event(enable_timing=True)
+        a.record()
+        r = fn()
+        b.record()
+        self.timed.setdefault(name, []).append((a, b))
+        return r
+
+    # ---- memory
+    def field(self, layout, qty):
+        return self.ti.TorchArray(self.ctx.field_shape(layout, qty), self.device)
+
+    def vec(self, layout, qty0):
+        return self.ti.TorchVec(self.ctx, layout, qty0, self.device)
+
+    def zero(self, h):
+        h.t.zero_()
+
+    def copy(self, dst, src):
+        self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, dst.ptr, src.ptr, src.size * 8))
+
+    def set_field(self, h, host):
+        h.t.copy_(self.torch.from_numpy(np.ascontiguousarray(host)).to(self.device))
+
+    def get_field(self, h):
+        return h.t.cpu().numpy()
+
+    def particles(self, capacity):
+        return self.ti.TorchParticles(self.dim, capacity, self.device)
+
+    def set_particles(self, store, icell, delta, weight, charge, v):
+        t = self.torch
+        n = len(weight)
+        for d in range(self.dim):
+            store.icell[d][:n] = t.from_numpy(np.ascontiguousarray(icell[:, d], dtype=np.int32)).to(self.device)
+            store.delta[d][:n] = t.from_numpy(np.ascontiguousarray(delta[:, d])).to(self.device)
+        for k in range(3):
+            store.v[k][:n] = t.from_numpy(np.ascontiguousarray(v[:, k])).to(self.device)
+        store.weight[:n] = t.from_numpy(np.ascontiguousarray(weight)).to(self.device)
+        store.charge[:n] = t.from_numpy(np.ascontiguousarray(charge)).to(self.device)
+        store.n = n
+
+    def get_particles(self, store, first=0, last=None):
+        last = store.n if last is None else last
+        sl = slice(first, last)
+        icell = np.stack([c[sl].cpu().numpy() for c in store.icell], 1)
+        delta = np.stack([c[sl].cpu().numpy() for c in store.delta], 1)
+        v = np.stack([c[sl].cpu().numpy() for c in store.v], 1)
+        return icell, delta, store.weight[sl].cpu().numpy(), store.charge[sl].cpu().numpy(), v
+
+    def count(self, store):
+        return store.n
+
+    def set_count(self, store, n):
+        store.n = n
+
+    def capacity(self, store):
+        return store.capacity
+
+    def alias_weight_charge(self, store, other):
+        """view of `store` whose weight/charge columns are `other`'s (a pushed copy never changes them,
+        boris.hpp:197-199), so the out-of-place push does not have to write them"""
+        class View:
+            pass
+        v = View()
+        v.c = abi.Particles()
+        C.memmove(C.byref(v.c), C.byref(store.c), C.sizeof(abi.Particles))
+        v.c.weight, v.c.charge = other.c.weight, other.c.charge
+        v.keep = (store, other)
+        return v
+
+    def particles_copy(self, src, first, count, dst, dst_first):
+        self.ctx._check(self.ctx.lib.phb_particles_copy(self.ctx.h, C.byref(src.c), first, count, C.byref(dst.c),
+                                                        dst_first))
+
+    def cell_start(self, nkeys):
+        return self.ti.TorchArray((nkeys + 1,), self.device, dtype=self.torch.int32)
+
+    def bin_nkeys(self, layout, domain):
+        return self.ctx.bin_nkeys(layout, domain)
+
+    # ---- operators
+    def push(self, layout, E, B, pin, pout, mass, dt, first_selector=None):
+        self._timed("push", lambda: self.ctx.push(layout, E, B, pin, pout, mass, dt, first_selector))
+        if hasattr(pout, "n") and hasattr(pin, "n"):
+            pout.n = pin.n
+
+    def deposit(self, layout, parts, rho_n, rho_q, F, coef=1.0, first=0, last=None, sel=(), domain=None,
+                cell_start=None):
+        self._timed("deposit" if cell_start is not None else "deposit_unordered",
+                    lambda: self.ctx.deposit(layout, parts, rho_n, rho_q, F, coef, first, last, sel, domain, cell_start))
+
+    def bin(self, layout, pin, pout, domain, keep, cell_start):
+        return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
+
+    def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
+        return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
+
+    def faraday(self, layout, B, E, Bnew, dt):
+        self.ctx.faraday(layout, B, E, Bnew, dt)
+
+    def ampere(self, layout, B, J):
+        self.ctx.ampere(layout, B, J)
+
+    def ohm(self, layout, n, Ve, Pe, B, J, Enew, eta, nu, hyper_mode):
+        self.ctx.ohm(layout, n, Ve, Pe, B, J, Enew, eta, nu, hyper_mode)
+
+    def electrons_update(self, layout, Ne, Vi, J, Te, Ve, Pe):
+        self.ctx.electrons_update(layout, Ne, Vi, J, Te, Ve, Pe)
+
+    def ions_totals(self, rho_n, rho_q, flux, mass, rho_q_tot, rho_m_tot, V):
+        self.ctx.ions_totals(rho_n, rho_q, flux, mass, rho_q_tot, rho_m_tot, V)
+
+    def average(self, a, b, avg):
+        self.ctx.average(a, b, avg)
+
+    def poll_error(self):
+        """returns 0 or the phb status raised by a kernel (message in last_error)"""
+        rc = self.ctx.lib.phb_poll_error(self.ctx.h)
+        self.last_error = self.ctx.lib.phb_last_error(self.ctx.h).decode() if rc else ""
+        return rc
+
+    def sync(self):
+        self.ctx.sync()
+
+    # ---- batched box operations (K8)
+    def compile_box_ops(self, entries):
+        """entries: (dst handle, dst_lo, src handle, src_lo, extent, op) -> device descriptor table"""
+        if not entries:
+            return None
+        descs = (abi.BoxDesc * len(entries))()
+        first = 0
+        for i, (dst, dlo, src, slo, ext, op) in enumerate(entries):
+            d = descs[i]
+            d.dst, d.src, d.op, d.first = dst.ptr, src.ptr, op, first
+            nd = len(ext)
+            for k in range(3):
+                d.dst_shape[k] = dst.shape[k] if k < nd else 1
+                d.src_shape[k] = src.shape[k] if k < nd else 1
+                d.dst_lo[k] = int(dlo[k]) if k < nd else 0
+                d.src_lo[k] = int(slo[k]) if k < nd else 0
+                d.ext[k] = int(ext[k]) if k < nd else 1
+            first += int(np.prod(ext))
+        raw = np.frombuffer(bytes(descs), dtype=np.uint8)
+        table = self.torch.from_numpy(raw.copy()).to(self.device)
+        return (table, len(entries), first)
+
+    def run_box_ops(self, compiled):
+        if compiled is None:
+            return
+        table, n, total = compiled
+        self.ctx._check(self.ctx.lib.phb_box_op_batch(self.ctx.h, table.data_ptr(), n, total))
+
+    def new_buffer(self, n):
+        return self.ti.TorchArray((max(int(n), 0),), self.device)
+
+    def buffer_slice(self, buf, off, ext):
+        t = buf.t[off:off + int(np.prod(ext))].view(*[int(e) for e in ext])
+        return self.ti.TorchArray(None, self.device, tensor=t)
+
+    def as_tensor(self, buf):
+        return buf.t if hasattr(buf, "t") else buf
+
+    def size(self, buf):
+        return buf.t.numel() if hasattr(buf, "t") else buf.numel()
+
+    # ---- particle staging for migration between ranks
+    def staging_particles(self, layout, capacity):
+        return self.particles(capacity)
+
+    def grow_particles(self, layout, store, capacity):
+        new = self.particles(int(capacity * 1.5) + 16)
+        self.ctx._check(self.ctx.lib.phb_particles_copy(self.ctx.h, C.byref(store.c), 0, store.n, C.byref(new.c), 0))
+        new.n = store.n
+        return new
+
+    def _columns(self, store):
+        return [(c, 4) for c in store.icell] + [(c, 8) for c in store.delta] + [(c, 8) for c in store.v] \
+            + [(store.weight, 8), (store.charge, 8)]
+
+    def particle_bytes(self):
+        return 4 * self.dim + 8 * self.dim + 24 + 16
+
+    def pack_particles(self, layout, stores):
+        """flat byte buffer: for every column, the stores back to back"""
+        total = sum(s.n for s in stores)
+        buf = self.torch.empty(total * self.particle_bytes(), dtype=self.torch.uint8, device=self.device)
+        off = 0
+        ncol = len(self._columns(stores[0]))
+        for ci in range(ncol):
+            for s in stores:
+                col, esz = self._columns(s)[ci]
+                nb = s.n * esz
+                if nb:
+                    self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, buf.data_ptr() + off, col.data_ptr(), nb))
+                off += nb
+        return buf
+
+    def new_particle_buffer(self, layout, total):
+        return self.torch.empty(total * self.particle_bytes(), dtype=self.torch.uint8, device=self.device)
+
+    def unpack_particles(self, layout, buf, off, n, total, dst):
+        if dst.n + n > dst.capacity:
+            raise RuntimeError("particle store capacity exceeded while receiving migrating particles")
+        base = 0
+        for col, esz in self._columns(dst):
+            self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, col.data_ptr() + dst.n * esz,
+                                                 buf.data_ptr() + base + off * esz, n * esz))
+            base += total * esz
+        dst.n = dst.n + n
+
+
+# ---------------------------------------------------------------------------------------------------
+class Population:
+    """IonPopulation (src/core/data/ions/ion_population/ion_population.hpp:19-140): moments + particle arrays"""
+
+    def __init__(self, ops, layout, name, mass, capacity, nkeys):
+        self.name, self.mass = name, mass
+        self.rho_n, self.rho_q = ops.field(layout, abi.RHO), ops.field(layout, abi.RHO)
+        self.flux = ops.vec(layout, abi.VX)
+        self.scratch = [ops.field(layout, abi.RHO) for _ in range(5)]  # sumField_/sumVec_ of the messenger
+        self.domain = ops.particles(capacity)      # domainParticles, cell-ordered in [0, n_sorted)
+        self.spare = ops.particles(capacity)       # tmp_particles_ of IonUpdater / sort target
+        self.cell_start = ops.cell_start(nkeys)
+        self.n_sorted = 0
+        self.patch_ghost = ops.particles(capacity // 8 + 4096)  # patchGhostParticles (leavers of this step)
+
+    def moments(self):
+        return [self.rho_n, self.rho_q, self.flux[0], self.flux[1], self.flux[2]]
+
+
+class Patch:
+    """one patch of the level: GridLayout + HybridState (src/core/models/hybrid_state.hpp:27-45) + solver scratch"""
+
+    def __init__(self, ops, geom, layout, pops_spec, capacity_factor=1.3):
+        self.geom, self.layout = geom, layout
+        dim = layout.dim
+        self.domain_box = abi.make_box(geom.box.lo, geom.box.hi)
+        pg = 1 if layout.interp == 1 else 2
+        self.ghost_box = abi.make_box(geom.box.lo - pg, geom.box.hi + pg)
+        # nonLevelGhostBox (amr_utils.hpp:233-253): on a periodic single level every ghost cell has a neighbour
+        self.non_level_ghost = [self.ghost_box]
+        V = lambda q: ops.vec(layout, q)
+        self.E, self.B, self.J = V(abi.EX), V(abi.BX), V(abi.JX)
+        self.Epred, self.Bpred = V(abi.EX), V(abi.BX)      # electromagPred_
+        self.Eavg, self.Bavg = V(abi.EX), V(abi.BX)        # electromagAvg_
+        self.Bold = V(abi.BX)                              # Bold_ (prepareStep)
+        self.Ve, self.Vi = V(abi.VX), V(abi.VX)
+        self.Pe = ops.field(layout, abi.P)
+        self.Ne = ops.field(layout, abi.RHO)               # ions.chargeDensity == electron density
+        self.rho_m = ops.field(layout, abi.RHO)
+        nkeys = ops.bin_nkeys(layout, self.domain_box)
+        self.pops = [Population(ops, layout, s["name"], s["mass"], int(s["n"] * capacity_factor) + 4096, nkeys)
+                     for s in pops_spec]
+
+
+class IonUpdater:
+    """IonUpdater<Ions, Electromag, GridLayout> (ion_updater.hpp:24-83) on the device-resident store.
+    The pusher is named in dict["pusher"]["name"]; only "modified_boris" exists (pusher_factory.hpp:20-30)."""
+
+    def __init__(self, ops, pusher_name="modified_boris"):
+        if pusher_name != "modified_boris":
+            raise RuntimeError("Error : Invalid Pusher name")
+        self.ops = ops
+
+    def update_populations(self, patch, E, B, dt, mode):
+        ops, L = self.ops, patch.layout
+        for pop in patch.pops:
+            for m in pop.moments():  # resetMoments (moments.hpp:15-23)
+                ops.zero(m)
+            n = ops.count(pop.domain)
+            if mode == DOMAIN_ONLY:
+                # updateAndDepositDomain_ (:171-219): push a COPY (tmp_particles_), deposit those that end in the
+                # nonLevelGhostBox; the domain array itself is untouched
+                tmp = ops.alias_weight_charge(pop.spare, pop.domain)
+                ops.push(L, E, B, pop.domain, tmp, pop.mass, dt)
+                self._deposit(patch, pop, tmp, n)
+            else:
+                # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
+                # are deposited; then the store is re-binned: [domain | new patch ghosts | erased]
+                ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
+                self._deposit(patch, pop, pop.domain, n)
+                counts = ops.bin(L, pop.domain, pop.spare, patch.domain_box, patch.non_level_ghost, pop.cell_start)
+                pop.domain, pop.spare = pop.spare, pop.domain
+                pop.n_sorted = counts[0]
+                # "copy out new patch ghosts" (:248-254) then "drop all ghosts" (:273)
+                if ops.capacity(pop.patch_ghost) < counts[1]:
+                    pop.patch_ghost = ops.particles(int(counts[1] * 1.5) + 4096)
+                ops.particles_copy(pop.domain, counts[0], counts[1], pop.patch_ghost, 0)
+                ops.set_count(pop.patch_ghost, counts[1])
+                ops.set_count(pop.domain, counts[0])
+
+    def _deposit(self, patch, pop, store, n):
+        ops, L = self.ops, patch.layout
+        # cell-ordered part (tolerates particles that changed cell since the last binning) ...
+        if pop.n_sorted:
+            ops.deposit(L, store, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, pop.n_sorted, patch.non_level_ghost,
+                        patch.domain_box, pop.cell_start)
+        # ... and the particles received from neighbours since then (appended, not ordered yet)
+        if n > pop.n_sorted:
+            ops.deposit(L, store, pop.rho_n, pop.rho_q, pop.flux, 1.0, pop.n_sorted, n, patch.non_level_ghost)
+
+    def update_ions(self, patch):
+        """Ions::computeChargeDensity + computeBulkVelocity (ion_updater.hpp:112-116)"""
+        pops = patch.pops
+        self.ops.ions_totals([p.rho_n for p in pops], [p.rho_q for p in pops], [p.flux for p in pops],
+                             [p.mass for p in pops], patch.Ne, patch.rho_m, patch.Vi)
+
+
+class SolverPPC:
+    """SolverPPC<HybridModel, AMR_Types> (solver_ppc.hpp:31-186) for one periodic level."""
+
+    def __init__(self, ops, patches, geom, comm=None, resistivity=0.0, hyper_resistivity=1e-4, hyper_mode=0, Te=0.12,
+                 pusher_name="modified_boris"):
+        self.ops, self.patches, self.geom = ops, patches, geom
+        self.comm = comm or LocalComm()
+        self.messenger = HybridMessenger(geom, ops, self.comm)
+        self.updater = IonUpdater(ops, pusher_name)
+        self.eta, self.nu, self.hyper_mode, self.Te = resistivity, hyper_resistivity, hyper_mode, Te
+        self.layouts = {p.geom.id: p.layout for p in patches}
+
+    # ---- helpers
+    def _by_id(self, attr):
+        return {p.geom.id: getattr(p, attr) for p in self.patches}
+
+    def _field_solve(self, Bsrc, Esrc, Bdst, Edst, dt, tag):
+        """Faraday -> fillMagneticGhosts -> Ampere -> fillCurrentGhosts -> electrons.update -> Ohm
+        (the common body of predictor1_/predictor2_/corrector_, solver_ppc.hpp:347-479)"""
+        ops, msg = self.ops, self.messenger
+        for p in self.patches:
+            ops.faraday(p.layout, getattr(p, Bsrc), getattr(p, Esrc), getattr(p, Bdst), dt)
+        msg.fill_ghosts(Bdst, abi.BX, self._by_id(Bdst))
+        for p in self.patches:
+            ops.ampere(p.layout, getattr(p, Bdst), p.J)
+        msg.fill_ghosts("J", abi.JX, self._by_id("J"))
+        for p in self.patches:
+            ops.electrons_update(p.layout, p.Ne, p.Vi, p.J, self.Te, p.Ve, p.Pe)
+            ops.ohm(p.layout, p.Ne, p.Ve, p.Pe, getattr(p, Bdst), p.J, getattr(p, Edst), self.eta, self.nu,
+                    self.hyper_mode)
+
+    def _average(self):
+        """average_ (solver_ppc.hpp:484-510)"""
+        ops = self.ops
+        for p in self.patches:
+            for c in range(3):
+                ops.average(p.B[c], p.Bpred[c], p.Bavg[c])
+                ops.average(p.E[c], p.Epred[c], p.Eavg[c])
+        self.messenger.fill_ghosts("Eavg", abi.EX, self._by_id("Eavg"))
+
+    def _move_ions(self, dt, mode):
+        """moveIons_ (solver_ppc.hpp:538-598)"""
+        ops, msg = self.ops, self.messenger
+        for p in self.patches:
+            self.updater.update_populations(p, p.Eavg, p.Bavg, dt, mode)
+        # mpi::any_errors(): every rank learns whether any kernel flagged a particle (:549-563)
+        err = ops.poll_error()
+        if self.comm.allreduce_max(err):
+            raise RuntimeError("Updater::updatePopulations: " + (getattr(ops, "last_error", "") or "error on another rank"))
+        npop = len(self.patches[0].pops) if self.patches else 0
+        for i in range(npop):
+            # fillFluxBorders + fillDensityBorders
+            msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in self.patches},
+                            {p.geom.id: p.pops[i].scratch for p in self.patches})
+        # fillIonPopMomentGhosts: level > 0 only (no-op on the root level)
+        if mode == ALL:
+            for i in range(npop):  # fillIonGhostParticles, then patchGhostParticles.clear()
+                msg.migrate_particles(self.layouts,
+                                      {p.geom.id: (p.pops[i].patch_ghost, 0, ops.count(p.pops[i].patch_ghost))
+                                       for p in self.patches},
+                                      {p.geom.id: p.pops[i].domain for p in self.patches})
+                for p in self.patches:
+                    ops.set_count(p.pops[i].patch_ghost, 0)
+        for p in self.patches:
+            self.updater.update_ions(p)
+        # fillIonBorders: SetMax on total mass density, charge density and bulk velocity
+        msg.max_borders("ions", {p.geom.id: [p.rho_m, p.Ne, p.Vi[0], p.Vi[1], p.Vi[2]] for p in self.patches})
+
+    # ---- public
+    def prepare_step(self):
+        """Bold <- B (solver_ppc.hpp:242-259)"""
+        for p in self.patches:
+            for c in range(3):
+                self.ops.copy(p.Bold[c], p.B[c])
+
+    def advance_level(self, dt):
+        """solver_ppc.hpp:315-341"""
+        self.prepare_step()
+        self._field_solve("B", "E", "Bpred", "Epred", dt, "predictor1")
+        self._average()
+        self._move_ions(dt, DOMAIN_ONLY)
+        self._field_solve("B", "Eavg", "Bpred", "Epred", dt, "predictor2")
+        self._average()
+        self._move_ions(dt, ALL)
+        self._field_solve("B", "Eavg", "B", "E", dt, "corrector")
+        self.messenger.fill_ghosts("E", abi.EX, self._by_id("E"))
+
+    def initialize(self):
+        """HybridLevelInitializer::initialize, root level (hybrid_level_initializer.hpp:100-182): particles and B
+        are already loaded; derive moments, J and E."""
+        ops, msg = self.ops, self.messenger
+        npop = len(self.patches[0].pops) if self.patches else 0
+        for p in self.patches:
+            for pop in p.pops:
+                # first binning of the freshly loaded particles (the reference's CellMap is built on emplace_back)
+                counts = ops.bin(p.layout, pop.domain, pop.spare, p.domain_box, p.non_level_ghost, pop.cell_start)
+                pop.domain, pop.spare = pop.spare, pop.domain
+                pop.n_sorted = counts[0]
+                ops.set_count(pop.domain, counts[0])
+                for m in pop.moments():
+                    ops.zero(m)
+                # depositParticles(DomainDeposit)
+                ops.deposit(p.layout, pop.domain, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, pop.n_sorted, (),
+                            p.domain_box, pop.cell_start)
+        for i in range(npop):
+            msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in self.patches},
+                            {p.geom.id: p.pops[i].scratch for p in self.patches})
+        for p in self.patches:
+            self.updater.update_ions(p)
+        msg.max_borders("ions", {p.geom.id: [p.rho_m, p.Ne, p.Vi[0], p.Vi[1], p.Vi[2]] for p in self.patches})
+        for p in self.patches:
+            ops.ampere(p.layout, p.B, p.J)
+        msg.fill_ghosts("J", abi.JX, self._by_id("J"))
+        for p in self.patches:
+            ops.electrons_update(p.layout, p.Ne, p.Vi, p.J, self.Te, p.Ve, p.Pe)
+            ops.ohm(p.layout, p.Ne, p.Ve, p.Pe, p.B, p.J, p.E, self.eta, self.nu, self.hyper_mode)
+        msg.fill_ghosts("E", abi.EX, self._by_id("E"))
+        self.prepare_step()
+
+
+# ---------------------------------------------------------------------------------------------------
+def make_level(domain_cells, patch_grid, interp, dx, nranks=1):
+    """Split a periodic domain into a Cartesian grid of patches and deal them to ranks in order.
+    Returns (LevelGeom, [layout per patch])."""
+    dim = len(domain_cells)
+    edges = []
+    for d in range(dim):
+        n, k = domain_cells[d], patch_grid[d]
+        cuts = [round(i * n / k) for i in range(k + 1)]
+        edges.append(cuts)
+    patches, layouts = [], []
+    idx = np.ndindex(*patch_grid)
+    npatch = int(np.prod(patch_grid))
+    for pid, ijk in enumerate(idx):
+        lo = [edges[d][ijk[d]] for d in range(dim)]
+        hi = [edges[d][ijk[d] + 1] - 1 for d in range(dim)]
+        owner = pid * nranks // npatch
+        patches.append(PatchGeom(pid, Box(lo, hi), owner))
+        ncells = [hi[d] - lo[d] + 1 for d in range(dim)]
+        origin = [lo[d] * dx[d] for d in range(dim)]
+        layouts.append(abi.make_layout(dim, interp, ncells, dx, amr_lower=lo, origin=origin))
+    return LevelGeom(domain_cells, patches, interp), layouts

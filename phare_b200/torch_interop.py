@@ -67,7 +67,7 @@ def current_stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
-def uniform_sorted_particles(ctx, layout, ppc, vth, device, seed=0, capacity_factor=1.0):
+def uniform_sorted_particles(ctx, layout, ppc, vth, device, seed=0, capacity_factor=1.0, store=None):
     """ppc particles per domain cell in row-major cell order: synthetic input created on the device."""
     dim = layout.dim
     nc = [int(layout.ncells[d]) for d in range(dim)]
@@ -75,7 +75,8 @@ def uniform_sorted_particles(ctx, layout, ppc, vth, device, seed=0, capacity_fac
     for n_ in nc:
         ncell *= n_
     n = ncell * ppc
-    P = TorchParticles(dim, int(n * capacity_factor) + 1024, device)
+    P = store if store is not None else TorchParticles(dim, int(n * capacity_factor) + 1024, device)
+    assert P.capacity >= n
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     cell = torch.arange(ncell, device=device, dtype=torch.int64).repeat_interleave(ppc)
