@@ -1,11 +1,8 @@
 """ctypes view of the C ABI declared in include/phare_b200.h.
 
-The structs here are shared by three libraries that take the same argument types:
-  * phare_b200/lib/libphare_b200.so  (phb_*)  the product: CUDA kernels, DEVICE pointers
-  * oracle/liboracle.so              (pho_*)  test-only CPU restatement, HOST pointers
-  * oracle/_ref/libphare_ref.so      (phr_*)  test-only: the reference itself, HOST pointers
-This module only loads the product library; tests/ and bench.py load the other two through
-phare_b200.testing (never imported by the product path).
+This module loads only the product library, phare_b200/lib/libphare_b200.so (phb_* entry points, CUDA
+kernels, DEVICE pointers).  The test-only CPU checkers under the top-level checker package reuse these
+struct definitions with HOST pointers; nothing in phare_b200/ imports or links them.
 """
 import ctypes as C
 import os
