@@ -204,10 +204,10 @@ class GpuOps:
         return self.ti.TorchArray(None, self.device, tensor=t)
 
     def as_tensor(self, buf):
-        return buf.t if hasattr(buf, "t") else buf
+        return buf.t if isinstance(buf, self.ti.TorchArray) else buf
 
     def size(self, buf):
-        return buf.t.numel() if hasattr(buf, "t") else buf.numel()
+        return self.as_tensor(buf).numel()
 
     # ---- particle staging for migration between ranks
     def staging_particles(self, layout, capacity):
