@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushP
 // stages with cp.async.bulk (completion on an mbarrier).  The 8 warps of the CTA pick their
 // particle out of the stage, release it at once, and do gather + Boris + stores while the next
 // PUSH_STAGES-1 tiles are already in flight (thread 0 issues the copies; no warp is set aside, so
-// three CTAs stay resident per SM).  Persistent CTAs, tiles handed out round-robin.
+// three CTAs stay resident per SM).  Persistent CTAs, one contiguous run of tiles each.
 constexpr int PUSH_TILE   = 256;
 constexpr int PUSH_STAGES = 3;
 template<int DIM> __host__ __device__ constexpr int push_ncol8(bool copy_wq) { return DIM + 3 + 1 + (copy_wq ? 1 : 0); }
@@ -127,8 +127,12 @@ __global__ void __launch_bounds__(PUSH_TILE, 3)
     uint64_t* full  = reinterpret_cast<uint64_t*>(smem + PUSH_STAGES * BYTES);
     uint64_t* empty = full + PUSH_STAGES;
 
-    // number of tiles this CTA processes: blockIdx.x, blockIdx.x + gridDim.x, ...
-    unsigned const my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // this CTA processes a CONTIGUOUS run of tiles: consecutive tiles are consecutive cells of the
+    // cell-ordered store, so the E,B lines one tile pulls into L1 (a 128-B line holds 16 nodes along the
+    // fastest direction) are reused by the next ones instead of thrashing between unrelated cells
+    unsigned const per_cta  = ntiles / gridDim.x, extra = ntiles % gridDim.x;
+    unsigned const my_tiles = per_cta + (blockIdx.x < extra ? 1u : 0u);
+    size_t const tile0      = size_t(blockIdx.x) * per_cta + (blockIdx.x < extra ? blockIdx.x : extra);
 
     uint64_t pol = 0;
     // producer step j: fill stage j % STAGES with this CTA's j-th tile (thread 0 only)
@@ -137,7 +141,7 @@ __global__ void __launch_bounds__(PUSH_TILE, 3)
         mbar_wait(empty + s, ((j / PUSH_STAGES) & 1) ^ 1);
         mbar_expect_tx(full + s, BYTES);
         unsigned char* st = smem + s * BYTES;
-        size_t const i0   = (size_t(blockIdx.x) + size_t(j) * gridDim.x) * PUSH_TILE;
+        size_t const i0   = (tile0 + j) * PUSH_TILE;
         int c8            = 0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d)
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(PUSH_TILE, 3)
         __syncwarp();
         if ((threadIdx.x & 31) == 0)
             mbar_arrive(empty + s); // the stage can be refilled while we compute
-        size_t const i = (size_t(blockIdx.x) + size_t(it) * gridDim.x) * PUSH_TILE + threadIdx.x;
+        size_t const i = (tile0 + it) * PUSH_TILE + threadIdx.x;
         if constexpr (COPY_WQ)
         {
             __stcs(P.out.charge + i, charge);
