@@ -18,6 +18,14 @@
 // the order in which contributions are summed into a node differs (FP64 addition is not
 // associative: agreement with the sequential reference is ~1e-16*sqrt(N) relative).
 #include "particle_math.cuh"
+#include "pipeline.cuh"
+
+#include <cstdlib>
+
+namespace phb
+{
+constexpr int DEPOSIT_DEPTH = 4; // particles in flight per lane (cp.async ring)
+}
 
 namespace phb
 {
@@ -95,6 +103,15 @@ __device__ __forceinline__ void scatter_atomic(const DevLayout& L, const MomentV
                                   dep[f] * w[0][ix] * w[1][iy] * w[2][iz]);
         }
     }
+}
+
+// out-of-line copy for the rare "particle left its cell" path of the cell-ordered kernel: keeps its
+// registers (weights, 64-bit addresses) out of the hot loop's allocation
+template<int DIM, int ORDER>
+__device__ __noinline__ void scatter_atomic_cold(const DevLayout& L, const MomentViews& M, const int* icell,
+                                                 const double* delta, const double (&dep)[5])
+{
+    scatter_atomic<DIM, ORDER>(L, M, icell, delta, dep);
 }
 
 template<int DIM, int ORDER>
@@ -222,16 +239,54 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
         begin = begin > A.first ? begin : A.first;
         end   = end < A.last ? end : A.last;
         bool const cell_selected = selected<DIM>(A.sel, cell);
-        // software pipeline: the columns of the lane's next particle are requested before the
-        // current one is processed, so each lane keeps ~2 x 13 loads in flight
-        Loaded<DIM> nxt;
-        if (begin + sub < end)
-            nxt = load_particle<DIM>(A.P, begin + sub);
+        // asynchronous prefetch ring: every lane keeps the columns of its next DEPOSIT_DEPTH particles in
+        // flight with cp.async (LDGSTS) into its private shared-memory slots ([slot][column][thread], so the
+        // later LDS are conflict-free) and holds no prefetch registers; one commit group per iteration
+        extern __shared__ __align__(16) unsigned char ring_raw[];
+        double* const ring8 = reinterpret_cast<double*>(ring_raw);
+        int* const ring4    = reinterpret_cast<int*>(ring_raw + size_t(DEPOSIT_DEPTH) * (DIM + 5) * 256 * 8);
+        auto issue = [&](size_t p, int slot) {
+            if (p < end)
+            {
+                int c8 = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    cp_async8(ring8 + (slot * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.delta[d] + p);
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    cp_async8(ring8 + (slot * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.v[c] + p);
+                cp_async8(ring8 + (slot * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.weight + p);
+                cp_async8(ring8 + (slot * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.charge + p);
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    cp_async4(ring4 + (slot * DIM + d) * 256 + threadIdx.x, A.P.icell[d] + p);
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int s = 0; s < DEPOSIT_DEPTH; ++s)
+            issue(begin + sub + size_t(s) * GS, s);
+        int slot = 0;
         for (size_t p = begin + sub; p < end; p += GS)
         {
-            Loaded<DIM> const cur = nxt;
-            if (p + GS < end)
-                nxt = load_particle<DIM>(A.P, p + GS);
+            cp_async_wait<DEPOSIT_DEPTH - 1>(); // the oldest group (this particle) has landed
+            Loaded<DIM> cur;
+            {
+                int c8 = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    cur.delta[d] = ring8[(slot * (DIM + 5) + c8++) * 256 + threadIdx.x];
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+                    cur.v[c] = ring8[(slot * (DIM + 5) + c8++) * 256 + threadIdx.x];
+                cur.weight = ring8[(slot * (DIM + 5) + c8++) * 256 + threadIdx.x];
+                cur.charge = ring8[(slot * (DIM + 5) + c8++) * 256 + threadIdx.x];
+#pragma unroll
+                for (int d = 0; d < DIM; ++d)
+                    cur.icell[d] = ring4[(slot * DIM + d) * 256 + threadIdx.x];
+            }
+            issue(p + size_t(DEPOSIT_DEPTH) * GS, slot); // refill the slot just read
+            slot = slot + 1 == DEPOSIT_DEPTH ? 0 : slot + 1;
             int icell[DIM];
             double delta[DIM];
             bool same = true;
@@ -272,6 +327,10 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
                             wf[d][s] = w[s];
                     }
                 }
+                // node sums: the partial products (dep*wx), ((dep*wx)*wy) are shared by the nodes of a row
+                // and rounded like the reference's left-to-right product; the last multiply is fused
+                // with the accumulation (one rounding instead of two: the summation order already differs
+                // from the sequential reference, so this stays far inside the 1e-10 bound)
 #pragma unroll
                 for (int f = 0; f < 5; ++f)
                 {
@@ -279,31 +338,40 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
                     {
 #pragma unroll
                         for (int ix = 0; ix < S; ++ix)
-                            acc[ix * 5 + f] += dep[f] * wf[0][ix];
+                            acc[ix * 5 + f] = fma(dep[f], wf[0][ix], acc[ix * 5 + f]);
                     }
                     else if constexpr (DIM == 2)
                     {
 #pragma unroll
                         for (int ix = 0; ix < S; ++ix)
+                        {
+                            double const tx = dep[f] * wf[0][ix];
 #pragma unroll
                             for (int iy = 0; iy < S; ++iy)
-                                acc[(ix * S + iy) * 5 + f] += dep[f] * wf[0][ix] * wf[1][iy];
+                                acc[(ix * S + iy) * 5 + f] = fma(tx, wf[1][iy], acc[(ix * S + iy) * 5 + f]);
+                        }
                     }
                     else
                     {
 #pragma unroll
                         for (int ix = 0; ix < S; ++ix)
+                        {
+                            double const tx = dep[f] * wf[0][ix];
 #pragma unroll
                             for (int iy = 0; iy < S; ++iy)
+                            {
+                                double const txy = tx * wf[1][iy];
 #pragma unroll
                                 for (int iz = 0; iz < S; ++iz)
                                     acc[((ix * S + iy) * S + iz) * 5 + f]
-                                        += dep[f] * wf[0][ix] * wf[1][iy] * wf[2][iz];
+                                        = fma(txy, wf[2][iz], acc[((ix * S + iy) * S + iz) * 5 + f]);
+                            }
+                        }
                     }
                 }
             }
             else if (selected<DIM>(A.sel, icell))
-                scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+                scatter_atomic_cold<DIM, ORDER>(A.L, A.M, icell, delta, dep);
         }
     }
 
@@ -342,7 +410,14 @@ void launch_cells(phb_ctx* ctx, const DepositParams<DIM>& A)
     constexpr int BS     = 256;
     size_t const threads = size_t(A.nkeys) * GS;
     unsigned const grid  = unsigned((threads + BS - 1) / BS);
-    deposit_cells_kernel<DIM, ORDER, GS><<<grid, BS, 0, ctx->stream>>>(A);
+    constexpr int smem = DEPOSIT_DEPTH * ((DIM + 5) * 8 + DIM * 4) * BS; // the lanes' prefetch slots
+    static bool configured = false; // per instantiation
+    if (!configured)
+    {
+        cudaFuncSetAttribute(deposit_cells_kernel<DIM, ORDER, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+    }
+    deposit_cells_kernel<DIM, ORDER, GS><<<grid, BS, smem, ctx->stream>>>(A);
 }
 
 template<int DIM, int ORDER>
@@ -356,7 +431,9 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
     {
         if (cells && A.nkeys > 0)
         {
-            size_t const ppc = (A.last - A.first) / A.nkeys;
+            size_t ppc = (A.last - A.first) / A.nkeys;
+            if (const char* e = getenv("PHB_DEPOSIT_GS")) // tuning override: lanes per cell
+                ppc = atoi(e) == 16 ? 96 : atoi(e) == 8 ? 24 : atoi(e) == 4 ? 6 : 1;
             if (ppc >= 96)
                 launch_cells<DIM, ORDER, 16>(ctx, A);
             else if (ppc >= 24)

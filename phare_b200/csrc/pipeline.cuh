@@ -50,6 +50,23 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
         ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)), "l"(policy)
         : "memory");
 }
+// per-thread asynchronous copies global -> shared (cp.async, SASS LDGSTS): 4- or 8-byte elements, so no
+// alignment beyond the element's own is needed; grouped with commit / wait_group
+__device__ __forceinline__ void cp_async8(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template<int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ uint64_t policy_evict_first()
 {
     uint64_t p;
