@@ -51,6 +51,8 @@ struct DepositParams
     DevBox keybox;             // cell-ordered kernel: key -> cell
     const uint32_t* cell_start;
     unsigned nkeys;
+    uint32_t* mover_list;  // cell-ordered kernel: indices of the particles that left their cell ...
+    unsigned* mover_count; // ... handled afterwards by deposit_list_kernel
 };
 
 template<int DIM>
@@ -105,13 +107,31 @@ __device__ __forceinline__ void scatter_atomic(const DevLayout& L, const MomentV
     }
 }
 
-// out-of-line copy for the rare "particle left its cell" path of the cell-ordered kernel: keeps its
-// registers (weights, 64-bit addresses) out of the hot loop's allocation
+// Particles that left their cell since the store was ordered are not scattered from inside the cell-ordered
+// kernel (one active lane doing 5*(o+1)^d atomics stalls its warp): the kernel only appends their index to
+// a list; this kernel then handles the list densely, one thread per listed particle.
 template<int DIM, int ORDER>
-__device__ __noinline__ void scatter_atomic_cold(const DevLayout& L, const MomentViews& M, const int* icell,
-                                                 const double* delta, const double (&dep)[5])
+__global__ void __launch_bounds__(256)
+    deposit_list_kernel(const __grid_constant__ DepositParams<DIM> A, const uint32_t* __restrict__ list,
+                        const unsigned* __restrict__ count)
 {
-    scatter_atomic<DIM, ORDER>(L, M, icell, delta, dep);
+    unsigned const n = *count;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    {
+        size_t const i = list[t];
+        int icell[DIM];
+        double delta[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+        {
+            icell[d] = A.P.icell[d][i];
+            delta[d] = A.P.delta[d][i];
+        }
+        double const weight = A.P.weight[i];
+        double const dep[5] = {1. * weight * A.coef, A.P.charge[i] * weight * A.coef, A.P.v[0][i] * weight * A.coef,
+                               A.P.v[1][i] * weight * A.coef, A.P.v[2][i] * weight * A.coef};
+        scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+    }
 }
 
 template<int DIM, int ORDER>
@@ -371,7 +391,7 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
                 }
             }
             else if (selected<DIM>(A.sel, icell))
-                scatter_atomic_cold<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+                A.mover_list[atomicAdd(A.mover_count, 1u)] = uint32_t(p);
         }
     }
 
@@ -429,8 +449,14 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
     constexpr bool cell_kernel_ok = ipow(cell_support<ORDER>(), DIM) <= 16;
     if constexpr (cell_kernel_ok)
     {
-        if (cells && A.nkeys > 0)
+        if (cells && A.nkeys > 0 && A.last < 0xffffffffull)
         {
+            // scratch: [count | list of at most (last-first) particle indices]
+            if (int rc = ensure_scratch(ctx, (A.last - A.first + 4) * sizeof(uint32_t)))
+                return rc;
+            A.mover_count = static_cast<unsigned*>(ctx->scratch);
+            A.mover_list  = static_cast<uint32_t*>(ctx->scratch) + 4;
+            PHB_CUDA(ctx, cudaMemsetAsync(A.mover_count, 0, sizeof(unsigned), ctx->stream));
             size_t ppc = (A.last - A.first) / A.nkeys;
             if (const char* e = getenv("PHB_DEPOSIT_GS")) // tuning override: lanes per cell
                 ppc = atoi(e) == 16 ? 96 : atoi(e) == 8 ? 24 : atoi(e) == 4 ? 6 : 1;
@@ -442,6 +468,8 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
                 launch_cells<DIM, ORDER, 4>(ctx, A);
             else
                 launch_cells<DIM, ORDER, 2>(ctx, A);
+            PHB_LAUNCH_CHECK(ctx);
+            deposit_list_kernel<DIM, ORDER><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(A, A.mover_list, A.mover_count);
             PHB_LAUNCH_CHECK(ctx);
             return PHB_OK;
         }

@@ -95,6 +95,10 @@ def run(name, cfg):
         report("deposit[atomic]", ms, bpp_dep)
     ms, _ = timeit(lambda: ctx.push(L, E, B, P, P, 1.0, 0.0))  # dt = 0: in place, store stays sorted
     report("push[exact] in place", ms, bpp_push)
+    # the way the step uses it: deposit right after a real push, on the stale order (movers -> list kernel)
+    ctx.push(L, E, B, P, P, 1.0, dt)
+    ms, _ = timeit(dep_cells)
+    report("deposit[cells, stale order]", ms, bpp_dep)
     ctx.poll_error()
     ctx.close()
     return out
