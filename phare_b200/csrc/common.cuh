@@ -167,6 +167,8 @@ struct phb_ctx
     void* scratch         = nullptr;
     size_t scratch_bytes  = 0;
     uint32_t* h_counts    = nullptr; // pinned, 8 entries
+    double* em_pack       = nullptr; // node-interleaved copy of E,B used by the push kernels
+    size_t em_bytes       = 0;
 };
 
 namespace phb

@@ -86,6 +86,8 @@ void phb_destroy(phb_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->scratch)
         cudaFree(ctx->scratch);
+    if (ctx->em_pack)
+        cudaFree(ctx->em_pack);
     if (ctx->d_err)
         cudaFree(ctx->d_err);
     if (ctx->h_err)

@@ -127,6 +127,13 @@ class LocalComm:
     def exchange(self, sends, recvs):
         assert not sends and not recvs
 
+    def prepare(self, sends, recvs):
+        assert not sends and not recvs
+        return None
+
+    def run(self, prepared):
+        pass
+
     def allreduce_max(self, v):
         return v
 
@@ -151,6 +158,16 @@ class TorchComm:
             ops.append(self.dist.P2POp(self.dist.isend, sends[peer], peer))
         if ops:
             for r in self.dist.batch_isend_irecv(ops):
+                r.wait()
+
+    def prepare(self, sends, recvs):
+        ops = [self.dist.P2POp(self.dist.irecv, recvs[peer], peer) for peer in sorted(recvs)]
+        ops += [self.dist.P2POp(self.dist.isend, sends[peer], peer) for peer in sorted(sends)]
+        return ops
+
+    def run(self, prepared):
+        if prepared:
+            for r in self.dist.batch_isend_irecv(prepared):
                 r.wait()
 
     def allreduce_max(self, v):
@@ -205,14 +222,15 @@ class HybridMessenger:
 
     def _run(self, phase):
         ops = self.ops
-        for peer, ph in phase["peers"].items():
-            ops.run_box_ops(ph["pack"])
-        ops.run_box_ops(phase["local"])
+        ops.run_box_ops(phase["pre"])      # packs for every peer (+ the local copies when they are independent)
+        ops.run_box_ops(phase["local"])    # local operations that must follow the packs (in-place max)
         if phase["peers"]:
-            self.comm.exchange({p: ops.as_tensor(ph["sbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["sbuf"])},
-                               {p: ops.as_tensor(ph["rbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["rbuf"])})
-            for peer, ph in phase["peers"].items():
-                ops.run_box_ops(ph["unpack"])
+            if "p2p" not in phase:         # the grouped send/recv list is built once per phase
+                phase["p2p"] = self.comm.prepare(
+                    {p: ops.as_tensor(ph["sbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["sbuf"])},
+                    {p: ops.as_tensor(ph["rbuf"]) for p, ph in phase["peers"].items() if ops.size(ph["rbuf"])})
+            self.comm.run(phase["p2p"])
+            ops.run_box_ops(phase["post"]) # unpack (copy / += / max) of everything received
 
     # ---- public API, named after the reference messenger --------------------------------------
     def fill_ghosts(self, name, qty0, vecs):
@@ -250,13 +268,15 @@ class HybridMessenger:
         self._run(self._compile(("max", name), "border", [abi.RHO] * n, arrays, 2))
 
     def _finish(self, local, send_items, recv_items, op):
+        """One launch packs for all peers, one launch unpacks from all peers (K8 batch tables)."""
         ops = self.ops
-        phase = dict(local=ops.compile_box_ops(local), peers={})
+        phase = dict(peers={})
+        pack, unpack = [], []
         for peer in sorted(set(send_items) | set(recv_items)):
             s_items, r_items = send_items.get(peer, []), recv_items.get(peer, [])
             sbuf = ops.new_buffer(sum(int(np.prod(e)) for _, _, e in s_items))
             rbuf = ops.new_buffer(sum(int(np.prod(e)) for _, _, e in r_items))
-            pack, unpack, off = [], [], 0
+            off = 0
             for (arr, lo, ext) in s_items:
                 pack.append((ops.buffer_slice(sbuf, off, ext), [0] * len(ext), arr, lo, ext, 0))
                 off += int(np.prod(ext))
@@ -264,8 +284,14 @@ class HybridMessenger:
             for (arr, lo, ext) in r_items:
                 unpack.append((arr, lo, ops.buffer_slice(rbuf, off, ext), [0] * len(ext), ext, op))
                 off += int(np.prod(ext))
-            phase["peers"][peer] = dict(pack=ops.compile_box_ops(pack), unpack=ops.compile_box_ops(unpack),
-                                        sbuf=sbuf, rbuf=rbuf)
+            phase["peers"][peer] = dict(sbuf=sbuf, rbuf=rbuf)
+        if op == 2:
+            # in-place max: what is packed must be the value before any local update of this phase
+            phase["pre"], phase["local"] = ops.compile_box_ops(pack), ops.compile_box_ops(local)
+        else:
+            # copy / += : packs read interiors (or the scratch copies), local ops write ghosts: independent
+            phase["pre"], phase["local"] = ops.compile_box_ops(pack + local), None
+        phase["post"] = ops.compile_box_ops(unpack)
         return phase
 
     def migrate_particles(self, layouts, patch_ghost, domain):
