@@ -269,6 +269,14 @@ class Population:
         self.cell_start = ops.cell_start(nkeys)
         self.n_sorted = 0
         self.patch_ghost = ops.particles(capacity // 8 + 4096)  # patchGhostParticles (leavers of this step)
+        # levelGhostParticles (+Old/New, particle_pack.hpp:20-36): only exist on refined levels
+        self.level_ghost = self.level_ghost_spare = self.level_ghost_old = self.level_ghost_new = None
+
+    def set_level_ghosts(self, ops, capacity):
+        self.level_ghost = ops.particles(capacity)
+        self.level_ghost_spare = ops.particles(capacity)
+        self.level_ghost_old = ops.particles(capacity)
+        self.level_ghost_new = ops.particles(capacity)
 
     def moments(self):
         return [self.rho_n, self.rho_q, self.flux[0], self.flux[1], self.flux[2]]
@@ -320,6 +328,13 @@ class IonUpdater:
                 tmp = ops.alias_weight_charge(pop.spare, pop.domain)
                 ops.push(L, E, B, pop.domain, tmp, pop.mass, dt)
                 self._deposit(patch, pop, tmp, n)
+                nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
+                if nlg:
+                    # pushAndAccumulateGhosts (:195-217): a copy of the level ghosts is pushed while inside the
+                    # ghost box (first selector), those that end in the domain box are deposited
+                    ops.push(L, E, B, pop.level_ghost, pop.level_ghost_spare, pop.mass, dt, patch.ghost_box)
+                    ops.deposit(L, pop.level_ghost_spare, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg,
+                                [patch.domain_box])
             else:
                 # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
                 # are deposited; then the store is re-binned: [domain | new patch ghosts | erased]
@@ -334,6 +349,28 @@ class IonUpdater:
                 ops.particles_copy(pop.domain, counts[0], counts[1], pop.patch_ghost, 0)
                 ops.set_count(pop.patch_ghost, counts[1])
                 ops.set_count(pop.domain, counts[0])
+                nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
+                if nlg:
+                    # level ghosts (:275-288): pushed in place while inside the ghost box; those that entered the
+                    # domain are deposited with, and appended to, the domain particles; only those still in the
+                    # ghost layer (ghost box minus domain) remain level ghosts
+                    lg = pop.level_ghost
+                    ops.push(L, E, B, lg, lg, pop.mass, dt, patch.ghost_box)
+                    ops.deposit(L, lg, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg, [patch.domain_box])
+                    ops.export(L, lg, 0, nlg, patch.domain_box, pop.domain)
+                    ops.set_count(pop.level_ghost_spare, 0)
+                    ops.export(L, lg, 0, nlg, patch.ghost_box, pop.level_ghost_spare, minus=patch.domain_box)
+                    pop.level_ghost, pop.level_ghost_spare = pop.level_ghost_spare, lg
+
+    def fill_pop_moment_ghosts(self, patch, alpha):
+        """fillIonPopMomentGhosts (hybrid_hybrid_messenger_strategy.hpp:508-547, level > 0): the level-ghost
+        contribution to the border moments, time-interpolated between the coarse steps:
+        deposit(levelGhostOld, coef = 1 - alpha) + deposit(levelGhostNew, coef = alpha)"""
+        ops, L = self.ops, patch.layout
+        for pop in patch.pops:
+            for store, coef in ((pop.level_ghost_old, 1. - alpha), (pop.level_ghost_new, alpha)):
+                if store is not None and ops.count(store):
+                    ops.deposit(L, store, pop.rho_n, pop.rho_q, pop.flux, coef, 0, ops.count(store))
 
     def _deposit(self, patch, pop, store, n):
         ops, L = self.ops, patch.layout
