@@ -155,6 +155,14 @@ int phb_export(phb_ctx*, const phb_layout*, const phb_particles* src, size_t fir
                const phb_box* box, const phb_box* minus, const int shift[3], phb_particles* dst,
                size_t* h_appended);
 
+/* the same for `nbox` disjoint boxes in ONE pass (two kernels, one synchronisation): particle k of
+ * src[first,last) whose cell lies in boxes[b] is appended to *dsts[b] with iCell += shifts[3b..3b+2].
+ * dsts may repeat. This is the whole sender side of fillIonGhostParticles
+ * (hybrid_hybrid_messenger_strategy.hpp:410-419) for one patch. host-returning: h_appended[nbox].
+ * The order of the appended particles is unspecified. nbox <= 28. */
+int phb_export_multi(phb_ctx*, const phb_layout*, const phb_particles* src, size_t first, size_t last, int nbox,
+                     const phb_box* boxes, const int* shifts, phb_particles* const* dsts, size_t* h_appended);
+
 /* ---- K3 moment deposit ----------------------------------------------------------------------
  * Interpolator::operator()(range, particleDensity, chargeDensity, flux, layout, coef)
  * (interpolator.hpp:468-504) restricted to particles [first,last) whose cell is in one of

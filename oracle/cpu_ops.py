@@ -143,6 +143,9 @@ class CpuOps:
         assert rc == 0, rc
         return int(n.value)
 
+    def export_multi(self, layout, src, first, last, boxes, shifts, dsts):
+        return [self.export(layout, src, first, last, b, d, shift=s) for b, s, d in zip(boxes, shifts, dsts)]
+
     def faraday(self, layout, B, E, Bnew, dt):
         assert self.lib.pho_faraday(C.byref(layout), C.byref(B.c), C.byref(E.c), C.byref(Bnew.c), C.c_double(dt)) == 0
 

@@ -114,6 +114,8 @@ _PROTOS = {
     "phb_export": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t,
                              C.POINTER(Box), C.POINTER(Box), c_int_p, C.POINTER(Particles),
                              C.POINTER(C.c_size_t)]),
+    "phb_export_multi": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_int,
+                                   C.POINTER(Box), c_int_p, C.POINTER(C.POINTER(Particles)), C.POINTER(C.c_size_t)]),
     "phb_deposit": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t,
                               C.c_void_p, C.c_void_p, C.POINTER(VecField), C.c_double, C.POINTER(Box), C.c_int,
                               C.POINTER(Box), C.c_void_p]),

@@ -380,6 +380,131 @@ int export_dim(phb_ctx* ctx, const phb_particles* src, size_t first, size_t last
     *h_appended = total;
     return PHB_OK;
 }
+// ---------------------------------------------------------------- export to several destinations at once
+// One pass classifies every particle of src[first,last) against up to MAX_BOXES disjoint boxes (the images of
+// the neighbouring patches' cell boxes inside this patch's particle ghost box), one host read returns all
+// counts, one pass moves the particles: the whole of fillIonGhostParticles' packing
+// (particles_data.hpp:702-784) in two kernels and one synchronisation instead of one per neighbour.
+template<int DIM>
+struct MultiParams
+{
+    PartView src;
+    size_t first, count;
+    int nbox;
+    DevBox box[MAX_BOXES];
+    int shift[MAX_BOXES][3];
+    PartView dst[MAX_BOXES];
+    unsigned long long dst_first[MAX_BOXES];
+};
+
+template<int DIM>
+__global__ void __launch_bounds__(256)
+    export_classify_kernel(const MultiParams<DIM>* __restrict__ A, uint32_t* __restrict__ counts,
+                           uint32_t* __restrict__ tag, uint32_t* __restrict__ rank)
+{
+    size_t const t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= A->count)
+        return;
+    int c[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+        c[d] = A->src.icell[d][A->first + t];
+    uint32_t b = 0xffffffffu;
+    for (int k = 0; k < A->nbox; ++k)
+        if (in_box<DIM>(c, A->box[k]))
+        {
+            b = uint32_t(k);
+            break;
+        }
+    tag[t] = b;
+    if (b != 0xffffffffu)
+        rank[t] = atomicAdd(counts + b, 1u);
+}
+
+template<int DIM>
+__global__ void __launch_bounds__(256)
+    export_scatter_kernel(const MultiParams<DIM>* __restrict__ A, const uint32_t* __restrict__ tag,
+                          const uint32_t* __restrict__ rank)
+{
+    size_t const t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= A->count)
+        return;
+    uint32_t const b = tag[t];
+    if (b == 0xffffffffu)
+        return;
+    size_t const i = A->first + t, j = A->dst_first[b] + rank[t];
+    const PartView& D = A->dst[b];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+    {
+        D.icell[d][j] = A->src.icell[d][i] + A->shift[b][d];
+        D.delta[d][j] = A->src.delta[d][i];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        D.v[k][j] = A->src.v[k][i];
+    D.weight[j] = A->src.weight[i];
+    D.charge[j] = A->src.charge[i];
+}
+
+template<int DIM>
+int export_multi_dim(phb_ctx* ctx, const phb_particles* src, size_t first, size_t last, int nbox, const phb_box* boxes,
+                     const int* shifts, phb_particles* const* dsts, size_t* h_appended)
+{
+    size_t const count = last - first;
+    for (int k = 0; k < nbox; ++k)
+        h_appended[k] = 0;
+    if (count == 0 || nbox == 0)
+        return PHB_OK;
+    // scratch: [params | counts[MAX_BOXES] | tag[count] | rank[count]]
+    size_t const pbytes = (sizeof(MultiParams<DIM>) + 255) / 256 * 256;
+    if (int rc = ensure_scratch(ctx, pbytes + (MAX_BOXES + 2 * count + 8) * sizeof(uint32_t)))
+        return rc;
+    auto* d_par      = static_cast<MultiParams<DIM>*>(ctx->scratch);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(static_cast<char*>(ctx->scratch) + pbytes);
+    uint32_t* tag    = counts + MAX_BOXES;
+    uint32_t* rank   = tag + count;
+    static thread_local MultiParams<DIM> h; // staged through pageable memory: cudaMemcpyAsync copies it at call time
+    h.src   = make_part(*src);
+    h.first = first;
+    h.count = count;
+    h.nbox  = nbox;
+    for (int k = 0; k < nbox; ++k)
+    {
+        h.box[k] = make_box(boxes[k], DIM);
+        for (int d = 0; d < 3; ++d)
+            h.shift[k][d] = (shifts && d < DIM) ? shifts[3 * k + d] : 0;
+        h.dst[k]       = make_part(*dsts[k]);
+        h.dst_first[k] = 0;
+    }
+    PHB_CUDA(ctx, cudaMemsetAsync(counts, 0, MAX_BOXES * sizeof(uint32_t), ctx->stream));
+    PHB_CUDA(ctx, cudaMemcpyAsync(d_par, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    constexpr int BS    = 256;
+    unsigned const grid = unsigned((count + BS - 1) / BS);
+    export_classify_kernel<DIM><<<grid, BS, 0, ctx->stream>>>(d_par, counts, tag, rank);
+    PHB_LAUNCH_CHECK(ctx);
+    uint32_t h_counts[MAX_BOXES];
+    PHB_CUDA(ctx, cudaMemcpyAsync(h_counts, counts, nbox * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // destinations may repeat (several images of the same patch): hand out consecutive ranges
+    size_t total = 0;
+    for (int k = 0; k < nbox; ++k)
+    {
+        h.dst_first[k] = dsts[k]->n;
+        if (dsts[k]->n + h_counts[k] > dsts[k]->capacity)
+            return set_error(ctx, PHB_ERR_CAPACITY, "phb_export_multi: destination capacity exceeded");
+        dsts[k]->n += h_counts[k]; // later boxes with the same store start after this one
+        h_appended[k] = h_counts[k];
+        total += h_counts[k];
+    }
+    if (total)
+    {
+        PHB_CUDA(ctx, cudaMemcpyAsync(d_par, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+        export_scatter_kernel<DIM><<<grid, BS, 0, ctx->stream>>>(d_par, tag, rank);
+        PHB_LAUNCH_CHECK(ctx);
+    }
+    return PHB_OK;
+}
 } // namespace phb
 
 extern "C" {
@@ -434,4 +559,19 @@ int phb_export(phb_ctx* ctx, const phb_layout* L, const phb_particles* src, size
         default: return phb::export_dim<3>(ctx, src, first, last, box, minus, shift, dst, h_appended);
     }
 }
+}
+
+extern "C" int phb_export_multi(phb_ctx* ctx, const phb_layout* L, const phb_particles* src, size_t first, size_t last,
+                                int nbox, const phb_box* boxes, const int* shifts, phb_particles* const* dsts,
+                                size_t* h_appended)
+{
+    if (!phb::valid_layout(ctx, L) || !src || nbox < 0 || nbox > phb::MAX_BOXES || (nbox && (!boxes || !dsts || !h_appended))
+        || last > src->n || first > last)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_export_multi: invalid argument");
+    switch (L->dim)
+    {
+        case 1: return phb::export_multi_dim<1>(ctx, src, first, last, nbox, boxes, shifts, dsts, h_appended);
+        case 2: return phb::export_multi_dim<2>(ctx, src, first, last, nbox, boxes, shifts, dsts, h_appended);
+        default: return phb::export_multi_dim<3>(ctx, src, first, last, nbox, boxes, shifts, dsts, h_appended);
+    }
 }

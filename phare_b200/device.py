@@ -213,6 +213,21 @@ class Context:
                                         C.byref(n)))
         return int(n.value)
 
+    def export_multi(self, layout, src, first, last, boxes, shifts, dsts):
+        """boxes: abi.Box list; shifts: list of int triples; dsts: stores (may repeat). Returns counts per box."""
+        nb = len(boxes)
+        if nb == 0 or last <= first:
+            return [0] * nb
+        sh = (C.c_int * (3 * nb))()
+        for k, s in enumerate(shifts):
+            for d in range(len(s)):
+                sh[3 * k + d] = int(s[d])
+        ptrs = (C.POINTER(abi.Particles) * nb)(*[C.pointer(d.c) for d in dsts])
+        out = (C.c_size_t * nb)()
+        self._check(self.lib.phb_export_multi(self.h, C.byref(layout), C.byref(src.c), first, last, nb,
+                                              abi.box_array(boxes), sh, ptrs, out))
+        return [int(x) for x in out]
+
     def deposit(self, layout, parts, rho_n, rho_q, flux, coef=1.0, first=0, last=None, sel=(), domain=None,
                 cell_start=None):
         last = parts.n if last is None else last

@@ -301,22 +301,32 @@ class HybridMessenger:
         ops, me = self.ops, self.me
         received = {pid: 0 for pid in domain}
         remote = {}  # (dst owner, dst pid) -> staging store
+        by_src = {}
         for (s, d, box, shift) in self._migration:
-            if s.owner != me:
-                continue
-            store, first, last = patch_ghost[s.id]
+            if s.owner == me:
+                by_src.setdefault(s.id, []).append((d, box, shift))
+        for sid, items in by_src.items():
+            store, first, last = patch_ghost[sid]
             if last <= first:
                 continue
-            if d.owner == me:
-                received[d.id] += ops.export(layouts[s.id], store, first, last, box, domain[d.id], shift=shift)
-            else:
-                key = (d.owner, d.id)
-                if key not in remote:
-                    remote[key] = ops.staging_particles(layouts[s.id], max(last - first, 1))
-                st = remote[key]
-                if ops.capacity(st) < ops.count(st) + (last - first):
-                    st = remote[key] = ops.grow_particles(layouts[s.id], st, ops.count(st) + (last - first))
-                ops.export(layouts[s.id], store, first, last, box, st, shift=shift)
+            dsts = []
+            for (d, box, shift) in items:
+                if d.owner == me:
+                    dsts.append(domain[d.id])
+                else:
+                    key = (d.owner, d.id)
+                    need = (ops.count(remote[key]) if key in remote else 0) + (last - first)
+                    if key not in remote:
+                        remote[key] = ops.staging_particles(layouts[sid], need)
+                    elif ops.capacity(remote[key]) < need:
+                        remote[key] = ops.grow_particles(layouts[sid], remote[key], need)
+                    dsts.append(remote[key])
+            # every image box of this source patch in one classification pass (K2 export_multi)
+            counts = ops.export_multi(layouts[sid], store, first, last, [b for _, b, _ in items],
+                                      [sh for _, _, sh in items], dsts)
+            for (d, _, _), c in zip(items, counts):
+                if d.owner == me:
+                    received[d.id] += c
         if self.comm.size > 1:
             self._exchange_particles(layouts, remote, domain, received)
         return received

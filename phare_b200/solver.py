@@ -141,6 +141,9 @@ class GpuOps:
     def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
         return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
 
+    def export_multi(self, layout, src, first, last, boxes, shifts, dsts):
+        return self.ctx.export_multi(layout, src, first, last, boxes, shifts, dsts)
+
     def faraday(self, layout, B, E, Bnew, dt):
         self.ctx.faraday(layout, B, E, Bnew, dt)
 

@@ -378,3 +378,30 @@ def test_aos_soa_roundtrip(ctxs, dim):
     p2 = DeviceParticles(ctx, 1234).upload_aos(raw)
     for g, w in zip(p2.download_soa(), soa):
         assert bit_equal(np.asarray(g), np.ascontiguousarray(w))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_export_multi_matches_sequential_exports(ctxs, cpu_oracle, dim):
+    """one-pass export to several (possibly repeated) destinations == the oracle's box-by-box exports"""
+    ctx = ctxs(dim, 1)
+    rng = np.random.default_rng(70 + dim)
+    L = small_layout(dim, 1)
+    soa = random_particles(rng, L, 8000)
+    dom = domain_box(L)
+    lo = [dom.lower[d] for d in range(dim)]
+    hi = [dom.upper[d] for d in range(dim)]
+    # the ghost strips below and above the domain in x (disjoint), and one interior box
+    boxes = [abi.make_box([lo[0] - 1] + lo[1:], [lo[0] - 1] + hi[1:]),
+             abi.make_box([hi[0] + 1] + lo[1:], [hi[0] + 1] + hi[1:]),
+             abi.make_box([lo[0] + 2] + lo[1:], [lo[0] + 3] + hi[1:])]
+    shifts = [[int(L.ncells[0])] + [0] * (dim - 1), [-int(L.ncells[0])] + [0] * (dim - 1), [0] * dim]
+    src = HostParticles.from_soa(*soa)
+    w0, w1 = HostParticles(dim, 8000), HostParticles(dim, 8000)
+    want_counts = [cpu_oracle.export(L, src, 50, 7900, boxes[0], w0, shift=shifts[0]),
+                   cpu_oracle.export(L, src, 50, 7900, boxes[1], w1, shift=shifts[1]),
+                   cpu_oracle.export(L, src, 50, 7900, boxes[2], w0, shift=shifts[2])]
+    d0, d1 = DeviceParticles(ctx, 8000), DeviceParticles(ctx, 8000)
+    got_counts = ctx.export_multi(L, dev_particles(ctx, soa), 50, 7900, boxes, shifts, [d0, d1, d0])
+    assert got_counts == want_counts and d0.n == w0.n and d1.n == w1.n and min(want_counts) > 0
+    assert np.array_equal(canonical_rows(*d0.download_soa()), canonical_rows(*w0.soa()))
+    assert np.array_equal(canonical_rows(*d1.download_soa()), canonical_rows(*w1.soa()))

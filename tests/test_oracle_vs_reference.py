@@ -83,3 +83,33 @@ def test_field_operators_bitexact(cpu_oracle, cpu_ref, dim, interp):
     for a, b in zip(to[2], tr[2]):
         assert bit_equal(a, b)
     assert bit_equal(o.average(n, Pe), r.average(n, Pe))
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_reference_maxwellian_initializer_feeds_both_sides(cpu_oracle, cpu_ref, dim):
+    """MaxwellianParticleInitializer::loadParticles (maxwellian_particle_initializer.hpp:138-199), run unmodified
+    through oracle/_ref with a fixed seed: identical initial particles for the oracle and the reference."""
+    L = small_layout(dim, 1)
+    ncell = int(np.prod([L.ncells[d] for d in range(dim)]))
+    n = 1.0 + 0.5 * np.arange(ncell) / ncell
+    zeros, vth = np.zeros(ncell), np.full(ncell, 0.3)
+    ppc = 7
+    P1 = cpu_ref.maxwellian(L, n, [zeros] * 3, [vth] * 3, 1.0, ppc, 1337)
+    P2 = cpu_ref.maxwellian(L, n, [zeros] * 3, [vth] * 3, 1.0, ppc, 1337)
+    assert P1.n == ncell * ppc
+    for a, b in zip(P1.soa(), P2.soa()):
+        assert bit_equal(a, b)  # seeded std::mt19937_64 stream is reproducible
+    ic, de, w, q, v = P1.soa()
+    assert np.all((de >= 0) & (de < 1)) and np.all(q == 1.0)
+    assert np.allclose(w.reshape(ncell, ppc), (n / ppc)[:, None], rtol=0, atol=0)
+    # row-major cell order over the patch box
+    lo = np.array([L.amr_lower[d] for d in range(dim)])
+    idx = np.stack(np.unravel_index(np.arange(ncell), [L.ncells[d] for d in range(dim)]), 1) + lo
+    assert np.array_equal(ic.reshape(ncell, ppc, dim)[:, 0, :], idx)
+    rng = np.random.default_rng(0)
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.1)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.1)
+    _, po = cpu_oracle.push(L, E, B, P1, 1.0, 0.02)
+    _, pr = cpu_ref.push(L, E, B, P1, 1.0, 0.02)
+    for a, b in zip(po.soa(), pr.soa()):
+        assert bit_equal(a, b)
