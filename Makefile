@@ -4,7 +4,7 @@ NVCC      ?= /usr/local/cuda/bin/nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: products and sums are rounded separately, like the reference's default CPU build;
 # the few deliberate fusions are explicit fma() calls.
-NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 SRC       := $(wildcard phare_b200/csrc/*.cu)
 OBJ       := $(patsubst phare_b200/csrc/%.cu,build/%.o,$(SRC))
 LIB       := phare_b200/lib/libphare_b200.so

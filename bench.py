@@ -178,10 +178,14 @@ def our_arm(args):
     if push_ms:
         alg = n_local * BYTES_PUSH[3]
         ach = alg / (avg(push_ms) * 1e-3) / 1e9
+        # DRAM traffic per launch: dram__bytes_read+write of one `ncu --set full` capture of this kernel
+        # (profiles/traffic_c5s.json, taken on the same kernel at 16.8 M particles), scaled per particle
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        prof = os.path.join(ROOT, "profiles", "traffic_c5s.json")
         if os.path.exists(prof):
-            traffic = json.load(open(prof)).get("push_tma_kernel<3,1>", {}).get("dram_bytes_per_launch")
+            for k, v in json.load(open(prof)).items():
+                if k.startswith("push_tma_kernel<3, 1"):
+                    traffic = v["dram_bytes_per_particle"] * n_local
         roofline = dict(bound="hbm", kernel="push (K1 fused interpolate+Boris)", achieved=round(ach, 1), peak=peak,
                         unit="GB/s", frac=round(ach / peak, 4), traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg, avg_launch_ms=round(avg(push_ms), 4),

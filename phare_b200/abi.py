@@ -9,7 +9,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "lib", "libphare_b200.so")
+LIB_PATH = os.environ.get("PHB_LIB") or os.path.join(_HERE, "lib", "libphare_b200.so")  # PHB_LIB: tuning builds
 
 PHB_OK, PHB_ERR_INVALID, PHB_ERR_CUDA, PHB_ERR_MOVE_TWO_CELL = 0, 1, 2, 3
 PHB_ERR_OUTSIDE_GHOST, PHB_ERR_CAPACITY, PHB_ERR_NO_DEVICE = 4, 5, 6

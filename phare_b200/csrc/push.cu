@@ -212,8 +212,18 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushP
 // particle out of the stage, release it at once, and do gather + Boris + stores while the next
 // PUSH_STAGES-1 tiles are already in flight (thread 0 issues the copies; no warp is set aside, so
 // three CTAs stay resident per SM).  Persistent CTAs, one contiguous run of tiles each.
-constexpr int PUSH_TILE   = 256;
-constexpr int PUSH_STAGES = 3;
+#ifndef PHB_PUSH_TILE
+#define PHB_PUSH_TILE 256
+#endif
+#ifndef PHB_PUSH_STAGES
+#define PHB_PUSH_STAGES 2 // measured at config 5: 2 -> 3.70 ms, 3 -> 3.91 ms, 4 -> 4.62 ms (stages eat L1 that the E,B lines need)
+#endif
+#ifndef PHB_PUSH_CTAS
+#define PHB_PUSH_CTAS 3
+#endif
+constexpr int PUSH_TILE   = PHB_PUSH_TILE;   // particles per tile = threads per CTA
+constexpr int PUSH_STAGES = PHB_PUSH_STAGES; // tiles in flight per CTA
+constexpr int PUSH_CTAS   = PHB_PUSH_CTAS;   // resident CTAs per SM
 template<int DIM> __host__ __device__ constexpr int push_ncol8(bool copy_wq) { return DIM + 3 + 1 + (copy_wq ? 1 : 0); }
 template<int DIM> __host__ __device__ constexpr int push_stage_bytes(bool copy_wq)
 {
@@ -221,7 +231,7 @@ template<int DIM> __host__ __device__ constexpr int push_stage_bytes(bool copy_w
 }
 
 template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool COPY_WQ>
-__global__ void __launch_bounds__(PUSH_TILE, 3)
+__global__ void __launch_bounds__(PUSH_TILE, PUSH_CTAS)
     push_tma_kernel(const __grid_constant__ PushParams<DIM> P, unsigned ntiles)
 {
     constexpr int NC8   = push_ncol8<DIM>(COPY_WQ);
@@ -327,7 +337,7 @@ int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P)
     {
         bool const wq      = P.copy_weight_charge;
         size_t const smem  = size_t(PUSH_STAGES) * push_stage_bytes<DIM>(wq) + 2 * PUSH_STAGES * sizeof(uint64_t);
-        unsigned const grid = unsigned(std::min<size_t>(ntiles, size_t(ctx->sm_count) * 3));
+        unsigned const grid = unsigned(std::min<size_t>(ntiles, size_t(ctx->sm_count) * PUSH_CTAS));
         auto launch = [&](auto kernel) -> int {
             PHB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
             kernel<<<grid, PUSH_TILE, smem, ctx->stream>>>(P, unsigned(ntiles));
