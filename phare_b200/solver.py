@@ -320,18 +320,28 @@ class IonUpdater:
         self.ops = ops
 
     def update_populations(self, patch, E, B, dt, mode):
+        """IonUpdater::updatePopulations (ion_updater.hpp:90-109).  For mode == all the work is split in two
+        halves that touch independent data: update_moments (push + deposit: everything the moments need) and
+        maintain_arrays (re-binning, patch-ghost / level-ghost bookkeeping: only the particle arrays).
+        SolverPPC runs the second half after the corrector so that its host synchronisations (counts) do not
+        stall the field phases; calling this method runs both, exactly like the reference."""
+        self.update_moments(patch, E, B, dt, mode)
+        if mode == ALL:
+            self.maintain_arrays(patch)
+
+    def update_moments(self, patch, E, B, dt, mode):
         ops, L = self.ops, patch.layout
         for pop in patch.pops:
             for m in pop.moments():  # resetMoments (moments.hpp:15-23)
                 ops.zero(m)
             n = ops.count(pop.domain)
+            nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
             if mode == DOMAIN_ONLY:
                 # updateAndDepositDomain_ (:171-219): push a COPY (tmp_particles_), deposit those that end in the
                 # nonLevelGhostBox; the domain array itself is untouched
                 tmp = ops.alias_weight_charge(pop.spare, pop.domain)
                 ops.push(L, E, B, pop.domain, tmp, pop.mass, dt)
                 self._deposit(patch, pop, tmp, n)
-                nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
                 if nlg:
                     # pushAndAccumulateGhosts (:195-217): a copy of the level ghosts is pushed while inside the
                     # ghost box (first selector), those that end in the domain box are deposited
@@ -340,30 +350,37 @@ class IonUpdater:
                                 [patch.domain_box])
             else:
                 # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
-                # are deposited; then the store is re-binned: [domain | new patch ghosts | erased]
+                # are deposited (= the domain + new patchGhost deposits of :290-293)
                 ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
                 self._deposit(patch, pop, pop.domain, n)
-                counts = ops.bin(L, pop.domain, pop.spare, patch.domain_box, patch.non_level_ghost, pop.cell_start)
-                pop.domain, pop.spare = pop.spare, pop.domain
-                pop.n_sorted = counts[0]
-                # "copy out new patch ghosts" (:248-254) then "drop all ghosts" (:273)
-                if ops.capacity(pop.patch_ghost) < counts[1]:
-                    pop.patch_ghost = ops.particles(int(counts[1] * 1.5) + 4096)
-                ops.particles_copy(pop.domain, counts[0], counts[1], pop.patch_ghost, 0)
-                ops.set_count(pop.patch_ghost, counts[1])
-                ops.set_count(pop.domain, counts[0])
-                nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
                 if nlg:
                     # level ghosts (:275-288): pushed in place while inside the ghost box; those that entered the
-                    # domain are deposited with, and appended to, the domain particles; only those still in the
-                    # ghost layer (ghost box minus domain) remain level ghosts
-                    lg = pop.level_ghost
-                    ops.push(L, E, B, lg, lg, pop.mass, dt, patch.ghost_box)
-                    ops.deposit(L, lg, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg, [patch.domain_box])
-                    ops.export(L, lg, 0, nlg, patch.domain_box, pop.domain)
-                    ops.set_count(pop.level_ghost_spare, 0)
-                    ops.export(L, lg, 0, nlg, patch.ghost_box, pop.level_ghost_spare, minus=patch.domain_box)
-                    pop.level_ghost, pop.level_ghost_spare = pop.level_ghost_spare, lg
+                    # domain are deposited with the domain particles
+                    ops.push(L, E, B, pop.level_ghost, pop.level_ghost, pop.mass, dt, patch.ghost_box)
+                    ops.deposit(L, pop.level_ghost, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg, [patch.domain_box])
+
+    def maintain_arrays(self, patch):
+        """second half of updateAndDepositAll_: the store is re-binned into [domain | new patch ghosts | erased]
+        (partition + erase, :245-273), level ghosts that entered the domain are appended to it and only those
+        still in the ghost layer remain level ghosts (:281-287)"""
+        ops, L = self.ops, patch.layout
+        for pop in patch.pops:
+            counts = ops.bin(L, pop.domain, pop.spare, patch.domain_box, patch.non_level_ghost, pop.cell_start)
+            pop.domain, pop.spare = pop.spare, pop.domain
+            pop.n_sorted = counts[0]
+            # "copy out new patch ghosts" (:248-254) then "drop all ghosts" (:273)
+            if ops.capacity(pop.patch_ghost) < counts[1]:
+                pop.patch_ghost = ops.particles(int(counts[1] * 1.5) + 4096)
+            ops.particles_copy(pop.domain, counts[0], counts[1], pop.patch_ghost, 0)
+            ops.set_count(pop.patch_ghost, counts[1])
+            ops.set_count(pop.domain, counts[0])
+            nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
+            if nlg:
+                lg = pop.level_ghost
+                ops.export(L, lg, 0, nlg, patch.domain_box, pop.domain)
+                ops.set_count(pop.level_ghost_spare, 0)
+                ops.export(L, lg, 0, nlg, patch.ghost_box, pop.level_ghost_spare, minus=patch.domain_box)
+                pop.level_ghost, pop.level_ghost_spare = pop.level_ghost_spare, lg
 
     def fill_pop_moment_ghosts(self, patch, alpha):
         """fillIonPopMomentGhosts (hybrid_hybrid_messenger_strategy.hpp:508-547, level > 0): the level-ghost
@@ -433,32 +450,40 @@ class SolverPPC:
         self.messenger.fill_ghosts("Eavg", abi.EX, self._by_id("Eavg"))
 
     def _move_ions(self, dt, mode):
-        """moveIons_ (solver_ppc.hpp:538-598)"""
+        """moveIons_ (solver_ppc.hpp:538-598).  The particle-array half of the `all` sweep (re-binning and
+        fillIonGhostParticles) and the error vote are deferred to _finish_particles(): they do not feed the
+        moments, and their host synchronisations would otherwise stall the field phases that follow."""
         ops, msg = self.ops, self.messenger
         for p in self.patches:
-            self.updater.update_populations(p, p.Eavg, p.Bavg, dt, mode)
-        # mpi::any_errors(): every rank learns whether any kernel flagged a particle (:549-563)
-        err = ops.poll_error()
-        if self.comm.allreduce_max(err):
-            raise RuntimeError("Updater::updatePopulations: " + (getattr(ops, "last_error", "") or "error on another rank"))
+            self.updater.update_moments(p, p.Eavg, p.Bavg, dt, mode)
         npop = len(self.patches[0].pops) if self.patches else 0
         for i in range(npop):
             # fillFluxBorders + fillDensityBorders
             msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in self.patches},
                             {p.geom.id: p.pops[i].scratch for p in self.patches})
         # fillIonPopMomentGhosts: level > 0 only (no-op on the root level)
-        if mode == ALL:
-            for i in range(npop):  # fillIonGhostParticles, then patchGhostParticles.clear()
-                msg.migrate_particles(self.layouts,
-                                      {p.geom.id: (p.pops[i].patch_ghost, 0, ops.count(p.pops[i].patch_ghost))
-                                       for p in self.patches},
-                                      {p.geom.id: p.pops[i].domain for p in self.patches})
-                for p in self.patches:
-                    ops.set_count(p.pops[i].patch_ghost, 0)
         for p in self.patches:
             self.updater.update_ions(p)
         # fillIonBorders: SetMax on total mass density, charge density and bulk velocity
         msg.max_borders("ions", {p.geom.id: [p.rho_m, p.Ne, p.Vi[0], p.Vi[1], p.Vi[2]] for p in self.patches})
+
+    def _finish_particles(self):
+        """deferred half of moveIons_(all): re-binning, fillIonGhostParticles + patchGhostParticles.clear()
+        (:581-585), and mpi::any_errors() (:549-563) for both sweeps of the step"""
+        ops, msg = self.ops, self.messenger
+        for p in self.patches:
+            self.updater.maintain_arrays(p)
+        npop = len(self.patches[0].pops) if self.patches else 0
+        for i in range(npop):
+            msg.migrate_particles(self.layouts,
+                                  {p.geom.id: (p.pops[i].patch_ghost, 0, ops.count(p.pops[i].patch_ghost))
+                                   for p in self.patches},
+                                  {p.geom.id: p.pops[i].domain for p in self.patches})
+            for p in self.patches:
+                ops.set_count(p.pops[i].patch_ghost, 0)
+        err = ops.poll_error()
+        if self.comm.allreduce_max(err):
+            raise RuntimeError("Updater::updatePopulations: " + (getattr(ops, "last_error", "") or "error on another rank"))
 
     # ---- public
     def prepare_step(self):
@@ -478,6 +503,7 @@ class SolverPPC:
         self._move_ions(dt, ALL)
         self._field_solve("B", "Eavg", "B", "E", dt, "corrector")
         self.messenger.fill_ghosts("E", abi.EX, self._by_id("E"))
+        self._finish_particles()
 
     def initialize(self):
         """HybridLevelInitializer::initialize, root level (hybrid_level_initializer.hpp:100-182): particles and B
