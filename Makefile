@@ -13,7 +13,7 @@ all: lib oracle
 
 lib: $(LIB)
 
-build/%.o: phare_b200/csrc/%.cu phare_b200/csrc/common.cuh phare_b200/csrc/particle_math.cuh include/phare_b200.h
+build/%.o: phare_b200/csrc/%.cu $(wildcard phare_b200/csrc/*.cuh) include/phare_b200.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
 

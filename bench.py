@@ -233,27 +233,15 @@ def our_arm(args):
 def measure_e2e(solver, ops, args, world, device, n_total):
     import torch
     import torch.distributed as dist
-    patch = solver.patches[0]
-    ins = [patch.E[c] for c in range(3)] + [patch.B[c] for c in range(3)]
-    pop = patch.pops[0]
-    outs = ins + [patch.Ne, patch.Vi[0], patch.Vi[1], patch.Vi[2]] + pop.moments()
-    h_in = [torch.empty(a.t.shape, dtype=torch.float64).pin_memory() for a in ins]
-    h_out = [torch.empty(a.t.shape, dtype=torch.float64).pin_memory() for a in outs]
-    for h, a in zip(h_in, ins):
-        h.copy_(a.t)
-    bi = sum(h.numel() * 8 for h in h_in)
-    bo = sum(h.numel() * 8 for h in h_out)
+    from phare_b200.solver import HostStaging
+    staging = HostStaging(ops, solver.patches)
+    bi, bo = staging.h2d_bytes, staging.d2h_bytes
     steps = max(2, min(args.steps, 5))
 
     def one():
-        for h, a in zip(h_in, ins):
-            a.t.copy_(h, non_blocking=True)
-        solver.advance_level(DT)
-        for h, a in zip(h_out, outs):
-            h.copy_(a.t, non_blocking=True)
-        # the host-side E,B of the next step are this step's results: the first six result buffers ARE the
-        # next inputs (pointer swap on the host, no extra transfer)
-        h_in[:], h_out[:6] = h_out[:6], h_in[:]
+        # the public host-buffer call: E,B pinned host -> device, advanceLevel, moments + E,B -> pinned host
+        solver.advance_level(DT, staging=staging)
+        staging.results_become_inputs()
 
     one()
     torch.cuda.synchronize()
@@ -272,8 +260,10 @@ def measure_e2e(solver, ops, args, world, device, n_total):
         ms = float(t.item())
     out = dict(value=2 * n_total * steps / (ms * 1e-3), unit="particle-pushes/s", h2d_bytes_per_step=bi,
                d2h_bytes_per_step=bo, steps=steps,
-               what="per step: E,B from pinned host memory -> device, advanceLevel, moments + E,B -> pinned host; "
-                    "the particle store stays device-resident (it is solver state, like the reference's ParticlesData)")
+               what="SolverPPC.advance_level(dt, staging=HostStaging): per step E,B from pinned host memory -> device, "
+                    "advanceLevel, per-population + total moments and the new E,B -> pinned host (read back on a copy "
+                    "stream as soon as each is final, overlapping the particle re-binning that ends the step); the "
+                    "particle store stays device-resident (it is solver state, like the reference's ParticlesData)")
     # the naive drop-in for comparison: AoS Particle<3> records cross PCIe both ways around one sweep
     try:
         out["particles_roundtrip"] = particle_roundtrip(solver, ops)

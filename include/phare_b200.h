@@ -175,6 +175,24 @@ int phb_deposit(phb_ctx*, const phb_layout*, const phb_particles*, size_t first,
                 double* rho_n, double* rho_q, const phb_vecfield* flux, double coef,
                 const phb_box* sel, int nsel, const phb_box* domain, const uint32_t* d_cell_start);
 
+/* ---- K1+K3 fused: push and deposit in one pass ------------------------------------------------
+ * The body of IonUpdater::updateAndDepositDomain_ / updateAndDepositAll_ for one particle array
+ * (ion_updater.hpp:171-219, 228-295): pusher_->move(range, ...) followed by
+ * interpolator_(range, density, flux, layout), as ONE pass over parts[first,last): every particle is
+ * moved exactly like phb_push (same arithmetic, same first_selector meaning) and, if its NEW cell lies in
+ * one of sel[nsel] (nsel = 0: always), deposited exactly like phb_deposit with `coef`.
+ *   write_back = 1 : the moved state replaces the stored one (UpdaterMode::all, in place)
+ *   write_back = 0 : the store is left untouched (UpdaterMode::domain_only: the reference pushes a
+ *                    temporary copy, deposits it and drops it — here the copy is never materialised)
+ * d_cell_start/domain as in phb_deposit (cell-ordered kernel; [first,last) must then lie inside the
+ * particles of the domain keys, i.e. last <= h_counts[0] of phb_bin); NULL = any order.
+ * Errors (move of more than two cells) are raised through phb_poll_error like phb_push. */
+int phb_push_deposit(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,
+                     phb_particles* parts, size_t first, size_t last, double mass, double dt,
+                     const phb_box* first_selector, int write_back, double* rho_n, double* rho_q,
+                     const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
+                     const phb_box* domain, const uint32_t* d_cell_start);
+
 /* ---- K4-K7 field solvers and pointwise ops -------------------------------------------------- */
 /* Faraday::operator()(B,E,Bnew,dt)  faraday/faraday.hpp:28-97 */
 int phb_faraday(phb_ctx*, const phb_layout*, const phb_vecfield* B, const phb_vecfield* E,

@@ -126,6 +126,18 @@ class CpuOps:
                                   abi.box_array(list(sel)), C.c_int(len(sel)))
         assert rc == 0
 
+    def push_deposit(self, layout, E, B, parts, mass, dt, rho_n, rho_q, F, coef=1.0, first=0, last=None, sel=(),
+                     domain=None, cell_start=None, first_selector=None, write_back=True):
+        """checker for phb_push_deposit, literally the reference's two passes: move the range (into a temporary
+        when write_back is false), then deposit the moved range"""
+        last = parts.n if last is None else last
+        tmp = HostParticles(self.dim, max(parts.n, 1))
+        self.push(layout, E, B, parts, tmp, mass, dt, first_selector)
+        tmp.n = parts.n
+        self.deposit(layout, tmp, rho_n, rho_q, F, coef, first, last, sel)
+        if write_back and last > first:
+            self.particles_copy(tmp, first, last - first, parts, first)
+
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         counts = (C.c_size_t * 3)()
         rc = self.lib.pho_bin(C.byref(layout), C.byref(pin.c), C.byref(pout.c), C.byref(domain),

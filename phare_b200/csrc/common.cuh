@@ -156,6 +156,7 @@ struct phb_ctx
     int device = 0, dim = 0, interp = 0;
     bool exact            = true;
     bool no_tma           = false; // PHB_NO_TMA=1: force the plain (non bulk-copy) kernels
+    bool no_fused_cells   = false; // PHB_NO_FUSED_CELLS=1: phb_push_deposit uses the per-particle kernel only
     cudaStream_t stream   = nullptr;
     bool own_stream       = false;
     phb::DevError* d_err  = nullptr;

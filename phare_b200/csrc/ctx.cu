@@ -73,6 +73,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
     ctx->own_stream = true;
     if (const char* e = getenv("PHB_NO_TMA"))
         ctx->no_tma = e[0] == '1';
+    if (const char* e = getenv("PHB_NO_FUSED_CELLS"))
+        ctx->no_fused_cells = e[0] == '1';
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return PHB_OK;

@@ -17,8 +17,7 @@
 // Each contribution is computed exactly as the reference does: ((q*weight)*coef)*wx*wy*wz; only
 // the order in which contributions are summed into a node differs (FP64 addition is not
 // associative: agreement with the sequential reference is ~1e-16*sqrt(N) relative).
-#include "particle_math.cuh"
-#include "pipeline.cuh"
+#include "deposit_core.cuh"
 
 #include <cstdlib>
 
@@ -29,84 +28,6 @@ constexpr int DEPOSIT_DEPTH = 4; // particles in flight per lane (cp.async ring)
 
 namespace phb
 {
-struct MomentViews
-{
-    double* f[5]; // rho_n, rho_q, Fx, Fy, Fz : all primal, same shape
-    int n[3];
-    __device__ __forceinline__ size_t at(int i, int j, int k) const
-    {
-        return (size_t(i) * n[1] + j) * n[2] + k;
-    }
-};
-
-template<int DIM>
-struct DepositParams
-{
-    DevLayout L;
-    PartView P;
-    MomentViews M;
-    size_t first, last;
-    double coef;
-    BoxList sel;               // n == 0: everything selected
-    DevBox keybox;             // cell-ordered kernel: key -> cell
-    const uint32_t* cell_start;
-    unsigned nkeys;
-    uint32_t* mover_list;  // cell-ordered kernel: indices of the particles that left their cell ...
-    unsigned* mover_count; // ... handled afterwards by deposit_list_kernel
-};
-
-template<int DIM>
-__device__ __forceinline__ bool selected(const BoxList& sel, const int* c)
-{
-    if (sel.n == 0)
-        return true;
-    for (int b = 0; b < sel.n; ++b)
-        if (in_box<DIM>(c, sel.b[b]))
-            return true;
-    return false;
-}
-
-// per-particle atomic scatter (ParticleToMesh<DIM>, interpolator.hpp:278-363)
-template<int DIM, int ORDER>
-__device__ __forceinline__ void scatter_atomic(const DevLayout& L, const MomentViews& M, const int* icell,
-                                               const double* delta, const double (&dep)[5])
-{
-    int start[DIM];
-    double w[DIM][ORDER + 1];
-#pragma unroll
-    for (int d = 0; d < DIM; ++d)
-        start[d] = index_and_weights<ORDER, PRIMAL>(icell[d] - (L.amr_lower[d] - L.g), delta[d], w[d]);
-#pragma unroll
-    for (int f = 0; f < 5; ++f)
-    {
-        if constexpr (DIM == 1)
-        {
-#pragma unroll
-            for (int ix = 0; ix <= ORDER; ++ix)
-                atomicAdd(M.f[f] + M.at(start[0] + ix, 0, 0), dep[f] * w[0][ix]);
-        }
-        else if constexpr (DIM == 2)
-        {
-#pragma unroll
-            for (int ix = 0; ix <= ORDER; ++ix)
-#pragma unroll
-                for (int iy = 0; iy <= ORDER; ++iy)
-                    atomicAdd(M.f[f] + M.at(start[0] + ix, start[1] + iy, 0), dep[f] * w[0][ix] * w[1][iy]);
-        }
-        else
-        {
-#pragma unroll
-            for (int ix = 0; ix <= ORDER; ++ix)
-#pragma unroll
-                for (int iy = 0; iy <= ORDER; ++iy)
-#pragma unroll
-                    for (int iz = 0; iz <= ORDER; ++iz)
-                        atomicAdd(M.f[f] + M.at(start[0] + ix, start[1] + iy, start[2] + iz),
-                                  dep[f] * w[0][ix] * w[1][iy] * w[2][iz]);
-        }
-    }
-}
-
 // Particles that left their cell since the store was ordered are not scattered from inside the cell-ordered
 // kernel (one active lane doing 5*(o+1)^d atomics stalls its warp): the kernel only appends their index to
 // a list; this kernel then handles the list densely, one thread per listed particle.
@@ -155,71 +76,6 @@ __global__ void __launch_bounds__(256) deposit_atomic_kernel(const __grid_consta
                            __ldcs(A.P.v[0] + i) * weight * A.coef, __ldcs(A.P.v[1] + i) * weight * A.coef,
                            __ldcs(A.P.v[2] + i) * weight * A.coef};
     scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
-}
-
-// union of the primal supports of all particles of one cell, per direction:
-// order 1: {l, l+1}; order 2: {l-1 .. l+2} (start = l-1 or l); order 3: {l-1 .. l+2}
-template<int ORDER> constexpr int cell_support() { return ORDER == 1 ? 2 : 4; }
-template<int ORDER> constexpr int cell_base_shift() { return ORDER == 1 ? 0 : 1; }
-constexpr int ipow(int b, int e) { return e == 0 ? 1 : b * ipow(b, e - 1); }
-
-template<int NV, int GS, int NCHUNK, int MASK>
-struct GroupReduce
-{
-    // a[0 .. NCHUNK*5) valid on entry; after all steps the lane owns chunks [base, base+nleft)
-    __device__ static __forceinline__ void run(double (&a)[NV], int lane, int& base, int& nleft)
-    {
-        if constexpr (MASK < GS)
-        {
-            if constexpr (NCHUNK > 1)
-            {
-                constexpr int half = NCHUNK / 2;
-                bool const upper   = (lane & MASK) != 0;
-#pragma unroll
-                for (int i = 0; i < half * 5; ++i)
-                {
-                    double const send = upper ? a[i] : a[i + half * 5];
-                    double const keep = upper ? a[i + half * 5] : a[i];
-                    a[i]              = keep + __shfl_xor_sync(0xffffffffu, send, MASK);
-                }
-                base += upper ? half : 0;
-                GroupReduce<NV, GS, half, MASK * 2>::run(a, lane, base, nleft);
-            }
-            else
-            {
-#pragma unroll
-                for (int i = 0; i < 5; ++i)
-                    a[i] += __shfl_xor_sync(0xffffffffu, a[i], MASK);
-                GroupReduce<NV, GS, 1, MASK * 2>::run(a, lane, base, nleft);
-            }
-        }
-        else
-            nleft = NCHUNK;
-    }
-};
-
-template<int DIM>
-struct Loaded
-{
-    int icell[DIM];
-    double delta[DIM], v[3], weight, charge;
-};
-template<int DIM>
-__device__ __forceinline__ Loaded<DIM> load_particle(const PartView& P, size_t p)
-{
-    Loaded<DIM> r;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d)
-    {
-        r.icell[d] = __ldcs(P.icell[d] + p);
-        r.delta[d] = __ldcs(P.delta[d] + p);
-    }
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        r.v[c] = __ldcs(P.v[c] + p);
-    r.weight = __ldcs(P.weight + p);
-    r.charge = __ldcs(P.charge + p);
-    return r;
 }
 
 template<int DIM, int ORDER, int GS>
@@ -487,31 +343,8 @@ int deposit_dim(phb_ctx* ctx, const phb_layout* L, const phb_particles* P, size_
                 const phb_box* domain, const uint32_t* cell_start)
 {
     DepositParams<DIM> A;
-    A.L      = make_dev_layout(*L);
-    A.P      = make_part(*P);
-    A.M.f[0] = rho_n;
-    A.M.f[1] = rho_q;
-    for (int c = 0; c < 3; ++c)
-        A.M.f[2 + c] = flux->comp[c];
-    for (int d = 0; d < 3; ++d)
-        A.M.n[d] = alloc_extent(A.L, PHB_RHO, d);
-    A.first = first;
-    A.last  = last;
-    A.coef  = coef;
-    A.sel.n = nsel;
-    for (int b = 0; b < nsel; ++b)
-        A.sel.b[b] = make_box(sel[b], DIM);
-    A.cell_start = cell_start;
-    A.nkeys      = 0;
+    prepare_deposit<DIM>(L, P, first, last, rho_n, rho_q, flux, coef, sel, nsel, domain, cell_start, A);
     bool const cells = cell_start != nullptr && domain != nullptr;
-    if (cells)
-    {
-        A.keybox   = make_box(*domain, DIM);
-        size_t vol = 1;
-        for (int d = 0; d < DIM; ++d)
-            vol *= size_t(domain->upper[d] - domain->lower[d] + 1);
-        A.nkeys = unsigned(vol);
-    }
     switch (L->interp)
     {
         case 1: return deposit_order<DIM, 1>(ctx, A, cells);

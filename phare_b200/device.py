@@ -236,6 +236,15 @@ class Context:
             abi.box_array(list(sel)), len(sel), C.byref(domain) if domain is not None else None,
             cell_start.ptr if cell_start is not None else None))
 
+    def push_deposit(self, layout, E, B, parts, mass, dt, rho_n, rho_q, flux, coef=1.0, first=0, last=None, sel=(),
+                     domain=None, cell_start=None, first_selector=None, write_back=True):
+        last = parts.n if last is None else last
+        self._check(self.lib.phb_push_deposit(
+            self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(parts.c), first, last, mass, dt,
+            C.byref(first_selector) if first_selector is not None else None, 1 if write_back else 0,
+            rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel),
+            C.byref(domain) if domain is not None else None, cell_start.ptr if cell_start is not None else None))
+
     def faraday(self, layout, B, E, Bnew, dt):
         self._check(self.lib.phb_faraday(self.h, C.byref(layout), C.byref(B.c), C.byref(E.c), C.byref(Bnew.c), dt))
 

@@ -135,6 +135,13 @@ class GpuOps:
         self._timed("deposit" if cell_start is not None else "deposit_unordered",
                     lambda: self.ctx.deposit(layout, parts, rho_n, rho_q, F, coef, first, last, sel, domain, cell_start))
 
+    def push_deposit(self, layout, E, B, parts, mass, dt, rho_n, rho_q, F, coef=1.0, first=0, last=None, sel=(),
+                     domain=None, cell_start=None, first_selector=None, write_back=True):
+        """K1+K3 fused (phb_push_deposit): move parts[first,last) and deposit the moved particles in one pass"""
+        name = ("move" if cell_start is not None else "move_unordered") + ("_all" if write_back else "_domain_only")
+        self._timed(name, lambda: self.ctx.push_deposit(layout, E, B, parts, mass, dt, rho_n, rho_q, F, coef, first,
+                                                        last, sel, domain, cell_start, first_selector, write_back))
+
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
 
@@ -314,10 +321,15 @@ class IonUpdater:
     """IonUpdater<Ions, Electromag, GridLayout> (ion_updater.hpp:24-83) on the device-resident store.
     The pusher is named in dict["pusher"]["name"]; only "modified_boris" exists (pusher_factory.hpp:20-30)."""
 
-    def __init__(self, ops, pusher_name="modified_boris"):
+    # (dim, interp) pairs where the one-pass kernel measured faster than push + deposit on B200 (tools/microbench.py)
+    FUSED_AUTO = frozenset({(1, 1), (1, 2), (1, 3)})
+
+    def __init__(self, ops, pusher_name="modified_boris", fused="auto"):
         if pusher_name != "modified_boris":
             raise RuntimeError("Error : Invalid Pusher name")
         self.ops = ops
+        # fused: one pass per array and sweep (phb_push_deposit, K1+K3) instead of phb_push then phb_deposit
+        self.fused = fused
 
     def update_populations(self, patch, E, B, dt, mode):
         """IonUpdater::updatePopulations (ion_updater.hpp:90-109).  For mode == all the work is split in two
@@ -336,7 +348,21 @@ class IonUpdater:
                 ops.zero(m)
             n = ops.count(pop.domain)
             nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
-            if mode == DOMAIN_ONLY:
+            fused = self.fused if isinstance(self.fused, bool) else (L.dim, L.interp) in self.FUSED_AUTO
+            if fused:
+                # both modes are the same pass; domain_only simply never stores the moved copy
+                wb = mode == ALL
+                if pop.n_sorted:
+                    ops.push_deposit(L, E, B, pop.domain, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0,
+                                     pop.n_sorted, patch.non_level_ghost, patch.domain_box, pop.cell_start,
+                                     write_back=wb)
+                if n > pop.n_sorted:  # received since the last binning: not ordered yet
+                    ops.push_deposit(L, E, B, pop.domain, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux, 1.0,
+                                     pop.n_sorted, n, patch.non_level_ghost, write_back=wb)
+                if nlg:
+                    ops.push_deposit(L, E, B, pop.level_ghost, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0,
+                                     nlg, [patch.domain_box], first_selector=patch.ghost_box, write_back=wb)
+            elif mode == DOMAIN_ONLY:
                 # updateAndDepositDomain_ (:171-219): push a COPY (tmp_particles_), deposit those that end in the
                 # nonLevelGhostBox; the domain array itself is untouched
                 tmp = ops.alias_weight_charge(pop.spare, pop.domain)
@@ -413,11 +439,11 @@ class SolverPPC:
     """SolverPPC<HybridModel, AMR_Types> (solver_ppc.hpp:31-186) for one periodic level."""
 
     def __init__(self, ops, patches, geom, comm=None, resistivity=0.0, hyper_resistivity=1e-4, hyper_mode=0, Te=0.12,
-                 pusher_name="modified_boris"):
+                 pusher_name="modified_boris", fused="auto"):
         self.ops, self.patches, self.geom = ops, patches, geom
         self.comm = comm or LocalComm()
         self.messenger = HybridMessenger(geom, ops, self.comm)
-        self.updater = IonUpdater(ops, pusher_name)
+        self.updater = IonUpdater(ops, pusher_name, fused)
         self.eta, self.nu, self.hyper_mode, self.Te = resistivity, hyper_resistivity, hyper_mode, Te
         self.layouts = {p.geom.id: p.layout for p in patches}
 
@@ -492,8 +518,12 @@ class SolverPPC:
             for c in range(3):
                 self.ops.copy(p.Bold[c], p.B[c])
 
-    def advance_level(self, dt):
-        """solver_ppc.hpp:315-341"""
+    def advance_level(self, dt, staging=None):
+        """solver_ppc.hpp:315-341.  `staging` (HostStaging): the step takes E,B from pinned host buffers and
+        returns the moments and the new E,B to pinned host buffers; the read-back runs on a copy stream as soon
+        as each result is final, underneath the particle-array maintenance that ends the step."""
+        if staging is not None:
+            staging.upload()
         self.prepare_step()
         self._field_solve("B", "E", "Bpred", "Epred", dt, "predictor1")
         self._average()
@@ -501,9 +531,15 @@ class SolverPPC:
         self._field_solve("B", "Eavg", "Bpred", "Epred", dt, "predictor2")
         self._average()
         self._move_ions(dt, ALL)
+        if staging is not None:
+            staging.download_moments()  # final after the `all` sweep (solver_ppc.hpp:333)
         self._field_solve("B", "Eavg", "B", "E", dt, "corrector")
         self.messenger.fill_ghosts("E", abi.EX, self._by_id("E"))
+        if staging is not None:
+            staging.download_fields()
         self._finish_particles()
+        if staging is not None:
+            staging.join()
 
     def initialize(self):
         """HybridLevelInitializer::initialize, root level (hybrid_level_initializer.hpp:100-182): particles and B
@@ -539,6 +575,59 @@ class SolverPPC:
 
 
 # ---------------------------------------------------------------------------------------------------
+class HostStaging:
+    """Host-buffer face of the step for callers whose fields live in host memory (the reference's FieldData
+    buffers): pinned staging for the inputs (E, B of every local patch) and the results (per-population and
+    total moments, new E and B), and a copy stream.  upload() is ordered before the step on the compute
+    stream; download_*() are ordered after the kernels that produce each result (event) and run on the copy
+    stream, so they overlap whatever the compute stream does next; join() makes the compute stream wait
+    for them (a step is complete when its results are on the host)."""
+
+    def __init__(self, ops, patches):
+        t = ops.torch
+        self.t, self.patches = t, patches
+        self.copy_stream = t.cuda.Stream(device=ops.device)
+        self.inputs, self.moments, self.fields = [], [], []
+        for p in patches:
+            eb = [p.E[c] for c in range(3)] + [p.B[c] for c in range(3)]
+            self.inputs += eb
+            self.fields += eb
+            self.moments += [p.Ne, p.rho_m, p.Vi[0], p.Vi[1], p.Vi[2]]
+            for pop in p.pops:
+                self.moments += pop.moments()
+        pin = lambda arrs: [t.empty(a.t.shape, dtype=t.float64).pin_memory() for a in arrs]
+        self.h_in, self.h_moments, self.h_fields = pin(self.inputs), pin(self.moments), pin(self.fields)
+        for h, a in zip(self.h_in, self.inputs):
+            h.copy_(a.t)
+        self.h2d_bytes = sum(h.numel() * 8 for h in self.h_in)
+        self.d2h_bytes = sum(h.numel() * 8 for h in self.h_moments + self.h_fields)
+
+    def upload(self):
+        for h, a in zip(self.h_in, self.inputs):
+            a.t.copy_(h, non_blocking=True)
+
+    def _download(self, hosts, arrs):
+        ready = self.t.cuda.Event()
+        ready.record()
+        with self.t.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(ready)
+            for h, a in zip(hosts, arrs):
+                h.copy_(a.t, non_blocking=True)
+
+    def download_moments(self):
+        self._download(self.h_moments, self.moments)
+
+    def download_fields(self):
+        self._download(self.h_fields, self.fields)
+
+    def join(self):
+        self.t.cuda.current_stream().wait_stream(self.copy_stream)
+
+    def results_become_inputs(self):
+        """the host-side E,B of the next step are this step's results: swap the buffers (no transfer)"""
+        self.h_in, self.h_fields = self.h_fields, self.h_in
+
+
 def make_level(domain_cells, patch_grid, interp, dx, nranks=1):
     """Split a periodic domain into a Cartesian grid of patches and deal them to ranks in order.
     Returns (LevelGeom, [layout per patch])."""

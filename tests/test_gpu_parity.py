@@ -201,6 +201,134 @@ def test_deposit_known_answer_1d(ctxs):
         assert np.allclose(fx, 2.0 * rho, atol=1e-14) and np.allclose(fy, -rho, atol=1e-14) and np.allclose(fz, rho, atol=1e-14)
 
 
+# ------------------------------------------------------------------------------------------- K1+K3 fused
+def _ordered_store(rng, L, ppc, vth):
+    icell, delta, w, q, v = sorted_particles(rng, L, ppc, vth=vth)
+    q = np.where(rng.random(len(w)) < 0.5, 1.0, 2.0)
+    nd = int(np.prod([L.ncells[d] for d in range(L.dim)]))
+    return (icell, delta, w, q, v), nd
+
+
+@pytest.mark.parametrize("dim,interp", ALL_DIM_INTERP)
+@pytest.mark.parametrize("write_back", [False, True])
+def test_push_deposit_cell_ordered(ctxs, cpu_oracle, dim, interp, write_back):
+    """phb_push_deposit on a binned store == oracle push followed by oracle deposit of the pushed particles
+    restricted to the keep boxes; the stored particles are bit-identical to the oracle push (write_back) or
+    untouched (domain_only).  dt is large enough for ~20% of the particles to change cell."""
+    ctx = ctxs(dim, interp)
+    rng = np.random.default_rng(41 * dim + interp)
+    L = small_layout(dim, interp)
+    ppc = 30 if dim < 3 else 12
+    soa, nd = _ordered_store(rng, L, ppc, vth=1.0)
+    n = len(soa[2])
+    dom = domain_box(L)
+    cell_start = np.zeros(ctx.bin_nkeys(L, dom) + 1, np.uint32)
+    cell_start[:nd + 1] = np.arange(nd + 1) * ppc
+    cell_start[nd + 1:] = n
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.3)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.3)
+    keep_lo = [dom.lower[d] - particle_ghosts(interp) for d in range(dim)]
+    keep_lo[0] = dom.lower[0]  # one face is not a keep box (as at a coarse-fine boundary)
+    keep = [abi.make_box(keep_lo, [dom.upper[d] + particle_ghosts(interp) for d in range(dim)])]
+    rc, pushed = cpu_oracle.push(L, E, B, HostParticles.from_soa(*soa), 1.0, 0.08)
+    assert rc == 0
+    assert 0.05 < np.mean(np.any(pushed.soa()[0] != soa[0], axis=1)) < 0.9
+    want = cpu_oracle.deposit(L, pushed, coef=0.9, sel=keep)
+    (rn, rq), F = gpu_moments(ctx, L)
+    parts = dev_particles(ctx, soa)
+    cs = DeviceArray(ctx, cell_start.shape, np.uint32).upload(cell_start)
+    ctx.push_deposit(L, DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B), parts, 1.0, 0.08, rn, rq, F, 0.9,
+                     sel=keep, domain=dom, cell_start=cs, write_back=write_back)
+    ctx.poll_error()
+    assert_moments_close([rn.download(), rq.download()] + F.download(), want)
+    for g, w in zip(parts.download_soa(), pushed.soa() if write_back else soa):
+        assert bit_equal(g, w)
+
+
+@pytest.mark.parametrize("dim,interp", [(1, 1), (2, 2), (3, 1), (3, 3)])
+@pytest.mark.parametrize("write_back", [False, True])
+def test_push_deposit_unordered_with_first_selector(ctxs, cpu_oracle, dim, interp, write_back):
+    """the per-particle fused kernel: any order, sub-range [first,last), first selector = ghost box and
+    deposit restricted to the domain box (the level-ghost sweep of ion_updater.hpp:195-217, 275-288)"""
+    ctx = ctxs(dim, interp)
+    rng = np.random.default_rng(77 + dim + interp)
+    L = small_layout(dim, interp)
+    soa = random_particles(rng, L, 4000, spread=particle_ghosts(interp) + 1, vth=0.8)
+    dom = domain_box(L)
+    ghost = grown(dom, dim, particle_ghosts(interp))
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.3)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.3)
+    _, pushed = cpu_oracle.push(L, E, B, HostParticles.from_soa(*soa), 2.0, 0.1, first_selector=ghost)
+    sub = tuple(a[100:3900] for a in pushed.soa())
+    want = cpu_oracle.deposit(L, HostParticles.from_soa(*sub), coef=1.0, sel=[dom])
+    (rn, rq), F = gpu_moments(ctx, L)
+    parts = dev_particles(ctx, soa)
+    ctx.push_deposit(L, DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B), parts, 2.0, 0.1, rn, rq, F, 1.0,
+                     first=100, last=3900, sel=[dom], first_selector=ghost, write_back=write_back)
+    assert_moments_close([rn.download(), rq.download()] + F.download(), want)
+    got = parts.download_soa()
+    for g, w, o in zip(got, pushed.soa(), soa):
+        assert bit_equal(g[:100], o[:100]) and bit_equal(g[3900:], o[3900:])
+        assert bit_equal(g[100:3900], w[100:3900] if write_back else o[100:3900])
+
+
+def test_push_deposit_mover_record_overflow(ctxs, cpu_oracle):
+    """more cell-changing particles than the record buffer holds (n/16 + 65536): the overflow is scattered
+    inside the kernel and nothing is lost"""
+    ctx = ctxs(1, 1)
+    rng = np.random.default_rng(8)
+    L = small_layout(1, 1, ncells=[4096])
+    ppc = 300
+    soa, nd = _ordered_store(rng, L, ppc, vth=1.2)
+    n = len(soa[2])
+    dom = domain_box(L)
+    cell_start = np.zeros(ctx.bin_nkeys(L, dom) + 1, np.uint32)
+    cell_start[:nd + 1] = np.arange(nd + 1) * ppc
+    cell_start[nd + 1:] = n
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.1)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.1)
+    rc, pushed = cpu_oracle.push(L, E, B, HostParticles.from_soa(*soa), 1.0, 0.05)
+    assert rc == 0
+    movers = int(np.sum(pushed.soa()[0] != soa[0]))
+    assert movers > n // 16 + 65536 + 1000
+    keep = [grown(dom, 1, 1)]
+    want = cpu_oracle.deposit(L, pushed, coef=1.0, sel=keep)
+    (rn, rq), F = gpu_moments(ctx, L)
+    parts = dev_particles(ctx, soa)
+    cs = DeviceArray(ctx, cell_start.shape, np.uint32).upload(cell_start)
+    ctx.push_deposit(L, DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B), parts, 1.0, 0.05, rn, rq, F, 1.0,
+                     sel=keep, domain=dom, cell_start=cs, write_back=False)
+    assert_moments_close([rn.download(), rq.download()] + F.download(), want)
+
+
+def test_push_deposit_fma_mode_and_error(ctxs, cpu_oracle):
+    ctx = ctxs(2, 1)
+    rng = np.random.default_rng(12)
+    L = small_layout(2, 1)
+    soa = random_particles(rng, L, 3000, vth=0.3)
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.3)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.3)
+    _, pushed = cpu_oracle.push(L, E, B, HostParticles.from_soa(*soa), 1.0, 0.05)
+    want = cpu_oracle.deposit(L, pushed, coef=1.0, sel=[])
+    dE, dB = DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B)
+    (rn, rq), F = gpu_moments(ctx, L)
+    parts = dev_particles(ctx, soa)
+    ctx.set_exact(False)
+    try:
+        ctx.push_deposit(L, dE, dB, parts, 1.0, 0.05, rn, rq, F, 1.0, write_back=True)
+    finally:
+        ctx.set_exact(True)
+    assert_moments_close([rn.download(), rq.download()] + F.download(), want)
+    gv, wv = parts.download_soa()[4], pushed.soa()[4]
+    assert np.max(np.abs(gv - wv) / np.linalg.norm(wv, axis=1, keepdims=True)) <= 1e-12
+    # a particle that would move more than two cells raises through the poll, like phb_push
+    fast = (np.array([[8, 0]], np.int32), np.array([[0.5, 0.5]]), np.ones(1), np.ones(1), np.array([[100., 0, 0]]))
+    ctx.push_deposit(L, dE, dB, dev_particles(ctx, fast), 1.0, 0.1, rn, rq, F, 1.0, write_back=False)
+    with pytest.raises(PhbError) as e:
+        ctx.poll_error()
+    assert e.value.code == abi.PHB_ERR_MOVE_TWO_CELL
+
+
 # ------------------------------------------------------------------------------------------- K2 bin / export
 @pytest.mark.parametrize("dim,interp", CONFIG_DIM_INTERP + [(3, 3)])
 def test_bin_counts_offsets_and_multisets(ctxs, cpu_oracle, dim, interp):

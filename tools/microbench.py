@@ -25,12 +25,16 @@ CFGS = {
 }
 
 
-def timeit(fn, iters=5, warm=2):
+def timeit(fn, iters=5, warm=2, prep=None):
     for _ in range(warm):
+        if prep:
+            prep()
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
+        if prep:
+            prep()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         fn()
@@ -75,30 +79,57 @@ def run(name, cfg):
         print(f"{name:4s} {label:22s} {ms:9.3f} ms  {n / ms / 1e6:8.2f} Gp/s  {gbs:8.1f} GB/s  {gbs / HBM:6.3f} of HBM peak",
               flush=True)
 
-    for exact in (True, False):
-        ctx.set_exact(exact)
-        ms, _ = timeit(lambda: ctx.push(L, E, B, P, Q, 1.0, dt))
-        report(f"push[{'exact' if exact else 'fma'}] oop", ms, bpp_push + 16)
-    ctx.set_exact(True)
-    # bin first so that cell_start is valid (P is sorted already, Q pushed)
-    counts = ctx.bin(L, Q, P, dom, keep, cs)
-    ms, _ = timeit(lambda: ctx.bin(L, Q, P, dom, keep, cs))
-    report("bin (count+scan+scatter)", ms, 2 * bpp_dep)
-    print("   counts", counts, flush=True)
+    if os.environ.get('PHB_MB_ONLY') != 'fused':
+        for exact in (True, False):
+            ctx.set_exact(exact)
+            ms, _ = timeit(lambda: ctx.push(L, E, B, P, Q, 1.0, dt))
+            report(f"push[{'exact' if exact else 'fma'}] oop", ms, bpp_push + 16)
+        ctx.set_exact(True)
+        # bin first so that cell_start is valid (P is sorted already, Q pushed)
+        counts = ctx.bin(L, Q, P, dom, keep, cs)
+        ms, _ = timeit(lambda: ctx.bin(L, Q, P, dom, keep, cs))
+        report("bin (count+scan+scatter)", ms, 2 * bpp_dep)
+        print("   counts", counts, flush=True)
 
-    def dep_cells():
-        ctx.deposit(L, P, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=counts[0])
-    ms, _ = timeit(dep_cells)
-    report("deposit[cells]", ms, bpp_dep)
-    if n <= 40_000_000:
-        ms, _ = timeit(lambda: ctx.deposit(L, P, rn, rq, F, sel=keep), iters=2, warm=1)
-        report("deposit[atomic]", ms, bpp_dep)
-    ms, _ = timeit(lambda: ctx.push(L, E, B, P, P, 1.0, 0.0))  # dt = 0: in place, store stays sorted
-    report("push[exact] in place", ms, bpp_push)
-    # the way the step uses it: deposit right after a real push, on the stale order (movers -> list kernel)
-    ctx.push(L, E, B, P, P, 1.0, dt)
-    ms, _ = timeit(dep_cells)
-    report("deposit[cells, stale order]", ms, bpp_dep)
+        def dep_cells():
+            ctx.deposit(L, P, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=counts[0])
+        ms, _ = timeit(dep_cells)
+        report("deposit[cells]", ms, bpp_dep)
+        if n <= 40_000_000:
+            ms, _ = timeit(lambda: ctx.deposit(L, P, rn, rq, F, sel=keep), iters=2, warm=1)
+            report("deposit[atomic]", ms, bpp_dep)
+        ms, _ = timeit(lambda: ctx.push(L, E, B, P, P, 1.0, 0.0))  # dt = 0: in place, store stays sorted
+        report("push[exact] in place", ms, bpp_push)
+        # the way the step uses it: deposit right after a real push, on the stale order (movers -> list kernel)
+        ctx.push(L, E, B, P, P, 1.0, dt)
+        ms, _ = timeit(dep_cells)
+        report("deposit[cells, stale order]", ms, bpp_dep)
+    # K1+K3 fused (phb_push_deposit) on the freshly binned store, the way the step uses it
+    state = {"P": P, "Q": Q}
+
+    def rebin():
+        c = ctx.bin(L, state["P"], state["Q"], dom, keep, cs)
+        state["P"], state["Q"] = state["Q"], state["P"]
+        state["n"] = c[0]
+    rebin()
+
+    def fused(wb):
+        S = state["P"]
+        ctx.push_deposit(L, E, B, S, 1.0, dt, rn, rq, F, 1.0, 0, state["n"], keep, dom, cs, write_back=wb)
+    bpp_ro = bpp_dep
+    ms, _ = timeit(lambda: fused(False))
+    report("move[domain_only] fused", ms, bpp_ro)
+    ms, _ = timeit(lambda: fused(True), prep=rebin)
+    report("move[all] fused", ms, bpp_ro + 4 * dim + 8 * dim + 24)
+    # the two-pass equivalents on the same state
+    rebin()
+    S, T = state["P"], state["Q"]
+
+    def two_pass_domain_only():
+        ctx.push(L, E, B, S, T, 1.0, dt)
+        ctx.deposit(L, T, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=state["n"])
+    ms, _ = timeit(two_pass_domain_only)
+    report("push+deposit [domain_only]", ms, bpp_push + 16 + bpp_dep)
     ctx.poll_error()
     ctx.close()
     return out
@@ -111,4 +142,4 @@ if __name__ == "__main__":
         res[nm] = run(nm, CFGS[nm])
         torch.cuda.empty_cache()
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/microbench.json", "w"), indent=1)
+    json.dump(res, open(os.environ.get("PHB_MB_OUT", "gpurun_out/microbench.json"), "w"), indent=1)
