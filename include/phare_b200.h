@@ -120,6 +120,29 @@ int phb_particles_to_soa(phb_ctx*, const phb_particles* src, int* h_icell, doubl
 int phb_particles_copy(phb_ctx*, const phb_particles* src, size_t src_first, size_t count,
                        phb_particles* dst, size_t dst_first);
 
+/* ---- initial particle loading -------------------------------------------------------
+ * MaxwellianParticleInitializer::loadParticles (data/ions/particle_initializers/
+ * maxwellian_particle_initializer.hpp:138-199).  The user profile functions are evaluated by the caller at
+ * the cell centres (GridLayout::cellCenteredCoordinates) into per-cell arrays, row-major over the patch box
+ * (the order of layout.indices(AMRBox)): n[ncell], V[3][ncell], Vth[3][ncell] (, B[3][ncell] for Basis::Magnetic).
+ *
+ * phb_maxwellian_load_host: parity mode, HOST arrays in and out (ContiguousParticles layout), the
+ * reference's sequential std::mt19937_64 algorithm -> the reference's particles bit for bit for a given seed
+ * (has_seed = 0: std::random_device, like the reference).  Cells with n < density_cut_off load nothing. */
+int phb_maxwellian_load_host(const phb_layout*, const double* h_n, const double* const* h_V,
+                             const double* const* h_Vth, const double* const* h_B /* NULL: Basis::Cartesian */,
+                             double charge, uint32_t ppc, int has_seed, size_t seed, double density_cut_off,
+                             int* h_icell, double* h_delta, double* h_weight, double* h_charge, double* h_v,
+                             size_t capacity, size_t* h_count);
+/* phb_maxwellian_load: the same distribution sampled on the device with a counter-based generator
+ * (Philox4x32-10 keyed by `seed`, counter = (row-major index of the cell in the level's domain box of
+ * h_domain_cells[dim] cells) * ppc + i: independent of the patch decomposition; NULL = the patch itself), appended to `out` in cell order.  d_first[ncell+1] = index (relative to the first appended
+ * particle) of the first particle of each cell, each cell holding 0 (below the cut-off) or ppc particles;
+ * h_total = d_first[ncell].  Cartesian basis.  Statistically equivalent to the reference, not bit-identical. */
+int phb_maxwellian_load(phb_ctx*, const phb_layout*, const double* d_n, const phb_vecfield* d_V,
+                        const phb_vecfield* d_Vth, const uint32_t* d_first, size_t h_total, double charge,
+                        uint32_t ppc, uint64_t seed, const uint32_t* h_domain_cells, phb_particles* out);
+
 /* ---- K1 fused interpolate + Boris push ---------------------------------------------------
  * BorisPusher::move (pusher/boris.hpp:93-138) = prePushStep_ (:180-216), firstSelector,
  * Interpolator::operator()(particle, em, layout) (interpolator.hpp:420-456), accelerate_

@@ -106,6 +106,13 @@ _PROTOS = {
                                        C.c_void_p, C.c_void_p]),
     "phb_particles_copy": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t,
                                      C.POINTER(Particles), C.c_size_t]),
+    "phb_maxwellian_load_host": (C.c_int, [C.POINTER(Layout), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.POINTER(C.c_void_p), C.c_double, C.c_uint32, C.c_int, C.c_size_t,
+                                           C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_size_t, C.POINTER(C.c_size_t)]),
+    "phb_maxwellian_load": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_void_p, C.POINTER(VecField),
+                                      C.POINTER(VecField), C.c_void_p, C.c_size_t, C.c_double, C.c_uint32, C.c_uint64,
+                                      c_u32_p, C.POINTER(Particles)]),
     "phb_push": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
                            C.POINTER(Particles), C.POINTER(Particles), C.c_double, C.c_double, C.POINTER(Box)]),
     "phb_bin_nkeys": (C.c_size_t, [C.POINTER(Layout), C.POINTER(Box)]),

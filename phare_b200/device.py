@@ -245,6 +245,13 @@ class Context:
             rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel),
             C.byref(domain) if domain is not None else None, cell_start.ptr if cell_start is not None else None))
 
+    def maxwellian_load(self, layout, d_n, d_V, d_Vth, d_first, total, charge, ppc, seed, domain_cells, store):
+        """phb_maxwellian_load: d_n / d_first device arrays, d_V / d_Vth objects with a .c VecField of per-cell arrays"""
+        self._check(self.lib.phb_maxwellian_load(self.h, C.byref(layout), d_n.ptr, C.byref(d_V.c), C.byref(d_Vth.c),
+                                                 d_first.ptr, int(total), charge, int(ppc), int(seed) & (2 ** 64 - 1),
+                                                 (C.c_uint32 * 3)(*([int(c) for c in domain_cells] + [1] * (3 - len(domain_cells)))),
+                                                 C.byref(store.c)))
+
     def faraday(self, layout, B, E, Bnew, dt):
         self._check(self.lib.phb_faraday(self.h, C.byref(layout), C.byref(B.c), C.byref(E.c), C.byref(Bnew.c), dt))
 

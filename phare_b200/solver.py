@@ -142,6 +142,23 @@ class GpuOps:
         self._timed(name, lambda: self.ctx.push_deposit(layout, E, B, parts, mass, dt, rho_n, rho_q, F, coef, first,
                                                         last, sel, domain, cell_start, first_selector, write_back))
 
+    def maxwellian_load(self, layout, n, V, Vth, first, total, charge, ppc, seed, domain_cells, store):
+        """device loader (phb_maxwellian_load): per-cell host profiles are uploaded (7 small arrays), the
+        particles are created in place in the store, already in cell order"""
+        t, ti = self.torch, self.ti
+        up = lambda a, dt: ti.TorchArray(None, self.device, tensor=t.from_numpy(np.ascontiguousarray(a)).to(self.device, dt))
+
+        class CellVec:
+            def __init__(self, arrs):
+                self.keep = [up(a, t.float64) for a in arrs]
+                self.c = abi.VecField()
+                for k in range(3):
+                    self.c.comp[k] = self.keep[k].ptr
+        d_n, d_first = up(n, t.float64), up(first.astype(np.int64), t.int32)
+        self.ctx.maxwellian_load(layout, d_n, CellVec(V), CellVec(Vth), d_first, total, charge, ppc, seed,
+                                 domain_cells, store)
+        self.ctx.sync()  # the uploaded temporaries die with this frame
+
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
 

@@ -1,0 +1,94 @@
+"""pybindlibs.cpp_etc (src/python3/cpp_etc.cpp:74-143): life cycle, hierarchy factory, MPI queries, the array
+wrapper handed back by user init functions, build configuration."""
+import os
+import sys
+
+import numpy as np
+
+from phare_b200 import simulator as _sim
+
+
+class SamraiLifeCycle:
+    """SAMRAI/MPI start-up and shutdown in the reference (src/amr/samrai.hpp); here: nothing to start — the
+    process group, when there is one, is torch.distributed's and belongs to the launcher"""
+
+    def __init__(self):
+        pass
+
+    @staticmethod
+    def reset():
+        pass
+
+
+def make_hierarchy():
+    return _sim.make_hierarchy()
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except ImportError:
+        pass
+    return None
+
+
+def mpi_size():
+    d = _dist()
+    return d.get_world_size() if d else 1
+
+
+def mpi_rank():
+    d = _dist()
+    return d.get_rank() if d else 0
+
+
+def mpi_barrier():
+    d = _dist()
+    if d:
+        d.barrier()
+
+
+def mpi_initialized():
+    return _dist() is not None
+
+
+def makePyArrayWrapper(array):
+    """PyArrayWrapper<double> (src/python3/pybind_def.hpp): keeps the numpy array alive behind a Span"""
+    return np.ascontiguousarray(array, dtype=np.float64)
+
+
+def phare_build_config():
+    v = sys.version_info
+    return {"PYTHON_VERSION": f"Python {v.major}.{v.minor}.{v.micro}", "GIT_HASH": "phare_b200",
+            "BACKEND": "libphare_b200.so (sm_100a)"}
+
+
+def phare_deps():
+    """versions of the native dependencies, written into every diagnostic's attributes (diagnostics.py:163)"""
+    from phare_b200 import abi
+    try:
+        backend = abi.load().phb_version().decode()
+    except Exception:
+        backend = "libphare_b200.so (not built)"
+    return {"phare_b200": backend}
+
+
+AMRHierarchy = _sim.Hierarchy
+
+
+def samrai_restart_file(path):
+    raise RuntimeError("restart files are not supported by the B200 back end")
+
+
+def patch_data_ids(path):
+    raise RuntimeError("restart files are not supported by the B200 back end")
+
+
+def serialized_simulation_string(path):
+    raise RuntimeError("restart files are not supported by the B200 back end")
+
+
+def restart_path_for_time(path, time):
+    return os.path.join(path, "{:0>11.5f}".format(time))

@@ -1,0 +1,211 @@
+"""Front end: the pybindlibs drop-in modules, the PHAREDict, the simulator object pyphare
+drives, and the parity-mode particle loader.  CPU only: the compute back end is replaced by the checker
+(oracle/cpu_ops.py) through phare_b200.simulator.ops_factory; the GPU side is tests/test_simulator_gpu.py.
+When the reference tree is mounted, pyphare's own Simulator runs the reference's harris_2d.py input script
+unchanged through these modules."""
+import ctypes as C
+import importlib
+import os
+import sys
+from unittest import mock
+
+import numpy as np
+import pytest
+
+from phare_b200 import abi
+import phare_b200.simulator as S
+from frontend_util import populate, two_pop_1d, const, gather
+
+REF = "/root/reference"
+
+
+@pytest.fixture()
+def cpu_backend(cpu_oracle):
+    from oracle.cpu_ops import CpuOps
+    old = S.ops_factory
+    S.ops_factory = lambda dim, interp: CpuOps(dim, interp)
+    yield
+    S.ops_factory = old
+    S.dict_instance().stop()
+
+
+def test_dictator_is_typed_and_path_addressed():
+    import pybindlibs.dictator as pp
+    pp.stop()
+    pp.add_int("simulation/dimension", 2)
+    pp.add_double("simulation/grid/meshsize/x", 1)          # ints are accepted where pybind casts to double
+    pp.add_string("simulation/AMR/refinement/boxes/nbr_levels/", "trailing slash is ignored")
+    pp.add_optional_size_t("a/b/seed", None)
+    pp.add_array_as_vector("a/ts", np.arange(3.0))
+    d = S.dict_instance()
+    assert d["simulation/dimension"] == 2 and isinstance(d["simulation/grid/meshsize/x"], float)
+    assert d.contains("simulation/AMR/refinement/boxes/nbr_levels") and d["a/b/seed"] is None
+    assert not d.contains("simulation/nope") and d.get("simulation/nope", 5) == 5
+    for bad in (lambda: pp.add_int("x", 1.5), lambda: pp.add_size_t("x", -1), lambda: pp.add_bool("x", 1),
+                lambda: pp.add_string("x", 3), lambda: pp.addInitFunction1D("x", 3.0),
+                lambda: pp.add_array_as_vector("x", np.zeros((2, 2)))):
+        with pytest.raises((TypeError, RuntimeError)):
+            bad()
+    pp.stop()
+    assert not d.contains("simulation")
+
+
+def test_simulator_modules_exist_for_every_permutation():
+    for dim, interp, nref in ((1, 1, 2), (2, 3, 9), (3, 1, 6)):
+        m = importlib.import_module(f"pybindlibs.cpp_{dim}_{interp}_{nref}")
+        assert (m.Simulator.dims, m.Simulator.interp_order, m.Simulator.refined_particle_nbr) == (dim, interp, nref)
+        assert callable(m.make_simulator) and hasattr(m, "DataWrangler") and hasattr(m, "Splitter")
+    with pytest.raises(ImportError):
+        importlib.import_module("pybindlibs.cpp_4_1_2")
+    etc = importlib.import_module("pybindlibs.cpp_etc")
+    assert etc.mpi_size() == 1 and etc.mpi_rank() == 0 and not etc.mpi_initialized()
+    assert etc.phare_build_config()["PYTHON_VERSION"].startswith("Python 3")
+
+
+@pytest.mark.parametrize("dim", [1, 2, 3])
+def test_parity_loader_reproduces_the_reference_initializer(cpu_ref, dim):
+    """phb_maxwellian_load_host against MaxwellianParticleInitializer::loadParticles compiled from the reference
+    headers (oracle/_ref): same seed -> the same particles bit for bit, cells below the cut-off skipped"""
+    lib = abi.load()
+    nc = [9, 6, 5][:dim]
+    L = abi.make_layout(dim, 1, nc, [0.2] * dim, amr_lower=[3, -2, 7][:dim])
+    ncell, ppc = int(np.prod(nc)), 11
+    rng = np.random.default_rng(dim)
+    n = rng.random(ncell) + 0.5
+    n[3] = 1e-7
+    V = [rng.standard_normal(ncell) for _ in range(3)]
+    T = [rng.random(ncell) + 0.1 for _ in range(3)]
+    want = cpu_ref.maxwellian(L, n, V, T, 1.5, ppc, 1337)
+    cap = ncell * ppc
+    ic, de = np.zeros((cap, dim), np.int32), np.zeros((cap, dim))
+    w, q, v = np.zeros(cap), np.zeros(cap), np.zeros((cap, 3))
+    pv = (C.c_void_p * 3)(*[a.ctypes.data for a in V])
+    pt = (C.c_void_p * 3)(*[a.ctypes.data for a in T])
+    cnt = C.c_size_t()
+    rc = lib.phb_maxwellian_load_host(C.byref(L), n.ctypes.data, pv, pt, None, 1.5, ppc, 1, 1337, 1e-5, ic.ctypes.data,
+                                      de.ctypes.data, w.ctypes.data, q.ctypes.data, v.ctypes.data, cap, C.byref(cnt))
+    k = cnt.value
+    assert rc == 0 and k == want.n == (ncell - 1) * ppc
+    for g, x in zip((ic[:k], de[:k], w[:k], q[:k], v[:k]), want.soa()):
+        assert np.array_equal(g, x)
+    # capacity is checked
+    rc = lib.phb_maxwellian_load_host(C.byref(L), n.ctypes.data, pv, pt, None, 1.5, ppc, 1, 1337, 1e-5, ic.ctypes.data,
+                                      de.ctypes.data, w.ctypes.data, q.ctypes.data, v.ctypes.data, 5, C.byref(cnt))
+    assert rc == abi.PHB_ERR_CAPACITY
+
+
+def test_simulator_from_dict_matches_hand_driven_solver(cpu_backend, cpu_ref):
+    """the Simulator built from the dict == SolverPPC driven by hand from the same profiles, with the particles of
+    the REFERENCE initializer: bit-identical fields after 3 steps, whatever the patch cut"""
+    from oracle.cpu_ops import CpuOps
+    from phare_b200.messenger import LocalComm
+    from phare_b200.setup import build
+    cells, dl, interp = 64, 0.2, 1
+    pops, bfn = two_pop_1d(cells, dl)
+    populate([cells], [dl], interp, pops, bfn, largest=[16])
+    m = importlib.import_module("pybindlibs.cpp_1_1_2")
+    etc = importlib.import_module("pybindlibs.cpp_etc")
+    sim = m.make_simulator(etc.make_hierarchy())
+    sim.initialize()
+    assert len(sim.solver.patches) == 4 and sim.currentTime() == 0.0 and sim.endTime() == pytest.approx(0.02)
+    for _ in range(3):
+        sim.advance(sim.timeStep())
+    assert sim.currentTime() == pytest.approx(0.015)
+    with pytest.raises(RuntimeError):
+        sim.initialize()
+
+    def particles_fn(i, L, pid):
+        x = (np.arange(L.ncells[0]) + L.amr_lower[0] + 0.5) * dl
+        p = pops[i]
+        P = cpu_ref.maxwellian(L, p["density"](x), [p[k](x) for k in ("vx", "vy", "vz")],
+                               [p[k](x) for k in ("vthx", "vthy", "vthz")], p["charge"], p["ppc"], p["seed"])
+        return P.soa()
+    hand = build(CpuOps(1, interp), LocalComm(), [cells], (4,), interp, [dl],
+                 [dict(name=p["name"], mass=p["mass"]) for p in pops], lambda c, x: bfn[c](x), particles_fn,
+                 dict(resistivity=1e-3, hyper_resistivity=1e-3, Te=0.12))
+    for _ in range(3):
+        hand.advance_level(0.005)
+    for attr, comp in (("B", 1), ("B", 2), ("E", 0), ("E", 1), ("Ne", None), ("Vi", 0)):
+        got = gather(sim, attr, comp)
+        for p in hand.patches:
+            h = getattr(p, attr)
+            assert np.array_equal(got[p.geom.id], hand.ops.get_field(h[comp] if comp is not None else h)), (attr, comp)
+    # DataWrangler view: merged level-0 density over the physical nodes
+    dw = m.DataWrangler(sim, sim.hier)
+    merged = dw.sync_merge(dw.getPatchLevel(0).getDensity(), True)
+    assert merged.shape == (cells + 1,) and abs(merged.mean() - 1.1) < 0.05
+
+
+def test_refined_levels_and_open_boundaries_are_refused(cpu_backend):
+    import pybindlibs.dictator as pp
+    pops, bfn = two_pop_1d()
+    populate([64], [0.2], 1, pops, bfn)
+    pp.add_int("simulation/AMR/max_nbr_levels", 2)
+    with pytest.raises(NotImplementedError):
+        S.make_hierarchy()
+    pp.add_int("simulation/AMR/max_nbr_levels", 1)
+    pp.add_string("simulation/grid/boundary_type/x", "open")
+    with pytest.raises(NotImplementedError):
+        S.make_hierarchy()
+
+
+def test_diagnostics_written_at_requested_timestamps(cpu_backend, tmp_path):
+    pops, bfn = two_pop_1d(32)
+    populate([32], [0.2], 1, pops[:1], bfn, steps=2, diag_dir=str(tmp_path), diag_times=[0.0, 0.01])
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    assert sim.dump_diagnostics(0.0, 0.005)
+    sim.advance(0.005)
+    assert not sim.dump_diagnostics(0.005, 0.005)
+    sim.advance(0.005)
+    assert sim.dump_diagnostics(0.01, 0.005)
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 4 and files[0].startswith("electromag_EM_B_00000.00000")
+    z = np.load(tmp_path / files[-1])
+    key = [k for k in z.files if k.endswith("EM_E_x")][0]
+    assert key.startswith("t0.0100000000/pl0/p0/") and z[key].shape == (32 + 4,)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
+def test_pyphare_runs_the_reference_harris_script_unchanged(cpu_backend, tmp_path, monkeypatch):
+    """tests/functional/harris/harris_2d.py (config 3's input script), imported as is, driven by pyphare's own
+    Simulator through pybindlibs: populateDict -> make_hierarchy -> make_simulator -> initialize -> advance -> dumps.
+    Only the domain size (a module global of the script) is shrunk, and the root level alone is run."""
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections",
+                 "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py"):
+        if name not in sys.modules:  # plotting / HDF5 readers of pharesee, not installed here and not used
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    monkeypatch.setenv("PHARE_B200_SINGLE_LEVEL", "1")
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(REF)  # the script does `from tests.simulator import SimulatorTest`
+    stale = [k for k in sys.modules if k == "tests" or k.startswith("tests.")]
+    for k in stale:
+        monkeypatch.delitem(sys.modules, k)
+    h = importlib.import_module("tests.functional.harris.harris_2d")
+    h.cells, h.final_time, h.timestamps, h.diag_dir = (60, 100), 0.01, np.array([0.0, 0.01]), str(tmp_path / "out")
+    sim = h.config()
+    from pyphare.simulator.simulator import Simulator
+    import pyphare.pharein as ph
+    with pytest.warns(UserWarning, match="root level only"):
+        simulator = Simulator(sim, log_to_file=False)
+        simulator.initialize()
+    assert simulator.currentTime() == 0.0 and simulator.timeStep() == 0.005 and simulator.interp_order() == 1
+    simulator.advance().advance()
+    assert simulator.currentTime() == pytest.approx(0.01)
+    cpp_sim = simulator.cpp_sim
+    pop = cpp_sim.solver.patches[0].pops[0]
+    assert cpp_sim.solver.ops.count(pop.domain) == 60 * 100 * 100  # L0 particle number conserved
+    # seed 12334 in the script -> parity loader -> the reference's initial deltas; density follows the profile
+    dw = simulator.data_wrangler()
+    ne = dw.getPatchLevel(0).getDensity()[0]
+    rho = np.asarray(ne.data).reshape(60 + 1 + 4, 100 + 1 + 4)[2:-2, 2:-2]
+    y = np.arange(101) * 0.4
+    want = 0.4 + 1 / np.cosh((y - 12.0) / 0.5) ** 2 + 1 / np.cosh((y - 28.0) / 0.5) ** 2
+    err = np.abs(rho.mean(axis=0) - want)
+    assert np.max(err) < 0.2 and np.max(err[:15]) < 0.02  # the order-1 deposit smooths the 0.5-wide sheets over dl = 0.4
+    assert sorted(os.listdir(tmp_path / "out"))[0].startswith("electromag_EM_B_00000.00000")
+    simulator.reset()
+    ph.global_vars.sim = None
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        del sys.modules[k]

@@ -85,6 +85,11 @@ def run(name, cfg):
             ms, _ = timeit(lambda: ctx.push(L, E, B, P, Q, 1.0, dt))
             report(f"push[{'exact' if exact else 'fma'}] oop", ms, bpp_push + 16)
         ctx.set_exact(True)
+        if os.environ.get('PHB_MB_ONLY') == 'push':
+            ms, _ = timeit(lambda: ctx.push(L, E, B, P, P, 1.0, 0.0))
+            report("push[exact] in place", ms, bpp_push)
+            ctx.close()
+            return out
         # bin first so that cell_start is valid (P is sorted already, Q pushed)
         counts = ctx.bin(L, Q, P, dom, keep, cs)
         ms, _ = timeit(lambda: ctx.bin(L, Q, P, dom, keep, cs))
