@@ -195,8 +195,16 @@ def our_arm(args):
             extra["deposit"] = dict(achieved=round(a, 1), frac=round(a / peak, 4), avg_launch_ms=round(avg(dep_ms), 4))
         if bin_ms:
             extra["bin"] = dict(avg_ms=round(avg(bin_ms), 4))
-        extra["particle_kernels_share_of_step"] = round(
-            (sum(push_ms) + sum(dep_ms) + sum(bin_ms)) / ms, 4)
+        ds_ms, plan_ms = kernel_ms.get("deposit_scatter", []), kernel_ms.get("bin_plan", [])
+        if ds_ms:
+            # K3+K2 fused (the `all` sweep): reads the store + 4 B slot, writes the re-binned store
+            a = n_local * (2 * BYTES_DEPOSIT[3] + 4) / (avg(ds_ms) * 1e-3) / 1e9
+            extra["deposit_scatter"] = dict(achieved=round(a, 1), frac=round(a / peak, 4),
+                                            avg_launch_ms=round(avg(ds_ms), 4),
+                                            what="deposit carried by the re-binning scatter pass (phb_deposit_scatter)")
+            extra["bin_plan"] = dict(avg_ms=round(avg(plan_ms), 4))
+        extra["particle_kernels_share_of_step"] = round(sum(sum(v) for v in kernel_ms.values()) / ms, 4)
+        extra["kernel_ms_per_step"] = {k: round(sum(v) / args.steps, 3) for k, v in sorted(kernel_ms.items())}
         # whole-step fraction: 2 sweeps x (K1 + K3 algorithmic bytes) / step time
         extra["whole_step_frac_of_hbm"] = round(
             2 * n_local * (BYTES_PUSH[3] + BYTES_DEPOSIT[3]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)

@@ -170,6 +170,24 @@ size_t phb_bin_nkeys(const phb_layout*, const phb_box* domain);
 int phb_bin(phb_ctx*, const phb_layout*, const phb_particles* in, phb_particles* out,
             const phb_box* domain, const phb_box* keep, int nkeep, uint32_t* d_cell_start,
             size_t h_counts[3]);
+/* phb_bin in three parts, so that the scatter pass can carry the moment deposit (K3+K2 fused):
+ *   phb_bin_plan        keys, histogram, slot of every particle of `in`, scan -> d_cell_start (asynchronous);
+ *                       the slots stay in the context scratch until phb_deposit_scatter consumes them: no other
+ *                       scratch-using call (phb_bin, phb_export*, phb_deposit/phb_push_deposit with a cell_start)
+ *                       may come in between
+ *   phb_deposit_scatter phb_deposit(in[0,in->n), coef, sel) — cell-ordered kernel over in[0,n_sorted) grouped by
+ *                       d_cell_start_old for `domain`, per-particle kernel for the rest — and, in the same pass,
+ *                       out[d_cell_start_new[key] + slot] = particle: `out` ends up exactly as phb_bin leaves it
+ *                       (updateAndDepositAll_, ion_updater.hpp:245-293: partition/erase + both deposits)
+ *   phb_bin_counts      host-returning: h_counts as phb_bin, out->n = #domain + #patch-ghost */
+int phb_bin_plan(phb_ctx*, const phb_layout*, const phb_particles* in, const phb_box* domain, const phb_box* keep,
+                 int nkeep, uint32_t* d_cell_start);
+int phb_deposit_scatter(phb_ctx*, const phb_layout*, const phb_particles* in, size_t n_sorted, double* rho_n,
+                        double* rho_q, const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
+                        const phb_box* domain, const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep,
+                        phb_particles* out, const uint32_t* d_cell_start_new);
+int phb_bin_counts(phb_ctx*, const phb_layout*, const phb_box* domain, const uint32_t* d_cell_start,
+                   size_t h_counts[3], phb_particles* out);
 /* append to `dst` every particle of src[first,last) whose cell lies in `box` (minus `minus` when
  * not NULL), adding `shift` to its cell: ParticleArray::export_particles (particle_array.hpp
  * :135-160) and ParticlesData pack/unpack with periodic shift (particles_data.hpp:702-784).

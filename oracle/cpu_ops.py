@@ -145,6 +145,19 @@ class CpuOps:
         assert rc == 0, rc
         return tuple(int(c) for c in counts)
 
+    def bin_plan(self, layout, pin, domain, keep, cell_start_new):
+        pass  # the checker bins in one go inside deposit_scatter
+
+    def deposit_scatter(self, layout, pin, n_sorted, rho_n, rho_q, F, coef, sel, domain, cell_start_old, keep, pout,
+                        cell_start_new):
+        """checker for phb_bin_plan + phb_deposit_scatter: the reference's two separate steps"""
+        self.deposit(layout, pin, rho_n, rho_q, F, coef, 0, pin.n, sel)
+        self._counts = getattr(self, '_counts', {})
+        self._counts[id(cell_start_new)] = self.bin(layout, pin, pout, domain, keep, cell_start_new)
+
+    def bin_counts(self, layout, domain, cell_start, pout):
+        return self._counts.pop(id(cell_start))
+
     def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
         if not isinstance(box, abi.Box):
             box = abi.make_box(box.lo, box.hi)

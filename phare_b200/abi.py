@@ -118,6 +118,14 @@ _PROTOS = {
     "phb_bin_nkeys": (C.c_size_t, [C.POINTER(Layout), C.POINTER(Box)]),
     "phb_bin": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.POINTER(Particles),
                           C.POINTER(Box), C.POINTER(Box), C.c_int, C.c_void_p, C.POINTER(C.c_size_t)]),
+    "phb_bin_plan": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.POINTER(Box), C.POINTER(Box), C.c_int,
+                               C.c_void_p]),
+    "phb_deposit_scatter": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_void_p,
+                                      C.c_void_p, C.POINTER(VecField), C.c_double, C.POINTER(Box), C.c_int,
+                                      C.POINTER(Box), C.c_void_p, C.POINTER(Box), C.c_int, C.POINTER(Particles),
+                                      C.c_void_p]),
+    "phb_bin_counts": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Box), C.c_void_p, C.POINTER(C.c_size_t),
+                                 C.POINTER(Particles)]),
     "phb_export": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.c_size_t,
                              C.POINTER(Box), C.POINTER(Box), c_int_p, C.POINTER(Particles),
                              C.POINTER(C.c_size_t)]),

@@ -170,6 +170,7 @@ struct phb_ctx
     uint32_t* h_counts    = nullptr; // pinned, 8 entries
     double* em_pack       = nullptr; // node-interleaved copy of E,B used by the push kernels
     size_t em_bytes       = 0;
+    size_t plan_n         = size_t(-1); // particles covered by the pending phb_bin_plan (slots live in scratch)
 };
 
 namespace phb

@@ -150,6 +150,33 @@ __device__ __forceinline__ Loaded<DIM> load_particle(const PartView& P, size_t p
     return r;
 }
 
+// Particles that left their cell since the store was ordered are not scattered from inside the cell-ordered
+// kernel (one active lane doing 5*(o+1)^d atomics stalls its warp): the kernel only appends their index to
+// a list; this kernel then handles the list densely, one thread per listed particle.
+template<int DIM, int ORDER>
+__global__ void __launch_bounds__(256)
+    deposit_list_kernel(const __grid_constant__ DepositParams<DIM> A, const uint32_t* __restrict__ list,
+                        const unsigned* __restrict__ count)
+{
+    unsigned const n = *count;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    {
+        size_t const i = list[t];
+        int icell[DIM];
+        double delta[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+        {
+            icell[d] = A.P.icell[d][i];
+            delta[d] = A.P.delta[d][i];
+        }
+        double const weight = A.P.weight[i];
+        double const dep[5] = {1. * weight * A.coef, A.P.charge[i] * weight * A.coef, A.P.v[0][i] * weight * A.coef,
+                               A.P.v[1][i] * weight * A.coef, A.P.v[2][i] * weight * A.coef};
+        scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
+    }
+}
+
 // host side: fill the parameter block of a deposit on layout L
 template<int DIM>
 void prepare_deposit(const phb_layout* L, const phb_particles* P, size_t first, size_t last, double* rho_n,

@@ -202,6 +202,24 @@ class Context:
                                      abi.box_array(keep), len(keep), cell_start.ptr, counts))
         return tuple(int(c) for c in counts)
 
+    def bin_plan(self, layout, pin, domain, keep, cell_start_new):
+        self._check(self.lib.phb_bin_plan(self.h, C.byref(layout), C.byref(pin.c), C.byref(domain), abi.box_array(keep),
+                                          len(keep), cell_start_new.ptr))
+
+    def deposit_scatter(self, layout, pin, n_sorted, rho_n, rho_q, flux, coef, sel, domain, cell_start_old, keep, pout,
+                        cell_start_new):
+        self._check(self.lib.phb_deposit_scatter(
+            self.h, C.byref(layout), C.byref(pin.c), int(n_sorted), rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef,
+            abi.box_array(list(sel)), len(sel), C.byref(domain),
+            cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep),
+            C.byref(pout.c), cell_start_new.ptr))
+
+    def bin_counts(self, layout, domain, cell_start, pout):
+        counts = (C.c_size_t * 3)()
+        self._check(self.lib.phb_bin_counts(self.h, C.byref(layout), C.byref(domain), cell_start.ptr, counts,
+                                            C.byref(pout.c)))
+        return tuple(int(c) for c in counts)
+
     def bin_nkeys(self, layout, domain):
         return int(self.lib.phb_bin_nkeys(C.byref(layout), C.byref(domain)))
 

@@ -162,6 +162,18 @@ class GpuOps:
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
 
+    def bin_plan(self, layout, pin, domain, keep, cell_start_new):
+        self._timed("bin_plan", lambda: self.ctx.bin_plan(layout, pin, domain, keep, cell_start_new))
+
+    def deposit_scatter(self, layout, pin, n_sorted, rho_n, rho_q, F, coef, sel, domain, cell_start_old, keep, pout,
+                        cell_start_new):
+        """K3+K2 fused (phb_deposit_scatter): the scatter pass of the re-binning carries the moment deposit"""
+        self._timed("deposit_scatter", lambda: self.ctx.deposit_scatter(
+            layout, pin, n_sorted, rho_n, rho_q, F, coef, sel, domain, cell_start_old, keep, pout, cell_start_new))
+
+    def bin_counts(self, layout, domain, cell_start, pout):
+        return self.ctx.bin_counts(layout, domain, cell_start, pout)
+
     def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
         return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
 
@@ -294,6 +306,8 @@ class Population:
         self.domain = ops.particles(capacity)      # domainParticles, cell-ordered in [0, n_sorted)
         self.spare = ops.particles(capacity)       # tmp_particles_ of IonUpdater / sort target
         self.cell_start = ops.cell_start(nkeys)
+        self.cell_start_next = ops.cell_start(nkeys)  # written by bin_plan while the old order is still being read
+        self.pending_bin = False                      # spare holds the re-binned store, counts not read back yet
         self.n_sorted = 0
         self.patch_ghost = ops.particles(capacity // 8 + 4096)  # patchGhostParticles (leavers of this step)
         # levelGhostParticles (+Old/New, particle_pack.hpp:20-36): only exist on refined levels
@@ -341,10 +355,13 @@ class IonUpdater:
     # (dim, interp) pairs where the one-pass kernel measured faster than push + deposit on B200 (tools/microbench.py)
     FUSED_AUTO = frozenset({(1, 1), (1, 2), (1, 3)})
 
-    def __init__(self, ops, pusher_name="modified_boris", fused="auto"):
+    def __init__(self, ops, pusher_name="modified_boris", fused="auto", sort_with_deposit=True):
         if pusher_name != "modified_boris":
             raise RuntimeError("Error : Invalid Pusher name")
         self.ops = ops
+        # sort_with_deposit: in the `all` sweep the deposit rides on the scatter pass of the re-binning
+        # (phb_bin_plan + phb_deposit_scatter, K3+K2) instead of phb_deposit followed by phb_bin
+        self.sort_with_deposit = sort_with_deposit
         # fused: one pass per array and sweep (phb_push_deposit, K1+K3) instead of phb_push then phb_deposit
         self.fused = fused
 
@@ -395,7 +412,14 @@ class IonUpdater:
                 # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
                 # are deposited (= the domain + new patchGhost deposits of :290-293)
                 ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
-                self._deposit(patch, pop, pop.domain, n)
+                if self.sort_with_deposit and n:
+                    ops.bin_plan(L, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start_next)
+                    ops.deposit_scatter(L, pop.domain, pop.n_sorted, pop.rho_n, pop.rho_q, pop.flux, 1.0,
+                                        patch.non_level_ghost, patch.domain_box, pop.cell_start, patch.non_level_ghost,
+                                        pop.spare, pop.cell_start_next)
+                    pop.pending_bin = True
+                else:
+                    self._deposit(patch, pop, pop.domain, n)
                 if nlg:
                     # level ghosts (:275-288): pushed in place while inside the ghost box; those that entered the
                     # domain are deposited with the domain particles
@@ -408,7 +432,12 @@ class IonUpdater:
         still in the ghost layer remain level ghosts (:281-287)"""
         ops, L = self.ops, patch.layout
         for pop in patch.pops:
-            counts = ops.bin(L, pop.domain, pop.spare, patch.domain_box, patch.non_level_ghost, pop.cell_start)
+            if pop.pending_bin:  # the scatter already happened with the deposit: only the counts are missing
+                counts = ops.bin_counts(L, patch.domain_box, pop.cell_start_next, pop.spare)
+                pop.cell_start, pop.cell_start_next = pop.cell_start_next, pop.cell_start
+                pop.pending_bin = False
+            else:
+                counts = ops.bin(L, pop.domain, pop.spare, patch.domain_box, patch.non_level_ghost, pop.cell_start)
             pop.domain, pop.spare = pop.spare, pop.domain
             pop.n_sorted = counts[0]
             # "copy out new patch ghosts" (:248-254) then "drop all ghosts" (:273)
@@ -456,11 +485,11 @@ class SolverPPC:
     """SolverPPC<HybridModel, AMR_Types> (solver_ppc.hpp:31-186) for one periodic level."""
 
     def __init__(self, ops, patches, geom, comm=None, resistivity=0.0, hyper_resistivity=1e-4, hyper_mode=0, Te=0.12,
-                 pusher_name="modified_boris", fused="auto"):
+                 pusher_name="modified_boris", fused="auto", sort_with_deposit=True):
         self.ops, self.patches, self.geom = ops, patches, geom
         self.comm = comm or LocalComm()
         self.messenger = HybridMessenger(geom, ops, self.comm)
-        self.updater = IonUpdater(ops, pusher_name, fused)
+        self.updater = IonUpdater(ops, pusher_name, fused, sort_with_deposit)
         self.eta, self.nu, self.hyper_mode, self.Te = resistivity, hyper_resistivity, hyper_mode, Te
         self.layouts = {p.geom.id: p.layout for p in patches}
 

@@ -396,6 +396,56 @@ def test_bin_counts_offsets_and_multisets(ctxs, cpu_oracle, dim, interp):
     assert np.array_equal(cs.download()[:-1], got_cs[:-1])
 
 
+@pytest.mark.parametrize("dim,interp", ALL_DIM_INTERP)
+def test_deposit_scatter_equals_deposit_then_bin(ctxs, cpu_oracle, dim, interp):
+    """K3+K2 fused: phb_bin_plan + phb_deposit_scatter + phb_bin_counts on a store whose first part is cell-ordered
+    (with ~10% of the particles displaced, some out of the patch and out of the ghost box) and whose tail is
+    unordered == oracle deposit of the whole store followed by the oracle bin."""
+    ctx = ctxs(dim, interp)
+    rng = np.random.default_rng(700 + 10 * dim + interp)
+    L = small_layout(dim, interp)
+    ppc = {1: 40, 2: 30, 3: 12}[dim]
+    icell, delta, w, q, v = sorted_particles(rng, L, ppc, vth=0.5)
+    q = np.where(rng.random(len(w)) < 0.5, 1.0, 2.0)
+    n_sorted = len(w)
+    dom = domain_box(L)
+    pg = particle_ghosts(interp)
+    nd = int(np.prod([L.ncells[d] for d in range(dim)]))
+    old_start = np.zeros(ctx.bin_nkeys(L, dom) + 1, np.uint32)
+    old_start[:nd + 1] = np.arange(nd + 1) * ppc
+    old_start[nd + 1:] = n_sorted
+    movers = rng.random(n_sorted) < 0.1
+    icell = icell.copy()
+    icell[movers] += rng.integers(-pg - 1, pg + 2, size=(int(movers.sum()), dim)).astype(np.int32)
+    tail = random_particles(rng, L, 700, spread=pg + 1)
+    soa = tuple(np.concatenate([a, b]) for a, b in zip((icell, delta, w, q, v), tail))
+    G = grown(dom, dim, pg)
+    keep_lo = [G.lower[d] for d in range(dim)]
+    keep_lo[0] = dom.lower[0]
+    keep = [abi.make_box(keep_lo, [G.upper[d] for d in range(dim)])]
+    src = HostParticles.from_soa(*soa)
+    want_m = cpu_oracle.deposit(L, src, coef=1.0, sel=keep)
+    want, want_cs, want_counts = cpu_oracle.bin(L, src, dom, keep)
+    pin, pout = dev_particles(ctx, soa), DeviceParticles(ctx, len(soa[2]))
+    (rn, rq), F = gpu_moments(ctx, L)
+    cs_old = DeviceArray(ctx, old_start.shape, np.uint32).upload(old_start)
+    cs_new = DeviceArray(ctx, old_start.shape, np.uint32)
+    ctx.bin_plan(L, pin, dom, keep, cs_new)
+    ctx.deposit_scatter(L, pin, n_sorted, rn, rq, F, 1.0, keep, dom, cs_old, keep, pout, cs_new)
+    counts = ctx.bin_counts(L, dom, cs_new, pout)
+    assert counts == want_counts and pout.n == counts[0] + counts[1]
+    assert np.array_equal(cs_new.download(), want_cs)
+    assert_moments_close([rn.download(), rq.download()] + F.download(), want_m)
+    got = pout.download_soa()
+    assert np.array_equal(got[0], want.soa()[0])
+    assert np.array_equal(canonical_rows(*got), canonical_rows(*want.soa()))
+    for g, x in zip(pin.download_soa(), soa):  # the source store is only read
+        assert bit_equal(g, x)
+    # a scatter without its plan is refused
+    with pytest.raises(PhbError):
+        ctx.deposit_scatter(L, pin, n_sorted, rn, rq, F, 1.0, keep, dom, cs_old, keep, pout, cs_new)
+
+
 def test_bin_empty_and_single(ctxs):
     ctx = ctxs(1, 1)
     L = small_layout(1, 1)

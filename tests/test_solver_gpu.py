@@ -21,7 +21,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("fused", [True, False, "two_pass"])
 @pytest.mark.parametrize("domain,grid,interp,dx,ppc,npop,steps", CASES)
 def test_gpu_step_matches_cpu_oracle_step(domain, grid, interp, dx, ppc, npop, steps, fused):
     from phare_b200.solver import GpuOps
@@ -29,7 +29,7 @@ def test_gpu_step_matches_cpu_oracle_step(domain, grid, interp, dx, ppc, npop, s
     dim = len(domain)
     gparts = global_particles(domain, interp, dx, ppc, seed=3, pops=npop)
     cpu = make_solver(CpuOps(dim, interp), domain, grid, interp, dx, gparts)
-    gpu = make_solver(GpuOps(dim, interp, "cuda:0"), domain, grid, interp, dx, gparts, solver_kw=dict(fused=fused))
+    gpu = make_solver(GpuOps(dim, interp, "cuda:0"), domain, grid, interp, dx, gparts, solver_kw=dict(fused=fused is True, sort_with_deposit=fused != "two_pass"))
     for s in range(steps):
         cpu.advance_level(0.005)
         gpu.advance_level(0.005)

@@ -135,6 +135,23 @@ def run(name, cfg):
         ctx.deposit(L, T, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=state["n"])
     ms, _ = timeit(two_pass_domain_only)
     report("push+deposit [domain_only]", ms, bpp_push + 16 + bpp_dep)
+    # K3+K2 fused: the `all` sweep's deposit carried by the re-binning scatter, against deposit then bin
+    rebin()
+    S, T = state["P"], state["Q"]
+    ctx.push(L, E, B, S, S, 1.0, dt)
+    cs2 = TorchArray((ctx.bin_nkeys(L, dom) + 1,), dev, dtype=torch.int32)
+
+    def plan_and_scatter():
+        ctx.bin_plan(L, S, dom, keep, cs2)
+        ctx.deposit_scatter(L, S, state["n"], rn, rq, F, 1.0, keep, dom, cs, keep, T, cs2)
+
+    def deposit_then_bin():
+        ctx.deposit(L, S, rn, rq, F, sel=keep, domain=dom, cell_start=cs, last=state["n"])
+        ctx.bin(L, S, T, dom, keep, cs2)
+    ms, _ = timeit(plan_and_scatter)
+    report("plan + deposit_scatter [all]", ms, 3 * bpp_dep)
+    ms, _ = timeit(deposit_then_bin)
+    report("deposit + bin [all]", ms, 3 * bpp_dep)
     ctx.poll_error()
     ctx.close()
     return out
