@@ -29,7 +29,8 @@ typedef enum {
                                   (boris.hpp:164-165 MoveTwoCellException)                       */
     PHB_ERR_OUTSIDE_GHOST = 4, /* a particle left the ghost box (ion_updater.hpp:256-271, debug)   */
     PHB_ERR_CAPACITY      = 5, /* destination particle array too small                           */
-    PHB_ERR_NO_DEVICE     = 6
+    PHB_ERR_NO_DEVICE     = 6,
+    PHB_ERR_PEER_TIMEOUT  = 7  /* phb_peer_wait: a neighbour GPU never signalled                */
 } phb_status;
 
 /* HybridQuantity::Scalar subset used on the path (models/quantities/hybrid_quantities.hpp:16-40);
@@ -281,6 +282,21 @@ typedef struct {
     uint64_t      first;
 } phb_box_desc;
 int phb_box_op_batch(phb_ctx*, const phb_box_desc* d_ops, int nops, uint64_t total_elements);
+
+/* ---- peer-memory halo exchange over NVLink (one process per GPU, GPUs of one node) ---------------
+ * The receive areas of the field exchange phases live in ONE device allocation per rank (phb_malloc) that
+ * every other rank maps through CUDA IPC; phb_box_op_batch descriptors may then name a peer's memory as
+ * destination (the pack kernel stores straight into the neighbour GPU).  Ordering between the two GPUs:
+ *   phb_peer_signal(flags, v): after all work already enqueued on the stream, *flags[i] = v[i] (release.sys);
+ *                              flags[i] normally point into peer memory
+ *   phb_peer_wait(flags, v)  : the stream waits until every *flags[i] >= v[i] (acquire.sys); gives up after
+ *                              timeout_s -> PHB_ERR_PEER_TIMEOUT through phb_poll_error
+ * n <= 32 flag words per call. */
+int phb_ipc_export(phb_ctx*, void* d_ptr, unsigned char h_handle[64]);
+int phb_ipc_open(phb_ctx*, const unsigned char h_handle[64], void** d_peer_ptr);
+int phb_ipc_close(phb_ctx*, void* d_peer_ptr);
+int phb_peer_signal(phb_ctx*, int n, uint64_t* const* h_flag_ptrs, const uint64_t* h_values);
+int phb_peer_wait(phb_ctx*, int n, uint64_t* const* h_flag_ptrs, const uint64_t* h_values, double timeout_s);
 
 #ifdef __cplusplus
 }

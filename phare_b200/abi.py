@@ -12,7 +12,7 @@ ROOT = os.path.dirname(_HERE)
 LIB_PATH = os.environ.get("PHB_LIB") or os.path.join(_HERE, "lib", "libphare_b200.so")  # PHB_LIB: tuning builds
 
 PHB_OK, PHB_ERR_INVALID, PHB_ERR_CUDA, PHB_ERR_MOVE_TWO_CELL = 0, 1, 2, 3
-PHB_ERR_OUTSIDE_GHOST, PHB_ERR_CAPACITY, PHB_ERR_NO_DEVICE = 4, 5, 6
+PHB_ERR_OUTSIDE_GHOST, PHB_ERR_CAPACITY, PHB_ERR_NO_DEVICE, PHB_ERR_PEER_TIMEOUT = 4, 5, 6, 7
 
 # phb_qty
 BX, BY, BZ, EX, EY, EZ, JX, JY, JZ, RHO, VX, VY, VZ, P = range(14)
@@ -153,6 +153,11 @@ _PROTOS = {
                              c_u32_p, C.c_int]),
     "phb_box_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p]),
     "phb_box_op_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64]),
+    "phb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "phb_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "phb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phb_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    "phb_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_double]),
     "phb_box_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p,
                                  C.c_int]),
 }

@@ -149,6 +149,9 @@ int phb_poll_error(phb_ctx* ctx)
         // same text as the reference exception, boris.hpp:207-214
         snprintf(buf, sizeof buf, "Particle moved 2 cells with delta/vel: %g/%g (particle index %llu)",
                  ctx->h_err->delta, ctx->h_err->vel, ctx->h_err->index);
+    else if (code == PHB_ERR_PEER_TIMEOUT)
+        snprintf(buf, sizeof buf, "peer halo exchange timed out: flag %llu at %g, expected %g", ctx->h_err->index,
+                 ctx->h_err->delta, ctx->h_err->vel);
     else
         snprintf(buf, sizeof buf, "Updater::outsideGhostBox (particle index %llu)", ctx->h_err->index);
     ctx->last_error = buf;

@@ -186,6 +186,95 @@ class TorchComm:
         return dst.cpu().tolist()
 
 
+class RawArray:
+    """a box-op operand that is only an address (own or peer device memory) and a shape"""
+
+    def __init__(self, ptr, shape):
+        self.ptr, self.shape = int(ptr), tuple(int(x) for x in shape)
+        self.size = int(np.prod(self.shape)) if len(self.shape) else 1
+
+
+class PeerArena:
+    """NVLink peer-memory exchange area (csrc/peer.cu): ONE device allocation per rank holding the flag words and
+    the receive areas of every fixed-size exchange phase, mapped by every other rank of the node through CUDA IPC.
+    A neighbour's pack kernel stores straight into it; ordering is a flag per (source rank -> this rank) that
+    counts the phases delivered.  Built on GPU ranks with more than one process; otherwise the messenger stages
+    through torch.distributed send/recv."""
+    FLAGS = 4096  # bytes reserved for flag words (8 per source rank)
+
+    def __init__(self, ops, comm, nbytes=None):
+        import ctypes as C
+        import os
+        dist = comm.dist
+        ctx = ops.ctx
+        self.ctx, self.me, self.size = ctx, comm.rank, comm.size
+        self.nbytes = int(nbytes) if nbytes else int(os.environ.get("PHB_PEER_ARENA_MB", 1024)) << 20
+        p = C.c_void_p()
+        ctx._check(ctx.lib.phb_malloc(ctx.h, self.nbytes, C.byref(p)))
+        ctx._check(ctx.lib.phb_memset(ctx.h, p, 0, self.FLAGS))
+        ctx.sync()
+        handle = (C.c_ubyte * 64)()
+        ctx._check(ctx.lib.phb_ipc_export(ctx.h, p, handle))
+        handles = [None] * self.size
+        dist.all_gather_object(handles, bytes(handle))
+        self.base = {}
+        for r, h in enumerate(handles):
+            if r == self.me:
+                self.base[r] = p.value
+            else:
+                q = C.c_void_p()
+                ctx._check(ctx.lib.phb_ipc_open(ctx.h, (C.c_ubyte * 64)(*h), C.byref(q)))
+                self.base[r] = q.value
+        dist.barrier()
+        self.cursor = self.FLAGS
+        self.sent = [0] * self.size      # phases I delivered to each rank
+        self.received = [0] * self.size  # phases each rank delivered to me
+        self.timeout_s = float(os.environ.get("PHB_PEER_TIMEOUT_S", 20.0))
+        self._C = C
+
+    def alloc(self, nbytes):
+        """offset of a fresh 256-byte aligned region of MY arena"""
+        off = self.cursor
+        self.cursor += (int(nbytes) + 255) & ~255
+        if self.cursor > self.nbytes:
+            raise RuntimeError("peer arena exhausted: raise PHB_PEER_ARENA_MB")
+        return off
+
+    def exchange_offsets(self, mine):
+        """mine: {source rank: offset in my arena}; returns {destination rank: offset of my area in ITS arena}"""
+        everyone = [None] * self.size
+        self._dist().all_gather_object(everyone, mine)
+        return {r: everyone[r][self.me] for r in range(self.size) if r != self.me and self.me in everyone[r]}
+
+    def _dist(self):
+        import torch.distributed as dist
+        return dist
+
+    def signal(self, dsts):
+        C = self._C
+        if not dsts:
+            return
+        ptrs = (C.c_void_p * len(dsts))()
+        vals = (C.c_uint64 * len(dsts))()
+        for i, r in enumerate(dsts):
+            self.sent[r] += 1
+            ptrs[i] = self.base[r] + 8 * self.me  # my word in rank r's flag block
+            vals[i] = self.sent[r]
+        self.ctx._check(self.ctx.lib.phb_peer_signal(self.ctx.h, len(dsts), ptrs, vals))
+
+    def wait(self, srcs):
+        C = self._C
+        if not srcs:
+            return
+        ptrs = (C.c_void_p * len(srcs))()
+        vals = (C.c_uint64 * len(srcs))()
+        for i, r in enumerate(srcs):
+            self.received[r] += 1
+            ptrs[i] = self.base[self.me] + 8 * r
+            vals[i] = self.received[r]
+        self.ctx._check(self.ctx.lib.phb_peer_wait(self.ctx.h, len(srcs), ptrs, vals, self.timeout_s))
+
+
 class HybridMessenger:
     """Executes the plans of a LevelGeom on the patches owned by this rank.
     `ops` is the compute back end (phare_b200.solver.GpuOps in production)."""
@@ -196,6 +285,12 @@ class HybridMessenger:
         self._plans = {}
         self._compiled = {}
         self._migration = geom.migration_plan()
+        # fixed-size field phases go through NVLink peer memory when every rank drives a GPU of the same node
+        self.arena = None
+        import os
+        if comm.size > 1 and hasattr(ops, "ctx") and os.environ.get("PHB_PEER_HALO", "1") != "0":
+            self.arena = PeerArena(ops, comm)
+        self._last_peer_key = None
 
     def _plan(self, kind, qty):
         key = (kind, qty)
@@ -220,9 +315,20 @@ class HybridMessenger:
             self._compiled[key] = self._finish(local, send_items, recv_items, op)
         return self._compiled[key]
 
-    def _run(self, phase):
+    def _run(self, phase, key=None):
         ops = self.ops
         ops.run_box_ops(phase["pre"])      # packs for every peer (+ the local copies when they are independent)
+        if "peer_dsts" in phase:
+            # a receive area is reused every time its phase comes round: safe because some OTHER phase with the same
+            # neighbours always runs in between (the sender waits on it, and the receiver only signals it after
+            # having unpacked this one)
+            assert key is None or key != self._last_peer_key, f"phase {key} run twice in a row"
+            self._last_peer_key = key
+            self.arena.signal(phase["peer_dsts"])
+            ops.run_box_ops(phase["local"])
+            self.arena.wait(phase["peer_srcs"])
+            ops.run_box_ops(phase["post"])
+            return
         ops.run_box_ops(phase["local"])    # local operations that must follow the packs (in-place max)
         if phase["peers"]:
             if "p2p" not in phase:         # the grouped send/recv list is built once per phase
@@ -237,7 +343,7 @@ class HybridMessenger:
         """vecs: {patch id: vector field}; fillMagneticGhosts (qty0=BX), fillElectricGhosts (EX),
         fillCurrentGhosts (JX)"""
         arrays = {pid: [v[c] for c in range(3)] for pid, v in vecs.items()}
-        self._run(self._compile(("fill", name), "fill", [qty0, qty0 + 1, qty0 + 2], arrays, 0))
+        self._run(self._compile(("fill", name), "fill", [qty0, qty0 + 1, qty0 + 2], arrays, 0), ("fill", name))
 
     def sum_borders(self, name, arrays, scratch):
         """arrays/scratch: {patch id: [primal arrays]}: a += neighbours' ORIGINAL values on the ghost-box
@@ -260,15 +366,17 @@ class HybridMessenger:
                     elif q.owner == me:
                         send_items.setdefault(p.owner, []).append((scratch[q.id][ci], slo, ext))
             self._compiled[key] = self._finish(local, send_items, recv_items, 1)
-        self._run(self._compiled[key])
+        self._run(self._compiled[key], key)
 
     def max_borders(self, name, arrays):
         """fillIonBorders: a = max(a, neighbour) on the ghost-box overlaps"""
         n = len(next(iter(arrays.values())))
-        self._run(self._compile(("max", name), "border", [abi.RHO] * n, arrays, 2))
+        self._run(self._compile(("max", name), "border", [abi.RHO] * n, arrays, 2), ("max", name))
 
     def _finish(self, local, send_items, recv_items, op):
         """One launch packs for all peers, one launch unpacks from all peers (K8 batch tables)."""
+        if self.arena is not None:
+            return self._finish_peer(local, send_items, recv_items, op)
         ops = self.ops
         phase = dict(peers={})
         pack, unpack = [], []
@@ -290,6 +398,31 @@ class HybridMessenger:
             phase["pre"], phase["local"] = ops.compile_box_ops(pack), ops.compile_box_ops(local)
         else:
             # copy / += : packs read interiors (or the scratch copies), local ops write ghosts: independent
+            phase["pre"], phase["local"] = ops.compile_box_ops(pack + local), None
+        phase["post"] = ops.compile_box_ops(unpack)
+        return phase
+
+    def _finish_peer(self, local, send_items, recv_items, op):
+        """peer-memory variant: my receive areas live in my arena, the pack ops of my neighbours write into them
+        (and mine into theirs); called collectively, in the same order, by every rank"""
+        ops, arena = self.ops, self.arena
+        my_off = {src: arena.alloc(8 * sum(int(np.prod(e)) for _, _, e in items)) for src, items in sorted(recv_items.items())}
+        their_off = arena.exchange_offsets(my_off)
+        pack, unpack = [], []
+        for dst, items in sorted(send_items.items()):
+            at = arena.base[dst] + their_off[dst]
+            for (arr, lo, ext) in items:
+                pack.append((RawArray(at, ext), [0] * len(ext), arr, lo, ext, 0))
+                at += 8 * int(np.prod(ext))
+        for src, items in sorted(recv_items.items()):
+            at = arena.base[arena.me] + my_off[src]
+            for (arr, lo, ext) in items:
+                unpack.append((arr, lo, RawArray(at, ext), [0] * len(ext), ext, op))
+                at += 8 * int(np.prod(ext))
+        phase = dict(peers={}, peer_dsts=sorted(send_items), peer_srcs=sorted(recv_items))
+        if op == 2:
+            phase["pre"], phase["local"] = ops.compile_box_ops(pack), ops.compile_box_ops(local)
+        else:
             phase["pre"], phase["local"] = ops.compile_box_ops(pack + local), None
         phase["post"] = ops.compile_box_ops(unpack)
         return phase

@@ -362,6 +362,7 @@ class IonUpdater:
         # sort_with_deposit: in the `all` sweep the deposit rides on the scatter pass of the re-binning
         # (phb_bin_plan + phb_deposit_scatter, K3+K2) instead of phb_deposit followed by phb_bin
         self.sort_with_deposit = sort_with_deposit
+        self.defer_sort = False  # set per step by SolverPPC.advance_level
         # fused: one pass per array and sweep (phb_push_deposit, K1+K3) instead of phb_push then phb_deposit
         self.fused = fused
 
@@ -412,7 +413,7 @@ class IonUpdater:
                 # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
                 # are deposited (= the domain + new patchGhost deposits of :290-293)
                 ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
-                if self.sort_with_deposit and n:
+                if self.sort_with_deposit and not self.defer_sort and n:
                     ops.bin_plan(L, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start_next)
                     ops.deposit_scatter(L, pop.domain, pop.n_sorted, pop.rho_n, pop.rho_q, pop.flux, 1.0,
                                         patch.non_level_ghost, patch.domain_box, pop.cell_start, patch.non_level_ghost,
@@ -568,6 +569,9 @@ class SolverPPC:
         """solver_ppc.hpp:315-341.  `staging` (HostStaging): the step takes E,B from pinned host buffers and
         returns the moments and the new E,B to pinned host buffers; the read-back runs on a copy stream as soon
         as each result is final, underneath the particle-array maintenance that ends the step."""
+        # with host staging the re-binning is kept as a separate, deferred pass: it is the GPU work the result
+        # read-back (PCIe) hides under; without it the deposit rides on the scatter pass (one read of the store less)
+        self.updater.defer_sort = staging is not None
         if staging is not None:
             staging.upload()
         self.prepare_step()
