@@ -144,6 +144,15 @@ int phb_maxwellian_load(phb_ctx*, const phb_layout*, const double* d_n, const ph
                         const phb_vecfield* d_Vth, const uint32_t* d_first, size_t h_total, double charge,
                         uint32_t ppc, uint64_t seed, const uint32_t* h_domain_cells, phb_particles* out);
 
+/* flat message form of store ranges (ParticlesData::packStream / unpackStream, particles_data.hpp:702-784): a message
+ * of `total` particles is column-major, delta[d][total] | v[3][total] | weight[total] | charge[total] | icell[d][total]
+ * (phb_particles_flat_bytes bytes); pack copies src[first, first+count) into entries [off, off+count) of every
+ * column, unpack appends entries [off, off+count) to dst.  One launch each. */
+size_t phb_particles_flat_bytes(int dim, size_t total);
+int phb_particles_pack(phb_ctx*, const phb_particles* src, size_t first, size_t count, void* d_buf, size_t total,
+                       size_t off);
+int phb_particles_unpack(phb_ctx*, const void* d_buf, size_t total, size_t off, size_t count, phb_particles* dst);
+
 /* ---- K1 fused interpolate + Boris push ---------------------------------------------------
  * BorisPusher::move (pusher/boris.hpp:93-138) = prePushStep_ (:180-216), firstSelector,
  * Interpolator::operator()(particle, em, layout) (interpolator.hpp:420-456), accelerate_

@@ -106,6 +106,10 @@ _PROTOS = {
                                        C.c_void_p, C.c_void_p]),
     "phb_particles_copy": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t,
                                      C.POINTER(Particles), C.c_size_t]),
+    "phb_particles_flat_bytes": (C.c_size_t, [C.c_int, C.c_size_t]),
+    "phb_particles_pack": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                     C.c_size_t]),
+    "phb_particles_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(Particles)]),
     "phb_maxwellian_load_host": (C.c_int, [C.POINTER(Layout), C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                            C.POINTER(C.c_void_p), C.c_double, C.c_uint32, C.c_int, C.c_size_t,
                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -260,3 +260,77 @@ int phb_particles_copy(phb_ctx* ctx, const phb_particles* src, size_t src_first,
     return PHB_OK;
 }
 }
+
+// ---- flat packing of a store range for the migration messages (ParticlesData::packStream / unpackStream,
+// src/amr/data/particles/particles_data.hpp:702-784): ONE launch per store instead of one copy per column.
+// A message of `total` particles is column-major: delta[d][total] | v[3][total] | weight[total] | charge[total] |
+// icell[d][total]; a store range of n particles occupies entries [off, off+n) of every column.
+namespace phb
+{
+template<bool PACK>
+__global__ void __launch_bounds__(256)
+    particles_flat_kernel(PartView P, size_t first, size_t n, int dim, unsigned char* buf, size_t total, size_t off)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    double* b8 = reinterpret_cast<double*>(buf) + off;
+    int* b4    = reinterpret_cast<int*>(buf + size_t(dim + 5) * total * 8) + off;
+    int c      = 0;
+    auto mv8   = [&](double* col) {
+        if (PACK)
+            b8[size_t(c) * total + i] = col[first + i];
+        else
+            col[first + i] = b8[size_t(c) * total + i];
+        ++c;
+    };
+    for (int d = 0; d < dim; ++d)
+        mv8(P.delta[d]);
+    for (int k = 0; k < 3; ++k)
+        mv8(P.v[k]);
+    mv8(P.weight);
+    mv8(P.charge);
+    for (int d = 0; d < dim; ++d)
+    {
+        if (PACK)
+            b4[size_t(d) * total + i] = P.icell[d][first + i];
+        else
+            P.icell[d][first + i] = b4[size_t(d) * total + i];
+    }
+}
+} // namespace phb
+
+extern "C" {
+size_t phb_particles_flat_bytes(int dim, size_t total) { return total * size_t(8 * (dim + 5) + 4 * dim); }
+
+int phb_particles_pack(phb_ctx* ctx, const phb_particles* src, size_t first, size_t count, void* d_buf, size_t total,
+                       size_t off)
+{
+    if (!ctx || !src || first + count > src->capacity || (count && !d_buf) || off + count > total)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_particles_pack: invalid argument");
+    if (count == 0)
+        return PHB_OK;
+    phb::particles_flat_kernel<true><<<unsigned((count + 255) / 256), 256, 0, ctx->stream>>>(
+        phb::make_part(*src), first, count, ctx->dim, static_cast<unsigned char*>(d_buf), total, off);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+
+int phb_particles_unpack(phb_ctx* ctx, const void* d_buf, size_t total, size_t off, size_t count, phb_particles* dst)
+{
+    if (!ctx || !dst || (count && !d_buf) || off + count > total)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_particles_unpack: invalid argument");
+    if (dst->n + count > dst->capacity)
+        return phb::set_error(ctx, PHB_ERR_CAPACITY, "phb_particles_unpack: capacity");
+    if (count)
+    {
+        phb::particles_flat_kernel<false><<<unsigned((count + 255) / 256), 256, 0, ctx->stream>>>(
+            phb::make_part(*dst), dst->n, count, ctx->dim,
+            const_cast<unsigned char*>(static_cast<const unsigned char*>(d_buf)), total, off);
+        PHB_LAUNCH_CHECK(ctx);
+    }
+    dst->n += count;
+    return PHB_OK;
+}
+}
+

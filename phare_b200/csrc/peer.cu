@@ -121,9 +121,9 @@ int phb_peer_wait(phb_ctx* ctx, int n, uint64_t* const* h_flag_ptrs, const uint6
         F.p[i] = reinterpret_cast<unsigned long long*>(h_flag_ptrs[i]);
         F.v[i] = h_values[i];
     }
-    int khz = 1965000;
-    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, ctx->device);
-    long long const cycles = (long long)(timeout_s * 1e3 * double(khz));
+    // clock64 ticks at the SM clock; 2 GHz is an upper bound on B200 (1.965 GHz boost), so the timeout is at least
+    // timeout_s.  (cudaDevAttrClockRate is NOT queried here: it is a slow, driver-serialised attribute.)
+    long long const cycles = (long long)(timeout_s * 2.0e9);
     phb::peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(F, cycles, ctx->d_err);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;

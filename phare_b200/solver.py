@@ -266,18 +266,13 @@ class GpuOps:
         return 4 * self.dim + 8 * self.dim + 24 + 16
 
     def pack_particles(self, layout, stores):
-        """flat byte buffer: for every column, the stores back to back"""
+        """flat message: every column holds the stores back to back (phb_particles_pack, one launch per store)"""
         total = sum(s.n for s in stores)
         buf = self.torch.empty(total * self.particle_bytes(), dtype=self.torch.uint8, device=self.device)
         off = 0
-        ncol = len(self._columns(stores[0]))
-        for ci in range(ncol):
-            for s in stores:
-                col, esz = self._columns(s)[ci]
-                nb = s.n * esz
-                if nb:
-                    self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, buf.data_ptr() + off, col.data_ptr(), nb))
-                off += nb
+        for s in stores:
+            self.ctx._check(self.ctx.lib.phb_particles_pack(self.ctx.h, C.byref(s.c), 0, s.n, buf.data_ptr(), total, off))
+            off += s.n
         return buf
 
     def new_particle_buffer(self, layout, total):
@@ -286,12 +281,7 @@ class GpuOps:
     def unpack_particles(self, layout, buf, off, n, total, dst):
         if dst.n + n > dst.capacity:
             raise RuntimeError("particle store capacity exceeded while receiving migrating particles")
-        base = 0
-        for col, esz in self._columns(dst):
-            self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, col.data_ptr() + dst.n * esz,
-                                                 buf.data_ptr() + base + off * esz, n * esz))
-            base += total * esz
-        dst.n = dst.n + n
+        self.ctx._check(self.ctx.lib.phb_particles_unpack(self.ctx.h, buf.data_ptr(), total, off, n, C.byref(dst.c)))
 
 
 # ---------------------------------------------------------------------------------------------------

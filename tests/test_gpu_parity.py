@@ -477,6 +477,30 @@ def test_export_with_shift(ctxs, cpu_oracle, dim):
         assert bit_equal(g, w)  # export preserves source order
 
 
+def test_particles_pack_unpack_roundtrip(ctxs):
+    """the migration message: two store ranges packed into one column-major buffer and appended to a non-empty store"""
+    for dim in (1, 2, 3):
+        ctx = ctxs(dim, 1)
+        rng = np.random.default_rng(dim)
+        L = small_layout(dim, 1)
+        a, b, pre = (random_particles(rng, L, n) for n in (301, 77, 10))
+        A, B = dev_particles(ctx, a), dev_particles(ctx, b)
+        total = 200 + 77
+        nbytes = ctx.lib.phb_particles_flat_bytes(dim, total)
+        assert nbytes == total * (12 * dim + 40)
+        buf = DeviceArray(ctx, (nbytes,), np.uint8)
+        ctx._check(ctx.lib.phb_particles_pack(ctx.h, C.byref(A.c), 50, 200, buf.ptr, total, 0))
+        ctx._check(ctx.lib.phb_particles_pack(ctx.h, C.byref(B.c), 0, 77, buf.ptr, total, 200))
+        dst = dev_particles(ctx, pre, capacity=10 + total)
+        ctx._check(ctx.lib.phb_particles_unpack(ctx.h, buf.ptr, total, 200, 77, C.byref(dst.c)))
+        ctx._check(ctx.lib.phb_particles_unpack(ctx.h, buf.ptr, total, 0, 200, C.byref(dst.c)))
+        assert dst.n == 10 + total
+        for g, p0, x, y in zip(dst.download_soa(), pre, a, b):
+            assert bit_equal(g, np.concatenate([p0, y, x[50:250]]))
+        with pytest.raises(PhbError):
+            ctx._check(ctx.lib.phb_particles_unpack(ctx.h, buf.ptr, total, 0, 200, C.byref(dst.c)))  # capacity
+
+
 def test_export_capacity_error(ctxs):
     ctx = ctxs(1, 1)
     L = small_layout(1, 1)
