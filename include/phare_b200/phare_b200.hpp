@@ -430,7 +430,8 @@ struct IonPopulation // ion_population.hpp:19-140
     Field rho_n, rho_q;
     VecField F;
     ParticleArray<dim> domain, patchGhost, spare;
-    std::unique_ptr<DeviceBuffer> cell_start; // ordering of `domain` (replaces the CellMap)
+    std::unique_ptr<DeviceBuffer> cell_start;      // ordering of `domain` (replaces the CellMap)
+    std::unique_ptr<DeviceBuffer> cell_start_next; // written by phb_bin_plan while the old ordering is still read
     std::size_t n_sorted = 0;
 };
 
@@ -523,12 +524,21 @@ public:
             {
                 // updateAndDepositAll_ (:228-295)
                 ctx.check(phb_push(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.domain.c(), pop.mass(), dt, nullptr));
-                deposit(pop.domain.c());
-                if (!pop.cell_start)
-                    pop.cell_start = std::make_unique<DeviceBuffer>(ctx, (phb_bin_nkeys(layout.c(), &dom) + 2) / 2 + 1);
+                auto const words = (phb_bin_nkeys(layout.c(), &dom) + 2) / 2 + 1;
+                if (!pop.cell_start_next)
+                    pop.cell_start_next = std::make_unique<DeviceBuffer>(ctx, words);
+                uint32_t const* old_start
+                    = pop.cell_start ? reinterpret_cast<uint32_t const*>(pop.cell_start->data()) : nullptr;
+                auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
                 std::size_t counts[3];
-                ctx.check(phb_bin(ctx.get(), layout.c(), pop.domain.c(), pop.spare.c(), &dom, keep.data(), int(keep.size()),
-                                  reinterpret_cast<uint32_t*>(pop.cell_start->data()), counts));
+                // the deposit rides on the scatter pass of the re-binning (K3+K2 fused): partition + erase
+                // (:245-273) and both deposits (:290-293) in one walk over the pushed store
+                ctx.check(phb_bin_plan(ctx.get(), layout.c(), pop.domain.c(), &dom, keep.data(), int(keep.size()), new_start));
+                ctx.check(phb_deposit_scatter(ctx.get(), layout.c(), pop.domain.c(), old_start ? pop.n_sorted : 0,
+                                              pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), &dom,
+                                              old_start, keep.data(), int(keep.size()), pop.spare.c(), new_start));
+                ctx.check(phb_bin_counts(ctx.get(), layout.c(), &dom, new_start, counts, pop.spare.c()));
+                std::swap(pop.cell_start, pop.cell_start_next);
                 // stayers -> domain, leavers inside nonLevelGhostBox -> patchGhost (:248-254), the rest erased (:273)
                 ctx.check(phb_particles_copy(ctx.get(), pop.spare.c(), counts[0], counts[1], pop.patchGhost.c(),
                                              pop.patchGhost.size()));

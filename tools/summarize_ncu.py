@@ -62,7 +62,7 @@ def launches(src, dst, steps_hint=None):
     print(open(dst).read())
 
 
-def kernels(src, dst):
+def kernels(src, dst, particles=64 ** 3 * 64, what="python tools/microbench.py c5s` (3-D, order 1, 64^3 cells x 64 ppc = 16.8 M particles, > L2)"):
     raw = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -70,8 +70,7 @@ def kernels(src, dst):
     seen, traffic = set(), {}
     with open(dst, "w") as f:
         f.write(f"# ncu --set full summary ({os.path.basename(src)})\n\n"
-                "`ncu --set full --clock-control none --import-source on` over `python tools/microbench.py c5s` "
-                "(3-D, order 1, 64^3 cells x 64 ppc = 16.8 M particles, > L2), one launch per kernel shown.\n")
+                f"`ncu --set full --clock-control none --import-source on` over `{what}, one launch per kernel shown.\n")
         for r in rows[2:]:
             name = short(r[idx["Kernel Name"]])
             if name in seen:
@@ -87,16 +86,21 @@ def kernels(src, dst):
                 mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}
                 rd *= mult.get(units[idx["dram__bytes_read.sum"]], 1)
                 wr *= mult.get(units[idx["dram__bytes_write.sum"]], 1)
-                traffic[name] = dict(dram_bytes_per_launch=rd + wr, particles=64 ** 3 * 64,
-                                     dram_bytes_per_particle=(rd + wr) / (64 ** 3 * 64))
+                traffic[name] = dict(dram_bytes_per_launch=rd + wr, particles=particles,
+                                     dram_bytes_per_particle=(rd + wr) / particles)
             except Exception:
                 pass
-    json.dump(traffic, open(os.path.join(os.path.dirname(dst), "traffic_c5s.json"), "w"), indent=1)
+    tfile = os.path.join(os.path.dirname(dst), "traffic_c5s.json")
+    merged = json.load(open(tfile)) if os.path.exists(tfile) else {}
+    merged.update(traffic)  # keep the kernels captured in earlier reports
+    json.dump(merged, open(tfile, "w"), indent=1)
     print(open(dst).read())
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) > 4:  # kernels <rep> <md> <particles> <what>
+        kernels(sys.argv[2], sys.argv[3], int(sys.argv[4]), sys.argv[5])
     else:
         kernels(sys.argv[2], sys.argv[3])
