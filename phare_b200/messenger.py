@@ -209,23 +209,40 @@ class PeerArena:
         ctx = ops.ctx
         self.ctx, self.me, self.size = ctx, comm.rank, comm.size
         self.nbytes = int(nbytes) if nbytes else int(os.environ.get("PHB_PEER_ARENA_MB", 1024)) << 20
-        p = C.c_void_p()
-        ctx._check(ctx.lib.phb_malloc(ctx.h, self.nbytes, C.byref(p)))
-        ctx._check(ctx.lib.phb_memset(ctx.h, p, 0, self.FLAGS))
-        ctx.sync()
-        handle = (C.c_ubyte * 64)()
-        ctx._check(ctx.lib.phb_ipc_export(ctx.h, p, handle))
+        # every step of the set-up is agreed on by all ranks: if any rank cannot export or map (no peer access, IPC
+        # not permitted in this container, ...) everybody falls back to the staged send/recv path
+        p, handle, ok = C.c_void_p(), (C.c_ubyte * 64)(), True
+        try:
+            ctx._check(ctx.lib.phb_malloc(ctx.h, self.nbytes, C.byref(p)))
+            ctx._check(ctx.lib.phb_memset(ctx.h, p, 0, self.FLAGS))
+            ctx.sync()
+            ctx._check(ctx.lib.phb_ipc_export(ctx.h, p, handle))
+        except Exception as e:  # noqa: BLE001 - any failure means "no peer path on this rank"
+            ok, self.why = False, str(e)
         handles = [None] * self.size
-        dist.all_gather_object(handles, bytes(handle))
+        dist.all_gather_object(handles, (ok, bytes(handle)))
         self.base = {}
-        for r, h in enumerate(handles):
-            if r == self.me:
-                self.base[r] = p.value
-            else:
+        if all(h[0] for h in handles):
+            for r, (_, h) in enumerate(handles):
+                if r == self.me:
+                    self.base[r] = p.value
+                    continue
                 q = C.c_void_p()
-                ctx._check(ctx.lib.phb_ipc_open(ctx.h, (C.c_ubyte * 64)(*h), C.byref(q)))
-                self.base[r] = q.value
-        dist.barrier()
+                try:
+                    ctx._check(ctx.lib.phb_ipc_open(ctx.h, (C.c_ubyte * 64)(*h), C.byref(q)))
+                    self.base[r] = q.value
+                except Exception as e:  # noqa: BLE001
+                    ok, self.why = False, str(e)
+                    break
+        else:
+            ok = False
+        verdict = [None] * self.size
+        dist.all_gather_object(verdict, ok)
+        self.ok = all(verdict)
+        if not self.ok:
+            if p.value:
+                ctx.lib.phb_free(ctx.h, p)
+            return
         self.cursor = self.FLAGS
         self.sent = [0] * self.size      # phases I delivered to each rank
         self.received = [0] * self.size  # phases each rank delivered to me
@@ -289,7 +306,13 @@ class HybridMessenger:
         self.arena = None
         import os
         if comm.size > 1 and hasattr(ops, "ctx") and os.environ.get("PHB_PEER_HALO", "1") != "0":
-            self.arena = PeerArena(ops, comm)
+            arena = PeerArena(ops, comm)
+            if arena.ok:
+                self.arena = arena
+            elif comm.rank == 0:
+                import warnings
+                warnings.warn("NVLink peer-memory halo unavailable (" + getattr(arena, "why", "another rank failed")
+                              + "): field phases are staged through torch.distributed send/recv")
         self._last_peer_key = None
 
     def _plan(self, kind, qty):
