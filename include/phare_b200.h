@@ -244,6 +244,17 @@ int phb_push_deposit(phb_ctx*, const phb_layout*, const phb_vecfield* E, const p
                      const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
                      const phb_box* domain, const uint32_t* d_cell_start);
 
+/* ---- particle splitting (level refinement) ---------------------------------------
+ * ParticlesRefineOperator::refine_ (amr/data/particles/refine/particles_data_split.hpp:142-231) for one source
+ * array: every coarse particle of coarse[first,last) is moved to the fine index space (toFineGrid, :32-46), and if
+ * it lies within max_cell_distance cells of a destination box it is split with the (delta, weight) table of
+ * Splitter<dim, interp, nbRefinedPart> (splitter.hpp:71-106; h_deltas[nref*dim], h_weights[nref], float32 like the
+ * reference); the refined particles whose cell lies in that box are appended to `fine`.  Boxes are fine-level AMR
+ * cell boxes and must be disjoint.  host-returning: *h_appended.  Output order: source order, then pattern order. */
+int phb_split(phb_ctx*, const phb_particles* coarse, size_t first, size_t last, int nref, const float* h_deltas,
+              const float* h_weights, int max_cell_distance, const phb_box* fine_boxes, int nbox,
+              phb_particles* fine, size_t* h_appended);
+
 /* ---- K4-K7 field solvers and pointwise ops -------------------------------------------------- */
 /* Faraday::operator()(B,E,Bnew,dt)  faraday/faraday.hpp:28-97 */
 int phb_faraday(phb_ctx*, const phb_layout*, const phb_vecfield* B, const phb_vecfield* E,

@@ -342,6 +342,24 @@ class Cpu:
         return dict(rho_n=rho_n, rho_q=rho_q, flux=flux, rho_q_tot=q, rho_m_tot=m, V=V,
                     seconds=float(self.lib.phr_last_seconds()))
 
+    def split_pattern(self, dim, interp, nref):
+        """the reference Splitter<dim, interp, nref> flattened: (deltas float32 (nref, dim), weights, maxCellDistance)"""
+        assert self.impl == "ref"
+        d, w, m = np.zeros((nref, dim), np.float32), np.zeros(nref, np.float32), C.c_int()
+        rc = self._fn("split_pattern")(dim, interp, nref, d.ctypes.data_as(C.c_void_p), w.ctypes.data_as(C.c_void_p),
+                                       C.byref(m))
+        if rc != 0:
+            raise KeyError((dim, interp, nref))
+        return d, w, m.value
+
+    def split(self, dim, interp, nref, parts):
+        """toFineGrid + Splitter::operator() of the reference on every particle: nref refined particles each, in order"""
+        assert self.impl == "ref"
+        out = HostParticles(dim, max(parts.n * nref, 1))
+        rc = self._fn("split")(dim, interp, nref, C.byref(parts.c), C.byref(out.c))
+        assert rc == 0, rc
+        return out
+
     def maxwellian(self, layout, n, V, Vth, charge, ppc, seed):
         """MaxwellianParticleInitializer::loadParticles with per-cell profile arrays (row-major over the patch)."""
         assert self.impl == "ref"

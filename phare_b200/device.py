@@ -220,6 +220,16 @@ class Context:
                                             C.byref(pout.c)))
         return tuple(int(c) for c in counts)
 
+    def split(self, coarse, first, last, deltas, weights, max_cell_distance, fine_boxes, fine):
+        """phb_split: deltas (nref, dim) float32, weights (nref,) float32 — see phare_b200.split.pattern()"""
+        d = np.ascontiguousarray(deltas, dtype=np.float32)
+        w = np.ascontiguousarray(weights, dtype=np.float32)
+        n = C.c_size_t()
+        self._check(self.lib.phb_split(self.h, C.byref(coarse.c), first, last, len(w), d.ctypes.data, w.ctypes.data,
+                                       int(max_cell_distance), abi.box_array(list(fine_boxes)), len(fine_boxes),
+                                       C.byref(fine.c), C.byref(n)))
+        return int(n.value)
+
     def bin_nkeys(self, layout, domain):
         return int(self.lib.phb_bin_nkeys(C.byref(layout), C.byref(domain)))
 

@@ -16,14 +16,35 @@ def populate(module, dim, interp, nref):
         return Simulator(hier)
 
     class Splitter:
-        """amr::Splitter<dim, interp, nbRefinedPart> (src/amr/data/particles/refine/splitter.hpp): particle
-        splitting belongs to level refinement, which this back end does not drive yet"""
+        """amr::Splitter<dim, interp, nbRefinedPart> (src/amr/data/particles/refine/splitter.hpp, split_{1,2,3}d.hpp):
+        the flattened pattern table phb_split consumes (phare_b200/split.py)"""
 
         def __init__(self):
-            raise NotImplementedError("particle splitting (refined levels) is not available in this back end")
+            from phare_b200.split import pattern
+            self.deltas, self.weights, self.max_cell_distance = pattern(dim, interp, nref)
+            self.nbRefinedPart = nref
 
-    def split_pyarray_particles(*args, **kwargs):
-        raise NotImplementedError("particle splitting (refined levels) is not available in this back end")
+    def split_pyarray_particles(particles):
+        """splitPyArrayParticles (src/python3/particles.hpp): (iCell, delta, weight, charge, v) flat arrays of coarse
+        particles -> the same five arrays for their refined particles, on the fine index space (runs phb_split)"""
+        import numpy as np
+        from phare_b200 import abi
+        from phare_b200.device import Context, DeviceParticles
+        icell, delta, weight, charge, v = (np.asarray(a) for a in particles)
+        n = len(weight)
+        sp = Splitter()
+        ctx = Context(dim, interp)
+        try:
+            src = DeviceParticles(ctx, max(n, 1)).upload_soa(icell.reshape(n, dim), delta.reshape(n, dim), weight, charge,
+                                                             v.reshape(n, 3))
+            dst = DeviceParticles(ctx, max(n * nref, 1))
+            big = 2 ** 30
+            everywhere = abi.make_box([-big] * dim, [big] * dim)
+            ctx.split(src, 0, n, sp.deltas, sp.weights, sp.max_cell_distance, [everywhere], dst)
+            ic, de, w, q, vv = dst.download_soa()
+        finally:
+            ctx.close()
+        return ic.reshape(-1), de.reshape(-1), w, q, vv.reshape(-1)
 
     module.Simulator = Simulator
     module.make_simulator = make_simulator
