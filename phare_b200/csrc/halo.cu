@@ -4,7 +4,7 @@
 //   border sum  : FieldBorderOp with PlusEquals               (src/amr/data/field/field_data.hpp:446-462,
 //                                                              src/core/utilities/types.hpp:570-575)
 //   border max  : SetMax                                       (src/core/utilities/types.hpp:577-581)
-// Which boxes are exchanged is decided on the host (phare_b200/halo.py restates
+// Which boxes are exchanged is decided on the host (phare_b200/messenger.py + boxes.py restate
 // field_geometry.hpp:139-304 and field_variable_fill_pattern.hpp:30-313).
 #include "common.cuh"
 

@@ -544,9 +544,27 @@ class SolverPPC:
                                   {p.geom.id: p.pops[i].domain for p in self.patches})
             for p in self.patches:
                 ops.set_count(p.pops[i].patch_ghost, 0)
+        for p in self.patches:
+            for pop in p.pops:
+                self._ensure_headroom(pop)
         err = ops.poll_error()
         if self.comm.allreduce_max(err):
             raise RuntimeError("Updater::updatePopulations: " + (getattr(ops, "last_error", "") or "error on another rank"))
+
+    GROW_AT, GROW_BY = 0.85, 1.5
+
+    def _ensure_headroom(self, pop):
+        """the reference's ParticleArray is a std::vector and simply grows; the device stores are fixed-capacity, so a
+        population that fills 85 % of its stores (density pile-up, e.g. a compressing current sheet) gets 1.5x larger ones"""
+        ops = self.ops
+        n, cap = ops.count(pop.domain), ops.capacity(pop.domain)
+        if n <= self.GROW_AT * cap:
+            return
+        new_cap = int(cap * self.GROW_BY) + 4096
+        bigger = ops.particles(new_cap)
+        ops.particles_copy(pop.domain, 0, n, bigger, 0)
+        ops.set_count(bigger, n)
+        pop.domain, pop.spare = bigger, ops.particles(new_cap)
 
     # ---- public
     def prepare_step(self):

@@ -95,3 +95,19 @@ def test_fused_and_two_pass_sweeps_are_the_same_orchestration():
     for i in range(2):
         for x, y in zip(all_particles(a, i), all_particles(b, i)):
             assert np.array_equal(x, y)
+
+
+def test_particle_stores_grow_before_they_overflow():
+    """a population that fills its stores gets larger ones at the end of the step (std::vector growth in the reference)"""
+    domain, interp, dx = (32,), 1, (0.2,)
+    gparts = global_particles(domain, interp, dx, 10, seed=5)
+    s = make_solver(CpuOps(1, interp), domain, (2,), interp, dx, gparts)
+    pop = s.patches[0].pops[0]
+    n, cap0 = s.ops.count(pop.domain), s.ops.capacity(pop.domain)
+    s.GROW_AT = (n - 1) / cap0  # pretend the store is nearly full
+    before = all_particles(s, 0)
+    s.advance_level(0.005)
+    assert s.ops.capacity(pop.domain) == s.ops.capacity(pop.spare) > cap0
+    s.GROW_AT = 0.85
+    s.advance_level(0.005)  # and the step goes on with the new stores
+    assert len(all_particles(s, 0)[2]) == len(before[2])
