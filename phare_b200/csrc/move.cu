@@ -34,11 +34,12 @@
 namespace phb
 {
 constexpr int MOVE_DEPTH = 4; // particles in flight per lane (cp.async ring)
+// 128-thread CTAs, at least two resident (c1: 1.55 ms against 1.78 ms with 256 x 1; c2: 1.97 against 2.06 ms)
 #ifndef PHB_MOVE_BS
-#define PHB_MOVE_BS 256
+#define PHB_MOVE_BS 128
 #endif
 #ifndef PHB_MOVE_MINB
-#define PHB_MOVE_MINB 1
+#define PHB_MOVE_MINB 2
 #endif
 constexpr int MOVE_BS = PHB_MOVE_BS;
 

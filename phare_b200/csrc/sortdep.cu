@@ -21,15 +21,18 @@
 namespace phb
 {
 constexpr int SD_DEPTH = 4;
+// threads per CTA: 128 in 3-D (config 5: 5.63 ms against 5.82 ms with 256), 256 otherwise (c3: 3.58 against 3.73 ms)
+template<int DIM> constexpr int sd_bs() { return DIM == 3 ? 128 : 256; }
 
 template<int DIM, int ORDER, int GS>
-__global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(sd_bs<DIM>(), (ipow(cell_support<ORDER>(), DIM) <= 8 ? 2 : 1) * (256 / sd_bs<DIM>()))
     deposit_scatter_kernel(const __grid_constant__ DepositParams<DIM> A, const __grid_constant__ KeySpace<DIM> K,
                            PartView out, const uint32_t* __restrict__ new_start, const uint32_t* __restrict__ slot)
 {
     constexpr int S     = cell_support<ORDER>();
     constexpr int NODES = ipow(S, DIM);
     constexpr int NV    = NODES * 5;
+    constexpr int SD_BS = sd_bs<DIM>();
 
     unsigned const gtid = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned const key  = gtid / GS;
@@ -65,23 +68,23 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
         size_t const own_start   = __ldg(new_start + own_key);
         extern __shared__ __align__(16) unsigned char ring_raw[];
         double* const ring8 = reinterpret_cast<double*>(ring_raw);
-        int* const ring4    = reinterpret_cast<int*>(ring_raw + size_t(SD_DEPTH) * (DIM + 5) * 256 * 8);
+        int* const ring4    = reinterpret_cast<int*>(ring_raw + size_t(SD_DEPTH) * (DIM + 5) * SD_BS * 8);
         auto issue = [&](size_t p, int s) {
             if (p < end)
             {
                 int c8 = 0;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
-                    cp_async8(ring8 + (s * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.delta[d] + p);
+                    cp_async8(ring8 + (s * (DIM + 5) + c8++) * SD_BS + threadIdx.x, A.P.delta[d] + p);
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    cp_async8(ring8 + (s * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.v[c] + p);
-                cp_async8(ring8 + (s * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.weight + p);
-                cp_async8(ring8 + (s * (DIM + 5) + c8++) * 256 + threadIdx.x, A.P.charge + p);
+                    cp_async8(ring8 + (s * (DIM + 5) + c8++) * SD_BS + threadIdx.x, A.P.v[c] + p);
+                cp_async8(ring8 + (s * (DIM + 5) + c8++) * SD_BS + threadIdx.x, A.P.weight + p);
+                cp_async8(ring8 + (s * (DIM + 5) + c8++) * SD_BS + threadIdx.x, A.P.charge + p);
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
-                    cp_async4(ring4 + (s * (DIM + 1) + d) * 256 + threadIdx.x, A.P.icell[d] + p);
-                cp_async4(ring4 + (s * (DIM + 1) + DIM) * 256 + threadIdx.x, slot + p);
+                    cp_async4(ring4 + (s * (DIM + 1) + d) * SD_BS + threadIdx.x, A.P.icell[d] + p);
+                cp_async4(ring4 + (s * (DIM + 1) + DIM) * SD_BS + threadIdx.x, slot + p);
             }
             cp_async_commit();
         };
@@ -99,16 +102,16 @@ __global__ void __launch_bounds__(256, (ipow(cell_support<ORDER>(), DIM) <= 8 ? 
                 int c8 = 0;
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
-                    delta[d] = ring8[(s * (DIM + 5) + c8++) * 256 + threadIdx.x];
+                    delta[d] = ring8[(s * (DIM + 5) + c8++) * SD_BS + threadIdx.x];
 #pragma unroll
                 for (int c = 0; c < 3; ++c)
-                    v[c] = ring8[(s * (DIM + 5) + c8++) * 256 + threadIdx.x];
-                weight = ring8[(s * (DIM + 5) + c8++) * 256 + threadIdx.x];
-                charge = ring8[(s * (DIM + 5) + c8++) * 256 + threadIdx.x];
+                    v[c] = ring8[(s * (DIM + 5) + c8++) * SD_BS + threadIdx.x];
+                weight = ring8[(s * (DIM + 5) + c8++) * SD_BS + threadIdx.x];
+                charge = ring8[(s * (DIM + 5) + c8++) * SD_BS + threadIdx.x];
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
-                    icell[d] = ring4[(s * (DIM + 1) + d) * 256 + threadIdx.x];
-                my_slot = unsigned(ring4[(s * (DIM + 1) + DIM) * 256 + threadIdx.x]);
+                    icell[d] = ring4[(s * (DIM + 1) + d) * SD_BS + threadIdx.x];
+                my_slot = unsigned(ring4[(s * (DIM + 1) + DIM) * SD_BS + threadIdx.x]);
             }
             issue(p + size_t(SD_DEPTH) * GS, s);
             s = s + 1 == SD_DEPTH ? 0 : s + 1;
@@ -319,8 +322,9 @@ int launch_ds_cells(phb_ctx* ctx, const DepositParams<DIM>& A, const KeySpace<DI
                     const uint32_t* new_start, const uint32_t* slot)
 {
     size_t const threads = size_t(A.nkeys) * GS;
-    unsigned const grid  = unsigned((threads + 255) / 256);
-    constexpr int smem   = SD_DEPTH * ((DIM + 5) * 8 + (DIM + 1) * 4) * 256;
+    constexpr int SD_BS  = sd_bs<DIM>();
+    unsigned const grid  = unsigned((threads + SD_BS - 1) / SD_BS);
+    constexpr int smem   = SD_DEPTH * ((DIM + 5) * 8 + (DIM + 1) * 4) * SD_BS;
     static bool configured = false;
     if (!configured)
     {
@@ -328,7 +332,7 @@ int launch_ds_cells(phb_ctx* ctx, const DepositParams<DIM>& A, const KeySpace<DI
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    deposit_scatter_kernel<DIM, ORDER, GS><<<grid, 256, smem, ctx->stream>>>(A, K, out, new_start, slot);
+    deposit_scatter_kernel<DIM, ORDER, GS><<<grid, SD_BS, smem, ctx->stream>>>(A, K, out, new_start, slot);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
