@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(DEP_BS, (ipow(cell_support<ORDER>(), DIM) <= 8
                 }
             }
             else if (selected<DIM>(A.sel, icell))
-                A.mover_list[atomicAdd(A.mover_count, 1u)] = uint32_t(p);
+                mover_append<DIM>(A, p);
         }
     }
 
@@ -286,12 +286,12 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
     {
         if (cells && A.nkeys > 0 && A.last < 0xffffffffull)
         {
-            // scratch: [count | list of at most (last-first) particle indices]
-            if (int rc = ensure_scratch(ctx, (A.last - A.first + 4) * sizeof(uint32_t)))
+            // scratch: the sub-listed mover indices (deposit_core.cuh)
+            if (int rc = ensure_scratch(ctx, mover_scratch_words(A.last - A.first) * sizeof(uint32_t)))
                 return rc;
-            A.mover_count = static_cast<unsigned*>(ctx->scratch);
-            A.mover_list  = static_cast<uint32_t*>(ctx->scratch) + 4;
-            PHB_CUDA(ctx, cudaMemsetAsync(A.mover_count, 0, sizeof(unsigned), ctx->stream));
+            ctx->plan_n = size_t(-1); // a pending phb_bin_plan's slots live in the same scratch
+            set_mover_lists<DIM>(A, static_cast<uint32_t*>(ctx->scratch), A.last - A.first);
+            PHB_CUDA(ctx, cudaMemsetAsync(A.mover_count, 0, mover_counter_bytes(), ctx->stream));
             size_t ppc = (A.last - A.first) / A.nkeys;
             if (const char* e = getenv("PHB_DEPOSIT_GS")) // tuning override: lanes per cell
                 ppc = atoi(e) == 16 ? 96 : atoi(e) == 8 ? 24 : atoi(e) == 4 ? 6 : 1;
@@ -304,7 +304,7 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
             else
                 launch_cells<DIM, ORDER, 2>(ctx, A);
             PHB_LAUNCH_CHECK(ctx);
-            deposit_list_kernel<DIM, ORDER><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(A, A.mover_list, A.mover_count);
+            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A);
             PHB_LAUNCH_CHECK(ctx);
             return PHB_OK;
         }

@@ -49,28 +49,32 @@ struct MoverRecords
     int* icell[3];
     double* delta[3];
     double* dep[5];
-    unsigned cap;
-    unsigned* count;
+    unsigned cap;    // records per sub-list (MOVER_LISTS sub-lists chosen by CTA, like the mover index lists of K3)
+    unsigned* count; // MOVER_LISTS counters, 32 words apart
 };
 
 template<int DIM, int ORDER>
 __global__ void __launch_bounds__(256)
     deposit_records_kernel(const __grid_constant__ DepositParams<DIM> A, const __grid_constant__ MoverRecords R)
 {
-    unsigned const total = *R.count;
-    unsigned const n     = total < R.cap ? total : R.cap;
-    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x)
+    for (unsigned l = blockIdx.x; l < MOVER_LISTS; l += gridDim.x)
     {
-        int icell[DIM];
-        double delta[DIM];
-#pragma unroll
-        for (int d = 0; d < DIM; ++d)
+        unsigned const total = R.count[l * 32];
+        unsigned const n     = total < R.cap ? total : R.cap;
+        for (unsigned k = threadIdx.x; k < n; k += blockDim.x)
         {
-            icell[d] = R.icell[d][t];
-            delta[d] = R.delta[d][t];
+            size_t const t = size_t(l) * R.cap + k;
+            int icell[DIM];
+            double delta[DIM];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d)
+            {
+                icell[d] = R.icell[d][t];
+                delta[d] = R.delta[d][t];
+            }
+            double const dep[5] = {R.dep[0][t], R.dep[1][t], R.dep[2][t], R.dep[3][t], R.dep[4][t]};
+            scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
         }
-        double const dep[5] = {R.dep[0][t], R.dep[1][t], R.dep[2][t], R.dep[3][t], R.dep[4][t]};
-        scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
     }
 }
 
@@ -251,9 +255,11 @@ __global__ void __launch_bounds__(MOVE_BS, PHB_MOVE_MINB)
             }
             else if (selected<DIM>(A.sel, icell))
             {
-                unsigned const r = atomicAdd(R.count, 1u);
-                if (r < R.cap)
+                unsigned const l = blockIdx.x % MOVER_LISTS;
+                unsigned const k = atomicAdd(R.count + l * 32, 1u);
+                if (k < R.cap)
                 {
+                    size_t const r = size_t(l) * R.cap + k;
 #pragma unroll
                     for (int d = 0; d < DIM; ++d)
                     {
@@ -361,25 +367,27 @@ int launch_move_cells(phb_ctx* ctx, const PushParams<DIM>& P, const DepositParam
 template<int DIM, int ORDER, bool EXACT, bool WRITE>
 int move_cells(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>& A)
 {
-    // record buffer for the particles that leave their cell: [count | icell[d] | delta[d] | dep[5]] x cap
-    size_t const n = A.last - A.first;
-    size_t cap     = n / 16 + 65536;
-    cap            = (cap + 63) & ~size_t(63);
+    // record buffer for the particles that leave their cell: [counters | delta[d] | dep[5] | icell[d]] x cap
+    size_t const n      = A.last - A.first;
+    size_t const subcap = ((n / 16 + 65536) / MOVER_LISTS + 2) & ~size_t(1);
+    size_t const cap    = subcap * MOVER_LISTS;
+    size_t const head   = size_t(MOVER_LISTS) * 32 * sizeof(unsigned);
     size_t const rec_bytes = cap * (4 * DIM + 8 * DIM + 40);
-    if (int rc = ensure_scratch(ctx, 256 + rec_bytes))
+    if (int rc = ensure_scratch(ctx, head + rec_bytes))
         return rc;
+    ctx->plan_n = size_t(-1);
     MoverRecords R{};
     unsigned char* base = static_cast<unsigned char*>(ctx->scratch);
     R.count             = reinterpret_cast<unsigned*>(base);
-    R.cap               = unsigned(cap);
-    unsigned char* q    = base + 256;
+    R.cap               = unsigned(subcap);
+    unsigned char* q    = base + head;
     for (int d = 0; d < DIM; ++d, q += cap * 8)
         R.delta[d] = reinterpret_cast<double*>(q);
     for (int f = 0; f < 5; ++f, q += cap * 8)
         R.dep[f] = reinterpret_cast<double*>(q);
     for (int d = 0; d < DIM; ++d, q += cap * 4)
         R.icell[d] = reinterpret_cast<int*>(q);
-    PHB_CUDA(ctx, cudaMemsetAsync(R.count, 0, sizeof(unsigned), ctx->stream));
+    PHB_CUDA(ctx, cudaMemsetAsync(R.count, 0, head, ctx->stream));
 
     size_t ppc = n / A.nkeys;
     if (const char* e = getenv("PHB_DEPOSIT_GS")) // tuning override: lanes per cell
@@ -395,7 +403,7 @@ int move_cells(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>& A)
         rc = launch_move_cells<DIM, ORDER, 2, EXACT, WRITE>(ctx, P, A, R);
     if (rc)
         return rc;
-    deposit_records_kernel<DIM, ORDER><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(A, R);
+    deposit_records_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A, R);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(sd_bs<DIM>(), (ipow(cell_support<ORDER>(), DIM
                 }
             }
             else if (selected<DIM>(A.sel, icell))
-                A.mover_list[atomicAdd(A.mover_count, 1u)] = uint32_t(p); // deposited from the source store afterwards
+                mover_append<DIM>(A, p); // deposited from the source store afterwards
         }
     }
 
@@ -278,22 +278,21 @@ __global__ void __launch_bounds__(256)
     scatter_atomic<DIM, ORDER>(A.L, A.M, icell, delta, dep);
 }
 
-// scratch layout shared by phb_bin_plan and phb_deposit_scatter: [slot n][scan tmp][mover count 4][mover list n]
+// scratch layout shared by phb_bin_plan and phb_deposit_scatter: [slot n][scan tmp][mover counters and sub-lists]
 struct PlanScratch
 {
-    uint32_t *slot, *scan_tmp, *mover_count, *mover_list;
+    uint32_t *slot, *scan_tmp, *movers;
 };
 template<int DIM>
 int plan_scratch(phb_ctx* ctx, size_t n, size_t nk, PlanScratch& S)
 {
     size_t const scan_words = scan_scratch_words(nk + 1) + 8;
-    size_t const words      = n + scan_words + 4 + n + 8;
+    size_t const words      = n + scan_words + mover_scratch_words(n) + 8;
     if (int rc = ensure_scratch(ctx, words * sizeof(uint32_t)))
         return rc;
     S.slot        = static_cast<uint32_t*>(ctx->scratch);
     S.scan_tmp    = S.slot + n;
-    S.mover_count = S.scan_tmp + scan_words;
-    S.mover_list  = S.mover_count + 4;
+    S.movers      = S.scan_tmp + scan_words;
     return PHB_OK;
 }
 
@@ -362,9 +361,8 @@ int ds_order(phb_ctx* ctx, const phb_layout* L, const phb_particles* in, size_t 
         {
             DepositParams<DIM> A;
             prepare_deposit<DIM>(L, in, 0, n_sorted, rho_n, rho_q, flux, coef, sel, nsel, domain, old_start, A);
-            A.mover_count = S.mover_count;
-            A.mover_list  = S.mover_list;
-            PHB_CUDA(ctx, cudaMemsetAsync(A.mover_count, 0, sizeof(unsigned), ctx->stream));
+            set_mover_lists<DIM>(A, S.movers, n);
+            PHB_CUDA(ctx, cudaMemsetAsync(A.mover_count, 0, mover_counter_bytes(), ctx->stream));
             // lanes per cell: wider groups than phb_deposit's, because a group also writes its particles to
             // consecutive slots of the re-binned store and full 128/256-byte segments matter more here
             // (config 5, 64 ppc: 16 lanes 5.8 ms, 8 lanes 7.0 ms, 4 lanes 11.9 ms for plan + pass)
@@ -385,7 +383,7 @@ int ds_order(phb_ctx* ctx, const phb_layout* L, const phb_particles* in, size_t 
                 rc = launch_ds_cells<DIM, ORDER, 2>(ctx, A, K, o, new_start, S.slot);
             if (rc)
                 return rc;
-            deposit_list_kernel<DIM, ORDER><<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(A, A.mover_list, A.mover_count);
+            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A);
             PHB_LAUNCH_CHECK(ctx);
         }
     }
