@@ -102,7 +102,7 @@ def build_gpu_solver(n_gpus, rank, device):
         if pg.owner != rank:
             continue
         n = int(L.ncells[0]) * int(L.ncells[1]) * int(L.ncells[2]) * PPC
-        patch = Patch(ops, pg, L, [dict(name="protons", mass=1.0, n=n)], capacity_factor=1.08)
+        patch = Patch(ops, pg, L, [dict(name="protons", mass=1.0, n=n)], capacity_factor=1.2)  # below the 85 % fill at which the stores would grow
         pop = patch.pops[0]
         # uniform Maxwellian: n = 1, V = 0, vth = 0.3, charge 1 (functional uniform bench)
         P = uniform_sorted_particles(ops.ctx, L, PPC, 0.3, device, seed=1337 + pg.id, store=pop.domain)
