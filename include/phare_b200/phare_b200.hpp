@@ -24,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <utility>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -318,6 +319,7 @@ public:
     std::size_t size() const { return p_.n; }
     std::size_t capacity() const { return p_.capacity; }
     void clear() { p_.n = 0; }
+    void swap(ParticleArray& other) { std::swap(p_, other.p_); } // both stores belong to the same context
     void assign(std::vector<Particle_t> const& host) // std::vector<Particle> -> device
     {
         static_assert(sizeof(Particle_t) == (dim == 1 ? 56 : dim == 2 ? 64 : 80));
@@ -539,10 +541,11 @@ public:
                                               old_start, keep.data(), int(keep.size()), pop.spare.c(), new_start));
                 ctx.check(phb_bin_counts(ctx.get(), layout.c(), &dom, new_start, counts, pop.spare.c()));
                 std::swap(pop.cell_start, pop.cell_start_next);
-                // stayers -> domain, leavers inside nonLevelGhostBox -> patchGhost (:248-254), the rest erased (:273)
-                ctx.check(phb_particles_copy(ctx.get(), pop.spare.c(), counts[0], counts[1], pop.patchGhost.c(),
+                // stayers -> domain, leavers inside nonLevelGhostBox -> patchGhost (:248-254), the rest erased (:273):
+                // the re-binned store becomes the domain array (pointer swap), its patch-ghost range is copied out
+                pop.domain.swap(pop.spare);
+                ctx.check(phb_particles_copy(ctx.get(), pop.domain.c(), counts[0], counts[1], pop.patchGhost.c(),
                                              pop.patchGhost.size()));
-                ctx.check(phb_particles_copy(ctx.get(), pop.spare.c(), 0, counts[0], pop.domain.c(), 0));
                 pop.domain.c()->n = counts[0];
                 pop.n_sorted      = counts[0];
             }
