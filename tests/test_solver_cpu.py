@@ -111,3 +111,23 @@ def test_particle_stores_grow_before_they_overflow():
     s.GROW_AT = 0.85
     s.advance_level(0.005)  # and the step goes on with the new stores
     assert len(all_particles(s, 0)[2]) == len(before[2])
+
+
+def test_patch_without_particles_and_empty_population():
+    """a population absent from one patch (which receives its first particles by migration) and a population that is
+    empty everywhere, next to a normal one (the plasma density itself is never zero: Ohm divides by it): every sweep,
+    binning and exchange phase must cope with zero-length ranges"""
+    domain, interp, dx = (32,), 1, (0.2,)
+    full, second = global_particles(domain, interp, dx, 20, seed=8, pops=2)
+    left = second[0][:, 0] < 16
+    gparts = [full, tuple(a[left] for a in second), tuple(a[:0] for a in full)]
+    s = make_solver(CpuOps(1, interp), domain, (2,), interp, dx, gparts, masses=(1.0, 2.0, 1.0))
+    assert s.ops.count(s.patches[1].pops[1].domain) == 0
+    for _ in range(6):
+        s.advance_level(0.02)
+    n = [s.ops.count(p.pops[1].domain) for p in s.patches]
+    assert sum(n) == int(left.sum()) and n[1] > 0          # conserved, and some have crossed into the patch without any
+    assert sum(s.ops.count(p.pops[0].domain) for p in s.patches) == len(full[2])
+    assert all(s.ops.count(p.pops[2].domain) == 0 for p in s.patches)
+    for attr, comp, qty in FIELDS:
+        assert not np.isnan(gather_field(s, attr, comp, qty, domain)).any()

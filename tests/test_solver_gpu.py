@@ -73,3 +73,29 @@ def test_gpu_first_sweep_is_bit_exact_from_synchronised_inputs():
         b = gpu.ops.get_particles(pg.pops[0].patch_ghost)
         assert np.array_equal(canonical_rows(*a), canonical_rows(*b))
         assert np.array_equal(cpu.ops.get_field(pc.pops[0].cell_start), gpu.ops.get_field(pg.pops[0].cell_start))
+
+
+def test_gpu_patch_without_particles_and_empty_population():
+    """zero-length ranges through every CUDA entry point of the step (push, plan + deposit_scatter, bin, export, migration):
+    a population absent from one patch, another empty everywhere, next to a normal one"""
+    from phare_b200.solver import GpuOps
+    from oracle.cpu_ops import CpuOps
+    domain, interp, dx = (16, 12), 1, (0.4, 0.4)
+    full, second = global_particles(domain, interp, dx, 10, seed=8, pops=2)
+    left = second[0][:, 0] < 8
+    gparts = [full, tuple(a[left] for a in second), tuple(a[:0] for a in full)]
+    masses = (1.0, 2.0, 1.0)
+    cpu = make_solver(CpuOps(2, interp), domain, (2, 1), interp, dx, gparts, masses=masses)
+    gpu = make_solver(GpuOps(2, interp, "cuda:0"), domain, (2, 1), interp, dx, gparts, masses=masses)
+    for _ in range(4):
+        cpu.advance_level(0.02)
+        gpu.advance_level(0.02)
+    for pc, pg in zip(cpu.patches, gpu.patches):
+        for i in range(3):
+            assert cpu.ops.count(pc.pops[i].domain) == gpu.ops.count(pg.pops[i].domain)
+    assert gpu.ops.count(gpu.patches[1].pops[1].domain) > 0
+    for attr, comp, qty in FIELDS:
+        a, b = gather_field(cpu, attr, comp, qty, domain), gather_field(gpu, attr, comp, qty, domain)
+        assert not np.isnan(a).any() and not np.isnan(b).any()
+        scale = np.max(np.abs(a)) + 1e-30
+        assert np.max(np.abs(a - b)) <= 1e-10 * scale + 1e-13, (attr, comp)
