@@ -303,6 +303,44 @@ typedef struct {
 } phb_box_desc;
 int phb_box_op_batch(phb_ctx*, const phb_box_desc* d_ops, int nops, uint64_t total_elements);
 
+/* ---- coarse <-> fine level operators (refinement ratio 2) ---------------------------
+ * A phb_field_view is an array of one quantity together with the AMR field index of its first element
+ * (primal directions count nodes, dual directions count cells), i.e. what the reference passes to its
+ * refiners / coarseners as (Field, ghost field box): local index = AMR index - lo (AMRToLocal,
+ * amr/resources_manager/amr_utils.hpp).  Boxes are inclusive AMR FIELD-index boxes of `qty`. */
+typedef struct { double* data; uint32_t shape[3]; int32_t lo[3]; } phb_field_view;
+typedef enum {
+    PHB_REFINE_DEFAULT       = 0, /* DefaultFieldRefiner: linear, writes NaN nodes only (field_refiner.hpp:32-170,
+                                     field_linear_refine.hpp:29-129, linear_weighter.cpp:9-56)                        */
+    PHB_REFINE_MAGNETIC      = 1, /* MagneticFieldRefiner: coarse faces copied, NaN nodes only
+                                     (magnetic_field_refiner.hpp:28-195)                                              */
+    PHB_REFINE_MAGNETIC_INIT = 2, /* MagneticFieldInitRefiner: same, unconditional (magnetic_field_init_refiner.hpp)  */
+    PHB_REFINE_ELECTRIC      = 3  /* ElectricFieldRefiner: edge-conserving, NaN nodes only
+                                     (electric_field_refiner.hpp:30-345)                                              */
+} phb_refine_op;
+typedef enum {
+    PHB_COARSEN_ELECTRIC = 0, /* ElectricFieldCoarsener (electric_field_coarsener.hpp:38-150) */
+    PHB_COARSEN_MOMENTS  = 1  /* MomentsCoarsener: injection (moments_coarsener.hpp:30-84)     */
+} phb_coarsen_op;
+/* FieldRefineOperator::refine for one destination box (field_refine_operator.hpp:60-102): every fine index of
+ * `fine_box` gets refiner(coarse, fine, index).  The coarse view must hold coarsen(fine_box) (+1 for the linear and
+ * electric stencils). */
+int phb_field_refine(phb_ctx*, int dim, int op, int qty, const phb_field_view* coarse,
+                     const phb_field_view* fine, const phb_box* fine_box);
+/* MagneticRefinePatchStrategy::postprocessRefine (magnetic_refine_patch_strategy.hpp:66-125, 1-D :134-141,
+ * 2-D :143-190, 3-D :192-372): the NEW fine faces (odd index along the component's own direction) of the field boxes
+ * of the cell box `fine_cell_box` get the divergence-free Toth-Roe value from the coarse faces around them. */
+int phb_magnetic_postprocess(phb_ctx*, const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box);
+/* FieldCoarsenOperator::coarsen for one coarse box (field_coarsen_operator.hpp:95-121) */
+int phb_field_coarsen(phb_ctx*, int dim, int op, int qty, const phb_field_view* fine,
+                      const phb_field_view* coarse, const phb_box* coarse_box);
+/* setNaNsOnFieldGhosts (hybrid_hybrid_messenger_strategy.hpp:924-955) / zero(): dst[box] = value */
+int phb_box_fill(phb_ctx*, int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3],
+                 const uint32_t extent[3], double value);
+/* core::operate<PlusEqualsProduct> (utilities/algorithm.hpp:166-183, types.hpp:584-588): dst += src * coef;
+ * SolverPPC::accumulateFluxSum (solver_ppc.hpp:263-276) */
+int phb_axpy(phb_ctx*, size_t n, double* dst, const double* src, double coef);
+
 /* ---- peer-memory halo exchange over NVLink (one process per GPU, GPUs of one node) ---------------
  * The receive areas of the field exchange phases live in ONE device allocation per rank (phb_malloc) that
  * every other rank maps through CUDA IPC; phb_box_op_batch descriptors may then name a peer's memory as

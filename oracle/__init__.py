@@ -294,6 +294,46 @@ class Cpu:
                                  src.ctypes.data_as(C.c_void_p), u3(src.shape), u3(src_lo), u3(extent), C.c_int(op))
         assert rc == 0
 
+    # ------------------------------------------------------------------ coarse <-> fine level operators
+    @staticmethod
+    def _view(a, lo):
+        return abi.make_view(a.ctypes.data, a.shape, lo)
+
+    def field_refine(self, dim, op, qty, coarse, coarse_lo, fine, fine_lo, box_lo, box_hi):
+        """in place on `fine` (numpy, C order); *_lo = AMR field index of element 0; box = inclusive AMR field box"""
+        assert self.impl == "oracle"
+        cv, fv, b = self._view(coarse, coarse_lo), self._view(fine, fine_lo), abi.make_box(box_lo, box_hi)
+        rc = self.lib.pho_field_refine(C.c_int(dim), C.c_int(op), C.c_int(qty), C.byref(cv), C.byref(fv), C.byref(b))
+        assert rc == 0, rc
+
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+        assert self.impl == "oracle"
+        bv = host_vec(B)
+        for c in range(3):
+            bv.comp[c] = B[c].ctypes.data
+        b = abi.make_box(cell_lo, cell_hi)
+        rc = self.lib.pho_magnetic_postprocess(C.byref(layout), C.byref(bv), C.byref(b))
+        assert rc == 0, rc
+
+    def field_coarsen(self, dim, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
+        assert self.impl == "oracle"
+        fv, cv, b = self._view(fine, fine_lo), self._view(coarse, coarse_lo), abi.make_box(box_lo, box_hi)
+        rc = self.lib.pho_field_coarsen(C.c_int(dim), C.c_int(op), C.c_int(qty), C.byref(fv), C.byref(cv), C.byref(b))
+        assert rc == 0, rc
+
+    def box_fill(self, dim, dst, dst_lo, extent, value):
+        assert self.impl == "oracle"
+        u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))
+        rc = self.lib.pho_box_fill(C.c_int(dim), dst.ctypes.data_as(C.c_void_p), u3(dst.shape), u3(dst_lo), u3(extent),
+                                   C.c_double(value))
+        assert rc == 0
+
+    def axpy(self, dst, src, coef):
+        assert self.impl == "oracle"
+        rc = self.lib.pho_axpy(C.c_size_t(dst.size), dst.ctypes.data_as(C.c_void_p), src.ctypes.data_as(C.c_void_p),
+                               C.c_double(coef))
+        assert rc == 0
+
     def weights(self, order, dual, local_cell, delta):
         w = (C.c_double * 4)()
         self.lib.pho_weights.restype = C.c_int

@@ -849,3 +849,354 @@ int pho_box_op(int dim, double* dst, const uint32_t ds[3], const uint32_t dlo[3]
             }
     return 0;
 }
+
+/* =====================================================================================================
+ * coarse <-> fine level operators (refinement ratio 2)
+ * ===================================================================================================== */
+static inline size_t vat(const phb_field_view* v, const int idx[3])
+{ /* AMRToLocal(index, box) = index - box.lower (amr_utils.hpp), C order */
+    return ((size_t)(idx[0] - v->lo[0]) * v->shape[1] + (size_t)(idx[1] - v->lo[1])) * v->shape[2]
+           + (size_t)(idx[2] - v->lo[2]);
+}
+/* toCoarseIndex, amr_utils.hpp:128-135 */
+static inline int to_coarse(int i) { return (i >= 0) ? i / 2 : i / 2 + i % 2; }
+
+/* LinearWeighter for ratio 2 (linear_weighter.cpp:9-56): primal distances {0, 1/2}; dual (even ratio):
+ * {(0.5+0)*0.5, (0.5+1)*0.5} rotated by one -> {0.75, 0.25}; weights {1-d, d} */
+static void linear_weights(int centering, double w[2][2])
+{
+    double dist[2];
+    double const small = 1. / 2;
+    if (centering == PRIMAL)
+    {
+        dist[0] = (double)0 / 2;
+        dist[1] = (double)1 / 2;
+    }
+    else
+    {
+        dist[1] = (0.5 + (double)0) * small; /* after std::rotate by the middle */
+        dist[0] = (0.5 + (double)1) * small;
+    }
+    for (int i = 0; i < 2; ++i)
+    {
+        w[i][0] = 1. - dist[i];
+        w[i][1] = dist[i];
+    }
+}
+
+/* DefaultFieldRefiner::operator() (field_refiner.hpp:58-163) with FieldRefineIndexesAndWeights
+ * (field_linear_refine.hpp:55-118) */
+static void refine_default(int dim, const int cen[3], const phb_field_view* C, const phb_field_view* F, const int f[3])
+{
+    int start[3] = {C->lo[0], C->lo[1], C->lo[2]}, iw[3] = {0, 0, 0};
+    double w[3][2][2];
+    for (int d = 0; d < dim; ++d)
+    {
+        double const shift = cen[d] == PRIMAL ? 0. : 0.5;
+        start[d]           = (int)floor((double)(f[d] + shift) / 2 - shift);
+        iw[d]              = abs(f[d]) % 2;
+        linear_weights(cen[d], w[d]);
+    }
+    double value = 0.;
+    if (dim == 1)
+    {
+        for (int sx = 0; sx < 2; ++sx)
+        {
+            int const c[3] = {start[0] + sx, start[1], start[2]};
+            value += C->data[vat(C, c)] * w[0][iw[0]][sx];
+        }
+    }
+    else if (dim == 2)
+    {
+        for (int sx = 0; sx < 2; ++sx)
+        {
+            double Y = 0.;
+            for (int sy = 0; sy < 2; ++sy)
+            {
+                int const c[3] = {start[0] + sx, start[1] + sy, start[2]};
+                Y += C->data[vat(C, c)] * w[1][iw[1]][sy];
+            }
+            value += Y * w[0][iw[0]][sx];
+        }
+    }
+    else
+    {
+        for (int sx = 0; sx < 2; ++sx)
+        {
+            double Y = 0.;
+            for (int sy = 0; sy < 2; ++sy)
+            {
+                double Z = 0.;
+                for (int sz = 0; sz < 2; ++sz)
+                {
+                    int const c[3] = {start[0] + sx, start[1] + sy, start[2] + sz};
+                    Z += C->data[vat(C, c)] * w[2][iw[2]][sz];
+                }
+                Y += Z * w[1][iw[1]][sy];
+            }
+            value += Y * w[0][iw[0]][sx];
+        }
+    }
+    size_t const pf = vat(F, f);
+    if (isnan(F->data[pf]))
+        F->data[pf] = value;
+}
+
+/* MagneticFieldRefiner / MagneticFieldInitRefiner::operator() (magnetic_field_refiner.hpp:47-190,
+ * magnetic_field_init_refiner.hpp:40-150): a fine face lying on a coarse face takes the coarse value; the primal
+ * direction of the component must be even, the dual directions always qualify */
+static void refine_magnetic(int dim, const int cen[3], const phb_field_view* C, const phb_field_view* F, const int f[3],
+                            int only_nan)
+{
+    int c[3] = {C->lo[0], C->lo[1], C->lo[2]};
+    for (int d = 0; d < dim; ++d)
+    {
+        c[d] = to_coarse(f[d]);
+        if (cen[d] == PRIMAL && f[d] % 2 != 0)
+            return;
+    }
+    size_t const pf = vat(F, f);
+    if (!only_nan || isnan(F->data[pf]))
+        F->data[pf] = C->data[vat(C, c)];
+}
+
+/* ElectricFieldRefiner::operator() (electric_field_refiner.hpp:42-57): 1-D :75-82 (always the coarse value),
+ * 2-D :84-150, 3-D :153-338 */
+static void refine_electric(int dim, const int cen[3], const phb_field_view* C, const phb_field_view* F, const int f[3])
+{
+    size_t const pf = vat(F, f);
+    if (!isnan(F->data[pf]))
+        return;
+    int c[3] = {C->lo[0], C->lo[1], C->lo[2]};
+    for (int d = 0; d < dim; ++d)
+        c[d] = to_coarse(f[d]);
+#define CV(dx, dy, dz) C->data[vat(C, (int[3]){c[0] + (dx), c[1] + (dy), c[2] + (dz)})]
+    double value;
+    if (dim == 1)
+        value = CV(0, 0, 0);
+    else if (dim == 2)
+    {
+        int const onX = f[0] % 2 == 0, onY = f[1] % 2 == 0;
+        if (cen[0] == DUAL && cen[1] == PRIMAL) /* Ex */
+            value = onY ? CV(0, 0, 0) : 0.5 * (CV(0, 0, 0) + CV(0, 1, 0));
+        else if (cen[0] == PRIMAL && cen[1] == DUAL) /* Ey */
+            value = onX ? CV(0, 0, 0) : 0.5 * (CV(0, 0, 0) + CV(1, 0, 0));
+        else if (cen[0] == PRIMAL && cen[1] == PRIMAL) /* Ez */
+        {
+            if (onX && onY)
+                value = CV(0, 0, 0);
+            else if (onX)
+                value = 0.5 * (CV(0, 0, 0) + CV(0, 1, 0));
+            else if (onY)
+                value = 0.5 * (CV(0, 0, 0) + CV(1, 0, 0));
+            else
+                value = 0.25 * (CV(0, 0, 0) + CV(1, 0, 0) + CV(0, 1, 0) + CV(1, 1, 0));
+        }
+        else
+            return;
+    }
+    else
+    {
+        int const onX = f[0] % 2 == 0, onY = f[1] % 2 == 0, onZ = f[2] % 2 == 0;
+        if (cen[0] == DUAL && cen[1] == PRIMAL && cen[2] == PRIMAL) /* Ex :166-196 */
+        {
+            if (onY && onZ)
+                value = CV(0, 0, 0);
+            else if (onY)
+                value = 0.5 * (CV(0, 0, 0) + CV(0, 0, 1));
+            else if (onZ)
+                value = 0.5 * (CV(0, 0, 0) + CV(0, 1, 0));
+            else
+                value = 0.25 * (CV(0, 0, 0) + CV(0, 1, 0)) + 0.25 * (CV(0, 0, 1) + CV(0, 1, 1));
+        }
+        else if (cen[0] == PRIMAL && cen[1] == DUAL && cen[2] == PRIMAL) /* Ey :199-231 */
+        {
+            if (onX && onZ)
+                value = CV(0, 0, 0);
+            else if (onX)
+                value = 0.5 * (CV(0, 0, 0) + CV(0, 0, 1));
+            else if (onZ)
+                value = 0.5 * (CV(0, 0, 0) + CV(1, 0, 0));
+            else
+                value = 0.25 * (CV(0, 0, 0) + CV(1, 0, 0) + CV(0, 0, 1) + CV(1, 0, 1));
+        }
+        else if (cen[0] == PRIMAL && cen[1] == PRIMAL && cen[2] == DUAL) /* Ez :234-334 */
+        {
+            if (onX && onY)
+                value = CV(0, 0, 0);
+            else if (onX)
+                value = 0.5 * (CV(0, 0, 0) + CV(0, 1, 0));
+            else if (onY)
+                value = 0.5 * (CV(0, 0, 0) + CV(1, 0, 0));
+            else
+                value = 0.25 * (CV(0, 0, 0) + CV(1, 0, 0) + CV(0, 1, 0) + CV(1, 1, 0));
+        }
+        else
+            return;
+    }
+#undef CV
+    F->data[pf] = value;
+}
+
+int pho_field_refine(int dim, int op, int qty, const phb_field_view* coarse, const phb_field_view* fine,
+                     const phb_box* box)
+{
+    if (dim < 1 || dim > 3 || qty < 0 || qty >= PHB_NQTY)
+        return PHB_ERR_INVALID;
+    int lo[3] = {fine->lo[0], fine->lo[1], fine->lo[2]}, hi[3] = {fine->lo[0], fine->lo[1], fine->lo[2]};
+    for (int d = 0; d < dim; ++d)
+    {
+        lo[d] = box->lower[d];
+        hi[d] = box->upper[d];
+    }
+    for (int i = lo[0]; i <= hi[0]; ++i)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int k = lo[2]; k <= hi[2]; ++k)
+            {
+                int const f[3] = {i, j, k};
+                if (op == PHB_REFINE_DEFAULT)
+                    refine_default(dim, CENTERING[qty], coarse, fine, f);
+                else if (op == PHB_REFINE_MAGNETIC || op == PHB_REFINE_MAGNETIC_INIT)
+                    refine_magnetic(dim, CENTERING[qty], coarse, fine, f, op == PHB_REFINE_MAGNETIC);
+                else if (op == PHB_REFINE_ELECTRIC)
+                    refine_electric(dim, CENTERING[qty], coarse, fine, f);
+                else
+                    return PHB_ERR_INVALID;
+            }
+    return 0;
+}
+
+/* MagneticRefinePatchStrategy::postprocessRefine (magnetic_refine_patch_strategy.hpp:66-125); p_plus/p_minus/
+ * d_plus/d_minus :374-377 */
+static inline int p_plus(int i, int o) { return i + 2 - o; }
+static inline int p_minus(int i, int o) { return i - o; }
+static inline int d_plus(int i, int o) { return i + 1 - o; }
+static inline int d_minus(int i, int o) { return i - o; }
+
+int pho_magnetic_postprocess(const phb_layout* L, const phb_vecfield* B, const phb_box* cells)
+{
+    int const dim = L->dim, g = field_ghosts(L->interp);
+    if (dim == 3)
+        return PHB_ERR_INVALID; /* 3-D (:192-372) not restated yet */
+    fld const bx = view(L, B->comp[0], PHB_BX), by = view(L, B->comp[1], PHB_BY);
+    double *X = B->comp[0], *Y = B->comp[1];
+    for (int comp = 0; comp < dim; ++comp)
+    {
+        /* toFieldBox: primal directions gain one node on the upper side (field_geometry.hpp:139-181) */
+        int lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+        for (int d = 0; d < dim; ++d)
+        {
+            lo[d] = cells->lower[d];
+            hi[d] = cells->upper[d] + (CENTERING[PHB_BX + comp][d] == PRIMAL ? 1 : 0);
+        }
+        for (int i = lo[0]; i <= hi[0]; ++i)
+            for (int j = lo[1]; j <= hi[1]; ++j)
+            {
+                int const idx[2] = {i, j};
+                if (idx[comp] % 2 == 0) /* isNewFineFace :127-132 */
+                    continue;
+                int const ix = i - (L->amr_lower[0] - g);                  /* GridLayout::AMRToLocal */
+                int const iy = dim > 1 ? j - (L->amr_lower[1] - g) : 0;
+                if (dim == 1) /* postprocessBx1d :134-141 */
+                    X[at(&bx, ix, 0, 0)] = 0.5 * (X[at(&bx, ix - 1, 0, 0)] + X[at(&bx, ix + 1, 0, 0)]);
+                else if (comp == 0) /* postprocessBx2d :143-166 */
+                {
+                    int const xo = 1, yo = (j % 2 == 0) ? 0 : 1;
+                    X[at(&bx, ix, iy, 0)]
+                        = 0.5 * (X[at(&bx, ix - 1, iy, 0)] + X[at(&bx, ix + 1, iy, 0)])
+                          + 0.25
+                                * (Y[at(&by, d_minus(ix, xo), p_minus(iy, yo), 0)]
+                                   - Y[at(&by, d_minus(ix, xo), p_plus(iy, yo), 0)]
+                                   - Y[at(&by, d_plus(ix, xo), p_minus(iy, yo), 0)]
+                                   + Y[at(&by, d_plus(ix, xo), p_plus(iy, yo), 0)]);
+                }
+                else /* postprocessBy2d :168-190 */
+                {
+                    int const xo = (i % 2 == 0) ? 0 : 1, yo = 1;
+                    Y[at(&by, ix, iy, 0)]
+                        = 0.5 * (Y[at(&by, ix, iy - 1, 0)] + Y[at(&by, ix, iy + 1, 0)])
+                          + 0.25
+                                * (X[at(&bx, p_minus(ix, xo), d_minus(iy, yo), 0)]
+                                   - X[at(&bx, p_plus(ix, xo), d_minus(iy, yo), 0)]
+                                   - X[at(&bx, p_minus(ix, xo), d_plus(iy, yo), 0)]
+                                   + X[at(&bx, p_plus(ix, xo), d_plus(iy, yo), 0)]);
+                }
+            }
+    }
+    return 0;
+}
+
+/* ElectricFieldCoarsener / MomentsCoarsener::operator() (electric_field_coarsener.hpp:52-146,
+ * moments_coarsener.hpp:44-80); fineStartIndex = coarseIndex * 2 */
+int pho_field_coarsen(int dim, int op, int qty, const phb_field_view* fine, const phb_field_view* coarse,
+                      const phb_box* box)
+{
+    if (dim < 1 || dim > 3 || qty < 0 || qty >= PHB_NQTY)
+        return PHB_ERR_INVALID;
+    const int* cen = CENTERING[qty];
+    int lo[3] = {coarse->lo[0], coarse->lo[1], coarse->lo[2]}, hi[3] = {coarse->lo[0], coarse->lo[1], coarse->lo[2]};
+    for (int d = 0; d < dim; ++d)
+    {
+        lo[d] = box->lower[d];
+        hi[d] = box->upper[d];
+    }
+    int dual_dir = -1, ndual = 0;
+    for (int d = 0; d < dim; ++d)
+        if (cen[d] == DUAL)
+        {
+            dual_dir = d;
+            ++ndual;
+        }
+    if (op == PHB_COARSEN_MOMENTS && ndual)
+        return PHB_ERR_INVALID; /* assert(primal) */
+    if (op == PHB_COARSEN_ELECTRIC && ndual > 1)
+        return PHB_ERR_INVALID; /* "no electric field should end up here" */
+    for (int i = lo[0]; i <= hi[0]; ++i)
+        for (int j = lo[1]; j <= hi[1]; ++j)
+            for (int k = lo[2]; k <= hi[2]; ++k)
+            {
+                int const c[3] = {i, j, k};
+                int f0[3]      = {fine->lo[0], fine->lo[1], fine->lo[2]};
+                for (int d = 0; d < dim; ++d)
+                    f0[d] = c[d] * 2;
+                double value;
+                if (op == PHB_COARSEN_MOMENTS || ndual == 0)
+                    value = fine->data[vat(fine, f0)];
+                else
+                {
+                    int f1[3] = {f0[0], f0[1], f0[2]};
+                    f1[dual_dir] += 1;
+                    if (dim == 1) /* :69-72 : (fine(start+1) + fine(start)) */
+                        value = 0.5 * (fine->data[vat(fine, f1)] + fine->data[vat(fine, f0)]);
+                    else
+                        value = 0.5 * (fine->data[vat(fine, f0)] + fine->data[vat(fine, f1)]);
+                }
+                coarse->data[vat(coarse, c)] = value;
+            }
+    return 0;
+}
+
+int pho_box_fill(int dim, double* dst, const uint32_t ds[3], const uint32_t dlo[3], const uint32_t ext[3], double value)
+{
+    uint32_t e[3] = {1, 1, 1}, dS[3] = {1, 1, 1}, dl[3] = {0, 0, 0};
+    for (int d = 0; d < dim; ++d)
+    {
+        int const a = d + 3 - dim;
+        e[a]  = ext[d];
+        dS[a] = ds[d];
+        dl[a] = dlo[d];
+    }
+    for (uint32_t i = 0; i < e[0]; ++i)
+        for (uint32_t j = 0; j < e[1]; ++j)
+            for (uint32_t k = 0; k < e[2]; ++k)
+                dst[((size_t)(dl[0] + i) * dS[1] + (dl[1] + j)) * dS[2] + (dl[2] + k)] = value;
+    return 0;
+}
+
+/* PlusEqualsProduct (types.hpp:584-588): d += d0 * o */
+int pho_axpy(size_t n, double* dst, const double* src, double coef)
+{
+    for (size_t i = 0; i < n; ++i)
+        dst[i] += src[i] * coef;
+    return 0;
+}

@@ -50,6 +50,16 @@ int pho_box_op(int dim, double* dst, const uint32_t dst_shape[3], const uint32_t
                const double* src, const uint32_t src_shape[3], const uint32_t src_lo[3],
                const uint32_t extent[3], int op);
 
+/* coarse <-> fine level operators (see include/phare_b200.h for the reference lines) */
+int pho_field_refine(int dim, int op, int qty, const phb_field_view* coarse, const phb_field_view* fine,
+                     const phb_box* fine_box);
+int pho_magnetic_postprocess(const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box);
+int pho_field_coarsen(int dim, int op, int qty, const phb_field_view* fine, const phb_field_view* coarse,
+                      const phb_box* coarse_box);
+int pho_box_fill(int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3], const uint32_t extent[3],
+                 double value);
+int pho_axpy(size_t n, double* dst, const double* src, double coef);
+
 /* B-spline weights of one direction (Weighter<order>::computeWeight + computeStartLeftShift,
  * interpolator.hpp:54-125,519-549): returns the start index; w[order+1] */
 int pho_weights(int order, int dual, uint32_t local_cell, double delta, double* w);

@@ -46,6 +46,25 @@ class BoxDesc(C.Structure):
                 ("op", C.c_int32), ("first", C.c_uint64)]
 
 
+class FieldView(C.Structure):
+    """phb_field_view: array + AMR field index of its first element"""
+    _fields_ = [("data", C.c_void_p), ("shape", C.c_uint32 * 3), ("lo", C.c_int32 * 3)]
+
+
+# phb_refine_op / phb_coarsen_op
+REFINE_DEFAULT, REFINE_MAGNETIC, REFINE_MAGNETIC_INIT, REFINE_ELECTRIC = range(4)
+COARSEN_ELECTRIC, COARSEN_MOMENTS = range(2)
+
+
+def make_view(ptr, shape, lo):
+    v = FieldView()
+    v.data = ptr
+    for d in range(3):
+        v.shape[d] = int(shape[d]) if d < len(shape) else 1
+        v.lo[d] = int(lo[d]) if d < len(lo) else 0
+    return v
+
+
 def make_layout(dim, interp, ncells, dx, amr_lower=None, origin=None, level=0):
     L = Layout()
     L.dim, L.interp, L.level = dim, interp, level
@@ -159,6 +178,13 @@ _PROTOS = {
                              c_u32_p, C.c_int]),
     "phb_box_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p]),
     "phb_box_op_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64]),
+    "phb_field_refine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FieldView), C.POINTER(FieldView),
+                                   C.POINTER(Box)]),
+    "phb_magnetic_postprocess": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(Box)]),
+    "phb_field_coarsen": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FieldView), C.POINTER(FieldView),
+                                    C.POINTER(Box)]),
+    "phb_box_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_double]),
+    "phb_axpy": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_double]),
     "phb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "phb_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),

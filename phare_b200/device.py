@@ -312,3 +312,29 @@ class Context:
         sptr = src.ptr if hasattr(src, "ptr") else src
         self._check(self.lib.phb_box_op(self.h, dim, dptr, u3(dst_shape), u3(dst_lo), sptr, u3(src_shape),
                                         u3(src_lo), u3(extent), op))
+
+    # ---- coarse <-> fine level operators; arrays are DeviceArrays, *_lo the AMR field index of element 0
+    @staticmethod
+    def _view(a, lo):
+        return abi.make_view(a.ptr, a.shape, lo)
+
+    def field_refine(self, op, qty, coarse, coarse_lo, fine, fine_lo, box_lo, box_hi):
+        dim = len(box_lo)
+        cv, fv, b = self._view(coarse, coarse_lo), self._view(fine, fine_lo), abi.make_box(box_lo, box_hi)
+        self._check(self.lib.phb_field_refine(self.h, dim, op, qty, C.byref(cv), C.byref(fv), C.byref(b)))
+
+    def field_coarsen(self, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
+        dim = len(box_lo)
+        fv, cv, b = self._view(fine, fine_lo), self._view(coarse, coarse_lo), abi.make_box(box_lo, box_hi)
+        self._check(self.lib.phb_field_coarsen(self.h, dim, op, qty, C.byref(fv), C.byref(cv), C.byref(b)))
+
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+        b = abi.make_box(cell_lo, cell_hi)
+        self._check(self.lib.phb_magnetic_postprocess(self.h, C.byref(layout), C.byref(B.c), C.byref(b)))
+
+    def box_fill(self, dst, lo, extent, value):
+        u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))
+        self._check(self.lib.phb_box_fill(self.h, len(extent), dst.ptr, u3(dst.shape), u3(lo), u3(extent), float(value)))
+
+    def axpy(self, dst, src, coef):
+        self._check(self.lib.phb_axpy(self.h, dst.size, dst.ptr, src.ptr, float(coef)))
