@@ -41,6 +41,7 @@ class CpuOps:
         self.dim, self.interp = dim, interp
         self.err = 0
         self.last_error = ""
+        self._ref = None
 
     # ---- memory
     def field(self, layout, qty):
@@ -196,6 +197,67 @@ class CpuOps:
 
     def average(self, a, b, avg):
         assert self.lib.pho_average(C.c_size_t(a.size), C.c_void_p(a.ptr), C.c_void_p(b.ptr), C.c_void_p(avg.ptr)) == 0
+
+    # ---- coarse <-> fine level operators
+    def array(self, shape):
+        return Arr(np.zeros(tuple(int(x) for x in shape)))
+
+    def box_fill(self, arr, lo, ext, value):
+        self.orc.box_fill(len(ext), arr.a, lo, ext, value)
+
+    def field_refine(self, op, qty, coarse, coarse_lo, fine, fine_lo, box_lo, box_hi):
+        self.orc.field_refine(len(box_lo), op, qty, coarse.a, coarse_lo, fine.a, fine_lo, box_lo, box_hi)
+
+    def field_coarsen(self, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
+        self.orc.field_coarsen(len(box_lo), op, qty, fine.a, fine_lo, coarse.a, coarse_lo, box_lo, box_hi)
+
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+        self.orc.magnetic_postprocess(layout, [c.a for c in B.comps], cell_lo, cell_hi)
+
+    def axpy(self, dst, src, coef):
+        self.orc.axpy(dst.a, src.a, coef)
+
+    def split(self, nref, coarse, first, last, fine_boxes, fine):
+        """checker for phb_split: the reference's toFineGrid + Splitter (oracle/_ref) on the range, then the
+        destination-box filter of ParticlesRefineOperator::refine_ (particles_data_split.hpp:142-231)"""
+        if self._ref is None:
+            self._ref = Cpu("ref")
+        from phare_b200.split import pattern
+        _, _, maxd = pattern(self.dim, self.interp, nref)
+        sub = HostParticles(self.dim, max(last - first, 1))
+        self.particles_copy(coarse, first, last - first, sub, 0)
+        sub.n = last - first
+        ic, de, w, q, v = self._ref.split(self.dim, self.interp, nref, sub).soa()
+        # candidates: the coarse particle moved to the fine grid lies within maxd cells of a destination box
+        # (isInBox(splitBox, particleRefinedPos)); children are kept when inside the destination box itself
+        ric = np.repeat(self._to_fine_icell(sub), nref, axis=0)
+        keep = np.zeros(len(w), bool)
+        for b in fine_boxes:
+            cand = np.ones(len(w), bool)
+            inb = np.ones(len(w), bool)
+            for k in range(self.dim):
+                cand &= (ric[:, k] >= b.lower[k] - maxd) & (ric[:, k] <= b.upper[k] + maxd)
+                inb &= (ic[:, k] >= b.lower[k]) & (ic[:, k] <= b.upper[k])
+            keep |= cand & inb
+        n = int(keep.sum())
+        if fine.n + n > self.capacity(fine):
+            return None
+        at = fine.n
+        for d in range(self.dim):
+            fine.icell[d][at:at + n] = ic[keep, d]
+            fine.delta[d][at:at + n] = de[keep, d]
+        for k in range(3):
+            fine.v[k][at:at + n] = v[keep, k]
+        fine.weight[at:at + n] = w[keep]
+        fine.charge[at:at + n] = q[keep]
+        fine.n = at + n
+        return n
+
+    def _to_fine_icell(self, parts):
+        """toFineGrid (split.hpp:32-46): iCell*2 (+1 when delta*2 >= 1)"""
+        ic, de, _, _, _ = parts.soa()
+        fine_delta = de * 2
+        return ic * 2 + np.floor(fine_delta).astype(np.int64)
 
     def poll_error(self):
         rc, self.err = self.err, 0

@@ -1,0 +1,429 @@
+"""Refined levels: a static hierarchy of patch levels with refinement ratio 2, advanced with the
+reference's recursive sub-cycling, on top of the per-level SolverPPC of phare_b200.solver.
+
+What is restated here (file:line relative to the PHARE tree; SAMRAI itself cannot be built in this image, so the
+schedules it would create are explicit box plans):
+  MultiPhysicsIntegrator::advanceLevel / standardLevelSynchronization / getMaxFinerLevelDt
+                                   src/amr/multiphysics_integrator.hpp:435-450, 491-600
+                                   (fine dt = coarse dt / ratio^2 -> 4 sub-steps per coarser step)
+  HybridHybridMessengerStrategy    src/amr/messengers/hybrid_hybrid_messenger_strategy.hpp
+      initLevel :335-362, fill{Magnetic,Electric,Current}Ghosts :376-400 (+ setNaNsOnFieldGhosts :924-968),
+      fillIonPopMomentGhosts :508-547, firstStep :582-608, lastStep :619-645, synchronize :708-720, reflux :724-729,
+      postSynchronize :736-751; refiner kinds src/amr/messengers/refiner.hpp:36-133 (GhostField = same level, then the
+      next coarser level through the refine operator; static refiners: the coarse data as it is NOW, no time interpolation)
+  HybridLevelInitializer::initialize (level > 0)   src/amr/level_initializer/hybrid_level_initializer.hpp:100-182
+  SolverPPC::accumulateFluxSum / resetFluxSum / reflux     src/amr/solvers/solver_ppc.hpp:263-311
+  ParticlesRefineOperator (interior / coarseBoundaryOld / coarseBoundaryNew)
+                                   src/amr/data/particles/refine/particles_data_split.hpp:142-231
+  makeNonLevelGhostBoxFor          src/amr/resources_manager/amr_utils.hpp:233-253
+The field operators themselves are CUDA kernels behind the C ABI (csrc/level.cu, csrc/split.cu).
+
+Scope: refinement boxes are fixed (no tagging / regridding / load balancing), every level lives on one rank, and a
+refined level together with its ghost layers must lie inside the (periodic) root domain.
+"""
+import numpy as np
+
+from . import abi
+from .boxes import Box
+from .messenger import HybridMessenger, LevelGeom, LocalComm, PatchGeom, centering, PRIMAL
+from .solver import Patch, SolverPPC
+
+RATIO = 2                      # amr/amr_constants.hpp: refinementRatio
+SUBSTEPS = RATIO * RATIO       # getMaxFinerLevelDt: dt_fine = dt_coarse / ratio^2
+DEFAULT_NREF = {1: 2, 2: 4, 3: 6}
+
+
+def refine_box(b):
+    return Box(b.lo * RATIO, b.hi * RATIO + (RATIO - 1))
+
+
+def coarsen_box(b):
+    return Box(b.lo // RATIO, b.hi // RATIO)  # floor division == toCoarseIndex (amr_utils.hpp:128-135)
+
+
+def field_box(cells, qty):
+    """FieldGeometry::toFieldBox (field_geometry.hpp:139-181): one more node on the upper side of primal directions"""
+    hi = cells.hi.copy()
+    for d in range(cells.dim):
+        if centering(qty, d) == PRIMAL:
+            hi[d] += 1
+    return Box(cells.lo, hi)
+
+
+def minus_all(boxes, removed):
+    out = list(boxes)
+    for r in removed:
+        out = [piece for b in out for piece in b.minus(r)]
+    return out
+
+
+class RefinedLevelMessenger(HybridMessenger):
+    """Messenger of a level > 0: same-level exchanges as on the root level (non periodic), plus everything that comes
+    from the next coarser level: level-ghost field nodes (refine operators) and level-ghost particles (splitting)."""
+
+    REFINE_OP = {abi.BX: abi.REFINE_MAGNETIC, abi.EX: abi.REFINE_ELECTRIC, abi.JX: abi.REFINE_ELECTRIC}
+
+    def __init__(self, geom, ops, comm, coarse_solver):
+        super().__init__(geom, ops, comm)
+        self.coarse = coarse_solver
+        g, dim = geom.g, geom.dim
+        level_boxes = [p.box for p in geom.patches]
+        self._nan, self._scratch, self._lg_field_cells, self.lg_particle_boxes = {}, {}, {}, {}
+        for p in geom.patches:
+            # level-ghost cells: the ghost layer minus every patch of the level (fields: g cells, particles: pg cells)
+            self._lg_field_cells[p.id] = minus_all([p.box.grow(g)], level_boxes)
+            self.lg_particle_boxes[p.id] = minus_all([p.box.grow(geom.pg)], level_boxes)
+            for qty in range(abi.BX, abi.JZ + 1):
+                gfb = p.ghost_field_box(qty, g)
+                # setNaNsOnFieldGhosts: ghost field box minus the field boxes of the level's patches
+                nan = minus_all([gfb], [q.interior_field_box(qty) for q in geom.patches])
+                self._nan[(p.id, qty)] = [(b.lo - gfb.lo, b.shape()) for b in nan]
+                # coarse data under the ghost box, one node more for the two-point refine stencils
+                cbox = Box(gfb.lo // RATIO - 1, gfb.hi // RATIO + 1)
+                self._scratch[(p.id, qty)] = (ops.array(cbox.shape()), cbox)
+        self._gather = {}
+
+    # ---- coarse level -> scratch arrays
+    def _gather_plan(self, name, qty0):
+        """copies of the coarse level's `name` arrays into the scratch of every fine patch (what the RefineSchedule does
+        before it calls the refine operator); a coarse node is taken from the first patch that owns it"""
+        if name not in self._gather:
+            cs, entries = self.coarse, []
+            arrays = cs._by_id(name)
+            for p in self.geom.patches:
+                for c in range(3):
+                    qty = qty0 + c
+                    scratch, cbox = self._scratch[(p.id, qty)]
+                    todo = [cbox]
+                    for providers in ("interior", "ghost"):
+                        for q in cs.geom.patches:
+                            for t in cs.geom.shifts:
+                                src = q.interior_field_box(qty) if providers == "interior" else q.ghost_field_box(qty, cs.geom.g)
+                                src = src.shift(t)
+                                rest = []
+                                for piece in todo:
+                                    ov = piece * src
+                                    if ov is None:
+                                        rest.append(piece)
+                                        continue
+                                    entries.append((scratch, ov.lo - cbox.lo, arrays[q.id][c], q.local(ov.lo - t, cs.geom.g),
+                                                    ov.shape(), 0))
+                                    rest += piece.minus(ov)
+                                todo = rest
+                    if todo:
+                        raise RuntimeError(f"refined patch {p.box} is not nested in the coarser level (uncovered {todo})")
+            self._gather[name] = self.ops.compile_box_ops(entries)
+        return self._gather[name]
+
+    def _refine(self, name, qty0, vecs, op, boxes=None):
+        ops, g = self.ops, self.geom.g
+        ops.run_box_ops(self._gather_plan(name, qty0))
+        for p in self.geom.patches:
+            for c in range(3):
+                qty = qty0 + c
+                scratch, cbox = self._scratch[(p.id, qty)]
+                gfb = p.ghost_field_box(qty, g)
+                ops.field_refine(op, qty, scratch, cbox.lo, vecs[p.id][c], gfb.lo, gfb.lo, gfb.hi)
+        if qty0 == abi.BX:
+            # MagneticRefinePatchStrategy::postprocessRefine on the cells that were filled from the coarser level
+            layouts = {p.geom.id: p.layout for p in self._fine_patches}
+            for p in self.geom.patches:
+                for cells in (boxes[p.id] if boxes is not None else self._lg_field_cells[p.id]):
+                    ops.magnetic_postprocess(layouts[p.id], vecs[p.id], cells.lo, cells.hi)
+
+    def attach(self, fine_patches):
+        self._fine_patches = fine_patches
+
+    # ---- HybridMessenger interface
+    def fill_ghosts(self, name, qty0, vecs):
+        """fillMagneticGhosts / fillElectricGhosts / fillCurrentGhosts on a refined level: NaNs on the level-ghost nodes,
+        patch ghosts from the neighbours, what is still NaN from the coarser level"""
+        ops = self.ops
+        for p in self.geom.patches:
+            for c in range(3):
+                for lo, ext in self._nan[(p.id, qty0 + c)]:
+                    ops.box_fill(vecs[p.id][c], lo, ext, float("nan"))
+        super().fill_ghosts(name, qty0, vecs)
+        self._refine(name, qty0, vecs, self.REFINE_OP[qty0])
+
+    def fill_patch_ghosts(self, name, qty0, vecs):
+        """same-level part only (patchGhostRefluxedSchedules, refiner.hpp PatchGhostField)"""
+        super().fill_ghosts(name, qty0, vecs)
+
+    def init_fields(self, solver):
+        """initLevel (:335-345): B through MagneticFieldInitRefiner (+ post-process) over the whole ghost box, E through
+        ElectricFieldRefiner (which only writes NaN nodes: a fresh FieldData is all NaN, field_data.hpp:41-59)"""
+        ops, g = self.ops, self.geom.g
+        self._refine("B", abi.BX, solver._by_id("B"), abi.REFINE_MAGNETIC_INIT,
+                     boxes={p.id: [p.box.grow(g)] for p in self.geom.patches})
+        for p in solver.patches:
+            for c in range(3):
+                ops.box_fill(p.E[c], [0] * self.geom.dim, p.E[c].shape, float("nan"))
+        self._refine("E", abi.EX, solver._by_id("E"), abi.REFINE_ELECTRIC)
+
+    def split_from_coarser(self, ipop, nref, boxes_of, store_of):
+        """ParticlesRefineOperator::refine_: the coarser level's domain particles, moved to this level's index space and
+        split, land in store_of(patch) when their cell lies in one of boxes_of(patch)"""
+        ops = self.ops
+        for p in self._fine_patches:
+            boxes = [abi.make_box(b.lo, b.hi) for b in boxes_of(p)]
+            if not boxes:
+                continue
+            for q in self.coarse.patches:
+                src = q.pops[ipop].domain
+                n = ops.count(src)
+                if n == 0:
+                    continue
+                while True:
+                    store = store_of(p)
+                    got = ops.split(nref, src, 0, n, boxes, store)
+                    if got is not None:
+                        break
+                    grow_store(ops, p, ipop, store)  # too small: nothing was appended
+
+
+def grow_store(ops, patch, ipop, store):
+    """the reference's ParticleArray grows on push_back; the device stores are re-allocated 2x and swapped in place"""
+    pop = patch.pops[ipop]
+    new_cap = 2 * ops.capacity(store) + 4096
+    for attr in ("domain", "level_ghost", "level_ghost_old", "level_ghost_new"):
+        if getattr(pop, attr) is store:
+            bigger = ops.particles(new_cap)
+            n = ops.count(store)
+            if n:
+                ops.particles_copy(store, 0, n, bigger, 0)
+            ops.set_count(bigger, n)
+            setattr(pop, attr, bigger)
+            if attr == "domain":
+                pop.spare = ops.particles(new_cap)
+            if attr == "level_ghost":
+                pop.level_ghost_spare = ops.particles(new_cap)
+            return
+    raise RuntimeError("unknown particle store")
+
+
+class Level:
+    def __init__(self, number, geom, solver):
+        self.number, self.geom, self.solver = number, geom, solver
+        self.before_coarse_time = self.after_coarse_time = None
+        self.old_time = 0.0
+
+
+class Hierarchy:
+    """The patch hierarchy + MultiPhysicsIntegrator: levels[0] is the periodic root level (an initialised SolverPPC),
+    levels[i > 0] are refined levels built by add_level()."""
+
+    def __init__(self, ops, root_solver, nref=None):
+        self.ops = ops
+        self.levels = [Level(0, root_solver.geom, root_solver)]
+        self.nref = nref or DEFAULT_NREF[root_solver.geom.dim]
+        self.time = 0.0
+        self._ensure_flux_sum(root_solver)
+
+    def _ensure_flux_sum(self, solver):
+        for p in solver.patches:
+            if not hasattr(p, "fluxSumE"):
+                p.fluxSumE = self.ops.vec(p.layout, abi.EX)  # SolverPPC::fluxSumE_ (solver_ppc.hpp:60)
+
+    # ---------------------------------------------------------------------------------------- construction
+    def add_level(self, fine_boxes, capacity_factor=1.6):
+        """creates level len(levels) from cell boxes given in ITS OWN index space and initialises it from the current
+        finest level (MultiPhysicsIntegrator::initializeLevelData -> HybridLevelInitializer::initialize, level > 0)"""
+        ops = self.ops
+        coarse = self.levels[-1]
+        cs = coarse.solver
+        ilvl = len(self.levels)
+        interp = cs.patches[0].layout.interp
+        dim = cs.geom.dim
+        fine_domain = tuple(s * RATIO for s in coarse.geom.domain_shape)
+        dx = [cs.patches[0].layout.dx[d] / RATIO for d in range(dim)]
+        patches_g = [PatchGeom(i, b if isinstance(b, Box) else Box(*b), 0) for i, b in enumerate(fine_boxes)]
+        geom = LevelGeom(fine_domain, patches_g, interp, periodic=False)
+        # nesting: the level with its field ghost layer and the split stencil stays inside the root domain
+        margin = geom.g + 2 * RATIO
+        for pg in patches_g:
+            if np.any(pg.box.lo - margin < 0) or np.any(pg.box.hi + margin >= np.asarray(fine_domain)):
+                raise ValueError(f"refinement box {pg.box} is too close to the domain boundary")
+            if np.any(pg.box.lo % RATIO) or np.any((pg.box.hi + 1) % RATIO):
+                raise ValueError(f"refinement box {pg.box} is not aligned with the coarser cells")
+        for a in patches_g:
+            for b in patches_g:
+                if a.id < b.id and a.box * b.box is not None:
+                    raise ValueError("refinement boxes overlap")
+        msg = RefinedLevelMessenger(geom, ops, LocalComm(), cs)
+        # expected number of particles: nref children per coarse particle of the covered coarse cells
+        npop = len(cs.patches[0].pops)
+        ncoarse_cells = sum(int(np.prod([p.layout.ncells[d] for d in range(dim)])) for p in cs.patches)
+        per_cell = [sum(ops.count(p.pops[i].domain) for p in cs.patches) / max(ncoarse_cells, 1) for i in range(npop)]
+        patches = []
+        for pg in patches_g:
+            ncells = [int(x) for x in pg.box.shape()]
+            origin = [cs.patches[0].layout.origin[d] - cs.patches[0].layout.amr_lower[d] * cs.patches[0].layout.dx[d]
+                      + pg.box.lo[d] * dx[d] for d in range(dim)]
+            L = abi.make_layout(dim, interp, ncells, dx, amr_lower=list(pg.box.lo), origin=origin, level=ilvl)
+            ccells = int(np.prod(ncells)) / RATIO ** dim
+            spec = [dict(name=cs.patches[0].pops[i].name, mass=cs.patches[0].pops[i].mass,
+                         n=int(self.nref * per_cell[i] * ccells)) for i in range(npop)]
+            patch = Patch(ops, pg, L, spec, capacity_factor=capacity_factor)
+            # nonLevelGhostBox: the domain plus the part of the particle ghost layer that belongs to a neighbour patch
+            patch.non_level_ghost = [patch.domain_box] + [
+                abi.make_box(ov.lo, ov.hi) for ov in (pg.box.grow(geom.pg) * q.box for q in patches_g if q.id != pg.id)
+                if ov is not None]
+            lg_cells = sum(b.volume() for b in msg.lg_particle_boxes[pg.id]) / RATIO ** dim
+            for i, pop in enumerate(patch.pops):
+                pop.set_level_ghosts(ops, int(capacity_factor * self.nref * per_cell[i] * lg_cells) + 4096)
+            patches.append(patch)
+        msg.attach(patches)
+        solver = SolverPPC(ops, patches, geom, LocalComm(), resistivity=cs.eta, hyper_resistivity=cs.nu,
+                           hyper_mode=cs.hyper_mode, Te=cs.Te, fused=cs.updater.fused,
+                           sort_with_deposit=cs.updater.sort_with_deposit, messenger=msg)
+        self._ensure_flux_sum(solver)
+        level = Level(ilvl, geom, solver)
+        self.levels.append(level)
+        self._initialize_level(level)
+        return level
+
+    def _initialize_level(self, level):
+        ops, s, msg = self.ops, level.solver, level.solver.messenger
+        npop = len(s.patches[0].pops)
+        msg.init_fields(s)
+        for i in range(npop):
+            # domainParticlesRefiners_ (interior) and lvlGhostPartOldRefiners_ (coarseBoundaryOld)
+            msg.split_from_coarser(i, self.nref, lambda p: [p.geom.box], lambda p, i=i: p.pops[i].domain)
+            msg.split_from_coarser(i, self.nref, lambda p: msg.lg_particle_boxes[p.geom.id],
+                                   lambda p, i=i: p.pops[i].level_ghost_old)
+        for p in s.patches:
+            for i, pop in enumerate(p.pops):
+                self._copy_store(p, i, "level_ghost_old", "level_ghost")  # copyLevelGhostOldToPushable_
+                counts = ops.bin(p.layout, pop.domain, pop.spare, p.domain_box, p.non_level_ghost, pop.cell_start)
+                pop.domain, pop.spare = pop.spare, pop.domain
+                pop.n_sorted = counts[0]
+                ops.set_count(pop.domain, counts[0])
+                for m in pop.moments():
+                    ops.zero(m)
+                ops.deposit(p.layout, pop.domain, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, pop.n_sorted, (),
+                            p.domain_box, pop.cell_start)  # depositParticles(DomainDeposit)
+        for i in range(npop):
+            msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in s.patches},
+                            {p.geom.id: p.pops[i].scratch for p in s.patches})
+        for p in s.patches:
+            for pop in p.pops:
+                n = ops.count(pop.level_ghost_old)
+                if n:  # depositParticles(LevelGhostDeposit): levelGhostParticlesOld, coef 1
+                    ops.deposit(p.layout, pop.level_ghost_old, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, n)
+            s.updater.update_ions(p)
+        msg.max_borders("ions", {p.geom.id: [p.rho_m, p.Ne, p.Vi[0], p.Vi[1], p.Vi[2]] for p in s.patches})
+        s.prepare_step()
+
+    def _copy_store(self, patch, ipop, src_attr, dst_attr):
+        ops, pop = self.ops, patch.pops[ipop]
+        src = getattr(pop, src_attr)
+        n = ops.count(src)
+        while ops.capacity(getattr(pop, dst_attr)) < n:
+            grow_store(ops, patch, ipop, getattr(pop, dst_attr))
+        dst = getattr(pop, dst_attr)
+        ops.set_count(dst, 0)
+        if n:
+            ops.particles_copy(src, 0, n, dst, 0)
+        ops.set_count(dst, n)
+
+    # ---------------------------------------------------------------------------------------- time stepping
+    def advance(self, dt):
+        """one step of the root level and the sub-cycles of every finer level (TimeRefinementIntegrator::advanceHierarchy
+        driving MultiPhysicsIntegrator::advanceLevel / standardLevelSynchronization)"""
+        self._advance_level(0, self.time, self.time + dt, True, True)
+        self.time += dt
+        return self.time
+
+    def _advance_level(self, il, t0, t1, first, last):
+        lvl = self.levels[il]
+        s = lvl.solver
+        if first:
+            if il > 0:
+                self._first_step(lvl, self.levels[il - 1])
+            s.reset_flux_sum()
+        lvl.old_time = t0  # SolverPPC::prepareStep: oldTime_[level] (Bold <- B happens inside advance_level)
+        if il > 0:
+            # timeInterpCoef_ (:901-905) at afterPushTime = newTime, for both sweeps of the step
+            s.level_ghost_alpha = (t1 - lvl.before_coarse_time) / (lvl.after_coarse_time - lvl.before_coarse_time)
+            if s.level_ghost_alpha < 0 or s.level_ghost_alpha > 1:
+                raise RuntimeError(f"ion moment ghost time interp coef invalid : alpha: {s.level_ghost_alpha}")
+        s.advance_level(t1 - t0)
+        if last and il > 0:
+            self._last_step(lvl)
+        finest = il == len(self.levels) - 1
+        if il > 0 and finest:
+            s.accumulate_flux_sum(1. / (RATIO * RATIO))
+        if not finest:
+            sub = (t1 - t0) / SUBSTEPS
+            t = t0
+            self.levels[il + 1].coarser_times = (t0, t1)
+            for k in range(SUBSTEPS):
+                tn = t1 if k == SUBSTEPS - 1 else t + sub
+                self._advance_level(il + 1, t, tn, k == 0, k == SUBSTEPS - 1)
+                t = tn
+            self._synchronize(self.levels[il + 1], lvl, t1)
+
+    def _first_step(self, lvl, coarser):
+        """firstStep: levelGhostParticlesNew = split of the coarser level's particles, which are already at the end of its
+        step; the times bracket the interpolation of the level-ghost moments"""
+        ops, s, msg = self.ops, lvl.solver, lvl.solver.messenger
+        for p in s.patches:
+            for pop in p.pops:
+                ops.set_count(pop.level_ghost_new, 0)
+        for i in range(len(s.patches[0].pops)):
+            msg.split_from_coarser(i, self.nref, lambda p: msg.lg_particle_boxes[p.geom.id],
+                                   lambda p, i=i: p.pops[i].level_ghost_new)
+        lvl.before_coarse_time, lvl.after_coarse_time = lvl.coarser_times
+
+    def _last_step(self, lvl):
+        """lastStep: New becomes Old, New is emptied, the pushable level ghosts restart from Old"""
+        ops = self.ops
+        for p in lvl.solver.patches:
+            for i, pop in enumerate(p.pops):
+                pop.level_ghost_old, pop.level_ghost_new = pop.level_ghost_new, pop.level_ghost_old
+                ops.set_count(pop.level_ghost_new, 0)
+                self._copy_store(p, i, "level_ghost_old", "level_ghost")
+
+    def _synchronize(self, fine, coarse, sync_time):
+        """standardLevelSynchronization for one (fine, coarse) pair"""
+        ops, fs, cs = self.ops, fine.solver, coarse.solver
+        gf, gc = fine.geom.g, coarse.geom.g
+        # synchronize(): E (electric coarsener), ion charge density and bulk velocity (injection);
+        # reflux(): fluxSumE of the fine level onto Eavg of the coarse level
+        for p in fs.patches:
+            for q in cs.patches:
+                cells = coarsen_box(p.geom.box) * q.geom.box
+                if cells is None:
+                    continue
+                items = [(p.E[c], q.E[c], abi.EX + c, abi.COARSEN_ELECTRIC) for c in range(3)]
+                items += [(p.Ne, q.Ne, abi.RHO, abi.COARSEN_MOMENTS)]
+                items += [(p.Vi[c], q.Vi[c], abi.VX + c, abi.COARSEN_MOMENTS) for c in range(3)]
+                items += [(p.fluxSumE[c], q.Eavg[c], abi.EX + c, abi.COARSEN_ELECTRIC) for c in range(3)]
+                for fa, ca, qty, op in items:
+                    fb = field_box(cells, qty)
+                    ops.field_coarsen(op, qty, fa, p.geom.box.lo - gf, ca, q.geom.box.lo - gc, fb.lo, fb.hi)
+        # patchGhostRefluxedSchedules: the patch ghosts of Eavg agree again with the refluxed interiors
+        if isinstance(cs.messenger, RefinedLevelMessenger):
+            cs.messenger.fill_patch_ghosts("Eavg", abi.EX, cs._by_id("Eavg"))
+        else:
+            cs.messenger.fill_ghosts("Eavg", abi.EX, cs._by_id("Eavg"))
+        cs.reflux(sync_time - coarse.old_time)
+        if coarse.number != 0:
+            cs.accumulate_flux_sum(1. / (RATIO * RATIO))
+        # postSynchronize: ghosts of what was coarsened
+        cs.messenger.fill_ghosts("E", abi.EX, cs._by_id("E"))
+        cs.messenger.fill_ghost_list("Ni", [abi.RHO], {p.geom.id: [p.Ne] for p in cs.patches})
+        cs.messenger.fill_ghost_list("Vi", [abi.VX, abi.VY, abi.VZ], {p.geom.id: [p.Vi[0], p.Vi[1], p.Vi[2]] for p in cs.patches})
+
+
+def build_hierarchy(ops, domain_cells, patch_grid, interp, dx, pops, B_fn, particles_fn, refinement_boxes=(),
+                    solver_kw=None, nref=None):
+    """root level as phare_b200.setup.build, then one refined level per entry of refinement_boxes (a list, per level,
+    of (lower, upper) cell boxes in the index space of the level BELOW, as in pyphare's `refinement_boxes`)"""
+    from .setup import build
+    root = build(ops, LocalComm(), domain_cells, patch_grid, interp, dx, pops, B_fn, particles_fn, solver_kw)
+    h = Hierarchy(ops, root, nref)
+    for boxes in refinement_boxes:
+        h.add_level([refine_box(Box(lo, hi)) for lo, hi in boxes])
+    return h

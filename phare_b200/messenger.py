@@ -54,13 +54,17 @@ class PatchGeom:
 
 
 class LevelGeom:
-    def __init__(self, domain_shape, patches, interp):
+    """periodic=True: the root level (periodic in every direction); periodic=False: a refined level, whose patches
+    only see each other directly (its outer ghosts are level ghosts, filled from the next coarser level: amr.py)"""
+
+    def __init__(self, domain_shape, patches, interp, periodic=True):
         self.domain_shape = tuple(int(s) for s in domain_shape)
         self.dim = len(self.domain_shape)
         self.patches = patches
         self.g = 2 if interp == 1 else 4
         self.pg = 1 if interp == 1 else 2
-        self.shifts = periodic_shifts(self.domain_shape)
+        self.periodic = periodic
+        self.shifts = periodic_shifts(self.domain_shape) if periodic else [np.zeros(self.dim, dtype=np.int64)]
         self._nb = {}
 
     def neighbours(self, p):
@@ -367,6 +371,11 @@ class HybridMessenger:
         fillCurrentGhosts (JX)"""
         arrays = {pid: [v[c] for c in range(3)] for pid, v in vecs.items()}
         self._run(self._compile(("fill", name), "fill", [qty0, qty0 + 1, qty0 + 2], arrays, 0), ("fill", name))
+
+    def fill_ghost_list(self, name, qtys, arrays):
+        """same-level ghost fill of arbitrary quantities ({patch id: [array per qty]}): the PatchGhostField refiners of
+        postSynchronize (charge density, bulk velocity; hybrid_hybrid_messenger_strategy.hpp:736-751)"""
+        self._run(self._compile(("fill", name), "fill", list(qtys), arrays, 0), ("fill", name))
 
     def sum_borders(self, name, arrays, scratch):
         """arrays/scratch: {patch id: [primal arrays]}: a += neighbours' ORIGINAL values on the ghost-box

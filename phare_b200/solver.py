@@ -198,6 +198,38 @@ class GpuOps:
     def average(self, a, b, avg):
         self.ctx.average(a, b, avg)
 
+    # ---- coarse <-> fine level operators (phare_b200.amr); *_lo = AMR field index of element 0 of the array
+    def array(self, shape):
+        return self.ti.TorchArray(tuple(int(s) for s in shape), self.device)
+
+    def box_fill(self, arr, lo, ext, value):
+        self.ctx.box_fill(arr, lo, ext, value)
+
+    def field_refine(self, op, qty, coarse, coarse_lo, fine, fine_lo, box_lo, box_hi):
+        self.ctx.field_refine(op, qty, coarse, coarse_lo, fine, fine_lo, box_lo, box_hi)
+
+    def field_coarsen(self, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
+        self.ctx.field_coarsen(op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi)
+
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+        self.ctx.magnetic_postprocess(layout, B, cell_lo, cell_hi)
+
+    def axpy(self, dst, src, coef):
+        self.ctx.axpy(dst, src, coef)
+
+    def split(self, nref, coarse, first, last, fine_boxes, fine):
+        """phb_split with the Splitter<dim, interp, nref> pattern; returns the number appended, or None when `fine` is
+        too small (nothing appended)"""
+        from .split import pattern
+        from .device import PhbError
+        d, w, m = pattern(self.dim, self.interp, nref)
+        try:
+            return self.ctx.split(coarse, first, last, d, w, m, fine_boxes, fine)
+        except PhbError as e:
+            if e.code == abi.PHB_ERR_CAPACITY:
+                return None
+            raise
+
     def poll_error(self):
         """returns 0 or the phb status raised by a kernel (message in last_error)"""
         rc = self.ctx.lib.phb_poll_error(self.ctx.h)
@@ -476,10 +508,13 @@ class SolverPPC:
     """SolverPPC<HybridModel, AMR_Types> (solver_ppc.hpp:31-186) for one periodic level."""
 
     def __init__(self, ops, patches, geom, comm=None, resistivity=0.0, hyper_resistivity=1e-4, hyper_mode=0, Te=0.12,
-                 pusher_name="modified_boris", fused="auto", sort_with_deposit=True):
+                 pusher_name="modified_boris", fused="auto", sort_with_deposit=True, messenger=None):
         self.ops, self.patches, self.geom = ops, patches, geom
         self.comm = comm or LocalComm()
-        self.messenger = HybridMessenger(geom, ops, self.comm)
+        # a refined level brings its own messenger (phare_b200.amr.RefinedLevelMessenger: level ghosts from the coarser level)
+        self.messenger = messenger or HybridMessenger(geom, ops, self.comm)
+        # timeInterpCoef_ of fillIonPopMomentGhosts for the sweep being run; None on the root level (no level ghosts)
+        self.level_ghost_alpha = None
         self.updater = IonUpdater(ops, pusher_name, fused, sort_with_deposit)
         self.eta, self.nu, self.hyper_mode, self.Te = resistivity, hyper_resistivity, hyper_mode, Te
         self.layouts = {p.geom.id: p.layout for p in patches}
@@ -525,6 +560,9 @@ class SolverPPC:
             msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in self.patches},
                             {p.geom.id: p.pops[i].scratch for p in self.patches})
         # fillIonPopMomentGhosts: level > 0 only (no-op on the root level)
+        if self.level_ghost_alpha is not None:
+            for p in self.patches:
+                self.updater.fill_pop_moment_ghosts(p, self.level_ghost_alpha)
         for p in self.patches:
             self.updater.update_ions(p)
         # fillIonBorders: SetMax on total mass density, charge density and bulk velocity
@@ -572,6 +610,25 @@ class SolverPPC:
         for p in self.patches:
             for c in range(3):
                 self.ops.copy(p.Bold[c], p.B[c])
+
+    # ---- refluxing (levels of a refined hierarchy; driven by phare_b200.amr.Hierarchy)
+    def reset_flux_sum(self):
+        """resetFluxSum (solver_ppc.hpp:279-295)"""
+        for p in self.patches:
+            for c in range(3):
+                self.ops.zero(p.fluxSumE[c])
+
+    def accumulate_flux_sum(self, coef):
+        """accumulateFluxSum (solver_ppc.hpp:263-276): fluxSumE += Eavg * coef"""
+        for p in self.patches:
+            for c in range(3):
+                self.ops.axpy(p.fluxSumE[c], p.Eavg[c], coef)
+
+    def reflux(self, dt):
+        """reflux (solver_ppc.hpp:298-311): B = Bold - dt curl(Eavg) with the refluxed Eavg, then fillMagneticGhosts"""
+        for p in self.patches:
+            self.ops.faraday(p.layout, p.Bold, p.Eavg, p.B, dt)
+        self.messenger.fill_ghosts("B", abi.BX, self._by_id("B"))
 
     def advance_level(self, dt, staging=None):
         """solver_ppc.hpp:315-341.  `staging` (HostStaging): the step takes E,B from pinned host buffers and
