@@ -10,9 +10,10 @@ Mirrors (file:line relative to the PHARE tree):
                                              one MaxwellianParticleInitializer per population)
   DataWrangler / PatchLevel                  src/python3/data_wrangler.hpp, patch_level.hpp (getters used by pyphare.data.wrangler)
 
-Scope: one level (max_nbr_levels == 1), periodic boundaries, HybridModel.  Refined levels raise
-NotImplementedError.  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is
-the seam the CPU parity tests replace.
+Scope: periodic boundaries, HybridModel; one level, or a STATIC hierarchy given by `refinement_boxes` (phare_b200.amr:
+ratio 2, sub-cycling, refluxing; one rank).  Tagging-driven refinement (regridding) raises NotImplementedError
+(SURVEY §8f-2).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
+tests replace.
 """
 import ctypes as C
 import os
@@ -105,10 +106,25 @@ class Hierarchy:
         if any(b != "periodic" for b in self.boundary):
             raise NotImplementedError(f"boundary types {self.boundary}: only periodic domains (hierarchy.hpp:347-349)")
         self.max_nbr_levels = int(d[sim + "AMR/max_nbr_levels"])
-        if self.max_nbr_levels != 1 or d.contains(sim + "AMR/refinement/boxes"):
-            if os.environ.get("PHARE_B200_SINGLE_LEVEL", "0") != "1":
-                raise NotImplementedError("refined levels are not driven yet (SURVEY §8f-2): max_nbr_levels must be 1 "
-                                          "(PHARE_B200_SINGLE_LEVEL=1 runs the root level only)")
+        # static refinement (simulation/AMR/refinement/boxes/L<i>/B<j>/{lower,upper}/{x,y,z}, written by
+        # pyphare/pharein/initialize/general.py:123-150): boxes of level i+1 in the index space of level i
+        self.refinement_boxes = []
+        rb = sim + "AMR/refinement/boxes/"
+        single = os.environ.get("PHARE_B200_SINGLE_LEVEL", "0") == "1"
+        if d.contains(rb + "nbr_levels") and not single:
+            for il in range(int(d[rb + "nbr_levels"])):
+                lp = f"{rb}L{il}/"
+                boxes = []
+                for ib in range(int(d[lp + "nbr_boxes"])):
+                    lo = [int(d[f"{lp}B{ib}/lower/{XYZ[k]}"]) for k in range(self.dim)]
+                    hi = [int(d[f"{lp}B{ib}/upper/{XYZ[k]}"]) for k in range(self.dim)]
+                    boxes.append((lo, hi))
+                self.refinement_boxes.append(boxes)
+        elif self.max_nbr_levels != 1 or d.contains(rb + "nbr_levels"):
+            if not single:
+                raise NotImplementedError("tagging-driven refinement (regridding) is not driven (SURVEY §8f-2): give "
+                                          "refinement_boxes, or max_nbr_levels = 1 (PHARE_B200_SINGLE_LEVEL=1 runs the "
+                                          "root level only)")
             import warnings
             warnings.warn("PHARE_B200_SINGLE_LEVEL=1: refinement ignored, running the root level only")
         self.largest = d.get(sim + "AMR/largest_patch_size")
@@ -256,13 +272,28 @@ class Simulator:
         self.solver = SolverPPC(ops, patches, geom, comm, resistivity=self.eta, hyper_resistivity=self.nu,
                                 hyper_mode=self.hyper_mode, Te=self.Te, pusher_name=self.pusher)
         self.solver.initialize()
+        self.amr = None
+        if h.refinement_boxes:
+            if comm.size > 1:
+                raise NotImplementedError("refined levels are driven on one rank only")
+            from .amr import Hierarchy as PatchHierarchy, refine_box
+            from .boxes import Box
+            self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)
+            for boxes in h.refinement_boxes:
+                self.amr.add_level([refine_box(Box(lo, hi)) for lo, hi in boxes])
         self.is_initialized = True
+
+    def level_solvers(self):
+        return [lvl.solver for lvl in self.amr.levels] if getattr(self, "amr", None) else [self.solver]
 
     # ---- time stepping (simulator.hpp:566-607)
     def advance(self, dt):
         if self.solver is None:
             raise RuntimeError("Error - no valid integrator in the simulator")
-        self.solver.advance_level(dt)
+        if getattr(self, "amr", None):
+            self.amr.advance(dt)  # root step + sub-cycles of the finer levels + synchronisation
+        else:
+            self.solver.advance_level(dt)
         self.elapsed += dt  # ConstantTimeStamper (core/utilities/time_stamper.hpp)
         self.current_time = self.start_time + self.elapsed
         return dt
@@ -307,9 +338,10 @@ class Simulator:
                     continue
                 os.makedirs(path, exist_ok=True)
                 arrays = {}
-                for p in self.solver.patches:
-                    for key, a in self._diag_arrays(p, dtype, diag["quantity"]).items():
-                        arrays[f"t{timestamp:.10f}/pl0/p{p.geom.id}/{key}"] = a
+                for il, solver in enumerate(self.level_solvers()):
+                    for p in solver.patches:
+                        for key, a in self._diag_arrays(p, dtype, diag["quantity"]).items():
+                            arrays[f"t{timestamp:.10f}/pl{il}/p{p.geom.id}/{key}"] = a
                 fn = os.path.join(path, f"{dtype}_{diag['quantity'].strip('/').replace('/', '_')}_"
                                         f"{timestamp:011.5f}_rank{self.solver.comm.rank}.npz")
                 np.savez(fn, **arrays)
@@ -348,7 +380,7 @@ class PatchData:
 
     def __init__(self, patch, data, n_ghosts):
         L = patch.layout
-        self.patchID = f"0#{patch.geom.id}"
+        self.patchID = f"{L.level}#{patch.geom.id}"
         self.origin = ",".join(repr(float(L.origin[k])) for k in range(L.dim))
         self.lower = np.array([L.amr_lower[k] for k in range(L.dim)], dtype=np.uint64)
         self.upper = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)], dtype=np.uint64)
@@ -360,12 +392,13 @@ class PatchLevel:
     """src/python3/patch_level.hpp: per-patch copies of the level's fields / particles on the host"""
 
     def __init__(self, sim, lvl):
-        if lvl != 0:
-            raise RuntimeError("only level 0 exists")
-        self.sim = sim
+        solvers = sim.level_solvers()
+        if lvl < 0 or lvl >= len(solvers):
+            raise RuntimeError(f"level {lvl} does not exist ({len(solvers)} levels)")
+        self.sim, self.solver = sim, solvers[lvl]
 
     def _field(self, fn):
-        s = self.sim.solver
+        s = self.solver
         g = 2 if self.sim.interp_order == 1 else 4
         return [PatchData(p, s.ops.get_field(fn(p)).reshape(-1), g) for p in s.patches]
 
@@ -386,7 +419,7 @@ class PatchLevel:
     def getBulkVelocity(self): return {"Vix": self.getVix(), "Viy": self.getViy(), "Viz": self.getViz()}
 
     def _pops(self):
-        return [pop.name for pop in self.sim.solver.patches[0].pops] if self.sim.solver.patches else []
+        return [pop.name for pop in self.solver.patches[0].pops] if self.solver.patches else []
 
     def getPopDensities(self):
         return {name: self._field(lambda p, i=i: p.pops[i].rho_n) for i, name in enumerate(self._pops())}
@@ -400,7 +433,7 @@ class PatchLevel:
     def getFz(self): return {n: f["Fz"] for n, f in self.getPopFluxes().items()}
 
     def getParticles(self, userPopName="all"):
-        s = self.sim.solver
+        s = self.solver
         out = {}
         for i, name in enumerate(self._pops()):
             if userPopName not in ("all", name):
@@ -416,7 +449,7 @@ class DataWrangler:
         self.sim, self.hier = sim, hier
 
     def getNumberOfLevels(self):
-        return 1
+        return len(self.sim.level_solvers())
 
     def getPatchLevel(self, lvl):
         return PatchLevel(self.sim, lvl)

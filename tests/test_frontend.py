@@ -209,3 +209,78 @@ def test_pyphare_runs_the_reference_harris_script_unchanged(cpu_backend, tmp_pat
     ph.global_vars.sim = None
     for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
         del sys.modules[k]
+
+
+def test_static_refinement_boxes_run_through_the_dict(cpu_backend, cpu_ref, tmp_path):
+    """simulation/AMR/refinement/boxes/L0/B0/... -> a two-level hierarchy (phare_b200.amr): 4 sub-cycles of level 1 per
+    step, both levels visible through the DataWrangler and in the diagnostics"""
+    import pybindlibs.dictator as pp
+    pops, bfn = two_pop_1d(64)
+    populate([64], [0.2], 1, pops[:1], bfn, steps=2, largest=[32], diag_dir=str(tmp_path), diag_times=[0.0, 0.01])
+    pp.add_int("simulation/AMR/max_nbr_levels", 2)
+    pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 1)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/B0/lower/x/", 20)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/B0/upper/x/", 43)
+    hier = S.make_hierarchy()
+    assert hier.refinement_boxes == [[([20], [43])]]
+    sim = S.make_simulator(hier, 1, 1, 2)
+    sim.initialize()
+    assert len(sim.level_solvers()) == 2 and sim.level_solvers()[1].patches[0].layout.level == 1
+    m = importlib.import_module("pybindlibs.cpp_1_1_2")
+    dw = m.DataWrangler(sim, sim.hier)
+    assert dw.getNumberOfLevels() == 2
+    sim.advance(0.005)
+    sim.advance(0.005)
+    assert sim.currentTime() == pytest.approx(0.01) and sim.amr.time == pytest.approx(0.01)
+    fine = dw.getPatchLevel(1).getDensity()
+    assert len(fine) == 1 and fine[0].patchID == "1#0" and list(fine[0].lower) == [40] and list(fine[0].upper) == [87]
+    rho = np.asarray(fine[0].data)[2:-2]
+    assert rho.shape == (49,) and np.all(np.isfinite(rho)) and abs(rho.mean() - 1.0) < 0.3
+    with pytest.raises(RuntimeError):
+        dw.getPatchLevel(2)
+    assert sim.dump_diagnostics(0.01, 0.005)
+    z = np.load(tmp_path / sorted(os.listdir(tmp_path))[-1])
+    assert any("/pl1/p0/" in k for k in z.files) and any("/pl0/p1/" in k for k in z.files)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
+def test_pyphare_runs_the_reference_td1d_script_unchanged(cpu_backend, cpu_ref, tmp_path, monkeypatch):
+    """tests/functional/td/td1d.py (config 2: 1-D tangential discontinuity with refinement boxes on L0 AND L1, i.e. three
+    levels), imported as is and driven by pyphare's own Simulator through pybindlibs; two root steps = 8 + 32 sub-cycles"""
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections",
+                 "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(REF)
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        monkeypatch.delitem(sys.modules, k)
+    td = importlib.import_module("tests.functional.td.td1d")
+    sim = td.config()
+    from pyphare.simulator.simulator import Simulator
+    import pyphare.pharein as ph
+    simulator = Simulator(sim, log_to_file=False)
+    simulator.initialize()
+    cpp_sim = simulator.cpp_sim
+    levels = cpp_sim.level_solvers()
+    assert [len(s.patches) for s in levels] == [25, 1, 1]
+    assert [(int(s.patches[0].geom.box.lo[0]), int(s.patches[0].geom.box.hi[0])) for s in levels[1:]] == [(160, 361), (400, 601)]
+    simulator.advance().advance()
+    assert simulator.currentTime() == pytest.approx(0.02)
+    ops = cpp_sim.solver.ops
+    assert sum(ops.count(p.pops[0].domain) for p in levels[0].patches) == 500 * 100  # L0 particle number conserved
+    for s in levels[1:]:
+        p = s.patches[0]
+        n = ops.count(p.pops[0].domain)
+        assert abs(n - 101 * 100 * 2) < 0.03 * 101 * 100 * 2      # refined_particle_nbr = 2 children per coarse particle
+        by = ops.get_field(p.B[1])
+        assert np.all(np.isfinite(by)) and np.all(np.isfinite(ops.get_field(p.Ne)[2:-2]))
+    # the tangential discontinuity at x = L/4 = 125 lies inside both refined levels: By goes from -1 to +1 across it
+    by = ops.get_field(levels[2].patches[0].B[1])[2:-2]
+    assert by[0] < -0.9 and by[-1] > 0.9 and np.all(np.diff(by) > -0.05)
+    simulator.reset()
+    ph.global_vars.sim = None
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        del sys.modules[k]
