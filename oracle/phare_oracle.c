@@ -1073,11 +1073,100 @@ static inline int p_minus(int i, int o) { return i - o; }
 static inline int d_plus(int i, int o) { return i + 1 - o; }
 static inline int d_minus(int i, int o) { return i - o; }
 
+
+/* 3-D new fine faces (magnetic_refine_patch_strategy.hpp:192-372).  Every sum of the reference is a list of eight
+ * signed samples of another component at (minus|plus) positions per direction, evaluated left to right; TR_A/B/C are
+ * the second-order lists, TR_STD the third-order one (identical for the six places it appears in). */
+typedef struct { int sign, sx, sy, sz; } tr_term;
+static const tr_term TR_A[8]   = {{+1,0,0,0},{-1,0,1,0},{-1,1,0,0},{+1,1,1,0},{+1,0,0,1},{-1,0,1,1},{-1,1,0,1},{+1,1,1,1}};
+static const tr_term TR_B[8]   = {{+1,0,0,0},{+1,0,1,0},{-1,1,0,0},{-1,1,1,0},{-1,0,0,1},{-1,0,1,1},{+1,1,0,1},{+1,1,1,1}};
+static const tr_term TR_C[8]   = {{+1,0,0,0},{-1,0,1,0},{+1,1,0,0},{-1,1,1,0},{-1,0,0,1},{+1,0,1,1},{-1,1,0,1},{+1,1,1,1}};
+static const tr_term TR_STD[8] = {{+1,1,1,1},{-1,0,1,1},{-1,1,0,1},{-1,1,1,0},{+1,1,0,0},{+1,0,1,0},{+1,0,0,1},{-1,0,0,0}};
+
+/* sample of component `comp` (primal along its own direction, dual along the others) */
+static double tr_sample(const fld* f, const double* p, int comp, const int i[3], const int o[3], const tr_term* t)
+{
+    int const s[3] = {t->sx, t->sy, t->sz};
+    int idx[3];
+    for (int a = 0; a < 3; ++a)
+    {
+        if (a == comp)
+            idx[a] = s[a] ? p_plus(i[a], o[a]) : p_minus(i[a], o[a]);
+        else
+            idx[a] = s[a] ? d_plus(i[a], o[a]) : d_minus(i[a], o[a]);
+    }
+    return p[at(f, idx[0], idx[1], idx[2])];
+}
+static double tr_sum(const fld* f, const double* p, int comp, const int i[3], const int o[3], const tr_term* list)
+{
+    double acc = tr_sample(f, p, comp, i, o, &list[0]); /* every list starts with a + term */
+    for (int k = 1; k < 8; ++k)
+    {
+        double const v = tr_sample(f, p, comp, i, o, &list[k]);
+        acc            = list[k].sign > 0 ? acc + v : acc - v;
+    }
+    return acc;
+}
+
+static int postprocess_3d(const phb_layout* L, const phb_vecfield* B, const phb_box* cells)
+{
+    int const g = field_ghosts(L->interp);
+    static const int ijk_factor[2] = {-1, 1};
+    fld f[3];
+    for (int c = 0; c < 3; ++c)
+        f[c] = view(L, B->comp[c], PHB_BX + c);
+    double const Dx = L->dx[0], Dy = L->dx[1], Dz = L->dx[2];
+    for (int comp = 0; comp < 3; ++comp)
+    {
+        int lo[3], hi[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = cells->lower[d];
+            hi[d] = cells->upper[d] + (CENTERING[PHB_BX + comp][d] == PRIMAL ? 1 : 0);
+        }
+        /* the two other components in the order the reference adds their terms, their second-order lists, and the
+         * (offset index, mesh size of the numerator, the two mesh sizes of the denominator) of the third-order terms */
+        int o1, o2, k4, k5;          /* components of T2/T3 ; offset directions of T4/T5 */
+        const tr_term *l2, *l3;
+        double num4, den4, num5, den5;
+        if (comp == 0)      { o1 = 1; o2 = 2; l2 = TR_A; l3 = TR_B; k4 = 2; num4 = Dz; den4 = Dx * Dx + Dz * Dz; k5 = 1; num5 = Dy; den5 = Dx * Dx + Dy * Dy; }
+        else if (comp == 1) { o1 = 0; o2 = 2; l2 = TR_A; l3 = TR_C; k4 = 0; num4 = Dx; den4 = Dx * Dx + Dy * Dy; k5 = 2; num5 = Dz; den5 = Dy * Dy + Dz * Dz; }
+        else                { o1 = 0; o2 = 1; l2 = TR_B; l3 = TR_C; k4 = 1; num4 = Dy; den4 = Dy * Dy + Dz * Dz; k5 = 0; num5 = Dx; den5 = Dx * Dx + Dz * Dz; }
+        /* T4 samples the component T2 does for Bx (by) but the other one for By (bz) and Bz (bx): :243-262, :303-322, :352-371 */
+        int const c4 = comp == 0 ? o1 : (comp == 1 ? o2 : o1), c5 = comp == 0 ? o2 : (comp == 1 ? o1 : o2);
+        for (int i = lo[0]; i <= hi[0]; ++i)
+            for (int j = lo[1]; j <= hi[1]; ++j)
+                for (int k = lo[2]; k <= hi[2]; ++k)
+                {
+                    int const amr[3] = {i, j, k};
+                    if (amr[comp] % 2 == 0)
+                        continue;
+                    int loc[3], off[3];
+                    for (int d = 0; d < 3; ++d)
+                    {
+                        loc[d] = amr[d] - (L->amr_lower[d] - g);
+                        off[d] = d == comp ? 1 : ((amr[d] % 2 == 0) ? 0 : 1);
+                    }
+                    int m[3] = {loc[0], loc[1], loc[2]}, q[3] = {loc[0], loc[1], loc[2]};
+                    m[comp] -= 1;
+                    q[comp] += 1;
+                    double* const self = B->comp[comp];
+                    double const t1 = 0.5 * (self[at(&f[comp], m[0], m[1], m[2])] + self[at(&f[comp], q[0], q[1], q[2])]);
+                    double const t2 = 0.125 * tr_sum(&f[o1], B->comp[o1], o1, loc, off, l2);
+                    double const t3 = 0.125 * tr_sum(&f[o2], B->comp[o2], o2, loc, off, l3);
+                    double const t4 = (0.125 * ijk_factor[off[k4]] * num4 * num4 / den4) * tr_sum(&f[c4], B->comp[c4], c4, loc, off, TR_STD);
+                    double const t5 = (0.125 * ijk_factor[off[k5]] * num5 * num5 / den5) * tr_sum(&f[c5], B->comp[c5], c5, loc, off, TR_STD);
+                    self[at(&f[comp], loc[0], loc[1], loc[2])] = t1 + t2 + t3 + t4 + t5;
+                }
+    }
+    return 0;
+}
+
 int pho_magnetic_postprocess(const phb_layout* L, const phb_vecfield* B, const phb_box* cells)
 {
     int const dim = L->dim, g = field_ghosts(L->interp);
     if (dim == 3)
-        return PHB_ERR_INVALID; /* 3-D (:192-372) not restated yet */
+        return postprocess_3d(L, B, cells);
     fld const bx = view(L, B->comp[0], PHB_BX), by = view(L, B->comp[1], PHB_BY);
     double *X = B->comp[0], *Y = B->comp[1];
     for (int comp = 0; comp < dim; ++comp)

@@ -5,7 +5,7 @@
 //   MagneticFieldRefiner       src/amr/data/field/refine/magnetic_field_refiner.hpp:28-195
 //   MagneticFieldInitRefiner   src/amr/data/field/refine/magnetic_field_init_refiner.hpp:27-190
 //   ElectricFieldRefiner       src/amr/data/field/refine/electric_field_refiner.hpp:30-345
-//   postprocessRefine          src/amr/data/field/refine/magnetic_refine_patch_strategy.hpp:66-190 (Toth & Roe 2002)
+//   postprocessRefine          src/amr/data/field/refine/magnetic_refine_patch_strategy.hpp:66-372 (Toth & Roe 2002)
 //   ElectricFieldCoarsener     src/amr/data/field/coarsening/electric_field_coarsener.hpp:38-150
 //   MomentsCoarsener           src/amr/data/field/coarsening/moments_coarsener.hpp:30-84
 //   setNaNsOnFieldGhosts       src/amr/messengers/hybrid_hybrid_messenger_strategy.hpp:924-955
@@ -256,10 +256,11 @@ __global__ void __launch_bounds__(256) coarsen_kernel(const __grid_constant__ Le
 // ---- magnetic post-process: new fine faces from the coarse faces around them
 struct PostParams
 {
-    FieldView bx, by;
+    FieldView bx, by, bz;
     int lo[3], ext[3]; // field box of the component (AMR indices)
     int shift[3];      // local = AMR - shift  (GridLayout::AMRToLocal)
     int comp;
+    double dx[3];
 };
 
 __device__ __forceinline__ int p_plus(int i, int o) { return i + 2 - o; }
@@ -301,6 +302,77 @@ __global__ void __launch_bounds__(256) magnetic_postprocess_kernel(const __grid_
               + 0.25
                     * (X[A.bx.at(p_minus(ix, xo), d_minus(iy, yo), 0)] - X[A.bx.at(p_plus(ix, xo), d_minus(iy, yo), 0)]
                        - X[A.bx.at(p_minus(ix, xo), d_plus(iy, yo), 0)] + X[A.bx.at(p_plus(ix, xo), d_plus(iy, yo), 0)]);
+    }
+}
+
+
+// 3-D: postprocessBx3d :192-262, postprocessBy3d :264-322, postprocessBz3d :324-372.  The sums are written out in the
+// reference's order; BX/BY/BZ(sx, sy, sz) pick the minus (0) or plus (1) neighbour per direction: p_* along the
+// component's own (primal) direction, d_* along the two others.
+__global__ void __launch_bounds__(128) magnetic_postprocess_3d_kernel(const __grid_constant__ PostParams A)
+{
+    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= size_t(A.ext[0]) * A.ext[1] * A.ext[2])
+        return;
+    int const k = A.lo[2] + int(t % A.ext[2]);
+    t /= A.ext[2];
+    int const j = A.lo[1] + int(t % A.ext[1]);
+    int const i = A.lo[0] + int(t / A.ext[1]);
+    if ((A.comp == 0 ? i : A.comp == 1 ? j : k) % 2 == 0)
+        return;
+    int const ix = i - A.shift[0], iy = j - A.shift[1], iz = k - A.shift[2];
+    int const xo = A.comp == 0 ? 1 : ((i % 2 == 0) ? 0 : 1);
+    int const yo = A.comp == 1 ? 1 : ((j % 2 == 0) ? 0 : 1);
+    int const zo = A.comp == 2 ? 1 : ((k % 2 == 0) ? 0 : 1);
+    double const Dx = A.dx[0], Dy = A.dx[1], Dz = A.dx[2];
+    auto fac = [](int o) { return o == 0 ? -1 : 1; }; // ijk_factor_ :383
+    auto BX  = [&](int sx, int sy, int sz) {
+        return A.bx.p[A.bx.at(sx ? p_plus(ix, xo) : p_minus(ix, xo), sy ? d_plus(iy, yo) : d_minus(iy, yo),
+                              sz ? d_plus(iz, zo) : d_minus(iz, zo))];
+    };
+    auto BY = [&](int sx, int sy, int sz) {
+        return A.by.p[A.by.at(sx ? d_plus(ix, xo) : d_minus(ix, xo), sy ? p_plus(iy, yo) : p_minus(iy, yo),
+                              sz ? d_plus(iz, zo) : d_minus(iz, zo))];
+    };
+    auto BZ = [&](int sx, int sy, int sz) {
+        return A.bz.p[A.bz.at(sx ? d_plus(ix, xo) : d_minus(ix, xo), sy ? d_plus(iy, yo) : d_minus(iy, yo),
+                              sz ? p_plus(iz, zo) : p_minus(iz, zo))];
+    };
+    if (A.comp == 0)
+    {
+        double* const X = A.bx.p;
+        X[A.bx.at(ix, iy, iz)]
+            = 0.5 * (X[A.bx.at(ix - 1, iy, iz)] + X[A.bx.at(ix + 1, iy, iz)])
+              + 0.125 * (BY(0, 0, 0) - BY(0, 1, 0) - BY(1, 0, 0) + BY(1, 1, 0) + BY(0, 0, 1) - BY(0, 1, 1) - BY(1, 0, 1) + BY(1, 1, 1))
+              + 0.125 * (BZ(0, 0, 0) + BZ(0, 1, 0) - BZ(1, 0, 0) - BZ(1, 1, 0) - BZ(0, 0, 1) - BZ(0, 1, 1) + BZ(1, 0, 1) + BZ(1, 1, 1))
+              + (0.125 * fac(zo) * Dz * Dz / (Dx * Dx + Dz * Dz))
+                    * (BY(1, 1, 1) - BY(0, 1, 1) - BY(1, 0, 1) - BY(1, 1, 0) + BY(1, 0, 0) + BY(0, 1, 0) + BY(0, 0, 1) - BY(0, 0, 0))
+              + (0.125 * fac(yo) * Dy * Dy / (Dx * Dx + Dy * Dy))
+                    * (BZ(1, 1, 1) - BZ(0, 1, 1) - BZ(1, 0, 1) - BZ(1, 1, 0) + BZ(1, 0, 0) + BZ(0, 1, 0) + BZ(0, 0, 1) - BZ(0, 0, 0));
+    }
+    else if (A.comp == 1)
+    {
+        double* const Y = A.by.p;
+        Y[A.by.at(ix, iy, iz)]
+            = 0.5 * (Y[A.by.at(ix, iy - 1, iz)] + Y[A.by.at(ix, iy + 1, iz)])
+              + 0.125 * (BX(0, 0, 0) - BX(0, 1, 0) - BX(1, 0, 0) + BX(1, 1, 0) + BX(0, 0, 1) - BX(0, 1, 1) - BX(1, 0, 1) + BX(1, 1, 1))
+              + 0.125 * (BZ(0, 0, 0) - BZ(0, 1, 0) + BZ(1, 0, 0) - BZ(1, 1, 0) - BZ(0, 0, 1) + BZ(0, 1, 1) - BZ(1, 0, 1) + BZ(1, 1, 1))
+              + (0.125 * fac(xo) * Dx * Dx / (Dx * Dx + Dy * Dy))
+                    * (BZ(1, 1, 1) - BZ(0, 1, 1) - BZ(1, 0, 1) - BZ(1, 1, 0) + BZ(1, 0, 0) + BZ(0, 1, 0) + BZ(0, 0, 1) - BZ(0, 0, 0))
+              + (0.125 * fac(zo) * Dz * Dz / (Dy * Dy + Dz * Dz))
+                    * (BX(1, 1, 1) - BX(0, 1, 1) - BX(1, 0, 1) - BX(1, 1, 0) + BX(1, 0, 0) + BX(0, 1, 0) + BX(0, 0, 1) - BX(0, 0, 0));
+    }
+    else
+    {
+        double* const Z = A.bz.p;
+        Z[A.bz.at(ix, iy, iz)]
+            = 0.5 * (Z[A.bz.at(ix, iy, iz - 1)] + Z[A.bz.at(ix, iy, iz + 1)])
+              + 0.125 * (BX(0, 0, 0) + BX(0, 1, 0) - BX(1, 0, 0) - BX(1, 1, 0) - BX(0, 0, 1) - BX(0, 1, 1) + BX(1, 0, 1) + BX(1, 1, 1))
+              + 0.125 * (BY(0, 0, 0) - BY(0, 1, 0) + BY(1, 0, 0) - BY(1, 1, 0) - BY(0, 0, 1) + BY(0, 1, 1) - BY(1, 0, 1) + BY(1, 1, 1))
+              + (0.125 * fac(yo) * Dy * Dy / (Dy * Dy + Dz * Dz))
+                    * (BX(1, 1, 1) - BX(0, 1, 1) - BX(1, 0, 1) - BX(1, 1, 0) + BX(1, 0, 0) + BX(0, 1, 0) + BX(0, 0, 1) - BX(0, 0, 0))
+              + (0.125 * fac(xo) * Dx * Dx / (Dx * Dx + Dz * Dz))
+                    * (BY(1, 1, 1) - BY(0, 1, 1) - BY(1, 0, 1) - BY(1, 1, 0) + BY(1, 0, 0) + BY(0, 1, 0) + BY(0, 0, 1) - BY(0, 0, 0));
     }
 }
 
@@ -437,14 +509,15 @@ int phb_field_coarsen(phb_ctx* ctx, int dim, int op, int qty, const phb_field_vi
 int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vecfield* B, const phb_box* cells)
 {
     using namespace phb;
-    if (!ctx || !valid_layout(ctx, fine) || !B || !cells || !B->comp[0] || !B->comp[1])
+    if (!ctx || !valid_layout(ctx, fine) || !B || !cells || !B->comp[0] || !B->comp[1] || (fine->dim == 3 && !B->comp[2]))
         return set_error(ctx, PHB_ERR_INVALID, "phb_magnetic_postprocess: invalid argument");
-    if (fine->dim == 3)
-        return set_error(ctx, PHB_ERR_INVALID, "phb_magnetic_postprocess: the 3-D Toth-Roe stencil is not built yet");
     DevLayout const L = make_dev_layout(*fine);
     PostParams A;
     A.bx = make_view(L, B->comp[0], PHB_BX);
     A.by = make_view(L, B->comp[1], PHB_BY);
+    A.bz = make_view(L, B->comp[2], PHB_BZ);
+    for (int d = 0; d < 3; ++d)
+        A.dx[d] = L.dx[d];
     for (int comp = 0; comp < L.dim; ++comp)
     {
         size_t n = 1;
@@ -468,8 +541,10 @@ int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vec
         unsigned const grid = unsigned((n + 255) / 256);
         if (L.dim == 1)
             magnetic_postprocess_kernel<1><<<grid, 256, 0, ctx->stream>>>(A);
-        else
+        else if (L.dim == 2)
             magnetic_postprocess_kernel<2><<<grid, 256, 0, ctx->stream>>>(A);
+        else
+            magnetic_postprocess_3d_kernel<<<unsigned((n + 127) / 128), 128, 0, ctx->stream>>>(A);
         PHB_LAUNCH_CHECK(ctx);
     }
     return PHB_OK;

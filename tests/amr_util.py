@@ -15,6 +15,7 @@ CASES = {
     "1d_o1_three_levels": ([64], [0.2], [1], 1, 16, [[([16], [47])], [([48], [79])]]),
     "2d_o1": ([32, 24], [0.2, 0.25], [2, 1], 1, 8, [[([8, 6], [15, 13]), ([16, 6], [21, 13])]]),
     "2d_o2_L": ([28, 28], [0.25, 0.25], [1, 1], 2, 6, [[([8, 8], [19, 13]), ([8, 14], [13, 19])]]),
+    "3d_o1": ([16, 14, 12], [0.2, 0.25, 0.3], [2, 1, 1], 1, 4, [[([4, 4, 4], [9, 8, 7])]]),
 }
 
 
@@ -25,11 +26,12 @@ def B_init_nd(cells, dx):
     kx, ky = 2 * np.pi / Lx, 2 * np.pi / Ly
 
     def fn(c, x, y, *z):
+        zero = 0 * x + 0 * y + (0 * z[0] if z else 0)
         if c == 0:
-            return 1.0 - 0.1 * ky * np.cos(kx * x) * np.sin(ky * y)
+            return 1.0 - 0.1 * ky * np.cos(kx * x) * np.sin(ky * y) + zero
         if c == 1:
-            return 0.1 * kx * np.sin(kx * x) * np.cos(ky * y)
-        return 0.05 * np.cos(kx * x) + 0 * y
+            return 0.1 * kx * np.sin(kx * x) * np.cos(ky * y) + zero
+        return 0.05 * np.cos(kx * x) + zero
     return fn
 
 

@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,pops", [("1d_o1", 1), ("1d_o2_td", 2), ("1d_o3_two_patches", 1), ("1d_o1_three_levels", 1),
-                                       ("2d_o1", 2), ("2d_o2_L", 1)])
+                                       ("2d_o1", 2), ("2d_o2_L", 1), ("3d_o1", 1)])
 def test_gpu_hierarchy_matches_cpu_oracle_hierarchy(cpu_ref, name, pops):
     from phare_b200.solver import GpuOps
     from oracle.cpu_ops import CpuOps

@@ -201,7 +201,7 @@ def test_gpu_level_operators_match_oracle(cpu_oracle, ndim):
                 cpu.field_coarsen(ndim, cop, qty, fine, flo - g, want, lo - g, lo, lo + n - 1 + prim)
                 ctx.field_coarsen(cop, qty, dfz, flo - g, dcz, lo - g, lo, lo + n - 1 + prim)
                 assert bit_equal(dcz.download(), want), (ndim, qty)
-        if ndim < 3:
+        if True:
             layout = abi.make_layout(ndim, 1, list(fhi - flo + 1), [0.3, 0.2, 0.25][:ndim], amr_lower=list(flo))
             from phare_b200.device import DeviceVec
             B = [rng.standard_normal(tuple(2 * n + 2 * g + _prim(abi.BX + c, ndim))) for c in range(3)]
@@ -222,3 +222,66 @@ def test_gpu_level_operators_match_oracle(cpu_oracle, ndim):
         assert bit_equal(dd.download(), d)
     finally:
         ctx.close()
+
+
+def _curl_A_3d(rng, n, dx):
+    """discretely divergence-free B on a Yee grid of n cells (arrays WITHOUT ghosts): B = curl A, A random on the edges"""
+    nx, ny, nz = n
+    Ax, Ay, Az = rng.standard_normal((nx, ny + 1, nz + 1)), rng.standard_normal((nx + 1, ny, nz + 1)), rng.standard_normal((nx + 1, ny + 1, nz))
+    Bx = (Az[:, 1:, :] - Az[:, :-1, :]) / dx[1] - (Ay[:, :, 1:] - Ay[:, :, :-1]) / dx[2]
+    By = (Ax[:, :, 1:] - Ax[:, :, :-1]) / dx[2] - (Az[1:, :, :] - Az[:-1, :, :]) / dx[0]
+    Bz = (Ay[1:, :, :] - Ay[:-1, :, :]) / dx[0] - (Ax[:, 1:, :] - Ax[:, :-1, :]) / dx[1]
+    return [Bx, By, Bz]
+
+
+def test_magnetic_refinement_conserves_divergence_3d(cpu_oracle):
+    """3-D Toth-Roe (magnetic_refine_patch_strategy.hpp:192-372) with three different mesh sizes: the refined field is
+    divergence-free in every fine cell, which the second- AND third-order terms are needed for"""
+    cpu = cpu_oracle
+    rng = np.random.default_rng(8)
+    g, interp = 2, 1
+    n = np.array([5, 4, 6])
+    dxc = [0.6, 0.4, 0.5]
+    lo = np.array([-2, 3, 0])
+    coarse = _curl_A_3d(rng, n + 2 * g, dxc)  # the coarse patch with its ghost layers
+    assert max(np.abs((coarse[0][1:] - coarse[0][:-1]) / dxc[0] + (coarse[1][:, 1:] - coarse[1][:, :-1]) / dxc[1]
+                      + (coarse[2][:, :, 1:] - coarse[2][:, :, :-1]) / dxc[2]).max(), 0) < 1e-12
+    flo, fhi = 2 * lo, 2 * (lo + n - 1) + 1
+    dxf = [d / 2 for d in dxc]
+    layout = abi.make_layout(3, interp, list(2 * n), dxf, amr_lower=list(flo))
+    B = [np.full(tuple(2 * n + 2 * g + _prim(abi.BX + c, 3)), np.nan) for c in range(3)]
+    for c in range(3):
+        cpu.field_refine(3, abi.REFINE_MAGNETIC_INIT, abi.BX + c, np.ascontiguousarray(coarse[c]), lo - g, B[c], flo - g,
+                         flo - g, fhi + g + _prim(abi.BX + c, 3))
+    cpu.magnetic_postprocess(layout, B, flo - g, fhi + g)
+    assert not any(np.isnan(b).any() for b in B)
+    div = ((B[0][1:] - B[0][:-1]) / dxf[0] + (B[1][:, 1:] - B[1][:, :-1]) / dxf[1] + (B[2][:, :, 1:] - B[2][:, :, :-1]) / dxf[2])
+    assert np.abs(div).max() < 1e-11 * max(np.abs(b).max() for b in B) / min(dxf)
+    # the four fine faces on a coarse face carry its value
+    assert bit_equal(B[0][::2, ::2, 1::2], coarse[0][g // 2:g // 2 + n[0] + g + 1, g // 2:g // 2 + n[1] + g, g // 2:g // 2 + n[2] + g])
+
+
+def _refine_B_3d(cpu, coarse, n, dxc, lo, g=2):
+    flo, fhi = 2 * lo, 2 * (lo + n - 1) + 1
+    layout = abi.make_layout(3, 1, list(2 * n), [d / 2 for d in dxc], amr_lower=list(flo))
+    B = [np.full(tuple(2 * n + 2 * g + _prim(abi.BX + c, 3)), np.nan) for c in range(3)]
+    for c in range(3):
+        cpu.field_refine(3, abi.REFINE_MAGNETIC_INIT, abi.BX + c, np.ascontiguousarray(coarse[c]), lo - g, B[c], flo - g,
+                         flo - g, fhi + g + _prim(abi.BX + c, 3))
+    cpu.magnetic_postprocess(layout, B, flo - g, fhi + g)
+    return B
+
+
+def test_toth_roe_3d_is_invariant_under_cyclic_permutation_of_the_axes(cpu_oracle):
+    """the divergence does not see the third-order terms (they cancel in it); relabelling (x, y, z) -> (y, z, x) maps the
+    Bx formula on the By formula and so on, so the three restated formulas check each other, mesh-size factors and
+    ijk_factor signs included"""
+    rng = np.random.default_rng(8)
+    n, dxc, lo = np.array([5, 4, 6]), [0.6, 0.4, 0.5], np.array([-2, 3, 0])
+    coarse = _curl_A_3d(rng, n + 4, dxc)
+    B = _refine_B_3d(cpu_oracle, coarse, n, dxc, lo)
+    T = lambda a: np.ascontiguousarray(np.transpose(a, (2, 0, 1)))
+    perm = lambda v: np.array([v[2], v[0], v[1]])
+    Bp = _refine_B_3d(cpu_oracle, [T(coarse[2]), T(coarse[0]), T(coarse[1])], perm(n), list(perm(dxc)), perm(lo))
+    for got, want in ((Bp[0], T(B[2])), (Bp[1], T(B[0])), (Bp[2], T(B[1]))):
+        assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
