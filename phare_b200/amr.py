@@ -169,11 +169,12 @@ class RefinedLevelMessenger(HybridMessenger):
             boxes = [abi.make_box(b.lo, b.hi) for b in boxes_of(p)]
             if not boxes:
                 continue
+            reach = [coarsen_box(b.grow(RATIO * 2)) for b in boxes_of(p)]  # split stencil: <= 2 fine cells
             for q in self.coarse.patches:
                 src = q.pops[ipop].domain
                 n = ops.count(src)
-                if n == 0:
-                    continue
+                if n == 0 or not any(r * q.geom.box is not None for r in reach):
+                    continue  # no particle of this coarse patch can land in the destination boxes
                 while True:
                     store = store_of(p)
                     got = ops.split(nref, src, 0, n, boxes, store)

@@ -332,7 +332,7 @@ class Simulator:
             return False
         path = diags.get("filePath", "phare_output")
         written = False
-        for dtype in ("electromag", "fluid"):
+        for dtype in ("electromag", "fluid", "particle"):
             for name, diag in (diags.get(dtype) or {}).items():
                 if not isinstance(diag, dict) or not self._due(diag, timestamp, timestep):
                     continue
@@ -368,6 +368,14 @@ class Simulator:
                 return {"charge_density": get(pop.rho_q)}
             if q == f"ions/pop/{pop.name}/flux":
                 return {f"flux_{c}": get(pop.flux[i]) for i, c in enumerate(XYZ)}
+            # ParticleDiagnostics (diagnostic/detail/types/particle.hpp): the SoA keys of particle_packer.hpp:66-67
+            for kind, store in (("domain", pop.domain), ("levelGhost", pop.level_ghost)):
+                if q == f"ions/pop/{pop.name}/{kind}":
+                    if store is None:
+                        return {}
+                    ic, de, w, ch, v = self.solver.ops.get_particles(store)
+                    return {f"{kind}/iCell": ic, f"{kind}/delta": de, f"{kind}/weight": w, f"{kind}/charge": ch,
+                            f"{kind}/v": v}
         return {}
 
     def dump_restarts(self, timestamp, timestep):

@@ -60,6 +60,11 @@ def populate(cells, dl, interp, pops, bfn, time_step=0.005, steps=4, eta=1e-3, n
             pp.add_string(f"simulation/diagnostics/electromag/{q}/type", "electromag")
             pp.add_string(f"simulation/diagnostics/electromag/{q}/quantity", "/" + q)
             pp.add_array_as_vector(f"simulation/diagnostics/electromag/{q}/write_timestamps", np.asarray(diag_times, float))
+        for i, p in enumerate(pops):
+            q = f"/ions/pop/{p['name']}/domain"
+            pp.add_string(f"simulation/diagnostics/particle/part{i}/type", "particle")
+            pp.add_string(f"simulation/diagnostics/particle/part{i}/quantity", q)
+            pp.add_array_as_vector(f"simulation/diagnostics/particle/part{i}/write_timestamps", np.asarray(diag_times[-1:], float))
         pp.add_string("simulation/diagnostics/filePath", diag_dir)
 
 

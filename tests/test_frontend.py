@@ -160,10 +160,14 @@ def test_diagnostics_written_at_requested_timestamps(cpu_backend, tmp_path):
     sim.advance(0.005)
     assert sim.dump_diagnostics(0.01, 0.005)
     files = sorted(os.listdir(tmp_path))
-    assert len(files) == 4 and files[0].startswith("electromag_EM_B_00000.00000")
-    z = np.load(tmp_path / files[-1])
+    assert len(files) == 5 and files[0].startswith("electromag_EM_B_00000.00000")
+    z = np.load(tmp_path / [f for f in files if f.startswith("electromag_EM_E")][-1])
     key = [k for k in z.files if k.endswith("EM_E_x")][0]
     assert key.startswith("t0.0100000000/pl0/p0/") and z[key].shape == (32 + 4,)
+    # particle diagnostics: the domain particles of the population with the reference's SoA keys, last timestamp only
+    z = np.load(tmp_path / [f for f in files if f.startswith("particle_")][0])
+    assert z["t0.0100000000/pl0/p0/domain/iCell"].shape == (32 * 40, 1) and z["t0.0100000000/pl0/p0/domain/v"].shape == (32 * 40, 3)
+    assert abs(z["t0.0100000000/pl0/p0/domain/weight"].sum() / 32 - 1.0) < 0.2
 
 
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
