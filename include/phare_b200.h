@@ -293,7 +293,8 @@ int phb_box_unpack(phb_ctx*, int dim, double* dst, const uint32_t dst_shape[3],
 /* batched form: one launch executes `nops` box operations (a whole exchange phase).  Descriptors are
  * in DEVICE memory; shapes/lows/extents are padded with 1/0/1 in unused trailing directions;
  * `first` = running sum of the element counts of the preceding descriptors. Overlapping
- * destinations inside one batch are only allowed for op 0 with identical values and op 2. */
+ * destinations inside one batch are only allowed for op 0 with identical values and op 2.
+ * op 3 = fill with quiet NaN (setNaNsOnFieldGhosts of a refined level; src is ignored). */
 typedef struct {
     double*       dst;
     const double* src;
@@ -329,8 +330,11 @@ int phb_field_refine(phb_ctx*, int dim, int op, int qty, const phb_field_view* c
                      const phb_field_view* fine, const phb_box* fine_box);
 /* MagneticRefinePatchStrategy::postprocessRefine (magnetic_refine_patch_strategy.hpp:66-125, 1-D :134-141,
  * 2-D :143-190, 3-D :192-372): the NEW fine faces (odd index along the component's own direction) of the field boxes
- * of the cell box `fine_cell_box` get the divergence-free Toth-Roe value from the coarse faces around them. */
-int phb_magnetic_postprocess(phb_ctx*, const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box);
+ * of the cell box `fine_cell_box` get the divergence-free Toth-Roe value from the coarse faces around them.
+ * Faces whose cell lies in one of the `excluded` cell boxes (<= 27; the patches of the level) are left alone, so one
+ * call covers every fill box of a patch's level-ghost layer. */
+int phb_magnetic_postprocess(phb_ctx*, const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box,
+                             const phb_box* excluded, int nexcluded);
 /* FieldCoarsenOperator::coarsen for one coarse box (field_coarsen_operator.hpp:95-121) */
 int phb_field_coarsen(phb_ctx*, int dim, int op, int qty, const phb_field_view* fine,
                       const phb_field_view* coarse, const phb_box* coarse_box);

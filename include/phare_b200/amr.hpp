@@ -147,11 +147,16 @@ class MagneticRefinePatchStrategy
 {
 public:
     explicit MagneticRefinePatchStrategy(Context const& ctx) : ctx_{ctx} {}
-    void postprocessRefine(GridLayout_t const& fineLayout, VecField& B, Box<GridLayout_t::dimension> const& fine_box) const
+    // `levelBoxes`: cell boxes left untouched (the patches of the level) so that fine_box may be a whole ghost box
+    void postprocessRefine(GridLayout_t const& fineLayout, VecField& B, Box<GridLayout_t::dimension> const& fine_box,
+                           std::vector<Box<GridLayout_t::dimension>> const& levelBoxes = {}) const
     {
         auto b   = B.c();
         auto box = fine_box.c();
-        ctx_.check(phb_magnetic_postprocess(ctx_.get(), fineLayout.c(), &b, &box));
+        std::vector<phb_box> ex;
+        for (auto const& lb : levelBoxes)
+            ex.push_back(lb.c());
+        ctx_.check(phb_magnetic_postprocess(ctx_.get(), fineLayout.c(), &b, &box, ex.data(), int(ex.size())));
     }
 
 private:

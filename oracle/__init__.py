@@ -306,13 +306,14 @@ class Cpu:
         rc = self.lib.pho_field_refine(C.c_int(dim), C.c_int(op), C.c_int(qty), C.byref(cv), C.byref(fv), C.byref(b))
         assert rc == 0, rc
 
-    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi, excluded=()):
         assert self.impl == "oracle"
         bv = host_vec(B)
         for c in range(3):
             bv.comp[c] = B[c].ctypes.data
         b = abi.make_box(cell_lo, cell_hi)
-        rc = self.lib.pho_magnetic_postprocess(C.byref(layout), C.byref(bv), C.byref(b))
+        rc = self.lib.pho_magnetic_postprocess(C.byref(layout), C.byref(bv), C.byref(b), abi.box_array(list(excluded)),
+                                               C.c_int(len(excluded)))
         assert rc == 0, rc
 
     def field_coarsen(self, dim, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):

@@ -211,8 +211,8 @@ class CpuOps:
     def field_coarsen(self, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
         self.orc.field_coarsen(len(box_lo), op, qty, fine.a, fine_lo, coarse.a, coarse_lo, box_lo, box_hi)
 
-    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
-        self.orc.magnetic_postprocess(layout, [c.a for c in B.comps], cell_lo, cell_hi)
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi, excluded=()):
+        self.orc.magnetic_postprocess(layout, [c.a for c in B.comps], cell_lo, cell_hi, excluded)
 
     def axpy(self, dst, src, coef):
         self.orc.axpy(dst.a, src.a, coef)

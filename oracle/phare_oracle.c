@@ -844,6 +844,8 @@ int pho_box_op(int dim, double* dst, const uint32_t ds[3], const uint32_t dlo[3]
                     dst[pd] = src[ps];
                 else if (op == 1)
                     dst[pd] += src[ps];
+                else if (op == 3)
+                    dst[pd] = NAN; /* setNaNsOnFieldGhosts */
                 else
                     dst[pd] = (dst[pd] < src[ps]) ? src[ps] : dst[pd]; /* std::max(d, d0): NaN d stays, NaN d0 ignored */
             }
@@ -1108,7 +1110,20 @@ static double tr_sum(const fld* f, const double* p, int comp, const int i[3], co
     return acc;
 }
 
-static int postprocess_3d(const phb_layout* L, const phb_vecfield* B, const phb_box* cells)
+static int cell_excluded(int dim, const int c[3], const phb_box* ex, int nex)
+{
+    for (int b = 0; b < nex; ++b)
+    {
+        int in = 1;
+        for (int d = 0; d < dim; ++d)
+            in = in && c[d] >= ex[b].lower[d] && c[d] <= ex[b].upper[d];
+        if (in)
+            return 1;
+    }
+    return 0;
+}
+
+static int postprocess_3d(const phb_layout* L, const phb_vecfield* B, const phb_box* cells, const phb_box* ex, int nex)
 {
     int const g = field_ghosts(L->interp);
     static const int ijk_factor[2] = {-1, 1};
@@ -1139,7 +1154,7 @@ static int postprocess_3d(const phb_layout* L, const phb_vecfield* B, const phb_
                 for (int k = lo[2]; k <= hi[2]; ++k)
                 {
                     int const amr[3] = {i, j, k};
-                    if (amr[comp] % 2 == 0)
+                    if (amr[comp] % 2 == 0 || cell_excluded(3, amr, ex, nex))
                         continue;
                     int loc[3], off[3];
                     for (int d = 0; d < 3; ++d)
@@ -1162,11 +1177,11 @@ static int postprocess_3d(const phb_layout* L, const phb_vecfield* B, const phb_
     return 0;
 }
 
-int pho_magnetic_postprocess(const phb_layout* L, const phb_vecfield* B, const phb_box* cells)
+int pho_magnetic_postprocess(const phb_layout* L, const phb_vecfield* B, const phb_box* cells, const phb_box* ex, int nex)
 {
     int const dim = L->dim, g = field_ghosts(L->interp);
     if (dim == 3)
-        return postprocess_3d(L, B, cells);
+        return postprocess_3d(L, B, cells, ex, nex);
     fld const bx = view(L, B->comp[0], PHB_BX), by = view(L, B->comp[1], PHB_BY);
     double *X = B->comp[0], *Y = B->comp[1];
     for (int comp = 0; comp < dim; ++comp)
@@ -1181,8 +1196,10 @@ int pho_magnetic_postprocess(const phb_layout* L, const phb_vecfield* B, const p
         for (int i = lo[0]; i <= hi[0]; ++i)
             for (int j = lo[1]; j <= hi[1]; ++j)
             {
-                int const idx[2] = {i, j};
+                int const idx[3] = {i, j, 0};
                 if (idx[comp] % 2 == 0) /* isNewFineFace :127-132 */
+                    continue;
+                if (cell_excluded(dim, idx, ex, nex))
                     continue;
                 int const ix = i - (L->amr_lower[0] - g);                  /* GridLayout::AMRToLocal */
                 int const iy = dim > 1 ? j - (L->amr_lower[1] - g) : 0;

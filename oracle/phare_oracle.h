@@ -53,7 +53,8 @@ int pho_box_op(int dim, double* dst, const uint32_t dst_shape[3], const uint32_t
 /* coarse <-> fine level operators (see include/phare_b200.h for the reference lines) */
 int pho_field_refine(int dim, int op, int qty, const phb_field_view* coarse, const phb_field_view* fine,
                      const phb_box* fine_box);
-int pho_magnetic_postprocess(const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box);
+int pho_magnetic_postprocess(const phb_layout* fine, const phb_vecfield* B, const phb_box* fine_cell_box,
+                             const phb_box* excluded, int nexcluded);
 int pho_field_coarsen(int dim, int op, int qty, const phb_field_view* fine, const phb_field_view* coarse,
                       const phb_box* coarse_box);
 int pho_box_fill(int dim, double* dst, const uint32_t dst_shape[3], const uint32_t dst_lo[3], const uint32_t extent[3],

@@ -180,7 +180,8 @@ _PROTOS = {
     "phb_box_op_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint64]),
     "phb_field_refine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FieldView), C.POINTER(FieldView),
                                    C.POINTER(Box)]),
-    "phb_magnetic_postprocess": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(Box)]),
+    "phb_magnetic_postprocess": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(Box),
+                                           C.POINTER(Box), C.c_int]),
     "phb_field_coarsen": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(FieldView), C.POINTER(FieldView),
                                     C.POINTER(Box)]),
     "phb_box_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_double]),

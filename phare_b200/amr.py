@@ -68,10 +68,11 @@ class RefinedLevelMessenger(HybridMessenger):
         self.coarse = coarse_solver
         g, dim = geom.g, geom.dim
         level_boxes = [p.box for p in geom.patches]
-        self._nan, self._scratch, self._lg_field_cells, self.lg_particle_boxes = {}, {}, {}, {}
+        self._nan, self._scratch, self._lg_excluded, self.lg_particle_boxes = {}, {}, {}, {}
         for p in geom.patches:
             # level-ghost cells: the ghost layer minus every patch of the level (fields: g cells, particles: pg cells)
-            self._lg_field_cells[p.id] = minus_all([p.box.grow(g)], level_boxes)
+            self._lg_excluded[p.id] = [abi.make_box(ov.lo, ov.hi) for ov in (p.box.grow(g) * b for b in level_boxes)
+                                       if ov is not None]
             self.lg_particle_boxes[p.id] = minus_all([p.box.grow(geom.pg)], level_boxes)
             for qty in range(abi.BX, abi.JZ + 1):
                 gfb = p.ghost_field_box(qty, g)
@@ -81,7 +82,7 @@ class RefinedLevelMessenger(HybridMessenger):
                 # coarse data under the ghost box, one node more for the two-point refine stencils
                 cbox = Box(gfb.lo // RATIO - 1, gfb.hi // RATIO + 1)
                 self._scratch[(p.id, qty)] = (ops.array(cbox.shape()), cbox)
-        self._gather = {}
+        self._gather, self._nan_ops = {}, {}
 
     # ---- coarse level -> scratch arrays
     def _gather_plan(self, name, qty0):
@@ -115,7 +116,7 @@ class RefinedLevelMessenger(HybridMessenger):
             self._gather[name] = self.ops.compile_box_ops(entries)
         return self._gather[name]
 
-    def _refine(self, name, qty0, vecs, op, boxes=None):
+    def _refine(self, name, qty0, vecs, op, whole_ghost_box=False):
         ops, g = self.ops, self.geom.g
         ops.run_box_ops(self._gather_plan(name, qty0))
         for p in self.geom.patches:
@@ -125,11 +126,14 @@ class RefinedLevelMessenger(HybridMessenger):
                 gfb = p.ghost_field_box(qty, g)
                 ops.field_refine(op, qty, scratch, cbox.lo, vecs[p.id][c], gfb.lo, gfb.lo, gfb.hi)
         if qty0 == abi.BX:
-            # MagneticRefinePatchStrategy::postprocessRefine on the cells that were filled from the coarser level
+            # MagneticRefinePatchStrategy::postprocessRefine on the cells that were filled from the coarser level: the
+            # whole ghost box at level creation, otherwise the ghost box minus the level's patches (one launch per
+            # component: the kernel skips the faces of the excluded cell boxes)
             layouts = {p.geom.id: p.layout for p in self._fine_patches}
             for p in self.geom.patches:
-                for cells in (boxes[p.id] if boxes is not None else self._lg_field_cells[p.id]):
-                    ops.magnetic_postprocess(layouts[p.id], vecs[p.id], cells.lo, cells.hi)
+                cells = p.box.grow(g)
+                ops.magnetic_postprocess(layouts[p.id], vecs[p.id], cells.lo, cells.hi,
+                                         () if whole_ghost_box else self._lg_excluded[p.id])
 
     def attach(self, fine_patches):
         self._fine_patches = fine_patches
@@ -138,11 +142,11 @@ class RefinedLevelMessenger(HybridMessenger):
     def fill_ghosts(self, name, qty0, vecs):
         """fillMagneticGhosts / fillElectricGhosts / fillCurrentGhosts on a refined level: NaNs on the level-ghost nodes,
         patch ghosts from the neighbours, what is still NaN from the coarser level"""
-        ops = self.ops
-        for p in self.geom.patches:
-            for c in range(3):
-                for lo, ext in self._nan[(p.id, qty0 + c)]:
-                    ops.box_fill(vecs[p.id][c], lo, ext, float("nan"))
+        if name not in self._nan_ops:  # every NaN box of every patch and component in one batched launch (K8, op 3)
+            self._nan_ops[name] = self.ops.compile_box_ops(
+                [(vecs[p.id][c], lo, vecs[p.id][c], lo, ext, 3) for p in self.geom.patches for c in range(3)
+                 for lo, ext in self._nan[(p.id, qty0 + c)]])
+        self.ops.run_box_ops(self._nan_ops[name])
         super().fill_ghosts(name, qty0, vecs)
         self._refine(name, qty0, vecs, self.REFINE_OP[qty0])
 
@@ -154,8 +158,7 @@ class RefinedLevelMessenger(HybridMessenger):
         """initLevel (:335-345): B through MagneticFieldInitRefiner (+ post-process) over the whole ghost box, E through
         ElectricFieldRefiner (which only writes NaN nodes: a fresh FieldData is all NaN, field_data.hpp:41-59)"""
         ops, g = self.ops, self.geom.g
-        self._refine("B", abi.BX, solver._by_id("B"), abi.REFINE_MAGNETIC_INIT,
-                     boxes={p.id: [p.box.grow(g)] for p in self.geom.patches})
+        self._refine("B", abi.BX, solver._by_id("B"), abi.REFINE_MAGNETIC_INIT, whole_ghost_box=True)
         for p in solver.patches:
             for c in range(3):
                 ops.box_fill(p.E[c], [0] * self.geom.dim, p.E[c].shape, float("nan"))

@@ -93,6 +93,12 @@ __global__ void __launch_bounds__(256)
     size_t const ps  = (size_t(A.src_lo[0] + i) * A.src_shape[1] + (A.src_lo[1] + j)) * A.src_shape[2] + (A.src_lo[2] + k);
     // several overlaps of one phase may cover the same destination node (faces, edges and corners of the
     // ghost box): += and max must therefore be atomic; copies never overlap (the plan deduplicates them)
+    if (A.op == 3)
+    {
+        // setNaNsOnFieldGhosts (hybrid_hybrid_messenger_strategy.hpp:924-955): the source is not read
+        A.dst[pd] = __longlong_as_double(0x7ff8000000000000LL);
+        return;
+    }
     double const sv = A.src[ps];
     if (A.op == 0)
         A.dst[pd] = sv;

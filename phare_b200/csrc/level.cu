@@ -261,7 +261,19 @@ struct PostParams
     int shift[3];      // local = AMR - shift  (GridLayout::AMRToLocal)
     int comp;
     double dx[3];
+    BoxList excluded; // cell boxes whose faces are not touched (the patches of the level)
 };
+
+__device__ __forceinline__ bool post_excluded(const PostParams& A, int i, int j, int k)
+{
+    for (int b = 0; b < A.excluded.n; ++b)
+    {
+        DevBox const& e = A.excluded.b[b];
+        if (i >= e.lo[0] && i <= e.hi[0] && j >= e.lo[1] && j <= e.hi[1] && k >= e.lo[2] && k <= e.hi[2])
+            return true;
+    }
+    return false;
+}
 
 __device__ __forceinline__ int p_plus(int i, int o) { return i + 2 - o; }
 __device__ __forceinline__ int p_minus(int i, int o) { return i - o; }
@@ -277,6 +289,8 @@ __global__ void __launch_bounds__(256) magnetic_postprocess_kernel(const __grid_
     int const i = A.lo[0] + int(t / A.ext[1]);
     int const j = A.lo[1] + int(t % A.ext[1]);
     if ((A.comp == 0 ? i : j) % 2 == 0) // isNewFineFace :127-132 (AMR indices can be negative: != 0, not == 1)
+        return;
+    if (post_excluded(A, i, j, 0))
         return;
     int const ix = i - A.shift[0], iy = DIM > 1 ? j - A.shift[1] : 0;
     double* const X = A.bx.p;
@@ -319,6 +333,8 @@ __global__ void __launch_bounds__(128) magnetic_postprocess_3d_kernel(const __gr
     int const j = A.lo[1] + int(t % A.ext[1]);
     int const i = A.lo[0] + int(t / A.ext[1]);
     if ((A.comp == 0 ? i : A.comp == 1 ? j : k) % 2 == 0)
+        return;
+    if (post_excluded(A, i, j, k))
         return;
     int const ix = i - A.shift[0], iy = j - A.shift[1], iz = k - A.shift[2];
     int const xo = A.comp == 0 ? 1 : ((i % 2 == 0) ? 0 : 1);
@@ -506,10 +522,12 @@ int phb_field_coarsen(phb_ctx* ctx, int dim, int op, int qty, const phb_field_vi
     return PHB_OK;
 }
 
-int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vecfield* B, const phb_box* cells)
+int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vecfield* B, const phb_box* cells,
+                             const phb_box* excluded, int nexcluded)
 {
     using namespace phb;
-    if (!ctx || !valid_layout(ctx, fine) || !B || !cells || !B->comp[0] || !B->comp[1] || (fine->dim == 3 && !B->comp[2]))
+    if (!ctx || !valid_layout(ctx, fine) || !B || !cells || !B->comp[0] || !B->comp[1] || (fine->dim == 3 && !B->comp[2])
+        || nexcluded < 0 || nexcluded > MAX_BOXES || (nexcluded && !excluded))
         return set_error(ctx, PHB_ERR_INVALID, "phb_magnetic_postprocess: invalid argument");
     DevLayout const L = make_dev_layout(*fine);
     PostParams A;
@@ -518,6 +536,9 @@ int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vec
     A.bz = make_view(L, B->comp[2], PHB_BZ);
     for (int d = 0; d < 3; ++d)
         A.dx[d] = L.dx[d];
+    A.excluded.n = nexcluded;
+    for (int b = 0; b < nexcluded; ++b)
+        A.excluded.b[b] = make_box(excluded[b], L.dim);
     for (int comp = 0; comp < L.dim; ++comp)
     {
         size_t n = 1;

@@ -328,9 +328,10 @@ class Context:
         fv, cv, b = self._view(fine, fine_lo), self._view(coarse, coarse_lo), abi.make_box(box_lo, box_hi)
         self._check(self.lib.phb_field_coarsen(self.h, dim, op, qty, C.byref(fv), C.byref(cv), C.byref(b)))
 
-    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi, excluded=()):
         b = abi.make_box(cell_lo, cell_hi)
-        self._check(self.lib.phb_magnetic_postprocess(self.h, C.byref(layout), C.byref(B.c), C.byref(b)))
+        self._check(self.lib.phb_magnetic_postprocess(self.h, C.byref(layout), C.byref(B.c), C.byref(b),
+                                                      abi.box_array(list(excluded)), len(excluded)))
 
     def box_fill(self, dst, lo, extent, value):
         u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))

@@ -211,8 +211,8 @@ class GpuOps:
     def field_coarsen(self, op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi):
         self.ctx.field_coarsen(op, qty, fine, fine_lo, coarse, coarse_lo, box_lo, box_hi)
 
-    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi):
-        self.ctx.magnetic_postprocess(layout, B, cell_lo, cell_hi)
+    def magnetic_postprocess(self, layout, B, cell_lo, cell_hi, excluded=()):
+        self.ctx.magnetic_postprocess(layout, B, cell_lo, cell_hi, excluded)
 
     def axpy(self, dst, src, coef):
         self.ctx.axpy(dst, src, coef)

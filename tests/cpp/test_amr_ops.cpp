@@ -143,10 +143,11 @@ void run()
     }
     amr::MagneticRefinePatchStrategy<Layout> strat{ctx};
     Box<dim> cells = grow(fineCells, g);
-    strat.postprocessRefine(fineLayout, B, cells);
+    strat.postprocessRefine(fineLayout, B, cells, {fineCells}); // the level-ghost layer only, in one call
     phb_vecfield hv{{hB[0].data(), hB[1].data(), hB[2].data()}};
     auto cb = cells.c();
-    CHECK(pho_magnetic_postprocess(fineLayout.c(), &hv, &cb) == 0);
+    auto ex = fineCells.c();
+    CHECK(pho_magnetic_postprocess(fineLayout.c(), &hv, &cb, &ex, 1) == 0);
     for (int c = 0; c < 3; ++c)
     {
         std::vector<double> got(hB[c].size());
