@@ -141,7 +141,9 @@ class RefinedLevelMessenger(HybridMessenger):
     # ---- HybridMessenger interface
     def fill_ghosts(self, name, qty0, vecs):
         """fillMagneticGhosts / fillElectricGhosts / fillCurrentGhosts on a refined level: NaNs on the level-ghost nodes,
-        patch ghosts from the neighbours, what is still NaN from the coarser level"""
+        patch ghosts from the neighbours, what is still NaN from the coarser level.  Only the refiner registered under
+        the name of the given field runs (RefinerPool::fill(vec, ...), refiner_pool.hpp:125-133): e.g. the level ghosts of
+        the model's B are those of its last own fill (the corrector) until the next one."""
         if name not in self._nan_ops:  # every NaN box of every patch and component in one batched launch (K8, op 3)
             self._nan_ops[name] = self.ops.compile_box_ops(
                 [(vecs[p.id][c], lo, vecs[p.id][c], lo, ext, 3) for p in self.geom.patches for c in range(3)

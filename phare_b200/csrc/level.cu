@@ -52,20 +52,56 @@ struct LevelOpParams
 // toCoarseIndex (amr_utils.hpp:128-135)
 __device__ __forceinline__ int to_coarse(int i) { return (i >= 0) ? i / 2 : i / 2 + i % 2; }
 
+// Thread -> node of a box without integer division: threadIdx.x runs along the fastest used direction, threadIdx.y /
+// blockIdx.y along the next one, blockIdx.z along the slowest (1-D: 256 x 1 threads, 2-D / 3-D: 32 x 8).
+template<int DIM>
+__device__ __forceinline__ bool box_index(const int (&ext)[3], int (&idx)[3])
+{
+    idx[0] = idx[1] = idx[2] = 0;
+    if constexpr (DIM == 1)
+    {
+        idx[0] = int(blockIdx.x * blockDim.x + threadIdx.x);
+        return idx[0] < ext[0];
+    }
+    else if constexpr (DIM == 2)
+    {
+        idx[1] = int(blockIdx.x * blockDim.x + threadIdx.x);
+        idx[0] = int(blockIdx.y * blockDim.y + threadIdx.y);
+        return idx[1] < ext[1] && idx[0] < ext[0];
+    }
+    else
+    {
+        idx[2] = int(blockIdx.x * blockDim.x + threadIdx.x);
+        idx[1] = int(blockIdx.y * blockDim.y + threadIdx.y);
+        idx[0] = int(blockIdx.z);
+        return idx[2] < ext[2] && idx[1] < ext[1];
+    }
+}
+inline void box_launch_dims(int dim, const int ext[3], dim3& grid, dim3& block)
+{
+    if (dim == 1)
+    {
+        block = dim3(256, 1, 1);
+        grid  = dim3(unsigned(ext[0] + 255) / 256, 1, 1);
+    }
+    else if (dim == 2)
+    {
+        block = dim3(32, 8, 1);
+        grid  = dim3(unsigned(ext[1] + 31) / 32, unsigned(ext[0] + 7) / 8, 1);
+    }
+    else
+    {
+        block = dim3(32, 8, 1);
+        grid  = dim3(unsigned(ext[2] + 31) / 32, unsigned(ext[1] + 7) / 8, unsigned(ext[0]));
+    }
+}
+
 template<int DIM>
 __device__ __forceinline__ bool node_of_thread(const LevelOpParams& A, int f[3])
 {
-    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= size_t(A.ext[0]) * A.ext[1] * A.ext[2])
+    int idx[3];
+    if (!box_index<DIM>(A.ext, idx))
         return false;
-    // the box is stored right-aligned like the arrays: the last used direction is the fastest
-    int idx[3] = {0, 0, 0};
-#pragma unroll
-    for (int d = DIM - 1; d >= 0; --d)
-    {
-        idx[d] = int(t % A.ext[d]);
-        t /= A.ext[d];
-    }
 #pragma unroll
     for (int d = 0; d < 3; ++d)
         f[d] = d < DIM ? A.lo[d] + idx[d] : 0;
@@ -283,11 +319,11 @@ __device__ __forceinline__ int d_minus(int i, int o) { return i - o; }
 template<int DIM>
 __global__ void __launch_bounds__(256) magnetic_postprocess_kernel(const __grid_constant__ PostParams A)
 {
-    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= size_t(A.ext[0]) * A.ext[1])
+    int idx[3];
+    if (!box_index<DIM>(A.ext, idx))
         return;
-    int const i = A.lo[0] + int(t / A.ext[1]);
-    int const j = A.lo[1] + int(t % A.ext[1]);
+    int const i = A.lo[0] + idx[0];
+    int const j = A.lo[1] + idx[1];
     if ((A.comp == 0 ? i : j) % 2 == 0) // isNewFineFace :127-132 (AMR indices can be negative: != 0, not == 1)
         return;
     if (post_excluded(A, i, j, 0))
@@ -323,15 +359,12 @@ __global__ void __launch_bounds__(256) magnetic_postprocess_kernel(const __grid_
 // 3-D: postprocessBx3d :192-262, postprocessBy3d :264-322, postprocessBz3d :324-372.  The sums are written out in the
 // reference's order; BX/BY/BZ(sx, sy, sz) pick the minus (0) or plus (1) neighbour per direction: p_* along the
 // component's own (primal) direction, d_* along the two others.
-__global__ void __launch_bounds__(128) magnetic_postprocess_3d_kernel(const __grid_constant__ PostParams A)
+__global__ void __launch_bounds__(256) magnetic_postprocess_3d_kernel(const __grid_constant__ PostParams A)
 {
-    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= size_t(A.ext[0]) * A.ext[1] * A.ext[2])
+    int idx[3];
+    if (!box_index<3>(A.ext, idx))
         return;
-    int const k = A.lo[2] + int(t % A.ext[2]);
-    t /= A.ext[2];
-    int const j = A.lo[1] + int(t % A.ext[1]);
-    int const i = A.lo[0] + int(t / A.ext[1]);
+    int const i = A.lo[0] + idx[0], j = A.lo[1] + idx[1], k = A.lo[2] + idx[2];
     if ((A.comp == 0 ? i : A.comp == 1 ? j : k) % 2 == 0)
         return;
     if (post_excluded(A, i, j, k))
@@ -395,19 +428,16 @@ __global__ void __launch_bounds__(128) magnetic_postprocess_3d_kernel(const __gr
 struct FillParams
 {
     double* dst;
-    int dn[3], dlo[3], ext[3];
+    int dn[3], dlo[3], ext[3]; // left-aligned: unused trailing directions are 1 / 0 / 1
     double value;
 };
+template<int DIM>
 __global__ void __launch_bounds__(256) box_fill_kernel(const __grid_constant__ FillParams A)
 {
-    size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (t >= size_t(A.ext[0]) * A.ext[1] * A.ext[2])
+    int idx[3];
+    if (!box_index<DIM>(A.ext, idx))
         return;
-    int const k = int(t % A.ext[2]);
-    t /= A.ext[2];
-    int const j = int(t % A.ext[1]);
-    int const i = int(t / A.ext[1]);
-    A.dst[(size_t(A.dlo[0] + i) * A.dn[1] + (A.dlo[1] + j)) * A.dn[2] + (A.dlo[2] + k)] = A.value;
+    A.dst[(size_t(A.dlo[0] + idx[0]) * A.dn[1] + (A.dlo[1] + idx[1])) * A.dn[2] + (A.dlo[2] + idx[2])] = A.value;
 }
 
 __global__ void __launch_bounds__(256) axpy_kernel(size_t n, double* __restrict__ dst, const double* __restrict__ src,
@@ -471,13 +501,14 @@ int phb_field_refine(phb_ctx* ctx, int dim, int op, int qty, const phb_field_vie
         if (clo < A.src.lo[d] || chi > A.src.lo[d] + A.src.n[d] - 1)
             return set_error(ctx, PHB_ERR_INVALID, "phb_field_refine: the coarse view does not cover the stencil");
     }
-    unsigned const grid = unsigned((n + 255) / 256);
+    dim3 grid, block;
+    box_launch_dims(dim, A.ext, grid, block);
     if (dim == 1)
-        refine_kernel<1><<<grid, 256, 0, ctx->stream>>>(A);
+        refine_kernel<1><<<grid, block, 0, ctx->stream>>>(A);
     else if (dim == 2)
-        refine_kernel<2><<<grid, 256, 0, ctx->stream>>>(A);
+        refine_kernel<2><<<grid, block, 0, ctx->stream>>>(A);
     else
-        refine_kernel<3><<<grid, 256, 0, ctx->stream>>>(A);
+        refine_kernel<3><<<grid, block, 0, ctx->stream>>>(A);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
@@ -511,13 +542,14 @@ int phb_field_coarsen(phb_ctx* ctx, int dim, int op, int qty, const phb_field_vi
         if (flo < A.src.lo[d] || fhi > A.src.lo[d] + A.src.n[d] - 1)
             return set_error(ctx, PHB_ERR_INVALID, "phb_field_coarsen: the fine view does not cover the box");
     }
-    unsigned const grid = unsigned((n + 255) / 256);
+    dim3 grid, block;
+    box_launch_dims(dim, A.ext, grid, block);
     if (dim == 1)
-        coarsen_kernel<1><<<grid, 256, 0, ctx->stream>>>(A, dual_dir);
+        coarsen_kernel<1><<<grid, block, 0, ctx->stream>>>(A, dual_dir);
     else if (dim == 2)
-        coarsen_kernel<2><<<grid, 256, 0, ctx->stream>>>(A, dual_dir);
+        coarsen_kernel<2><<<grid, block, 0, ctx->stream>>>(A, dual_dir);
     else
-        coarsen_kernel<3><<<grid, 256, 0, ctx->stream>>>(A, dual_dir);
+        coarsen_kernel<3><<<grid, block, 0, ctx->stream>>>(A, dual_dir);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
@@ -558,14 +590,15 @@ int phb_magnetic_postprocess(phb_ctx* ctx, const phb_layout* fine, const phb_vec
         }
         if (n == 0)
             continue;
-        A.comp              = comp;
-        unsigned const grid = unsigned((n + 255) / 256);
+        A.comp = comp;
+        dim3 grid, block;
+        box_launch_dims(L.dim, A.ext, grid, block);
         if (L.dim == 1)
-            magnetic_postprocess_kernel<1><<<grid, 256, 0, ctx->stream>>>(A);
+            magnetic_postprocess_kernel<1><<<grid, block, 0, ctx->stream>>>(A);
         else if (L.dim == 2)
-            magnetic_postprocess_kernel<2><<<grid, 256, 0, ctx->stream>>>(A);
+            magnetic_postprocess_kernel<2><<<grid, block, 0, ctx->stream>>>(A);
         else
-            magnetic_postprocess_3d_kernel<<<unsigned((n + 127) / 128), 128, 0, ctx->stream>>>(A);
+            magnetic_postprocess_3d_kernel<<<grid, block, 0, ctx->stream>>>(A);
         PHB_LAUNCH_CHECK(ctx);
     }
     return PHB_OK;
@@ -578,20 +611,26 @@ int phb_box_fill(phb_ctx* ctx, int dim, double* dst, const uint32_t dst_shape[3]
     if (!ctx || dim < 1 || dim > 3 || !dst)
         return set_error(ctx, PHB_ERR_INVALID, "phb_box_fill: invalid argument");
     FillParams A;
-    A.dst = dst;
-    // right-aligned like phb_box_op: the last used direction is the fastest
+    A.dst    = dst;
+    size_t n = 1;
     for (int d = 0; d < 3; ++d)
     {
-        int const s = d - (3 - dim);
-        A.dn[d]     = s >= 0 ? int(dst_shape[s]) : 1;
-        A.dlo[d]    = s >= 0 ? int(dst_lo[s]) : 0;
-        A.ext[d]    = s >= 0 ? int(extent[s]) : 1;
+        A.dn[d]  = d < dim ? int(dst_shape[d]) : 1;
+        A.dlo[d] = d < dim ? int(dst_lo[d]) : 0;
+        A.ext[d] = d < dim ? int(extent[d]) : 1;
+        n *= size_t(A.ext[d]);
     }
-    A.value        = value;
-    size_t const n = size_t(A.ext[0]) * A.ext[1] * A.ext[2];
+    A.value = value;
     if (n == 0)
         return PHB_OK;
-    box_fill_kernel<<<unsigned((n + 255) / 256), 256, 0, ctx->stream>>>(A);
+    dim3 grid, block;
+    box_launch_dims(dim, A.ext, grid, block);
+    if (dim == 1)
+        box_fill_kernel<1><<<grid, block, 0, ctx->stream>>>(A);
+    else if (dim == 2)
+        box_fill_kernel<2><<<grid, block, 0, ctx->stream>>>(A);
+    else
+        box_fill_kernel<3><<<grid, block, 0, ctx->stream>>>(A);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
