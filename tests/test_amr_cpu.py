@@ -148,3 +148,18 @@ def test_refinement_boxes_are_validated(cpu_ops_factory):
     h2.levels.pop()
     with pytest.raises(ValueError):
         h2.add_level([Box([40], [79]), Box([70], [99])])  # overlapping patches
+
+
+def test_two_populations_on_a_refined_level(cpu_ops_factory):
+    """every population carries its own domain / level-ghost stores and moments; the totals are their sum"""
+    ops = cpu_ops_factory(1, 2)
+    h = make_hierarchy(ops, "1d_o2_td", pops=2)
+    h.advance(0.004)
+    p = h.levels[1].solver.patches[0]
+    assert len(p.pops) == 2 and all(ops.count(pop.domain) > 0 and ops.count(pop.level_ghost_old) > 0 for pop in p.pops)
+    g = 4
+    total = sum(ops.get_field(pop.rho_q) for pop in p.pops)
+    assert np.allclose(ops.get_field(p.Ne)[g:-g], total[g:-g], rtol=1e-13)
+    # heavier second population: mass density = sum m_i n_i
+    mass = sum(pop.mass * ops.get_field(pop.rho_n) for pop in p.pops)
+    assert np.allclose(ops.get_field(p.rho_m)[g:-g], mass[g:-g], rtol=1e-13)
