@@ -232,6 +232,20 @@ void prepare_deposit(const phb_layout* L, const phb_particles* P, size_t first, 
     A.sel.n = nsel;
     for (int b = 0; b < nsel; ++b)
         A.sel.b[b] = make_box(sel[b], DIM);
+    if (nsel == 0)
+    {
+        // "everything" = every cell whose (order+1)^d primal stencil fits the arrays (nodes -g .. n+g): order 1 touches
+        // the nodes c, c+1 -> the patch grown by g cells; orders 2 and 3 touch c-1 .. c+2 -> grown by g-1.  A particle
+        // left far outside by a move-two-cells error (reported at the next poll) is skipped instead of scattered out of
+        // bounds; everything the reference could deposit is still deposited.
+        int const grow = A.L.interp == 1 ? A.L.g : A.L.g - 1;
+        A.sel.n        = 1;
+        for (int d = 0; d < 3; ++d)
+        {
+            A.sel.b[0].lo[d] = d < DIM ? A.L.amr_lower[d] - grow : 0;
+            A.sel.b[0].hi[d] = d < DIM ? A.L.amr_lower[d] + A.L.ncells[d] - 1 + grow : 0;
+        }
+    }
     A.cell_start  = cell_start;
     A.nkeys       = 0;
     A.mover_list  = nullptr;

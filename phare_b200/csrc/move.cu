@@ -166,6 +166,12 @@ __global__ void __launch_bounds__(MOVE_BS, PHB_MOVE_MINB)
             bool ok = true;
             double bad_delta = 0, bad_vel = 0;
             move_particle<DIM, ORDER, EXACT, false>(P, icell, delta, v, charge, ok, bad_delta, bad_vel);
+            if (!ok)
+            {
+                // reported at the next poll; the offender stays as it was in the store and deposits nothing
+                report_move_error(P.err, ok, bad_delta, bad_vel, p);
+                continue;
+            }
             if constexpr (WRITE)
             {
 #pragma unroll
@@ -326,6 +332,11 @@ __global__ void __launch_bounds__(256)
     bool ok             = true;
     double bad_delta = 0, bad_vel = 0;
     move_particle<DIM, ORDER, EXACT, HAS_FIRST>(P, icell, delta, v, charge, ok, bad_delta, bad_vel);
+    if (!ok)
+    {
+        report_move_error(P.err, ok, bad_delta, bad_vel, i);
+        return;
+    }
     if constexpr (WRITE)
     {
 #pragma unroll

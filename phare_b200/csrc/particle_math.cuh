@@ -197,19 +197,12 @@ __device__ __forceinline__ void advance_position(const double* h, int* icell, do
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
     {
-        double t = __dadd_rn(delta[d], __dmul_rn(h[d], v[d]));
-        if (fabs(t) > 2)
+        double const t = __dadd_rn(delta[d], __dmul_rn(h[d], v[d]));
+        if (fabs(t) > 2 && ok) // the reference throws at the first offending direction
         {
-            if (ok) // the reference throws at the first offending direction
-            {
-                ok        = false;
-                bad_delta = t;
-                bad_vel   = v[d];
-            }
-            // the reference's sweep ends here with an exception; this one is reported at the next poll, so the
-            // particle is parked in its cell: everything that still runs on it (the gather of this push, a deposit,
-            // the re-binning) keeps indexing inside the arrays
-            t = 0.5;
+            ok        = false;
+            bad_delta = t;
+            bad_vel   = v[d];
         }
         int const s = int(floor(t));
         delta[d]    = t - double(s);

@@ -134,6 +134,12 @@ __device__ __forceinline__ void move_particle(const PushParams<DIM>& P, int (&ic
                                               double& bad_vel)
 {
     advance_position<DIM>(P.h, icell, delta, v, ok, bad_delta, bad_vel);
+    // The reference's sweep ends with an exception at the first particle that moves more than two cells; here the
+    // error is reported at the next poll and the sweep goes on, so the offender must not index anything: no gather
+    // (its cell may lie anywhere).  It is stored where the half step left it; the deposit and re-binning kernels only
+    // touch particles inside their selection boxes (by default the cells whose stencil fits the arrays), so they skip it.
+    if (!ok)
+        return;
 
     bool selected = true;
     if constexpr (HAS_FIRST)
