@@ -211,8 +211,9 @@ def grow_store(ops, patch, ipop, store):
 class Level:
     def __init__(self, number, geom, solver):
         self.number, self.geom, self.solver = number, geom, solver
-        self.before_coarse_time = self.after_coarse_time = None
-        self.old_time = 0.0
+        self.before_coarse_time = self.after_coarse_time = None  # beforePushCoarseTime_ / afterPushCoarseTime_
+        self.coarser_times = None  # (start, end) of the coarser level's current step (subcycleStart/EndTimes_[i-1])
+        self.old_time = 0.0        # SolverPPC::oldTime_[level]
 
 
 class Hierarchy:

@@ -163,3 +163,41 @@ def test_two_populations_on_a_refined_level(cpu_ops_factory):
     # heavier second population: mass density = sum m_i n_i
     mass = sum(pop.mass * ops.get_field(pop.rho_n) for pop in p.pops)
     assert np.allclose(ops.get_field(p.rho_m)[g:-g], mass[g:-g], rtol=1e-13)
+
+
+def test_particle_stores_grow_when_the_split_overflows_them(cpu_ops_factory):
+    """the device stores have a fixed capacity; a level created with stores that are too small re-allocates them (2x)
+    and retries the split: same result as with roomy stores, bit for bit"""
+    from phare_b200.amr import Hierarchy, refine_box
+    from phare_b200.boxes import Box
+    from phare_b200.setup import build
+    from phare_b200.messenger import LocalComm
+    from amr_util import SOLVER_KW
+    from solver_util import global_particles, B_init
+    cells, dx, interp, ppc = [64], [0.2], 1, 200
+    gparts = global_particles(cells, interp, dx, ppc, 7)
+
+    def particles_fn(i, L, pid):
+        return gparts[i]
+
+    def make(capacity_factor):
+        ops = cpu_ops_factory(1, interp)
+        root = build(ops, LocalComm(), cells, [1], interp, dx, [dict(name="p", mass=1.0)], B_init(cells, dx), particles_fn,
+                     SOLVER_KW)
+        h = Hierarchy(ops, root)
+        h.add_level([refine_box(Box([20], [43]))], capacity_factor=capacity_factor)
+        return ops, h
+
+    ops_a, small = make(0.1)
+    ops_b, roomy = make(1.6)
+    pa, pb = small.levels[1].solver.patches[0], roomy.levels[1].solver.patches[0]
+    n = ops_a.count(pa.pops[0].domain)
+    assert n == ops_b.count(pb.pops[0].domain) and n > int(0.1 * 2 * ppc * 24) + 4096   # did not fit at first
+    assert ops_a.capacity(pa.pops[0].domain) >= n and ops_a.capacity(pa.pops[0].spare) >= n
+    small.advance(0.004)
+    roomy.advance(0.004)
+    for attr in ("Ne", "rho_m"):
+        assert bit_equal(ops_a.get_field(getattr(pa, attr)), ops_b.get_field(getattr(pb, attr)))
+    for c in range(3):
+        assert bit_equal(ops_a.get_field(pa.E[c]), ops_b.get_field(pb.E[c]))
+        assert bit_equal(ops_a.get_field(pa.B[c]), ops_b.get_field(pb.B[c]))
