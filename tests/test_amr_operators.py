@@ -285,3 +285,78 @@ def test_toth_roe_3d_is_invariant_under_cyclic_permutation_of_the_axes(cpu_oracl
     Bp = _refine_B_3d(cpu_oracle, [T(coarse[2]), T(coarse[0]), T(coarse[1])], perm(n), list(perm(dxc)), perm(lo))
     for got, want in ((Bp[0], T(B[2])), (Bp[1], T(B[0])), (Bp[2], T(B[1]))):
         assert np.abs(got - want).max() < 1e-13 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("ndim", [1, 2, 3])
+def test_default_refiner_is_multilinear_interpolation(cpu_oracle, ndim):
+    """DefaultFieldRefiner against an independent numpy statement of what it is: linear interpolation, per direction, of
+    the coarse samples at the position of the fine node (primal: x_f = i/2; dual: x_f = (i + 1/2)/2 - 1/2 in coarse
+    index units).  Exact for fields that are linear in the coordinates, which also checks the weights / start indices
+    for negative AMR indices."""
+    rng = np.random.default_rng(40 + ndim)
+    g, n = 2, np.array([6, 5, 4][:ndim])
+    lo = np.array([-5, 2, -1][:ndim])
+    for qty in (abi.BX, abi.EX, abi.EZ, abi.BZ, abi.RHO):
+        prim = _prim(qty, ndim)
+        cshape = tuple(n + 2 * g + prim)
+        # a field linear in the coarse coordinates + a random part
+        axes = [np.arange(cshape[d]) + (lo[d] - g) + (0.0 if prim[d] else 0.5) for d in range(ndim)]
+        X = np.meshgrid(*axes, indexing="ij")
+        coef = rng.standard_normal(ndim)
+        linear = sum(c * x for c, x in zip(coef, X)) + 0.3
+        for coarse in (linear, rng.standard_normal(cshape)):
+            flo, fhi = 2 * lo, 2 * (lo + n - 1) + 1
+            fine = np.full(tuple(2 * n + 2 * g + prim), np.nan)
+            blo, bhi = flo - g + 1, fhi + g + prim - 1
+            cpu_oracle.field_refine(ndim, abi.REFINE_DEFAULT, qty, np.ascontiguousarray(coarse), lo - g, fine, flo - g, blo, bhi)
+            # numpy: position of every fine node of the box in coarse index units, then separable linear interpolation
+            want = np.ascontiguousarray(coarse)
+            for d in range(ndim):
+                fi = np.arange(blo[d], bhi[d] + 1)
+                xc = fi / 2.0 if prim[d] else (fi + 0.5) / 2.0 - 0.5
+                i0 = np.floor(xc).astype(int)
+                w1 = xc - i0
+                a = np.take(want, i0 - (lo[d] - g), axis=d)
+                b = np.take(want, i0 + 1 - (lo[d] - g), axis=d)
+                shape = [1] * ndim
+                shape[d] = len(fi)
+                want = a * (1 - w1).reshape(shape) + b * w1.reshape(shape)
+            got = fine[tuple(slice(int(blo[d] - (flo[d] - g)), int(bhi[d] - (flo[d] - g)) + 1) for d in range(ndim))]
+            assert np.abs(got - want).max() <= 1e-14 * max(1.0, np.abs(want).max()), (ndim, qty)
+            if coarse is linear:  # the refined field is the same linear function at the fine nodes
+                faxes = [(np.arange(blo[d], bhi[d] + 1) + (0.0 if prim[d] else 0.5)) / 2.0 for d in range(ndim)]
+                FX = np.meshgrid(*faxes, indexing="ij")
+                exact = sum(c * x for c, x in zip(coef, FX)) + 0.3
+                assert np.abs(got - exact).max() <= 1e-13 * max(1.0, np.abs(exact).max()), (ndim, qty)
+
+
+@pytest.mark.parametrize("ndim", [2, 3])
+def test_electric_refiner_reproduces_edge_averages(cpu_oracle, ndim):
+    """ElectricFieldRefiner in 2-D / 3-D (no usable upstream Python restatement): along its own (dual) direction a fine
+    edge takes the coarse edge it lies on; across a primal direction it takes the coarse edge it lies on (even index) or
+    the mean of the two neighbouring ones (odd index).  Independent numpy statement: piecewise constant along the dual
+    direction, linear interpolation at the half-way point along the primal ones."""
+    rng = np.random.default_rng(60 + ndim)
+    g, n = 2, np.array([6, 5, 4][:ndim])
+    lo = np.array([-3, 4, 1][:ndim])
+    for c in range(3):
+        qty = abi.EX + c
+        prim = _prim(qty, ndim)
+        coarse = rng.standard_normal(tuple(n + 2 * g + prim))
+        flo, fhi = 2 * lo, 2 * (lo + n - 1) + 1
+        fine = np.full(tuple(2 * n + 2 * g + prim), np.nan)
+        blo, bhi = flo - g + 1, fhi + g + prim - 1
+        cpu_oracle.field_refine(ndim, abi.REFINE_ELECTRIC, qty, coarse, lo - g, fine, flo - g, blo, bhi)
+        want = coarse
+        for d in range(ndim):
+            fi = np.arange(blo[d], bhi[d] + 1)
+            ci = fi // 2 - (lo[d] - g)
+            a = np.take(want, ci, axis=d)
+            if prim[d]:
+                b = np.take(want, np.minimum(ci + 1, want.shape[d] - 1), axis=d)
+                odd = (fi % 2 != 0).reshape([len(fi) if k == d else 1 for k in range(ndim)])
+                want = np.where(odd, 0.5 * (a + b), a)
+            else:
+                want = a
+        got = fine[tuple(slice(int(blo[d] - (flo[d] - g)), int(bhi[d] - (flo[d] - g)) + 1) for d in range(ndim))]
+        assert np.abs(got - want).max() <= 4e-16 * max(1.0, np.abs(want).max()), (ndim, c)
