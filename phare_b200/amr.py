@@ -59,14 +59,17 @@ def minus_all(boxes, removed):
 
 class RefinedLevelMessenger(HybridMessenger):
     """Messenger of a level > 0: same-level exchanges as on the root level (non periodic), plus everything that comes
-    from the next coarser level: level-ghost field nodes (refine operators) and level-ghost particles (splitting)."""
+    from the next coarser level: level-ghost field nodes (refine operators) and level-ghost particles (splitting).
+    Every rank knows the geometry of every patch of both levels; a patch and its data live on its owner.  The
+    coarse -> fine transfers are one-directional (the owner of a coarse patch never waits on the fine level), so this
+    messenger always uses two-sided point-to-point messages, never the peer-memory arena of the root level."""
 
     REFINE_OP = {abi.BX: abi.REFINE_MAGNETIC, abi.EX: abi.REFINE_ELECTRIC, abi.JX: abi.REFINE_ELECTRIC}
 
     def __init__(self, geom, ops, comm, coarse_solver):
-        super().__init__(geom, ops, comm)
+        super().__init__(geom, ops, comm, peer_halo=False)
         self.coarse = coarse_solver
-        g, dim = geom.g, geom.dim
+        g = geom.g
         level_boxes = [p.box for p in geom.patches]
         self._nan, self._scratch, self._lg_excluded, self.lg_particle_boxes = {}, {}, {}, {}
         for p in geom.patches:
@@ -76,20 +79,30 @@ class RefinedLevelMessenger(HybridMessenger):
             self.lg_particle_boxes[p.id] = minus_all([p.box.grow(geom.pg)], level_boxes)
             for qty in range(abi.BX, abi.JZ + 1):
                 gfb = p.ghost_field_box(qty, g)
+                # coarse data under the ghost box, one node more for the two-point refine stencils
+                cbox = Box(gfb.lo // RATIO - 1, gfb.hi // RATIO + 1)
+                if p.owner != self.me:
+                    self._scratch[(p.id, qty)] = (None, cbox)
+                    continue
                 # setNaNsOnFieldGhosts: ghost field box minus the field boxes of the level's patches
                 nan = minus_all([gfb], [q.interior_field_box(qty) for q in geom.patches])
                 self._nan[(p.id, qty)] = [(b.lo - gfb.lo, b.shape()) for b in nan]
-                # coarse data under the ghost box, one node more for the two-point refine stencils
-                cbox = Box(gfb.lo // RATIO - 1, gfb.hi // RATIO + 1)
                 self._scratch[(p.id, qty)] = (ops.array(cbox.shape()), cbox)
         self._gather, self._nan_ops = {}, {}
+        self._fine_patches = []
+
+    def attach(self, fine_patches):
+        """the Patch objects (data) of the fine patches this rank owns"""
+        self._fine_patches = fine_patches
 
     # ---- coarse level -> scratch arrays
-    def _gather_plan(self, name, qty0):
+    def _gather_phase(self, name, qty0):
         """copies of the coarse level's `name` arrays into the scratch of every fine patch (what the RefineSchedule does
-        before it calls the refine operator); a coarse node is taken from the first patch that owns it"""
+        before it calls the refine operator); a coarse node is taken from the first patch that owns it.  Compiled once
+        per field into an exchange phase: local box copies, plus one packed message per (coarse owner, fine owner)."""
         if name not in self._gather:
-            cs, entries = self.coarse, []
+            cs, me = self.coarse, self.me
+            local, send_items, recv_items = [], {}, {}
             arrays = cs._by_id(name)
             for p in self.geom.patches:
                 for c in range(3):
@@ -107,36 +120,37 @@ class RefinedLevelMessenger(HybridMessenger):
                                     if ov is None:
                                         rest.append(piece)
                                         continue
-                                    entries.append((scratch, ov.lo - cbox.lo, arrays[q.id][c], q.local(ov.lo - t, cs.geom.g),
-                                                    ov.shape(), 0))
+                                    dlo, slo, ext = ov.lo - cbox.lo, q.local(ov.lo - t, cs.geom.g), ov.shape()
+                                    if p.owner == me and q.owner == me:
+                                        local.append((scratch, dlo, arrays[q.id][c], slo, ext, 0))
+                                    elif p.owner == me:
+                                        recv_items.setdefault(q.owner, []).append((scratch, dlo, ext))
+                                    elif q.owner == me:
+                                        send_items.setdefault(p.owner, []).append((arrays[q.id][c], slo, ext))
                                     rest += piece.minus(ov)
                                 todo = rest
                     if todo:
                         raise RuntimeError(f"refined patch {p.box} is not nested in the coarser level (uncovered {todo})")
-            self._gather[name] = self.ops.compile_box_ops(entries)
+            self._gather[name] = self._finish(local, send_items, recv_items, 0)
         return self._gather[name]
 
     def _refine(self, name, qty0, vecs, op, whole_ghost_box=False):
         ops, g = self.ops, self.geom.g
-        ops.run_box_ops(self._gather_plan(name, qty0))
-        for p in self.geom.patches:
+        self._run(self._gather_phase(name, qty0), ("gather", name))
+        for patch in self._fine_patches:
+            p = patch.geom
             for c in range(3):
                 qty = qty0 + c
                 scratch, cbox = self._scratch[(p.id, qty)]
                 gfb = p.ghost_field_box(qty, g)
                 ops.field_refine(op, qty, scratch, cbox.lo, vecs[p.id][c], gfb.lo, gfb.lo, gfb.hi)
-        if qty0 == abi.BX:
-            # MagneticRefinePatchStrategy::postprocessRefine on the cells that were filled from the coarser level: the
-            # whole ghost box at level creation, otherwise the ghost box minus the level's patches (one launch per
-            # component: the kernel skips the faces of the excluded cell boxes)
-            layouts = {p.geom.id: p.layout for p in self._fine_patches}
-            for p in self.geom.patches:
+            if qty0 == abi.BX:
+                # MagneticRefinePatchStrategy::postprocessRefine on the cells that were filled from the coarser level:
+                # the whole ghost box at level creation, otherwise the ghost box minus the level's patches (one launch
+                # per component: the kernel skips the faces of the excluded cell boxes)
                 cells = p.box.grow(g)
-                ops.magnetic_postprocess(layouts[p.id], vecs[p.id], cells.lo, cells.hi,
+                ops.magnetic_postprocess(patch.layout, vecs[p.id], cells.lo, cells.hi,
                                          () if whole_ghost_box else self._lg_excluded[p.id])
-
-    def attach(self, fine_patches):
-        self._fine_patches = fine_patches
 
     # ---- HybridMessenger interface
     def fill_ghosts(self, name, qty0, vecs):
@@ -146,46 +160,73 @@ class RefinedLevelMessenger(HybridMessenger):
         the model's B are those of its last own fill (the corrector) until the next one."""
         if name not in self._nan_ops:  # every NaN box of every patch and component in one batched launch (K8, op 3)
             self._nan_ops[name] = self.ops.compile_box_ops(
-                [(vecs[p.id][c], lo, vecs[p.id][c], lo, ext, 3) for p in self.geom.patches for c in range(3)
-                 for lo, ext in self._nan[(p.id, qty0 + c)]])
+                [(vecs[p.geom.id][c], lo, vecs[p.geom.id][c], lo, ext, 3) for p in self._fine_patches for c in range(3)
+                 for lo, ext in self._nan[(p.geom.id, qty0 + c)]])
         self.ops.run_box_ops(self._nan_ops[name])
-        super().fill_ghosts(name, qty0, vecs)
+        HybridMessenger.fill_ghosts(self, name, qty0, vecs)
         self._refine(name, qty0, vecs, self.REFINE_OP[qty0])
 
     def fill_patch_ghosts(self, name, qty0, vecs):
         """same-level part only (patchGhostRefluxedSchedules, refiner.hpp PatchGhostField)"""
-        super().fill_ghosts(name, qty0, vecs)
+        HybridMessenger.fill_ghosts(self, name, qty0, vecs)
 
     def init_fields(self, solver):
         """initLevel (:335-345): B through MagneticFieldInitRefiner (+ post-process) over the whole ghost box, E through
         ElectricFieldRefiner (which only writes NaN nodes: a fresh FieldData is all NaN, field_data.hpp:41-59)"""
-        ops, g = self.ops, self.geom.g
+        ops = self.ops
         self._refine("B", abi.BX, solver._by_id("B"), abi.REFINE_MAGNETIC_INIT, whole_ghost_box=True)
         for p in solver.patches:
             for c in range(3):
                 ops.box_fill(p.E[c], [0] * self.geom.dim, p.E[c].shape, float("nan"))
         self._refine("E", abi.EX, solver._by_id("E"), abi.REFINE_ELECTRIC)
 
-    def split_from_coarser(self, ipop, nref, boxes_of, store_of):
+    def split_from_coarser(self, ipop, nref, boxes_of, attr):
         """ParticlesRefineOperator::refine_: the coarser level's domain particles, moved to this level's index space and
-        split, land in store_of(patch) when their cell lies in one of boxes_of(patch)"""
-        ops = self.ops
-        for p in self._fine_patches:
-            boxes = [abi.make_box(b.lo, b.hi) for b in boxes_of(p)]
+        split, land in the store `attr` of the population of a fine patch when their cell lies in one of
+        boxes_of(patch geometry).  Every rank splits the particles of the coarse patches it owns; children for a fine
+        patch owned elsewhere are staged and shipped like migrating particles."""
+        ops, me = self.ops, self.me
+        mine = {p.geom.id: p for p in self._fine_patches}
+        remote = {}
+
+        def try_split(src, n, boxes, get, grow):
+            while True:
+                if ops.split(nref, src, 0, n, boxes, get()) is not None:
+                    return
+                grow()  # too small: nothing was appended
+
+        for pg in self.geom.patches:
+            fine_boxes = boxes_of(pg)
+            boxes = [abi.make_box(b.lo, b.hi) for b in fine_boxes]
             if not boxes:
                 continue
-            reach = [coarsen_box(b.grow(RATIO * 2)) for b in boxes_of(p)]  # split stencil: <= 2 fine cells
+            reach = [coarsen_box(b.grow(RATIO * 2)) for b in fine_boxes]  # split stencil: <= 2 fine cells
             for q in self.coarse.patches:
                 src = q.pops[ipop].domain
                 n = ops.count(src)
                 if n == 0 or not any(r * q.geom.box is not None for r in reach):
                     continue  # no particle of this coarse patch can land in the destination boxes
-                while True:
-                    store = store_of(p)
-                    got = ops.split(nref, src, 0, n, boxes, store)
-                    if got is not None:
-                        break
-                    grow_store(ops, p, ipop, store)  # too small: nothing was appended
+                if pg.owner == me:
+                    patch = mine[pg.id]
+                    try_split(src, n, boxes, lambda: getattr(patch.pops[ipop], attr),
+                              lambda: grow_store(ops, patch, ipop, getattr(patch.pops[ipop], attr)))
+                else:
+                    key = (pg.owner, pg.id)
+                    if key not in remote:
+                        remote[key] = ops.staging_particles(q.layout, 4096)
+
+                    def grow_remote(key=key, q=q):
+                        remote[key] = ops.grow_particles(q.layout, remote[key], 2 * ops.capacity(remote[key]) + 4096)
+                    try_split(src, n, boxes, lambda key=key: remote[key], grow_remote)
+        if self.comm.size > 1:
+            def ensure(pid, needed):
+                patch = mine[pid]
+                while ops.capacity(getattr(patch.pops[ipop], attr)) < needed:
+                    grow_store(ops, patch, ipop, getattr(patch.pops[ipop], attr))
+                return getattr(patch.pops[ipop], attr)
+            self._exchange_particles({pid: p.layout for pid, p in mine.items()}, remote,
+                                     {pid: getattr(p.pops[ipop], attr) for pid, p in mine.items()},
+                                     {pid: 0 for pid in mine}, ensure)
 
 
 def grow_store(ops, patch, ipop, store):
@@ -209,21 +250,34 @@ def grow_store(ops, patch, ipop, store):
 
 
 class Level:
-    def __init__(self, number, geom, solver):
+    def __init__(self, number, geom, solver, interp, dx, origin, pops):
         self.number, self.geom, self.solver = number, geom, solver
+        # what every rank must know about the level even when it owns none of its patches
+        self.interp, self.dx, self.origin, self.pops = interp, dx, origin, pops  # origin: position of AMR index 0
         self.before_coarse_time = self.after_coarse_time = None  # beforePushCoarseTime_ / afterPushCoarseTime_
         self.coarser_times = None  # (start, end) of the coarser level's current step (subcycleStart/EndTimes_[i-1])
         self.old_time = 0.0        # SolverPPC::oldTime_[level]
+        self.sync_phase = None     # compiled fine -> coarse exchange of the synchronisation (ranks > 1)
 
 
 class Hierarchy:
     """The patch hierarchy + MultiPhysicsIntegrator: levels[0] is the periodic root level (an initialised SolverPPC),
-    levels[i > 0] are refined levels built by add_level()."""
+    levels[i > 0] are refined levels built by add_level().  With several ranks (one per GPU) every patch of every level
+    has an owner: a refined patch goes to the owner of the coarser patch under its lower corner; the exchanges between
+    a level and the next coarser one (gather for the refine operators, split particles, coarsened data) cross ranks
+    as packed point-to-point messages, like the same-level phases."""
 
     def __init__(self, ops, root_solver, nref=None):
         self.ops = ops
-        self.levels = [Level(0, root_solver.geom, root_solver)]
-        self.nref = nref or DEFAULT_NREF[root_solver.geom.dim]
+        self.comm = root_solver.comm
+        if not root_solver.patches:
+            raise RuntimeError("every rank must own at least one patch of the root level")
+        L0 = root_solver.patches[0].layout
+        dim = root_solver.geom.dim
+        origin = [L0.origin[d] - L0.amr_lower[d] * L0.dx[d] for d in range(dim)]
+        pops = [(pop.name, pop.mass) for pop in root_solver.patches[0].pops]
+        self.levels = [Level(0, root_solver.geom, root_solver, L0.interp, [L0.dx[d] for d in range(dim)], origin, pops)]
+        self.nref = nref or DEFAULT_NREF[dim]
         self.time = 0.0
         self._ensure_flux_sum(root_solver)
 
@@ -236,15 +290,22 @@ class Hierarchy:
     def add_level(self, fine_boxes, capacity_factor=1.6):
         """creates level len(levels) from cell boxes given in ITS OWN index space and initialises it from the current
         finest level (MultiPhysicsIntegrator::initializeLevelData -> HybridLevelInitializer::initialize, level > 0)"""
-        ops = self.ops
+        ops, me = self.ops, self.comm.rank
         coarse = self.levels[-1]
         cs = coarse.solver
         ilvl = len(self.levels)
-        interp = cs.patches[0].layout.interp
-        dim = cs.geom.dim
+        interp, dim = coarse.interp, cs.geom.dim
         fine_domain = tuple(s * RATIO for s in coarse.geom.domain_shape)
-        dx = [cs.patches[0].layout.dx[d] / RATIO for d in range(dim)]
-        patches_g = [PatchGeom(i, b if isinstance(b, Box) else Box(*b), 0) for i, b in enumerate(fine_boxes)]
+        dx = [coarse.dx[d] / RATIO for d in range(dim)]
+        boxes = [b if isinstance(b, Box) else Box(*b) for b in fine_boxes]
+
+        def owner_of(box):  # the owner of the coarser patch under the lower corner
+            corner = Box(box.lo // RATIO, box.lo // RATIO)
+            for q in coarse.geom.patches:
+                if q.box.contains(corner):
+                    return q.owner
+            raise ValueError(f"refinement box {box} does not start inside the coarser level")
+        patches_g = [PatchGeom(i, b, owner_of(b)) for i, b in enumerate(boxes)]
         geom = LevelGeom(fine_domain, patches_g, interp, periodic=False)
         # nesting: the level with its field ghost layer and the split stencil stays inside the root domain
         margin = geom.g + 2 * RATIO
@@ -257,20 +318,22 @@ class Hierarchy:
             for b in patches_g:
                 if a.id < b.id and a.box * b.box is not None:
                     raise ValueError("refinement boxes overlap")
-        msg = RefinedLevelMessenger(geom, ops, LocalComm(), cs)
-        # expected number of particles: nref children per coarse particle of the covered coarse cells
-        npop = len(cs.patches[0].pops)
+        msg = RefinedLevelMessenger(geom, ops, self.comm, cs)
+        # expected number of particles: nref children per coarse particle of the covered coarse cells (estimated from the
+        # coarse patches of this rank; a store that turns out too small is re-allocated)
+        npop = len(coarse.pops)
         ncoarse_cells = sum(int(np.prod([p.layout.ncells[d] for d in range(dim)])) for p in cs.patches)
         per_cell = [sum(ops.count(p.pops[i].domain) for p in cs.patches) / max(ncoarse_cells, 1) for i in range(npop)]
         patches = []
         for pg in patches_g:
+            if pg.owner != me:
+                continue
             ncells = [int(x) for x in pg.box.shape()]
-            origin = [cs.patches[0].layout.origin[d] - cs.patches[0].layout.amr_lower[d] * cs.patches[0].layout.dx[d]
-                      + pg.box.lo[d] * dx[d] for d in range(dim)]
+            origin = [coarse.origin[d] + pg.box.lo[d] * dx[d] for d in range(dim)]
             L = abi.make_layout(dim, interp, ncells, dx, amr_lower=list(pg.box.lo), origin=origin, level=ilvl)
             ccells = int(np.prod(ncells)) / RATIO ** dim
-            spec = [dict(name=cs.patches[0].pops[i].name, mass=cs.patches[0].pops[i].mass,
-                         n=int(self.nref * per_cell[i] * ccells)) for i in range(npop)]
+            spec = [dict(name=coarse.pops[i][0], mass=coarse.pops[i][1], n=int(self.nref * per_cell[i] * ccells))
+                    for i in range(npop)]
             patch = Patch(ops, pg, L, spec, capacity_factor=capacity_factor)
             # nonLevelGhostBox: the domain plus the part of the particle ghost layer that belongs to a neighbour patch
             patch.non_level_ghost = [patch.domain_box] + [
@@ -281,27 +344,28 @@ class Hierarchy:
                 pop.set_level_ghosts(ops, int(capacity_factor * self.nref * per_cell[i] * lg_cells) + 4096)
             patches.append(patch)
         msg.attach(patches)
-        solver = SolverPPC(ops, patches, geom, LocalComm(), resistivity=cs.eta, hyper_resistivity=cs.nu,
+        solver = SolverPPC(ops, patches, geom, self.comm, resistivity=cs.eta, hyper_resistivity=cs.nu,
                            hyper_mode=cs.hyper_mode, Te=cs.Te, fused=cs.updater.fused,
-                           sort_with_deposit=cs.updater.sort_with_deposit, messenger=msg)
+                           sort_with_deposit=cs.updater.sort_with_deposit, messenger=msg, npop=npop)
         self._ensure_flux_sum(solver)
-        level = Level(ilvl, geom, solver)
+        level = Level(ilvl, geom, solver, interp, dx, coarse.origin, coarse.pops)
         self.levels.append(level)
         self._initialize_level(level)
         return level
 
     def _initialize_level(self, level):
         ops, s, msg = self.ops, level.solver, level.solver.messenger
-        npop = len(s.patches[0].pops)
+        npop = s.npop
         msg.init_fields(s)
         for i in range(npop):
             # domainParticlesRefiners_ (interior) and lvlGhostPartOldRefiners_ (coarseBoundaryOld)
-            msg.split_from_coarser(i, self.nref, lambda p: [p.geom.box], lambda p, i=i: p.pops[i].domain)
-            msg.split_from_coarser(i, self.nref, lambda p: msg.lg_particle_boxes[p.geom.id],
-                                   lambda p, i=i: p.pops[i].level_ghost_old)
+            msg.split_from_coarser(i, self.nref, lambda pg: [pg.box], "domain")
+            msg.split_from_coarser(i, self.nref, lambda pg: msg.lg_particle_boxes[pg.id], "level_ghost_old")
         for p in s.patches:
             for i, pop in enumerate(p.pops):
                 self._copy_store(p, i, "level_ghost_old", "level_ghost")  # copyLevelGhostOldToPushable_
+                while ops.capacity(pop.spare) < ops.count(pop.domain):     # the split may have re-allocated `domain`
+                    pop.spare = ops.particles(ops.capacity(pop.domain))
                 counts = ops.bin(p.layout, pop.domain, pop.spare, p.domain_box, p.non_level_ghost, pop.cell_start)
                 pop.domain, pop.spare = pop.spare, pop.domain
                 pop.n_sorted = counts[0]
@@ -347,7 +411,7 @@ class Hierarchy:
         s = lvl.solver
         if first:
             if il > 0:
-                self._first_step(lvl, self.levels[il - 1])
+                self._first_step(lvl)
             s.reset_flux_sum()
         lvl.old_time = t0  # SolverPPC::prepareStep: oldTime_[level] (Bold <- B happens inside advance_level)
         if il > 0:
@@ -371,16 +435,15 @@ class Hierarchy:
                 t = tn
             self._synchronize(self.levels[il + 1], lvl, t1)
 
-    def _first_step(self, lvl, coarser):
+    def _first_step(self, lvl):
         """firstStep: levelGhostParticlesNew = split of the coarser level's particles, which are already at the end of its
         step; the times bracket the interpolation of the level-ghost moments"""
         ops, s, msg = self.ops, lvl.solver, lvl.solver.messenger
         for p in s.patches:
             for pop in p.pops:
                 ops.set_count(pop.level_ghost_new, 0)
-        for i in range(len(s.patches[0].pops)):
-            msg.split_from_coarser(i, self.nref, lambda p: msg.lg_particle_boxes[p.geom.id],
-                                   lambda p, i=i: p.pops[i].level_ghost_new)
+        for i in range(s.npop):
+            msg.split_from_coarser(i, self.nref, lambda pg: msg.lg_particle_boxes[pg.id], "level_ghost_new")
         lvl.before_coarse_time, lvl.after_coarse_time = lvl.coarser_times
 
     def _last_step(self, lvl):
@@ -392,24 +455,52 @@ class Hierarchy:
                 ops.set_count(pop.level_ghost_new, 0)
                 self._copy_store(p, i, "level_ghost_old", "level_ghost")
 
+    # what standardLevelSynchronization moves from a level to the next coarser one:
+    # (attribute of the fine patch, component, attribute of the coarse patch, first quantity, coarsener)
+    SYNC_ITEMS = ([("E", c, "E", abi.EX, abi.COARSEN_ELECTRIC) for c in range(3)]            # synchronize(): electric
+                  + [("Ne", None, "Ne", abi.RHO, abi.COARSEN_MOMENTS)]                       # ion charge density
+                  + [("Vi", c, "Vi", abi.VX, abi.COARSEN_MOMENTS) for c in range(3)]         # ion bulk velocity
+                  + [("fluxSumE", c, "Eavg", abi.EX, abi.COARSEN_ELECTRIC) for c in range(3)])  # reflux()
+
     def _synchronize(self, fine, coarse, sync_time):
         """standardLevelSynchronization for one (fine, coarse) pair"""
-        ops, fs, cs = self.ops, fine.solver, coarse.solver
+        ops, fs, cs, me = self.ops, fine.solver, coarse.solver, self.comm.rank
         gf, gc = fine.geom.g, coarse.geom.g
+        fine_patch = {p.geom.id: p for p in fs.patches}
+        coarse_patch = {q.geom.id: q for q in cs.patches}
+        arr = lambda patch, attr, c: getattr(patch, attr) if c is None else getattr(patch, attr)[c]
         # synchronize(): E (electric coarsener), ion charge density and bulk velocity (injection);
-        # reflux(): fluxSumE of the fine level onto Eavg of the coarse level
-        for p in fs.patches:
-            for q in cs.patches:
-                cells = coarsen_box(p.geom.box) * q.geom.box
-                if cells is None:
+        # reflux(): fluxSumE of the fine level onto Eavg of the coarse level.
+        # A fine patch coarsens onto the coarse patch directly when both live here, else into a staging array that is
+        # shipped to the owner of the coarse patch (one packed message per pair of ranks, compiled once).
+        staged, send_items, recv_items = [], {}, {}
+        for pg in fine.geom.patches:
+            for qg in coarse.geom.patches:
+                cells = coarsen_box(pg.box) * qg.box
+                if cells is None or (pg.owner != me and qg.owner != me):
                     continue
-                items = [(p.E[c], q.E[c], abi.EX + c, abi.COARSEN_ELECTRIC) for c in range(3)]
-                items += [(p.Ne, q.Ne, abi.RHO, abi.COARSEN_MOMENTS)]
-                items += [(p.Vi[c], q.Vi[c], abi.VX + c, abi.COARSEN_MOMENTS) for c in range(3)]
-                items += [(p.fluxSumE[c], q.Eavg[c], abi.EX + c, abi.COARSEN_ELECTRIC) for c in range(3)]
-                for fa, ca, qty, op in items:
+                for k, (fattr, c, cattr, qty0, op) in enumerate(self.SYNC_ITEMS):
+                    qty = qty0 + (c or 0)
                     fb = field_box(cells, qty)
-                    ops.field_coarsen(op, qty, fa, p.geom.box.lo - gf, ca, q.geom.box.lo - gc, fb.lo, fb.hi)
+                    if pg.owner == me and qg.owner == me:
+                        ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), pg.box.lo - gf,
+                                          arr(coarse_patch[qg.id], cattr, c), qg.box.lo - gc, fb.lo, fb.hi)
+                    elif pg.owner == me:
+                        if fine.sync_phase is None:
+                            stage = ops.array(fb.shape())
+                            send_items.setdefault(qg.owner, []).append((stage, [0] * fb.dim, fb.shape()))
+                        else:
+                            stage = fine.sync_phase["stages"][len(staged)]
+                        staged.append(stage)
+                        ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), pg.box.lo - gf, stage, fb.lo, fb.lo, fb.hi)
+                    elif fine.sync_phase is None:
+                        recv_items.setdefault(pg.owner, []).append(
+                            (arr(coarse_patch[qg.id], cattr, c), fb.lo - (qg.box.lo - gc), fb.shape()))
+        if self.comm.size > 1:
+            if fine.sync_phase is None:
+                fine.sync_phase = fs.messenger._finish([], send_items, recv_items, 0)
+                fine.sync_phase["stages"] = staged
+            fs.messenger._run(fine.sync_phase, ("sync", fine.number))
         # patchGhostRefluxedSchedules: the patch ghosts of Eavg agree again with the refluxed interiors
         if isinstance(cs.messenger, RefinedLevelMessenger):
             cs.messenger.fill_patch_ghosts("Eavg", abi.EX, cs._by_id("Eavg"))
@@ -425,11 +516,11 @@ class Hierarchy:
 
 
 def build_hierarchy(ops, domain_cells, patch_grid, interp, dx, pops, B_fn, particles_fn, refinement_boxes=(),
-                    solver_kw=None, nref=None):
+                    solver_kw=None, nref=None, comm=None):
     """root level as phare_b200.setup.build, then one refined level per entry of refinement_boxes (a list, per level,
     of (lower, upper) cell boxes in the index space of the level BELOW, as in pyphare's `refinement_boxes`)"""
     from .setup import build
-    root = build(ops, LocalComm(), domain_cells, patch_grid, interp, dx, pops, B_fn, particles_fn, solver_kw)
+    root = build(ops, comm or LocalComm(), domain_cells, patch_grid, interp, dx, pops, B_fn, particles_fn, solver_kw)
     h = Hierarchy(ops, root, nref)
     for boxes in refinement_boxes:
         h.add_level([refine_box(Box(lo, hi)) for lo, hi in boxes])

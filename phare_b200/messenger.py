@@ -300,7 +300,7 @@ class HybridMessenger:
     """Executes the plans of a LevelGeom on the patches owned by this rank.
     `ops` is the compute back end (phare_b200.solver.GpuOps in production)."""
 
-    def __init__(self, geom, ops, comm):
+    def __init__(self, geom, ops, comm, peer_halo=True):
         self.geom, self.ops, self.comm = geom, ops, comm
         self.me = comm.rank
         self._plans = {}
@@ -309,7 +309,7 @@ class HybridMessenger:
         # fixed-size field phases go through NVLink peer memory when every rank drives a GPU of the same node
         self.arena = None
         import os
-        if comm.size > 1 and hasattr(ops, "ctx") and os.environ.get("PHB_PEER_HALO", "1") != "0":
+        if peer_halo and comm.size > 1 and hasattr(ops, "ctx") and os.environ.get("PHB_PEER_HALO", "1") != "0":
             arena = PeerArena(ops, comm)
             if arena.ok:
                 self.arena = arena
@@ -384,7 +384,7 @@ class HybridMessenger:
         for pid, lst in arrays.items():
             for a, s in zip(lst, scratch[pid]):
                 ops.copy(s, a)
-        n = len(next(iter(arrays.values())))
+        n = len(next(iter(arrays.values()))) if arrays else 0  # a rank may own no patch of a refined level
         key = ("sum", name)
         if key not in self._compiled:
             # destination = arrays, source = scratch copies (local) / packed from scratch (remote)
@@ -402,7 +402,7 @@ class HybridMessenger:
 
     def max_borders(self, name, arrays):
         """fillIonBorders: a = max(a, neighbour) on the ghost-box overlaps"""
-        n = len(next(iter(arrays.values())))
+        n = len(next(iter(arrays.values()))) if arrays else 0
         self._run(self._compile(("max", name), "border", [abi.RHO] * n, arrays, 2), ("max", name))
 
     def _finish(self, local, send_items, recv_items, op):
@@ -459,7 +459,7 @@ class HybridMessenger:
         phase["post"] = ops.compile_box_ops(unpack)
         return phase
 
-    def migrate_particles(self, layouts, patch_ghost, domain):
+    def migrate_particles(self, layouts, patch_ghost, domain, ensure=None):
         """fillIonGhostParticles for one population.
         patch_ghost: {pid: (store, first, last)} the new patch-ghost particles of my patches;
         domain: {pid: store} destination stores of my patches.  Returns the number received per patch."""
@@ -493,10 +493,12 @@ class HybridMessenger:
                 if d.owner == me:
                     received[d.id] += c
         if self.comm.size > 1:
-            self._exchange_particles(layouts, remote, domain, received)
+            self._exchange_particles(layouts, remote, domain, received, ensure)
         return received
 
-    def _exchange_particles(self, layouts, remote, domain, received):
+    def _exchange_particles(self, layouts, remote, domain, received, ensure=None):
+        """remote: {(owner rank, patch id): staging store} -> appended to domain[patch id] on the owner.
+        ensure(pid, needed) -> store: lets the caller re-allocate a destination store that is too small"""
         ops, comm, geom = self.ops, self.comm, self.geom
         # every rank announces, per destination patch, how many particles it ships
         npatch = len(geom.patches)
@@ -504,7 +506,7 @@ class HybridMessenger:
         for (owner, pid), st in remote.items():
             counts[owner][pid] = ops.count(st)
         incoming = comm.alltoall_counts(counts)  # incoming[src rank][pid]
-        any_layout = next(iter(layouts.values()))
+        any_layout = next(iter(layouts.values()), None)  # only carries dim / interp, which the back end knows
         sends, recvs, recv_meta = {}, {}, {}
         for peer in range(comm.size):
             if peer == self.me:
@@ -520,6 +522,8 @@ class HybridMessenger:
         for peer, inc in recv_meta.items():
             off = 0
             for pid, n in inc:
+                if ensure is not None:
+                    domain[pid] = ensure(pid, ops.count(domain[pid]) + n)
                 ops.unpack_particles(layouts[pid], recvs[peer], off, n, sum(m for _, m in inc), domain[pid])
                 received[pid] += n
                 off += n

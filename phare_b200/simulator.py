@@ -11,7 +11,7 @@ Mirrors (file:line relative to the PHARE tree):
   DataWrangler / PatchLevel                  src/python3/data_wrangler.hpp, patch_level.hpp (getters used by pyphare.data.wrangler)
 
 Scope: periodic boundaries, HybridModel; one level, or a STATIC hierarchy given by `refinement_boxes` (phare_b200.amr:
-ratio 2, sub-cycling, refluxing; one rank).  Tagging-driven refinement (regridding) raises NotImplementedError
+ratio 2, sub-cycling, refluxing; patches of every level dealt to the ranks).  Tagging-driven refinement (regridding) raises NotImplementedError
 (SURVEY §8f-2).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
 tests replace.
 """
@@ -274,8 +274,6 @@ class Simulator:
         self.solver.initialize()
         self.amr = None
         if h.refinement_boxes:
-            if comm.size > 1:
-                raise NotImplementedError("refined levels are driven on one rank only")
             from .amr import Hierarchy as PatchHierarchy, refine_box
             from .boxes import Box
             self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)

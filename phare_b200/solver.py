@@ -508,9 +508,12 @@ class SolverPPC:
     """SolverPPC<HybridModel, AMR_Types> (solver_ppc.hpp:31-186) for one periodic level."""
 
     def __init__(self, ops, patches, geom, comm=None, resistivity=0.0, hyper_resistivity=1e-4, hyper_mode=0, Te=0.12,
-                 pusher_name="modified_boris", fused="auto", sort_with_deposit=True, messenger=None):
+                 pusher_name="modified_boris", fused="auto", sort_with_deposit=True, messenger=None, npop=None):
         self.ops, self.patches, self.geom = ops, patches, geom
         self.comm = comm or LocalComm()
+        # number of populations: given explicitly when this rank may own no patch of the level (refined levels), because
+        # the per-population exchange phases are collective
+        self.npop = npop if npop is not None else (len(patches[0].pops) if patches else 0)
         # a refined level brings its own messenger (phare_b200.amr.RefinedLevelMessenger: level ghosts from the coarser level)
         self.messenger = messenger or HybridMessenger(geom, ops, self.comm)
         # timeInterpCoef_ of fillIonPopMomentGhosts for the sweep being run; None on the root level (no level ghosts)
@@ -554,7 +557,7 @@ class SolverPPC:
         ops, msg = self.ops, self.messenger
         for p in self.patches:
             self.updater.update_moments(p, p.Eavg, p.Bavg, dt, mode)
-        npop = len(self.patches[0].pops) if self.patches else 0
+        npop = self.npop
         for i in range(npop):
             # fillFluxBorders + fillDensityBorders
             msg.sum_borders(f"pop{i}", {p.geom.id: p.pops[i].moments() for p in self.patches},
@@ -574,7 +577,7 @@ class SolverPPC:
         ops, msg = self.ops, self.messenger
         for p in self.patches:
             self.updater.maintain_arrays(p)
-        npop = len(self.patches[0].pops) if self.patches else 0
+        npop = self.npop
         for i in range(npop):
             msg.migrate_particles(self.layouts,
                                   {p.geom.id: (p.pops[i].patch_ghost, 0, ops.count(p.pops[i].patch_ghost))
@@ -660,7 +663,7 @@ class SolverPPC:
         """HybridLevelInitializer::initialize, root level (hybrid_level_initializer.hpp:100-182): particles and B
         are already loaded; derive moments, J and E."""
         ops, msg = self.ops, self.messenger
-        npop = len(self.patches[0].pops) if self.patches else 0
+        npop = self.npop
         for p in self.patches:
             for pop in p.pops:
                 # first binning of the freshly loaded particles (the reference's CellMap is built on emplace_back)

@@ -1,0 +1,92 @@
+"""Refined hierarchies on two ranks (gloo, CPU back end): patches of both levels are dealt to the ranks, the
+coarse -> fine gathers, the split particles and the coarsened data of the synchronisation cross ranks as packed
+point-to-point messages.  The 2-rank result must equal the 1-process result."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _run(ops, name, comm=None, steps=2):
+    from amr_util import CASES, SOLVER_KW, B_init_nd
+    from phare_b200.amr import build_hierarchy
+    from solver_util import global_particles
+    cells, dx, grid, interp, ppc, boxes = CASES[name]
+    dim = len(cells)
+    gparts = global_particles(cells, interp, dx, ppc, 7)
+
+    def particles_fn(i, L, pid):
+        icell, delta, w, q, v = gparts[i]
+        inside = np.ones(len(w), bool)
+        for d in range(dim):
+            inside &= (icell[:, d] >= L.amr_lower[d]) & (icell[:, d] < L.amr_lower[d] + L.ncells[d])
+        return icell[inside], delta[inside], w[inside], q[inside], v[inside]
+
+    h = build_hierarchy(ops, cells, grid, interp, dx, [dict(name="pop0", mass=1.0)], B_init_nd(cells, dx), particles_fn,
+                        refinement_boxes=boxes, solver_kw=SOLVER_KW, comm=comm)
+    for _ in range(steps):
+        h.advance(0.004)
+    return h
+
+
+def _collect(h):
+    from amr_util import level_fields
+    res = {f"{k[0]}_{k[1]}_{k[2]}": v for k, v in level_fields(h).items()}
+    for lvl in h.levels:
+        for p in lvl.solver.patches:
+            pop = p.pops[0]
+            res[f"{lvl.number}_{p.geom.id}_counts"] = np.array(
+                [h.ops.count(pop.domain)] + [h.ops.count(s) if s is not None else -1
+                                             for s in (pop.level_ghost, pop.level_ghost_old, pop.level_ghost_new)])
+    return res
+
+
+def _worker(rank, world, port, name, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from phare_b200.messenger import TorchComm
+    from oracle.cpu_ops import CpuOps
+    from amr_util import CASES
+    cells, dx, grid, interp, ppc, boxes = CASES[name]
+    h = _run(CpuOps(len(cells), interp), name, comm=TorchComm(torch.device("cpu")))
+    owners = {f"owner_{lvl.number}_{pg.id}": np.array([pg.owner]) for lvl in h.levels for pg in lvl.geom.patches}
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **_collect(h), **(owners if rank == 0 else {}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["1d_o1", "1d_o2_three_levels_two_root_patches", "2d_o1", "3d_o1"])
+def test_two_ranks_equal_one_process(cpu_ref, name, tmp_path):
+    sys.path.insert(0, HERE)
+    from oracle.cpu_ops import CpuOps
+    from amr_util import CASES
+    cells, dx, grid, interp, ppc, boxes = CASES[name]
+    port = 29500 + (os.getpid() % 2000) + 7
+    mp.spawn(_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+    want = _collect(_run(CpuOps(len(cells), interp), name))
+    got = {}
+    for r in range(2):
+        got.update(np.load(os.path.join(str(tmp_path), f"rank{r}.npz")))
+    owners = {k: int(v[0]) for k, v in got.items() if k.startswith("owner_")}
+    # both ranks own root patches; the refined level is where the coarser patch under its corner is
+    assert {o for k, o in owners.items() if k.startswith("owner_0_")} == {0, 1}
+    assert set(want) == {k for k in got if not k.startswith("owner_")}
+    for key, w in want.items():
+        g = got[key]
+        if key.endswith("_counts"):
+            assert np.array_equal(g, w), key
+            continue
+        assert np.array_equal(np.isnan(g), np.isnan(w)), key
+        ok = ~np.isnan(w) & np.isfinite(w)
+        scale = np.max(np.abs(w[ok])) + 1e-30 if ok.any() else 1.0
+        # identical plans and arithmetic; only the order of sums over particles that arrive from another rank differs
+        assert np.max(np.abs(g[ok] - w[ok]), initial=0.0) <= 1e-11 * scale, key

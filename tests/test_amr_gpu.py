@@ -41,3 +41,52 @@ def test_gpu_hierarchy_matches_cpu_oracle_hierarchy(cpu_ref, name, pops):
         cpu.advance(0.004)
         gpu.advance(0.004)
         compare(f"step {step}")
+
+
+def _two_gpu_worker(rank, world, port, name, out_dir):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.dirname(here))
+    sys.path.insert(0, here)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), PHB_PEER_ARENA_MB="64", PHB_PEER_TIMEOUT_S="10")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
+    from phare_b200.messenger import TorchComm
+    from phare_b200.solver import GpuOps
+    from test_amr_gloo import _run, _collect
+    cells, dx, grid, interp, ppc, boxes = CASES[name]
+    h = _run(GpuOps(len(cells), interp, f"cuda:{rank}"), name, comm=TorchComm(torch.device(f"cuda:{rank}")))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **_collect(h))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["1d_o1", "2d_o1", "3d_o1"])
+def test_hierarchy_on_two_gpus_equals_one(cpu_ref, name, tmp_path):
+    """patches of both levels dealt to two GPUs (root level: NVLink peer-memory halo; between levels and on the refined
+    level: NCCL point-to-point) against the same hierarchy on one GPU.  Needs two GPUs: skipped on the single-GPU box."""
+    import os
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from phare_b200.solver import GpuOps
+    from test_amr_gloo import _run, _collect
+    cells, dx, grid, interp, ppc, boxes = CASES[name]
+    mp.spawn(_two_gpu_worker, args=(2, 29800 + (os.getpid() % 1000), name, str(tmp_path)), nprocs=2, join=True)
+    want = _collect(_run(GpuOps(len(cells), interp, "cuda:0"), name))
+    got = {}
+    for r in range(2):
+        got.update(np.load(os.path.join(str(tmp_path), f"rank{r}.npz")))
+    assert set(want) == set(got)
+    for key, w in want.items():
+        g = got[key]
+        if key.endswith("_counts"):
+            assert np.array_equal(g, w), key
+            continue
+        ok = ~np.isnan(w) & np.isfinite(w)
+        scale = np.max(np.abs(w[ok])) + 1e-30 if ok.any() else 1.0
+        assert np.array_equal(np.isnan(g), np.isnan(w)) and np.max(np.abs(g[ok] - w[ok]), initial=0.0) <= 1e-10 * scale, key
