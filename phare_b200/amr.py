@@ -18,8 +18,8 @@ schedules it would create are explicit box plans):
   makeNonLevelGhostBoxFor          src/amr/resources_manager/amr_utils.hpp:233-253
 The field operators themselves are CUDA kernels behind the C ABI (csrc/level.cu, csrc/split.cu).
 
-Scope: refinement boxes are fixed (no tagging / regridding / load balancing), every level lives on one rank, and a
-refined level together with its ghost layers must lie inside the (periodic) root domain.
+Scope: refinement boxes are fixed (no tagging / regridding / load balancing) and a refined level together with its
+ghost layers must lie inside the (periodic) root domain.  Patches of every level are dealt to the ranks (one per GPU).
 """
 import numpy as np
 
