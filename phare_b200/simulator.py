@@ -309,7 +309,8 @@ class Simulator:
         return self.dt
 
     def domain_box(self):
-        return ([0] * self.dims, [c - 1 for c in self.hier.cells])
+        """Hierarchy::domainBox() (hierarchy.hpp:120,161-166): the upper cell index per direction (shape - 1)"""
+        return [c - 1 for c in self.hier.cells]
 
     def cell_width(self):
         return list(self.hier.dl)
@@ -394,6 +395,18 @@ class PatchData:
         self.data = data
 
 
+class ContiguousParticles:
+    """core::ContiguousParticles as pybind exposes it (src/python3/particles.hpp, particle_array.hpp:255-354): flat
+    iCell / delta (n*dim), v (n*3), weight, charge arrays"""
+
+    def __init__(self, icell, delta, weight, charge, v):
+        self.iCell, self.delta = np.ascontiguousarray(icell).reshape(-1), np.ascontiguousarray(delta).reshape(-1)
+        self.v, self.weight, self.charge = np.ascontiguousarray(v).reshape(-1), np.asarray(weight), np.asarray(charge)
+
+    def size(self):
+        return len(self.weight)
+
+
 class PatchLevel:
     """src/python3/patch_level.hpp: per-patch copies of the level's fields / particles on the host"""
 
@@ -444,7 +457,11 @@ class PatchLevel:
         for i, name in enumerate(self._pops()):
             if userPopName not in ("all", name):
                 continue
-            out[name] = {"domain": [PatchData(p, s.ops.get_particles(p.pops[i].domain), 0) for p in s.patches]}
+            out[name] = {"domain": [PatchData(p, ContiguousParticles(*s.ops.get_particles(p.pops[i].domain)), 0)
+                                    for p in s.patches]}
+            if s.patches and s.patches[0].pops[i].level_ghost is not None:
+                out[name]["levelGhost"] = [
+                    PatchData(p, ContiguousParticles(*s.ops.get_particles(p.pops[i].level_ghost)), 0) for p in s.patches]
         return out
 
 

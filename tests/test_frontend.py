@@ -241,6 +241,11 @@ def test_static_refinement_boxes_run_through_the_dict(cpu_backend, cpu_ref, tmp_
     assert len(fine) == 1 and fine[0].patchID == "1#0" and list(fine[0].lower) == [40] and list(fine[0].upper) == [87]
     rho = np.asarray(fine[0].data)[2:-2]
     assert rho.shape == (49,) and np.all(np.isfinite(rho)) and abs(rho.mean() - 1.0) < 0.3
+    parts = dw.getPatchLevel(1).getParticles("protons")["protons"]
+    dom, lg = parts["domain"][0].data, parts["levelGhost"][0].data
+    assert dom.size() == sim.solver.ops.count(sim.level_solvers()[1].patches[0].pops[0].domain) > 0
+    assert dom.iCell.shape == (dom.size(),) and dom.v.shape == (3 * dom.size(),) and lg.size() > 0
+    assert dom.iCell.min() >= 40 and dom.iCell.max() <= 87 and sim.domain_box() == [63]
     with pytest.raises(RuntimeError):
         dw.getPatchLevel(2)
     assert sim.dump_diagnostics(0.01, 0.005)
