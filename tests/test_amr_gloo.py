@@ -90,3 +90,66 @@ def test_two_ranks_equal_one_process(cpu_ref, name, tmp_path):
         scale = np.max(np.abs(w[ok])) + 1e-30 if ok.any() else 1.0
         # identical plans and arithmetic; only the order of sums over particles that arrive from another rank differs
         assert np.max(np.abs(g[ok] - w[ok]), initial=0.0) <= 1e-11 * scale, key
+
+
+def _sim_run(world_rank=None):
+    """the dict-driven simulator with one refinement box, three steps; returns {key: array} of this rank's patches"""
+    import phare_b200.simulator as S
+    import pybindlibs.dictator as pp
+    from oracle.cpu_ops import CpuOps
+    from frontend_util import populate, two_pop_1d
+    S.ops_factory = lambda dim, interp: CpuOps(dim, interp)
+    pops, bfn = two_pop_1d(64)
+    populate([64], [0.2], 1, pops, bfn, steps=3, largest=[16])
+    pp.add_int("simulation/AMR/max_nbr_levels", 2)
+    pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 2)
+    for ib, (lo, hi) in enumerate(((10, 25), (26, 45))):   # two adjacent refined patches across root patch borders
+        pp.add_int(f"simulation/AMR/refinement/boxes/L0/B{ib}/lower/x/", lo)
+        pp.add_int(f"simulation/AMR/refinement/boxes/L0/B{ib}/upper/x/", hi)
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    for _ in range(3):
+        sim.advance(sim.timeStep())
+    res = {}
+    for il, solver in enumerate(sim.level_solvers()):
+        for p in solver.patches:
+            for name, h in (("By", p.B[1]), ("Ez", p.E[2]), ("Ne", p.Ne), ("Vx", p.Vi[0])):
+                res[f"{il}_{p.geom.id}_{name}"] = solver.ops.get_field(h)
+            res[f"{il}_{p.geom.id}_n"] = np.array([solver.ops.count(pop.domain) for pop in p.pops])
+    S.dict_instance().stop()
+    return res
+
+
+def _sim_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    np.savez(os.path.join(out_dir, f"sim_rank{rank}.npz"), **_sim_run())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_simulator_with_refinement_on_two_ranks_equals_one(cpu_ref, tmp_path):
+    """pyphare-style dict -> Simulator on two ranks: 4 root patches and 2 refined patches dealt to the ranks"""
+    sys.path.insert(0, HERE)
+    import phare_b200.simulator as S
+    old = S.ops_factory
+    try:
+        mp.spawn(_sim_worker, args=(2, 29500 + (os.getpid() % 2000) + 11, str(tmp_path)), nprocs=2, join=True)
+        want = _sim_run()
+    finally:
+        S.ops_factory = old
+    got = {}
+    for r in range(2):
+        got.update(np.load(os.path.join(str(tmp_path), f"sim_rank{r}.npz")))
+    assert set(got) == set(want) and len([k for k in want if k.startswith("1_")]) == 2 * 5
+    for k, w in want.items():
+        if k.endswith("_n"):
+            assert np.array_equal(got[k], w), k
+        else:
+            ok = np.isfinite(w)
+            assert np.array_equal(np.isnan(got[k]), np.isnan(w)), k
+            assert np.max(np.abs(got[k][ok] - w[ok]), initial=0.0) <= 1e-11 * (np.max(np.abs(w[ok])) + 1e-30), k
