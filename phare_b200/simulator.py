@@ -336,11 +336,20 @@ class Simulator:
                 if not isinstance(diag, dict) or not self._due(diag, timestamp, timestep):
                     continue
                 os.makedirs(path, exist_ok=True)
-                arrays = {}
+                # file attributes of the reference's h5 writer that pharesee needs to rebuild the hierarchy
+                # (diagnostic/detail/h5writer.hpp: interpOrder, domain_box, cell_width; per patch: origin, lower, upper)
+                arrays = {"_meta/interp_order": np.array(self.interp_order), "_meta/domain_cells": np.array(self.hier.cells),
+                          "_meta/cell_width": np.array(self.hier.dl), "_meta/time": np.array(float(timestamp)),
+                          "_meta/quantity": np.array(diag["quantity"])}
                 for il, solver in enumerate(self.level_solvers()):
                     for p in solver.patches:
+                        base = f"t{timestamp:.10f}/pl{il}/p{p.geom.id}/"
+                        L = p.layout
+                        arrays[base + "_lower"] = np.array([L.amr_lower[k] for k in range(L.dim)])
+                        arrays[base + "_upper"] = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)])
+                        arrays[base + "_origin"] = np.array([L.origin[k] for k in range(L.dim)])
                         for key, a in self._diag_arrays(p, dtype, diag["quantity"]).items():
-                            arrays[f"t{timestamp:.10f}/pl{il}/p{p.geom.id}/{key}"] = a
+                            arrays[base + key] = a
                 fn = os.path.join(path, f"{dtype}_{diag['quantity'].strip('/').replace('/', '_')}_"
                                         f"{timestamp:011.5f}_rank{self.solver.comm.rank}.npz")
                 np.savez(fn, **arrays)

@@ -61,6 +61,9 @@ def populate(cells, dl, interp, pops, bfn, time_step=0.005, steps=4, eta=1e-3, n
             pp.add_string(f"simulation/diagnostics/electromag/{q}/quantity", "/" + q)
             pp.add_array_as_vector(f"simulation/diagnostics/electromag/{q}/write_timestamps", np.asarray(diag_times, float))
         for i, p in enumerate(pops):
+            pp.add_string(f"simulation/diagnostics/fluid/flux{i}/type", "fluid")
+            pp.add_string(f"simulation/diagnostics/fluid/flux{i}/quantity", f"/ions/pop/{p['name']}/flux")
+            pp.add_array_as_vector(f"simulation/diagnostics/fluid/flux{i}/write_timestamps", np.asarray(diag_times[-1:], float))
             q = f"/ions/pop/{p['name']}/domain"
             pp.add_string(f"simulation/diagnostics/particle/part{i}/type", "particle")
             pp.add_string(f"simulation/diagnostics/particle/part{i}/quantity", q)

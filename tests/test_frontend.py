@@ -160,7 +160,8 @@ def test_diagnostics_written_at_requested_timestamps(cpu_backend, tmp_path):
     sim.advance(0.005)
     assert sim.dump_diagnostics(0.01, 0.005)
     files = sorted(os.listdir(tmp_path))
-    assert len(files) == 5 and files[0].startswith("electromag_EM_B_00000.00000")
+    assert len(files) == 6 and files[0].startswith("electromag_EM_B_00000.00000")
+    assert any(f.startswith("fluid_ions_pop_protons_flux_") for f in files)
     z = np.load(tmp_path / [f for f in files if f.startswith("electromag_EM_E")][-1])
     key = [k for k in z.files if k.endswith("EM_E_x")][0]
     assert key.startswith("t0.0100000000/pl0/p0/") and z[key].shape == (32 + 4,)
@@ -293,3 +294,72 @@ def test_pyphare_runs_the_reference_td1d_script_unchanged(cpu_backend, cpu_ref, 
     ph.global_vars.sim = None
     for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
         del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
+def test_pharesee_post_processing_runs_on_the_npz_diagnostics(cpu_backend, cpu_ref, tmp_path, monkeypatch):
+    """the dumps of a three-level run (the reference's td1d.py, unchanged) are loaded into pyphare's own
+    PatchHierarchy and pharesee's flat_finest_field assembles the finest available data over the whole domain"""
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections",
+                 "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(REF)
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        monkeypatch.delitem(sys.modules, k)
+    td = importlib.import_module("tests.functional.td.td1d")
+    sim = td.config()
+    from pyphare.simulator.simulator import Simulator
+    import pyphare.pharein as ph
+    simulator = Simulator(sim, log_to_file=False)
+    simulator.initialize()          # dumps t = 0 (td1d asks for E, B, charge density and bulk velocity)
+    from phare_b200.pharesee_npz import hierarchy_from_npz
+    from pyphare.pharesee.hierarchy.hierarchy_utils import flat_finest_field
+    hier = hierarchy_from_npz(str(tmp_path / "td_noflow"), time=0.0)
+    assert sorted(hier.levels().keys()) == [0, 1, 2] and [len(l.patches) for l in hier.levels().values()] == [25, 1, 1]
+    assert {"Bx", "By", "Bz", "Ex", "Ey", "Ez", "rho", "Vx", "Vy", "Vz"} <= set(hier.level(2).patches[0].patch_datas)
+    by, x = flat_finest_field(hier, "By")
+    order = np.argsort(x)
+    x, by = x[order], by[order]
+    # more points than the root level alone: the refined regions contribute their own nodes
+    assert len(x) > 500 + 100 and x.min() < 1.0 and x.max() > 499.0
+    assert np.min(np.diff(x[(x > 125) & (x < 150)])) == pytest.approx(0.25)   # level 2 mesh size inside its patch
+    S_ = lambda x, x0: 0.5 * (1 + np.tanh(x - x0))
+    want = -1 + 2 * (S_(x, 125.0) - S_(x, 375.0))
+    assert np.max(np.abs(by - want)) < 0.4 and np.max(np.abs(by - want)[np.abs(x - 125) > 10]) < 2e-2
+    rho, xr = flat_finest_field(hier, "rho")
+    assert abs(np.mean(rho[(xr > 5) & (xr < 495)]) - 1.0) < 0.05
+    simulator.reset()
+    ph.global_vars.sim = None
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
+def test_npz_reader_names_population_quantities(cpu_backend, cpu_ref, tmp_path, monkeypatch):
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections",
+                 "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    import pybindlibs.dictator as pp
+    pops, bfn = two_pop_1d(64)
+    populate([64], [0.2], 1, pops, bfn, steps=1, largest=[32], diag_dir=str(tmp_path), diag_times=[0.0])
+    pp.add_int("simulation/AMR/max_nbr_levels", 2)
+    pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 1)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/B0/lower/x/", 20)
+    pp.add_int("simulation/AMR/refinement/boxes/L0/B0/upper/x/", 43)
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    assert sim.dump_diagnostics(0.0, 0.005)
+    from phare_b200.pharesee_npz import hierarchy_from_npz
+    hier = hierarchy_from_npz(str(tmp_path))
+    fine = hier.level(1).patches[0]
+    assert {"Bx", "Ez", "protons_Fx", "beam_Fz"} <= set(fine.patch_datas) and fine.box.shape[0] == 48
+    fx = fine.patch_datas["beam_Fx"]
+    ops = sim.solver.ops
+    want = ops.get_field(sim.level_solvers()[1].patches[0].pops[1].flux[0])
+    assert np.array_equal(fx.dataset[:], want) and fx.ghosts_nbr[0] == 2 and abs(fx.x[2] - 40 * 0.1) < 1e-12
