@@ -30,6 +30,19 @@ def _mode1(sim, getter, primal):
 
 
 def test_alfven_wave_propagates_at_the_alfven_speed(cpu_backend):
+    _alfven_wave()
+
+
+@pytest.mark.gpu
+def test_alfven_wave_propagates_at_the_alfven_speed_on_the_gpu():
+    """the same run on the CUDA path (GpuOps through the C ABI)"""
+    try:
+        _alfven_wave()
+    finally:
+        S.dict_instance().stop()
+
+
+def _alfven_wave():
     cells, dl, ampl = 100, 1.0, 0.01
     Lx = cells * dl
     k = 2 * np.pi / Lx
