@@ -80,3 +80,59 @@ def _alfven_wave():
     dphi = np.angle(vy[1:] / by[1:])
     assert np.all(np.abs(np.abs(dphi) - np.pi) < 0.3) or np.all(np.abs(dphi) < 0.3)
     assert np.all(np.abs(np.abs(vy[1:]) - ampl) < 0.25 * ampl)
+
+
+def _phase_speed_and_sim(refine_box, ppc=60, dt=0.02, nsteps=500, every=50):
+    import pybindlibs.dictator as pp
+    cells, dl, ampl = 100, 1.0, 0.01
+    k = 2 * np.pi / (cells * dl)
+    pop = dict(name="protons", mass=1.0, charge=1.0, ppc=ppc, seed=1337, density=const(1.0),
+               vx=const(0.0), vy=lambda x: ampl * np.cos(k * x), vz=lambda x: ampl * np.sin(k * x),
+               vthx=const(0.01), vthy=const(0.01), vthz=const(0.01))
+    bfn = [const(1.0), lambda x: ampl * np.cos(k * x), lambda x: ampl * np.sin(k * x)]
+    populate([cells], [dl], 1, [pop], bfn, time_step=dt, steps=nsteps, eta=0.0, nu=1e-3, Te=0.0, largest=[50])
+    if refine_box is not None:
+        pp.add_int("simulation/AMR/max_nbr_levels", 2)
+        pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+        pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 1)
+        pp.add_int("simulation/AMR/refinement/boxes/L0/B0/lower/x/", refine_box[0])
+        pp.add_int("simulation/AMR/refinement/boxes/L0/B0/upper/x/", refine_box[1])
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    times, by = [0.0], [_mode1(sim, "getBy", False)]
+    for step in range(1, nsteps + 1):
+        sim.advance(dt)
+        if step % every == 0:
+            times.append(step * dt)
+            by.append(_mode1(sim, "getBy", False))
+    times, by = np.array(times), np.array(by)
+    assert np.all(np.abs(np.abs(by) - ampl) < 0.1 * ampl), np.abs(by)
+    phase = np.unwrap(np.angle(by))
+    fit = np.polyfit(times, phase, 1)
+    assert np.max(np.abs(phase - np.polyval(fit, times))) < 0.05
+    return abs(fit[0]) / k, sim
+
+
+def test_alfven_wave_crosses_a_refined_level_unperturbed(cpu_backend, cpu_ref):
+    """the same wave with 40 % of the domain refined (static box, 4 sub-cycles per step, level-ghost particles, refluxing):
+    the restated multi-level sequencing has no runnable reference here, so it is held to the physics: the wave keeps its
+    amplitude and its phase speed through the coarse-fine boundaries (against the single-level run over the same
+    interval, 0 < t < 10, where the initial transient still makes both 2 % faster than the asymptotic value), and both
+    levels carry the same field"""
+    ampl = 0.01
+    v_single, sim = _phase_speed_and_sim(None)
+    S.dict_instance().stop()
+    v_refined, sim = _phase_speed_and_sim((30, 69))
+    assert len(sim.level_solvers()) == 2
+    assert abs(v_refined - v_single) < 0.005 * v_single, (v_refined, v_single)     # measured: 1.0556 vs 1.0539
+    assert abs(v_refined - 1.0) < 0.07
+    # the refined level carries the same wave as the root level under it (By is dual: two fine cells per coarse cell)
+    ops = sim.solver.ops
+    fine = sim.level_solvers()[1].patches[0]
+    g = 2
+    by_f = ops.get_field(fine.B[1])[g:-g]
+    by_c = np.concatenate([ops.get_field(p.B[1])[g:-g] for p in sim.level_solvers()[0].patches])[30:70]
+    assert np.max(np.abs(0.5 * (by_f[0::2] + by_f[1::2]) - by_c)) < 0.1 * ampl
+    # and no particle pile-up or depletion at the level boundary
+    ne = ops.get_field(fine.Ne)[g:-g]
+    assert abs(ne.mean() - 1.0) < 0.02 and np.max(np.abs(ne - 1.0)) < 0.25
