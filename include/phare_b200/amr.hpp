@@ -19,6 +19,7 @@
 #define PHARE_B200_AMR_HPP
 
 #include "phare_b200.hpp"
+#include "split_patterns.hpp"
 
 #include <limits>
 #include <vector>
@@ -161,6 +162,40 @@ public:
 
 private:
     Context const& ctx_;
+};
+
+// Splitter<dim, interp, nbRefinedPart> (splitter.hpp:71-106) together with the loop of ParticlesRefineOperator::refine_
+// (particles_data_split.hpp:142-231): every coarse particle moved to the fine index space (toFineGrid) and within
+// maxCellDistanceFromSplit() cells of a destination box is split with the pattern's (delta, weight) table; the refined
+// particles whose cell lies in a destination box are appended to `fine`.  Returns how many were appended.
+template<std::size_t dim, std::size_t interp, std::size_t nbRefinedPart>
+class Splitter
+{
+public:
+    static constexpr std::size_t dimension = dim, interp_order = interp, nbRefinedParts = nbRefinedPart;
+    explicit Splitter(Context const& ctx) : ctx_{ctx}, pattern_{detail::find_split_pattern(int(dim), int(interp), int(nbRefinedPart))}
+    {
+        if (!pattern_)
+            throw std::runtime_error("no Splitter for this (dim, interp, nbRefinedPart)"); // meta_utilities.hpp:73-88
+    }
+    int maxCellDistanceFromSplit() const { return pattern_->max_cell_distance; }
+    float const* deltas() const { return pattern_->deltas; }
+    float const* weights() const { return pattern_->weights; }
+    std::size_t operator()(ParticleArray<dim> const& coarse, std::vector<Box<dim>> const& destinationBoxes,
+                           ParticleArray<dim>& fine) const
+    {
+        std::vector<phb_box> boxes;
+        for (auto const& b : destinationBoxes)
+            boxes.push_back(b.c());
+        std::size_t appended = 0;
+        ctx_.check(phb_split(ctx_.get(), coarse.c(), 0, coarse.size(), int(nbRefinedPart), pattern_->deltas, pattern_->weights,
+                             pattern_->max_cell_distance, boxes.data(), int(boxes.size()), fine.c(), &appended));
+        return appended;
+    }
+
+private:
+    Context const& ctx_;
+    detail::SplitPattern const* pattern_;
 };
 
 // setNaNsOnFieldGhosts for one box of local indices (hybrid_hybrid_messenger_strategy.hpp:924-955)

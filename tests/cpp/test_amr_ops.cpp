@@ -175,6 +175,67 @@ void run()
         pho_axpy(hS[c].size(), hS[c].data(), hB[c].data(), 0.25);
         CHECK(same_bits(got, hS[c]));
     }
+    // Splitter: nbRefinedPart children per coarse particle, kept when their cell lies in the destination box
+    {
+        constexpr std::size_t nref = dim == 1 ? 2 : dim == 2 ? 4 : 6;
+        amr::Splitter<dim, interp, nref> split{ctx};
+        CHECK(split.maxCellDistanceFromSplit() == 1);
+        std::vector<Particle<dim>> host(500);
+        for (auto& p : host)
+        {
+            for (std::size_t d = 0; d < dim; ++d)
+            {
+                p.iCell[d] = coarseCells.lower[d] + int(U(gen) * (coarseCells.upper[d] - coarseCells.lower[d] + 1));
+                p.delta[d] = U(gen);
+            }
+            p.weight = 0.5 + U(gen);
+            p.charge = 1;
+            p.v      = {N(gen), N(gen), N(gen)};
+        }
+        ParticleArray<dim> coarse{ctx, host.size()}, fineAll{ctx, host.size() * nref}, fineIn{ctx, host.size() * nref};
+        coarse.assign(host);
+        Box<dim> everywhere, inner = fineCells;
+        for (std::size_t d = 0; d < dim; ++d)
+        {
+            everywhere.lower[d] = -(1 << 28);
+            everywhere.upper[d] = 1 << 28;
+            inner.lower[d] += 3;
+        }
+        CHECK(split(coarse, {everywhere}, fineAll) == host.size() * nref);
+        auto children = fineAll.vector();
+        double wsum = 0;
+        for (std::size_t k = 0; k < nref; ++k)
+            wsum += double(split.weights()[k]);
+        bool ok = true;
+        for (std::size_t i = 0; i < host.size() && ok; ++i)
+        {
+            double w = 0, pos[dim] = {};
+            for (std::size_t k = 0; k < nref; ++k)
+            {
+                auto const& c = children[i * nref + k]; // source order, then pattern order
+                w += c.weight;
+                for (std::size_t d = 0; d < dim; ++d)
+                    pos[d] += (c.iCell[d] + c.delta[d]) / double(nref);
+                ok = ok && c.v == host[i].v && c.charge == host[i].charge;
+            }
+            // weights: pattern weight x parent weight x 2^dim (split.hpp dispatch); the pattern is symmetric around the
+            // parent's position in the fine index space, 2 x (iCell + delta)
+            ok = ok && std::abs(w - host[i].weight * wsum * double(1 << dim)) < 1e-12;
+            for (std::size_t d = 0; d < dim; ++d)
+                ok = ok && std::abs(pos[d] - 2. * (host[i].iCell[d] + host[i].delta[d])) < 1e-6;
+        }
+        CHECK(ok);
+        std::size_t const kept = split(coarse, {inner}, fineIn);
+        std::size_t expect     = 0;
+        for (auto const& c : children)
+        {
+            bool in = true;
+            for (std::size_t d = 0; d < dim; ++d)
+                in = in && c.iCell[d] >= inner.lower[d] && c.iCell[d] <= inner.upper[d];
+            expect += in ? 1 : 0;
+        }
+        CHECK(kept == expect && kept > 0 && kept < children.size() && fineIn.size() == kept);
+    }
     std::printf("dim %zu ok\n", dim);
 }
 
