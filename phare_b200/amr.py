@@ -134,7 +134,7 @@ class RefinedLevelMessenger(HybridMessenger):
             self._gather[name] = self._finish(local, send_items, recv_items, 0)
         return self._gather[name]
 
-    def _refine(self, name, qty0, vecs, op, whole_ghost_box=False):
+    def _refine(self, name, qty0, vecs, op, whole_ghost_box=False, excluded=None):
         ops, g = self.ops, self.geom.g
         self._run(self._gather_phase(name, qty0), ("gather", name))
         for patch in self._fine_patches:
@@ -149,8 +149,8 @@ class RefinedLevelMessenger(HybridMessenger):
                 # the whole ghost box at level creation, otherwise the ghost box minus the level's patches (one launch
                 # per component: the kernel skips the faces of the excluded cell boxes)
                 cells = p.box.grow(g)
-                ops.magnetic_postprocess(patch.layout, vecs[p.id], cells.lo, cells.hi,
-                                         () if whole_ghost_box else self._lg_excluded[p.id])
+                skip = () if whole_ghost_box else (excluded[p.id] if excluded is not None else self._lg_excluded[p.id])
+                ops.magnetic_postprocess(patch.layout, vecs[p.id], cells.lo, cells.hi, skip)
 
     # ---- HybridMessenger interface
     def fill_ghosts(self, name, qty0, vecs):
@@ -179,6 +179,30 @@ class RefinedLevelMessenger(HybridMessenger):
             for c in range(3):
                 ops.box_fill(p.E[c], [0] * self.geom.dim, p.E[c].shape, float("nan"))
         self._refine("E", abi.EX, solver._by_id("E"), abi.REFINE_ELECTRIC)
+
+    def regrid_fields(self, solver, old_solver):
+        """regrid (:265-280): B (magneticRegriding_: BregridAlgo with the NaN-only MagneticFieldRefiner and the patch
+        strategy, overwrite_interior) and E (electricInitRefiners_.regrid): a fresh, all-NaN array first takes what the
+        old level holds (its interior field boxes), the remaining NaN nodes are refined from the coarser level, and the
+        new fine faces of the cells that did not come from the old level get the Toth-Roe value"""
+        ops, g = self.ops, self.geom.g
+        old_boxes = [q.geom.box for q in old_solver.patches]
+        for name, qty0, op in (("B", abi.BX, abi.REFINE_MAGNETIC), ("E", abi.EX, abi.REFINE_ELECTRIC)):
+            vecs, old_vecs = solver._by_id(name), old_solver._by_id(name)
+            entries = []
+            for p in solver.patches:
+                for c in range(3):
+                    qty = qty0 + c
+                    ops.box_fill(vecs[p.geom.id][c], [0] * self.geom.dim, vecs[p.geom.id][c].shape, float("nan"))
+                    for q in old_solver.patches:
+                        ov = p.geom.ghost_field_box(qty, g) * q.geom.interior_field_box(qty)
+                        if ov is not None:
+                            entries.append((vecs[p.geom.id][c], p.geom.local(ov.lo, g), old_vecs[q.geom.id][c],
+                                            q.geom.local(ov.lo, g), ov.shape(), 0))
+            ops.run_box_ops(ops.compile_box_ops(entries))
+            excluded = {p.geom.id: [abi.make_box(ov.lo, ov.hi) for ov in (p.geom.box.grow(g) * b for b in old_boxes)
+                                    if ov is not None] for p in solver.patches}
+            self._refine(name, qty0, vecs, op, excluded=excluded)
 
     def split_from_coarser(self, ipop, nref, boxes_of, attr):
         """ParticlesRefineOperator::refine_: the coarser level's domain particles, moved to this level's index space and
@@ -287,9 +311,10 @@ class Hierarchy:
                 p.fluxSumE = self.ops.vec(p.layout, abi.EX)  # SolverPPC::fluxSumE_ (solver_ppc.hpp:60)
 
     # ---------------------------------------------------------------------------------------- construction
-    def add_level(self, fine_boxes, capacity_factor=1.6):
+    def add_level(self, fine_boxes, capacity_factor=1.6, old_level=None):
         """creates level len(levels) from cell boxes given in ITS OWN index space and initialises it from the current
-        finest level (MultiPhysicsIntegrator::initializeLevelData -> HybridLevelInitializer::initialize, level > 0)"""
+        finest level (MultiPhysicsIntegrator::initializeLevelData -> HybridLevelInitializer::initialize, level > 0);
+        old_level: the level it replaces (regrid())"""
         ops, me = self.ops, self.comm.rank
         coarse = self.levels[-1]
         cs = coarse.solver
@@ -350,16 +375,47 @@ class Hierarchy:
         self._ensure_flux_sum(solver)
         level = Level(ilvl, geom, solver, interp, dx, coarse.origin, coarse.pops)
         self.levels.append(level)
-        self._initialize_level(level)
+        self._initialize_level(level, old_level)
         return level
 
-    def _initialize_level(self, level):
+    def regrid(self, fine_boxes, capacity_factor=1.6):
+        """replaces the finest level by one made of `fine_boxes` (cell boxes in its own index space; none: the level is
+        removed).  HybridHybridMessengerStrategy::regrid (:265-311) + HybridLevelInitializer::initialize(isRegridding):
+        where the new level overlaps the old one its E, B and domain particles are COPIED from it, everywhere else they
+        come from the next coarser level exactly as at level creation (B: coarse faces + Toth-Roe on the cells that were
+        not copied; E: electric refiner; particles: splitting); level ghosts and moments are rebuilt.  One rank only."""
+        if len(self.levels) < 2:
+            raise RuntimeError("there is no refined level to regrid")
+        if self.comm.size > 1:
+            raise NotImplementedError("regridding moves data between owners: not driven across ranks yet")
+        old = self.levels.pop()
+        if not fine_boxes:
+            return None
+        return self.add_level(fine_boxes, capacity_factor, old_level=old)
+
+    def _initialize_level(self, level, old=None):
         ops, s, msg = self.ops, level.solver, level.solver.messenger
         npop = s.npop
-        msg.init_fields(s)
+        if old is None:
+            msg.init_fields(s)
+        else:
+            msg.regrid_fields(s, old.solver)
+        old_boxes = [q.box for q in old.geom.patches] if old is not None else []
         for i in range(npop):
-            # domainParticlesRefiners_ (interior) and lvlGhostPartOldRefiners_ (coarseBoundaryOld)
-            msg.split_from_coarser(i, self.nref, lambda pg: [pg.box], "domain")
+            if old is not None:
+                # domain particles of the old level that lie in a patch of the new one are kept as they are
+                for p in s.patches:
+                    for q in old.solver.patches:
+                        both = p.geom.box * q.geom.box
+                        n = ops.count(q.pops[i].domain)
+                        if both is None or n == 0:
+                            continue
+                        while ops.capacity(p.pops[i].domain) < ops.count(p.pops[i].domain) + n:
+                            grow_store(ops, p, i, p.pops[i].domain)
+                        ops.export(q.layout, q.pops[i].domain, 0, n, abi.make_box(both.lo, both.hi), p.pops[i].domain)
+            # domainParticlesRefiners_ (interior; on a regrid: the part of the interior the old level did not cover) and
+            # lvlGhostPartOldRefiners_ (coarseBoundaryOld)
+            msg.split_from_coarser(i, self.nref, lambda pg: minus_all([pg.box], old_boxes), "domain")
             msg.split_from_coarser(i, self.nref, lambda pg: msg.lg_particle_boxes[pg.id], "level_ghost_old")
         for p in s.patches:
             for i, pop in enumerate(p.pops):

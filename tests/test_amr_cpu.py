@@ -201,3 +201,76 @@ def test_particle_stores_grow_when_the_split_overflows_them(cpu_ops_factory):
     for c in range(3):
         assert bit_equal(ops_a.get_field(pa.E[c]), ops_b.get_field(pb.E[c]))
         assert bit_equal(ops_a.get_field(pa.B[c]), ops_b.get_field(pb.B[c]))
+
+
+def _domain_rows(ops, patch, ipop=0):
+    from oracle import canonical_rows
+    return canonical_rows(*ops.get_particles(patch.pops[ipop].domain))
+
+
+def test_regrid_onto_the_same_boxes_keeps_the_level(cpu_ops_factory):
+    """every patch of the new level lies in the old one: E, B on the physical nodes and the domain particles are copied"""
+    from phare_b200.boxes import Box
+    ops = cpu_ops_factory(2, 1)
+    h = make_hierarchy(ops, "2d_o1")
+    h.advance(0.004)
+    old = h.levels[1]
+    boxes = [Box(p.geom.box.lo, p.geom.box.hi) for p in old.solver.patches]
+    keep = {p.geom.id: ([ops.get_field(p.B[c]) for c in range(3)], [ops.get_field(p.E[c]) for c in range(3)],
+                        _domain_rows(ops, p)) for p in old.solver.patches}
+    new = h.regrid(boxes)
+    assert h.levels[1] is new and new is not old and len(h.levels) == 2
+    g = 2
+    for p in new.solver.patches:
+        B0, E0, rows0 = keep[p.geom.id]
+        phys = tuple(slice(g, -g) for _ in range(2))
+        for c in range(3):
+            assert bit_equal(ops.get_field(p.B[c])[phys], B0[c][phys]) and bit_equal(ops.get_field(p.E[c])[phys], E0[c][phys])
+            assert not np.isnan(ops.get_field(p.B[c])).any() and not np.isnan(ops.get_field(p.E[c])).any()
+        assert np.array_equal(_domain_rows(ops, p), rows0)
+        assert ops.count(p.pops[0].level_ghost) == ops.count(p.pops[0].level_ghost_old) > 0
+    h.advance(0.004)
+    for p in new.solver.patches:
+        assert np.isfinite(ops.get_field(p.Ne)[g:-g, g:-g]).all()
+
+
+def test_regrid_onto_shifted_boxes_copies_the_overlap_and_refines_the_rest(cpu_ops_factory):
+    from phare_b200.amr import refine_box
+    from phare_b200.boxes import Box
+    ops_a, ops_b = cpu_ops_factory(1, 1), cpu_ops_factory(1, 1)
+    h, fresh = make_hierarchy(ops_a, "1d_o1"), make_hierarchy(ops_b, "1d_o1")
+    for hh in (h, fresh):
+        hh.advance(0.004)
+    old = h.levels[1].solver.patches[0]                       # fine cells [40, 79]
+    oldE, oldB = [ops_a.get_field(old.E[c]) for c in range(3)], [ops_a.get_field(old.B[c]) for c in range(3)]
+    old_ic, old_rows = ops_a.get_particles(old.pops[0].domain)[0][:, 0], _domain_rows(ops_a, old)
+    shifted = refine_box(Box([26], [45]))                      # fine cells [52, 91]
+    new = h.regrid([shifted]).solver.patches[0]
+    # the same level created from scratch on the same coarse state: everything refined / split from the coarser level
+    fresh.levels.pop()
+    ref = fresh.add_level([shifted]).solver.patches[0]
+    g = 2
+    at = lambda patch, i: i - (int(patch.geom.box.lo[0]) - g)  # array index of AMR index i
+    for c in range(3):
+        E, B = ops_a.get_field(new.E[c]), ops_a.get_field(new.B[c])
+        assert not np.isnan(E).any() and not np.isnan(B).any()
+        hi = 80 if c == 0 else 81                              # Ex dual: cells 52..79 ; Ey, Ez primal: nodes 52..80
+        assert bit_equal(E[at(new, 52):at(new, hi)], oldE[c][at(old, 52):at(old, hi)])          # copied from the old level
+        assert bit_equal(E[at(new, 82):], ops_b.get_field(ref.E[c])[at(ref, 82):])              # refined from the coarser one
+        hiB = 81 if c == 0 else 80
+        assert bit_equal(B[at(new, 52):at(new, hiB)], oldB[c][at(old, 52):at(old, hiB)])
+        assert bit_equal(B[at(new, 83):], ops_b.get_field(ref.B[c])[at(ref, 83):])
+    # particles: the old ones in [52, 79], split coarse ones in [80, 91]
+    ic = ops_a.get_particles(new.pops[0].domain)[0][:, 0]
+    assert (ic >= 52).all() and (ic <= 91).all()
+    assert np.count_nonzero(ic <= 79) == np.count_nonzero(old_ic >= 52)
+    ric = ops_b.get_particles(ref.pops[0].domain)[0][:, 0]
+    assert np.count_nonzero(ic >= 80) == np.count_nonzero(ric >= 80)
+    # ... the very same particles: every old one with cell >= 52 is found again, bit for bit
+    as_set = lambda rows: {r.tobytes() for r in np.ascontiguousarray(rows)}
+    assert len(as_set(_domain_rows(ops_a, new)) & as_set(old_rows)) == np.count_nonzero(old_ic >= 52)
+    h.advance(0.004)
+    assert np.isfinite(ops_a.get_field(h.levels[1].solver.patches[0].Ne)[g:-g]).all()
+    # removing the level
+    assert h.regrid([]) is None and len(h.levels) == 1
+    h.advance(0.004)
