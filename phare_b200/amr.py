@@ -393,6 +393,32 @@ class Hierarchy:
             return None
         return self.add_level(fine_boxes, capacity_factor, old_level=old)
 
+    def regrid_tagged(self, tagger):
+        """GriddingAlgorithm::regridAllFinerLevels driven by the tagger: level by level from the root, the boxes of level
+        i+1 follow from the tags of level i (phare_b200.tagging); a level whose boxes (and whose coarser levels) did not
+        change is kept as it is, otherwise it is rebuilt by regrid() semantics from its old self and the level below.
+        Returns True when the hierarchy changed."""
+        if self.comm.size > 1:
+            raise NotImplementedError("tagging-driven regridding is driven on one rank only")
+        old_levels = self.levels[1:]
+        self.levels = self.levels[:1]
+        changed = False
+        for il in range(tagger.max_nbr_levels - 1):
+            boxes = tagger.boxes(self, il)
+            old = old_levels[il] if il < len(old_levels) else None
+            if not boxes:
+                changed = changed or old is not None
+                break
+            fine = [refine_box(b) for b in boxes]
+            same = (old is not None and not changed and len(fine) == len(old.geom.patches)
+                    and all(a == b.box for a, b in zip(fine, old.geom.patches)))
+            if same:
+                self.levels.append(old)
+            else:
+                self.add_level(fine, old_level=old)
+                changed = True
+        return changed or len(self.levels) - 1 != len(old_levels)
+
     def _initialize_level(self, level, old=None):
         ops, s, msg = self.ops, level.solver, level.solver.messenger
         npop = s.npop

@@ -11,8 +11,8 @@ Mirrors (file:line relative to the PHARE tree):
   DataWrangler / PatchLevel                  src/python3/data_wrangler.hpp, patch_level.hpp (getters used by pyphare.data.wrangler)
 
 Scope: periodic boundaries, HybridModel; one level, or a STATIC hierarchy given by `refinement_boxes` (phare_b200.amr:
-ratio 2, sub-cycling, refluxing; patches of every level dealt to the ranks).  Tagging-driven refinement (regridding) raises NotImplementedError
-(SURVEY §8f-2).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
+ratio 2, sub-cycling, refluxing; patches of every level dealt to the ranks), or `refinement="tagging"` (the
+reference's tagging criterion, our own tile clustering, regridding after every root step; one rank).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
 tests replace.
 """
 import ctypes as C
@@ -109,6 +109,7 @@ class Hierarchy:
         # static refinement (simulation/AMR/refinement/boxes/L<i>/B<j>/{lower,upper}/{x,y,z}, written by
         # pyphare/pharein/initialize/general.py:123-150): boxes of level i+1 in the index space of level i
         self.refinement_boxes = []
+        self.tagging = None
         rb = sim + "AMR/refinement/boxes/"
         single = os.environ.get("PHARE_B200_SINGLE_LEVEL", "0") == "1"
         if d.contains(rb + "nbr_levels") and not single:
@@ -121,12 +122,18 @@ class Hierarchy:
                     boxes.append((lo, hi))
                 self.refinement_boxes.append(boxes)
         elif self.max_nbr_levels != 1 or d.contains(rb + "nbr_levels"):
-            if not single:
-                raise NotImplementedError("tagging-driven refinement (regridding) is not driven (SURVEY §8f-2): give "
-                                          "refinement_boxes, or max_nbr_levels = 1 (PHARE_B200_SINGLE_LEVEL=1 runs the "
-                                          "root level only)")
-            import warnings
-            warnings.warn("PHARE_B200_SINGLE_LEVEL=1: refinement ignored, running the root level only")
+            if single:
+                import warnings
+                warnings.warn("PHARE_B200_SINGLE_LEVEL=1: refinement ignored, running the root level only")
+            elif d.get(sim + "AMR/refinement/tagging/method", "none") == "auto":
+                # refinement="tagging": DefaultTaggerStrategy + our own tile clustering (phare_b200.tagging)
+                self.tagging = dict(threshold=float(d.get(sim + "AMR/refinement/tagging/threshold", 0.1)),
+                                    tag_buffer=int(d.get(sim + "AMR/tag_buffer", 1)),
+                                    nesting_buffer=d.get(sim + "AMR/nesting_buffer", 1),
+                                    max_nbr_levels=self.max_nbr_levels)
+            else:
+                raise NotImplementedError("max_nbr_levels > 1 needs refinement_boxes or refinement='tagging' "
+                                          "(PHARE_B200_SINGLE_LEVEL=1 runs the root level only)")
         self.largest = d.get(sim + "AMR/largest_patch_size")
         self.smallest = d.get(sim + "AMR/smallest_patch_size")
         self.interp = int(d[sim + "interp_order"])
@@ -279,6 +286,13 @@ class Simulator:
             self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)
             for boxes in h.refinement_boxes:
                 self.amr.add_level([refine_box(Box(lo, hi)) for lo, hi in boxes])
+        self.tagger = None
+        if h.tagging:
+            from .amr import Hierarchy as PatchHierarchy
+            from .tagging import Tagger
+            self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)
+            self.tagger = Tagger(smallest_patch_size=h.smallest, largest_patch_size=h.largest, **h.tagging)
+            self.amr.regrid_tagged(self.tagger)  # the initial hierarchy: tag level 0, build level 1, tag it, ...
         self.is_initialized = True
 
     def level_solvers(self):
@@ -290,6 +304,8 @@ class Simulator:
             raise RuntimeError("Error - no valid integrator in the simulator")
         if getattr(self, "amr", None):
             self.amr.advance(dt)  # root step + sub-cycles of the finer levels + synchronisation
+            if getattr(self, "tagger", None):
+                self.amr.regrid_tagged(self.tagger)  # TimeRefinementIntegrator: regrid_interval = 1
         else:
             self.solver.advance_level(dt)
         self.elapsed += dt  # ConstantTimeStamper (core/utilities/time_stamper.hpp)
