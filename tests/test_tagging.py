@@ -190,3 +190,47 @@ def test_pyphare_runs_the_reference_tagged_script_unchanged(cpu_backend, tmp_pat
     ph.global_vars.sim = None
     for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
         del sys.modules[k]
+
+
+@pytest.mark.skipif(not __import__("os").path.isdir(REF + "/pyphare"), reason="reference tree not mounted")
+def test_pyphare_runs_the_reference_harris_script_with_its_tagging(cpu_backend, tmp_path, monkeypatch):
+    """tests/functional/harris/harris_2d.py as it is (refinement="tagging", two levels; only the domain is shrunk): the
+    refined level is made of two strips along the current sheets at y = 0.3 Ly and 0.7 Ly.  (The strips stop four root
+    cells short of the periodic x boundary: a refined level has to stay inside the root domain here.)"""
+    import importlib
+    import os
+    import sys
+    from unittest import mock
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections", "matplotlib.colors",
+                 "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py", "ddt"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.syspath_prepend(REF)
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        monkeypatch.delitem(sys.modules, k)
+    h = importlib.import_module("tests.functional.harris.harris_2d")
+    h.cells, h.final_time, h.timestamps, h.diag_dir = (60, 100), 0.005, np.array([0.0]), str(tmp_path / "out")
+    sim = h.config()
+    assert sim.refinement == "tagging" and sim.max_nbr_levels == 2
+    from pyphare.simulator.simulator import Simulator
+    import pyphare.pharein as ph
+    simulator = Simulator(sim, log_to_file=False)
+    simulator.initialize()
+    amr = simulator.cpp_sim.amr
+    assert len(amr.levels) == 2
+    boxes = sorted(((p.box.lo.tolist(), p.box.hi.tolist()) for p in amr.levels[1].geom.patches), key=lambda b: b[0][1])
+    assert len(boxes) == 2
+    for (lo, hi), y0 in zip(boxes, (0.3 * 40.0, 0.7 * 40.0)):
+        assert lo[1] * 0.2 < y0 - 1.0 and (hi[1] + 1) * 0.2 > y0 + 1.0          # the sheet (half width 0.5) is inside
+        assert (hi[1] - lo[1] + 1) * 0.2 < 8.0 and hi[0] - lo[0] + 1 >= 100     # a strip along x
+    simulator.advance()
+    ops = simulator.cpp_sim.solver.ops
+    assert sum(ops.count(p.pops[0].domain) for p in amr.levels[0].solver.patches) == 60 * 100 * 100
+    for p in simulator.cpp_sim.amr.levels[1].solver.patches:
+        assert not np.isnan(ops.get_field(p.B[0])).any() and np.isfinite(ops.get_field(p.Ne)[2:-2, 2:-2]).all()
+    simulator.reset()
+    ph.global_vars.sim = None
+    for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
+        del sys.modules[k]
