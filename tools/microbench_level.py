@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from phare_b200 import abi
 from phare_b200.device import Context
 from phare_b200.split import pattern
-from phare_b200.torch_interop import TorchArray, TorchVec, TorchParticles, current_stream_ptr, uniform_sorted_particles
+from phare_b200.torch_interop import TorchVec, TorchParticles, current_stream_ptr, uniform_sorted_particles
 import ctypes as C
 
 from microbench import timeit, HBM
