@@ -169,6 +169,19 @@ class CpuOps:
         assert rc == 0, rc
         return int(n.value)
 
+    def try_export(self, layout, src, first, last, box, dst, minus=None, shift=None):
+        """export(), but a destination that is too small yields None (nothing appended) instead of an error"""
+        n0 = dst.n
+        n = C.c_size_t()
+        sh = (C.c_int * 3)(*([int(s) for s in shift] + [0] * (3 - len(shift)))) if shift is not None else None
+        rc = self.lib.pho_export(C.byref(layout), C.byref(src.c), C.c_size_t(first), C.c_size_t(last), C.byref(box),
+                                 C.byref(minus) if minus is not None else None, sh, C.byref(dst.c), C.byref(n))
+        if rc == abi.PHB_ERR_CAPACITY:
+            dst.n = n0
+            return None
+        assert rc == 0, rc
+        return int(n.value)
+
     def export_multi(self, layout, src, first, last, boxes, shifts, dsts):
         return [self.export(layout, src, first, last, b, d, shift=s) for b, s, d in zip(boxes, shifts, dsts)]
 

@@ -18,8 +18,8 @@ schedules it would create are explicit box plans):
   makeNonLevelGhostBoxFor          src/amr/resources_manager/amr_utils.hpp:233-253
 The field operators themselves are CUDA kernels behind the C ABI (csrc/level.cu, csrc/split.cu).
 
-Scope: refinement boxes are fixed (no tagging / regridding / load balancing) and a refined level together with its
-ghost layers must lie inside the (periodic) root domain.  Patches of every level are dealt to the ranks (one per GPU).
+Scope: refinement boxes given by the user or by tagging (phare_b200.tagging; no load balancing); a refined level may reach
+or span a periodic boundary of the root domain.  Patches of every level are dealt to the ranks (one per GPU).
 """
 import numpy as np
 
@@ -29,6 +29,7 @@ from .messenger import HybridMessenger, LevelGeom, LocalComm, PatchGeom, centeri
 from .solver import Patch, SolverPPC
 
 RATIO = 2                      # amr/amr_constants.hpp: refinementRatio
+MAX_BOXES = 28                 # csrc/common.cuh: box lists passed to a kernel
 SUBSTEPS = RATIO * RATIO       # getMaxFinerLevelDt: dt_fine = dt_coarse / ratio^2
 DEFAULT_NREF = {1: 2, 2: 4, 3: 6}
 
@@ -70,7 +71,9 @@ class RefinedLevelMessenger(HybridMessenger):
         super().__init__(geom, ops, comm, peer_halo=False)
         self.coarse = coarse_solver
         g = geom.g
-        level_boxes = [p.box for p in geom.patches]
+        # the patches of the level and, when the level reaches a periodic boundary of the domain (geom.periodic), their
+        # periodic images: a ghost cell covered by an image belongs to the level, not to the coarser one
+        level_boxes = [p.box.shift(t) for p in geom.patches for t in geom.shifts]
         self._nan, self._scratch, self._lg_excluded, self.lg_particle_boxes = {}, {}, {}, {}
         for p in geom.patches:
             # level-ghost cells: the ghost layer minus every patch of the level (fields: g cells, particles: pg cells)
@@ -85,7 +88,7 @@ class RefinedLevelMessenger(HybridMessenger):
                     self._scratch[(p.id, qty)] = (None, cbox)
                     continue
                 # setNaNsOnFieldGhosts: ghost field box minus the field boxes of the level's patches
-                nan = minus_all([gfb], [q.interior_field_box(qty) for q in geom.patches])
+                nan = minus_all([gfb], [q.interior_field_box(qty).shift(t) for q in geom.patches for t in geom.shifts])
                 self._nan[(p.id, qty)] = [(b.lo - gfb.lo, b.shape()) for b in nan]
                 self._scratch[(p.id, qty)] = (ops.array(cbox.shape()), cbox)
         self._gather, self._nan_ops = {}, {}
@@ -105,30 +108,34 @@ class RefinedLevelMessenger(HybridMessenger):
             local, send_items, recv_items = [], {}, {}
             arrays = cs._by_id(name)
             for p in self.geom.patches:
+                # A coarse node on a patch border has one copy per patch, and the synchronisation only refreshes the
+                # copy of the patch the fine level overlaps: the coarse patches (images) under this fine patch come first.
+                under = coarsen_box(p.box)
+                sources = sorted(((q, t) for q in cs.geom.patches for t in cs.geom.shifts),
+                                 key=lambda qt: 0 if under * qt[0].box.shift(qt[1]) is not None else 1)
                 for c in range(3):
                     qty = qty0 + c
                     scratch, cbox = self._scratch[(p.id, qty)]
                     todo = [cbox]
                     for providers in ("interior", "ghost"):
-                        for q in cs.geom.patches:
-                            for t in cs.geom.shifts:
-                                src = q.interior_field_box(qty) if providers == "interior" else q.ghost_field_box(qty, cs.geom.g)
-                                src = src.shift(t)
-                                rest = []
-                                for piece in todo:
-                                    ov = piece * src
-                                    if ov is None:
-                                        rest.append(piece)
-                                        continue
-                                    dlo, slo, ext = ov.lo - cbox.lo, q.local(ov.lo - t, cs.geom.g), ov.shape()
-                                    if p.owner == me and q.owner == me:
-                                        local.append((scratch, dlo, arrays[q.id][c], slo, ext, 0))
-                                    elif p.owner == me:
-                                        recv_items.setdefault(q.owner, []).append((scratch, dlo, ext))
-                                    elif q.owner == me:
-                                        send_items.setdefault(p.owner, []).append((arrays[q.id][c], slo, ext))
-                                    rest += piece.minus(ov)
-                                todo = rest
+                        for q, t in sources:
+                            src = q.interior_field_box(qty) if providers == "interior" else q.ghost_field_box(qty, cs.geom.g)
+                            src = src.shift(t)
+                            rest = []
+                            for piece in todo:
+                                ov = piece * src
+                                if ov is None:
+                                    rest.append(piece)
+                                    continue
+                                dlo, slo, ext = ov.lo - cbox.lo, q.local(ov.lo - t, cs.geom.g), ov.shape()
+                                if p.owner == me and q.owner == me:
+                                    local.append((scratch, dlo, arrays[q.id][c], slo, ext, 0))
+                                elif p.owner == me:
+                                    recv_items.setdefault(q.owner, []).append((scratch, dlo, ext))
+                                elif q.owner == me:
+                                    send_items.setdefault(p.owner, []).append((arrays[q.id][c], slo, ext))
+                                rest += piece.minus(ov)
+                            todo = rest
                     if todo:
                         raise RuntimeError(f"refined patch {p.box} is not nested in the coarser level (uncovered {todo})")
             self._gather[name] = self._finish(local, send_items, recv_items, 0)
@@ -224,12 +231,29 @@ class RefinedLevelMessenger(HybridMessenger):
             boxes = [abi.make_box(b.lo, b.hi) for b in fine_boxes]
             if not boxes:
                 continue
+            if len(boxes) > MAX_BOXES:
+                raise RuntimeError(f"{len(boxes)} destination boxes for one patch (the kernels take {MAX_BOXES})")
             reach = [coarsen_box(b.grow(RATIO * 2)) for b in fine_boxes]  # split stencil: <= 2 fine cells
-            for q in self.coarse.patches:
+            for q, t in ((q, t) for q in self.coarse.patches for t in self.coarse.geom.shifts):
                 src = q.pops[ipop].domain
                 n = ops.count(src)
-                if n == 0 or not any(r * q.geom.box is not None for r in reach):
-                    continue  # no particle of this coarse patch can land in the destination boxes
+                if n == 0 or not any(r * q.geom.box.shift(t) is not None for r in reach):
+                    continue  # no particle of this coarse patch (image) can land in the destination boxes
+                if t.any():
+                    # a periodic image of the coarse patch: its particles near the destination, index-shifted like
+                    # ParticlesData::pack does for a periodic overlap (particles_data.hpp:745-756), then split
+                    image = ops.staging_particles(q.layout, 4096)
+                    taken = []  # the reaches of neighbouring destination boxes overlap: every particle once
+                    for r in reach:
+                        part = r.shift(-t) * q.geom.box
+                        for piece in (minus_all([part], taken) if part is not None else []):
+                            taken.append(piece)
+                            while ops.try_export(q.layout, src, 0, n, abi.make_box(piece.lo, piece.hi), image, None,
+                                                 [int(x) for x in t]) is None:
+                                image = ops.grow_particles(q.layout, image, 2 * ops.capacity(image) + 4096)
+                    src, n = image, ops.count(image)
+                    if n == 0:
+                        continue
                 if pg.owner == me:
                     patch = mine[pg.id]
                     try_split(src, n, boxes, lambda: getattr(patch.pops[ipop], attr),
@@ -331,12 +355,16 @@ class Hierarchy:
                     return q.owner
             raise ValueError(f"refinement box {box} does not start inside the coarser level")
         patches_g = [PatchGeom(i, b, owner_of(b)) for i, b in enumerate(boxes)]
-        geom = LevelGeom(fine_domain, patches_g, interp, periodic=False)
-        # nesting: the level with its field ghost layer and the split stencil stays inside the root domain
-        margin = geom.g + 2 * RATIO
+        # a level whose ghost layers (and split stencil) stay inside the domain never sees a periodic image; one that
+        # reaches the boundary is periodic like the domain (its patches then see their images across it)
+        margin = (2 if interp == 1 else 4) + 2 * RATIO
+        reaches = any(np.any(b.lo - margin < 0) or np.any(b.hi + margin >= np.asarray(fine_domain)) for b in boxes)
+        if reaches and not self.levels[0].geom.periodic:
+            raise ValueError("a refinement box reaches the boundary of a non periodic domain")
+        geom = LevelGeom(fine_domain, patches_g, interp, periodic=reaches)
         for pg in patches_g:
-            if np.any(pg.box.lo - margin < 0) or np.any(pg.box.hi + margin >= np.asarray(fine_domain)):
-                raise ValueError(f"refinement box {pg.box} is too close to the domain boundary")
+            if np.any(pg.box.lo < 0) or np.any(pg.box.hi >= np.asarray(fine_domain)):
+                raise ValueError(f"refinement box {pg.box} is outside the domain")
             if np.any(pg.box.lo % RATIO) or np.any((pg.box.hi + 1) % RATIO):
                 raise ValueError(f"refinement box {pg.box} is not aligned with the coarser cells")
         for a in patches_g:
@@ -362,8 +390,11 @@ class Hierarchy:
             patch = Patch(ops, pg, L, spec, capacity_factor=capacity_factor)
             # nonLevelGhostBox: the domain plus the part of the particle ghost layer that belongs to a neighbour patch
             patch.non_level_ghost = [patch.domain_box] + [
-                abi.make_box(ov.lo, ov.hi) for ov in (pg.box.grow(geom.pg) * q.box for q in patches_g if q.id != pg.id)
+                abi.make_box(ov.lo, ov.hi) for ov in (pg.box.grow(geom.pg) * q.box.shift(t) for q in patches_g
+                                                      for t in geom.shifts if q.id != pg.id or t.any())
                 if ov is not None]
+            if len(patch.non_level_ghost) > MAX_BOXES:
+                raise RuntimeError(f"patch {pg.box} has {len(patch.non_level_ghost) - 1} neighbours (the kernels take {MAX_BOXES - 1})")
             lg_cells = sum(b.volume() for b in msg.lg_particle_boxes[pg.id]) / RATIO ** dim
             for i, pop in enumerate(patch.pops):
                 pop.set_level_ghosts(ops, int(capacity_factor * self.nref * per_cell[i] * lg_cells) + 4096)

@@ -177,6 +177,16 @@ class GpuOps:
     def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
         return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
 
+    def try_export(self, layout, src, first, last, box, dst, minus=None, shift=None):
+        """export(), but a destination that is too small yields None (nothing appended) instead of an error"""
+        from .device import PhbError
+        try:
+            return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
+        except PhbError as e:
+            if e.code == abi.PHB_ERR_CAPACITY:
+                return None
+            raise
+
     def export_multi(self, layout, src, first, last, boxes, shifts, dsts):
         return self.ctx.export_multi(layout, src, first, last, boxes, shifts, dsts)
 

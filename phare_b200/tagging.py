@@ -169,13 +169,10 @@ class Tagger:
         mask, origin = level_tag_mask(level, hierarchy.ops, self.threshold)
         if self.tag_buffer:
             mask = _dilate(mask, self.tag_buffer)
-        # where level il+1 may live: inside the patches of level il shrunk by the nesting buffer (proper nesting) and,
-        # because a refined level with its ghost layers has to stay inside the periodic root domain here (amr.py), away
-        # from the domain boundary
+        # where level il+1 may live: anywhere on the root level; on a refined level inside its patches shrunk by the
+        # nesting buffer (proper nesting)
         nest = np.broadcast_to(self.nesting_buffer, (dim,)).astype(np.int64)
-        g = level.geom.g
-        margin = -(-(g + 4) // 2)  # add_level(): g + 2 * ratio cells of level il + 1
-        domain = Box([margin] * dim, [int(s) - 1 - margin for s in level.geom.domain_shape])
+        domain = Box([0] * dim, [int(s) - 1 for s in level.geom.domain_shape])
         if il == 0:
             allowed = [domain]
         else:

@@ -274,3 +274,83 @@ def test_regrid_onto_shifted_boxes_copies_the_overlap_and_refines_the_rest(cpu_o
     # removing the level
     assert h.regrid([]) is None and len(h.levels) == 1
     h.advance(0.004)
+
+
+def _shifted_run(ops, cells, dx, grid, interp, ppc, box, shift, steps=2):
+    """the hierarchy of a periodic problem translated by `shift` root cells (particles, B profile and refinement box)"""
+    from phare_b200.amr import build_hierarchy
+    from amr_util import SOLVER_KW, B_init_nd
+    from solver_util import global_particles
+    dim = len(cells)
+    icell, delta, w, q, v = global_particles(cells, interp, dx, ppc, 7)[0]
+    icell = (icell + np.asarray(shift)) % np.asarray(cells)
+    B0 = B_init_nd(cells, dx)
+    B_fn = lambda c, *x: B0(c, *[xi - shift[d] * dx[d] for d, xi in enumerate(x)])
+
+    def particles_fn(i, L, pid):
+        inside = np.ones(len(w), bool)
+        for d in range(dim):
+            inside &= (icell[:, d] >= L.amr_lower[d]) & (icell[:, d] < L.amr_lower[d] + L.ncells[d])
+        return icell[inside].astype(np.int32), delta[inside], w[inside], q[inside], v[inside]
+
+    lo, hi = box
+    sbox = ([int(a + s) for a, s in zip(lo, shift)], [int(a + s) for a, s in zip(hi, shift)])
+    h = build_hierarchy(ops, cells, grid, interp, dx, [dict(name="pop0", mass=1.0)], B_fn, particles_fn,
+                        refinement_boxes=[[sbox]], solver_kw=SOLVER_KW)
+    for _ in range(steps):
+        h.advance(0.004)
+    return h
+
+
+@pytest.mark.parametrize("case", [
+    # (translations by half the domain map the two root patches onto each other, so that both runs see the coarse-fine
+    # boundary on a root patch border: a coarse border node has one copy per patch and the synchronisation only updates
+    # the copy of the patch the fine level overlaps, in the reference as here)
+    ([64], [0.2], [2], 1, 20, ([32], [51]), [-32]),              # the refined level touches x = 0
+    ([64], [0.2], [2], 2, 12, ([8], [31]), [32]),                # ... and x = L (order 2: wider ghost layers)
+    ([24, 16], [0.25, 0.25], [2, 1], 1, 6, ([0, 5], [23, 10]), [0, 0]),   # a strip spanning the whole periodic x extent
+])
+def test_refined_level_at_a_periodic_boundary_is_translation_invariant(cpu_ops_factory, case):
+    """a refined level may reach (or span) a periodic boundary: its ghost cells beyond the boundary are then filled from
+    the periodic images (of the level itself, of the coarser fields, of the coarser particles).  The physics does not know
+    where the origin is: the same problem translated so that the level sits in the middle of the domain must give the
+    same result."""
+    from amr_util import level_fields
+    cells, dx, grid, interp, ppc, box, shift = case
+    dim = len(cells)
+    if dim == 2:
+        # the strip: compare the run with itself translated by 5 cells along x (the level spans x either way)
+        a = _shifted_run(cpu_ops_factory(dim, interp), cells, dx, grid, interp, ppc, box, [0, 0])
+        b = _shifted_run(cpu_ops_factory(dim, interp), cells, dx, [1, 1], interp, ppc, box, [0, 0])
+        pa, pb = a.levels[1].solver.patches[0], b.levels[1].solver.patches[0]
+        assert a.levels[1].geom.periodic and pa.geom.box.shape()[0] == 2 * cells[0]
+        for attr in ("B", "E", "Vi"):
+            for c in range(3):
+                x, y = a.ops.get_field(getattr(pa, attr)[c]), b.ops.get_field(getattr(pb, attr)[c])
+                ok = np.isfinite(y)
+                assert np.array_equal(np.isnan(x), np.isnan(y))
+                assert np.max(np.abs(x[ok] - y[ok])) <= 1e-10 * (np.max(np.abs(y[ok])) + 1e-30), (attr, c)
+        assert not np.isnan(a.ops.get_field(pa.B[0])).any()
+        assert a.ops.count(pa.pops[0].domain) == b.ops.count(pb.pops[0].domain)
+        return
+    mid = _shifted_run(cpu_ops_factory(dim, interp), cells, dx, grid, interp, ppc, box, [0])
+    edge = _shifted_run(cpu_ops_factory(dim, interp), cells, dx, grid, interp, ppc, box, shift)
+    assert not mid.levels[1].geom.periodic and edge.levels[1].geom.periodic
+    pm, pe = mid.levels[1].solver.patches[0], edge.levels[1].solver.patches[0]
+    assert int(pe.geom.box.lo[0]) == 0 or int(pe.geom.box.hi[0]) == 2 * cells[0] - 1
+    for pop_attr in ("domain", "level_ghost", "level_ghost_old"):
+        assert mid.ops.count(getattr(pm.pops[0], pop_attr)) == edge.ops.count(getattr(pe.pops[0], pop_attr)) > 0
+    for attr in ("B", "E", "Vi", "J"):
+        for c in range(3):
+            x, y = mid.ops.get_field(getattr(pm, attr)[c]), edge.ops.get_field(getattr(pe, attr)[c])
+            assert np.array_equal(np.isnan(x), np.isnan(y)), (attr, c)
+            ok = np.isfinite(x)
+            assert np.max(np.abs(x[ok] - y[ok]), initial=0.0) <= 1e-10 * (np.max(np.abs(x[ok])) + 1e-30), (attr, c)
+    x, y = mid.ops.get_field(pm.Ne), edge.ops.get_field(pe.Ne)
+    assert np.max(np.abs(x - y)) <= 1e-10 * np.max(np.abs(x))
+    # the root level: the same fields, rolled
+    g = mid.levels[0].geom.g
+    root = lambda h, fn: np.concatenate([h.ops.get_field(fn(p))[g:g + p.layout.ncells[0]] for p in h.levels[0].solver.patches])
+    for fn in (lambda p: p.B[1], lambda p: p.E[2], lambda p: p.Ne):
+        rm, re = root(mid, fn), root(edge, fn)
+        assert np.max(np.abs(np.roll(rm, shift[0]) - re)) <= 1e-10 * np.max(np.abs(rm))

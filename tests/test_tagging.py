@@ -195,8 +195,8 @@ def test_pyphare_runs_the_reference_tagged_script_unchanged(cpu_backend, tmp_pat
 @pytest.mark.skipif(not __import__("os").path.isdir(REF + "/pyphare"), reason="reference tree not mounted")
 def test_pyphare_runs_the_reference_harris_script_with_its_tagging(cpu_backend, tmp_path, monkeypatch):
     """tests/functional/harris/harris_2d.py as it is (refinement="tagging", two levels; only the domain is shrunk): the
-    refined level is made of two strips along the current sheets at y = 0.3 Ly and 0.7 Ly.  (The strips stop four root
-    cells short of the periodic x boundary: a refined level has to stay inside the root domain here.)"""
+    refined level is made of two strips along the current sheets at y = 0.3 Ly and 0.7 Ly, spanning the periodic x
+    extent of the domain (the level is then periodic in x like the domain)."""
     import importlib
     import os
     import sys
@@ -224,7 +224,8 @@ def test_pyphare_runs_the_reference_harris_script_with_its_tagging(cpu_backend, 
     assert len(boxes) == 2
     for (lo, hi), y0 in zip(boxes, (0.3 * 40.0, 0.7 * 40.0)):
         assert lo[1] * 0.2 < y0 - 1.0 and (hi[1] + 1) * 0.2 > y0 + 1.0          # the sheet (half width 0.5) is inside
-        assert (hi[1] - lo[1] + 1) * 0.2 < 8.0 and hi[0] - lo[0] + 1 >= 100     # a strip along x
+        assert (hi[1] - lo[1] + 1) * 0.2 < 8.0 and (lo[0], hi[0]) == (0, 119)   # a strip along the whole x extent
+    assert amr.levels[1].geom.periodic
     simulator.advance()
     ops = simulator.cpp_sim.solver.ops
     assert sum(ops.count(p.pops[0].domain) for p in amr.levels[0].solver.patches) == 60 * 100 * 100
