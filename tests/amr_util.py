@@ -14,6 +14,7 @@ CASES = {
     "1d_o3_two_patches": ([64], [0.2], [1], 3, 12, [[([12], [27]), ([28], [45])]]),
     "1d_o1_three_levels": ([64], [0.2], [1], 1, 16, [[([16], [47])], [([48], [79])]]),
     "1d_o2_three_levels_two_root_patches": ([64], [0.2], [2], 2, 12, [[([14], [47])], [([40], [71])]]),
+    "1d_o1_at_the_periodic_boundary": ([64], [0.2], [2], 1, 20, [[([0], [19])]]),
     "2d_o1": ([32, 24], [0.2, 0.25], [2, 1], 1, 8, [[([8, 6], [15, 13]), ([16, 6], [21, 13])]]),
     "2d_o2_L": ([28, 28], [0.25, 0.25], [1, 1], 2, 6, [[([8, 8], [19, 13]), ([8, 14], [13, 19])]]),
     "3d_o1": ([16, 14, 12], [0.2, 0.25, 0.3], [2, 1, 1], 1, 4, [[([4, 4, 4], [9, 8, 7])]]),

@@ -64,7 +64,8 @@ def _worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["1d_o1", "1d_o2_three_levels_two_root_patches", "2d_o1", "3d_o1"])
+@pytest.mark.parametrize("name", ["1d_o1", "1d_o2_three_levels_two_root_patches", "1d_o1_at_the_periodic_boundary", "2d_o1",
+                                  "3d_o1"])
 def test_two_ranks_equal_one_process(cpu_ref, name, tmp_path):
     sys.path.insert(0, HERE)
     from oracle.cpu_ops import CpuOps
