@@ -192,21 +192,30 @@ class RefinedLevelMessenger(HybridMessenger):
         strategy, overwrite_interior) and E (electricInitRefiners_.regrid): a fresh, all-NaN array first takes what the
         old level holds (its interior field boxes), the remaining NaN nodes are refined from the coarser level, and the
         new fine faces of the cells that did not come from the old level get the Toth-Roe value"""
-        ops, g = self.ops, self.geom.g
-        old_boxes = [q.geom.box for q in old_solver.patches]
+        ops, g, me = self.ops, self.geom.g, self.me
+        old_geom = old_solver.geom.patches
+        old_boxes = [q.box for q in old_geom]
         for name, qty0, op in (("B", abi.BX, abi.REFINE_MAGNETIC), ("E", abi.EX, abi.REFINE_ELECTRIC)):
             vecs, old_vecs = solver._by_id(name), old_solver._by_id(name)
-            entries = []
+            local, send_items, recv_items = [], {}, {}
             for p in solver.patches:
                 for c in range(3):
-                    qty = qty0 + c
                     ops.box_fill(vecs[p.geom.id][c], [0] * self.geom.dim, vecs[p.geom.id][c].shape, float("nan"))
-                    for q in old_solver.patches:
-                        ov = p.geom.ghost_field_box(qty, g) * q.geom.interior_field_box(qty)
-                        if ov is not None:
-                            entries.append((vecs[p.geom.id][c], p.geom.local(ov.lo, g), old_vecs[q.geom.id][c],
-                                            q.geom.local(ov.lo, g), ov.shape(), 0))
-            ops.run_box_ops(ops.compile_box_ops(entries))
+            for pg in self.geom.patches:
+                for c in range(3):
+                    qty = qty0 + c
+                    for qg in old_geom:
+                        ov = pg.ghost_field_box(qty, g) * qg.interior_field_box(qty)
+                        if ov is None:
+                            continue
+                        dlo, slo, ext = pg.local(ov.lo, g), qg.local(ov.lo, g), ov.shape()
+                        if pg.owner == me and qg.owner == me:
+                            local.append((vecs[pg.id][c], dlo, old_vecs[qg.id][c], slo, ext, 0))
+                        elif pg.owner == me:
+                            recv_items.setdefault(qg.owner, []).append((vecs[pg.id][c], dlo, ext))
+                        elif qg.owner == me:
+                            send_items.setdefault(pg.owner, []).append((old_vecs[qg.id][c], slo, ext))
+            self._run(self._finish(local, send_items, recv_items, 0), ("regrid", name))
             excluded = {p.geom.id: [abi.make_box(ov.lo, ov.hi) for ov in (p.geom.box.grow(g) * b for b in old_boxes)
                                     if ov is not None] for p in solver.patches}
             self._refine(name, qty0, vecs, op, excluded=excluded)
@@ -414,11 +423,10 @@ class Hierarchy:
         removed).  HybridHybridMessengerStrategy::regrid (:265-311) + HybridLevelInitializer::initialize(isRegridding):
         where the new level overlaps the old one its E, B and domain particles are COPIED from it, everywhere else they
         come from the next coarser level exactly as at level creation (B: coarse faces + Toth-Roe on the cells that were
-        not copied; E: electric refiner; particles: splitting); level ghosts and moments are rebuilt.  One rank only."""
+        not copied; E: electric refiner; particles: splitting); level ghosts and moments are rebuilt.  Old and new patches
+        may live on different ranks: the copies then travel as packed point-to-point messages."""
         if len(self.levels) < 2:
             raise RuntimeError("there is no refined level to regrid")
-        if self.comm.size > 1:
-            raise NotImplementedError("regridding moves data between owners: not driven across ranks yet")
         old = self.levels.pop()
         if not fine_boxes:
             return None
@@ -429,8 +437,6 @@ class Hierarchy:
         i+1 follow from the tags of level i (phare_b200.tagging); a level whose boxes (and whose coarser levels) did not
         change is kept as it is, otherwise it is rebuilt by regrid() semantics from its old self and the level below.
         Returns True when the hierarchy changed."""
-        if self.comm.size > 1:
-            raise NotImplementedError("tagging-driven regridding is driven on one rank only")
         old_levels = self.levels[1:]
         self.levels = self.levels[:1]
         changed = False
@@ -460,16 +466,37 @@ class Hierarchy:
         old_boxes = [q.box for q in old.geom.patches] if old is not None else []
         for i in range(npop):
             if old is not None:
-                # domain particles of the old level that lie in a patch of the new one are kept as they are
-                for p in s.patches:
-                    for q in old.solver.patches:
-                        both = p.geom.box * q.geom.box
-                        n = ops.count(q.pops[i].domain)
+                # domain particles of the old level that lie in a patch of the new one are kept as they are (shipped to
+                # the owner of the new patch when it is another rank)
+                mine = {p.geom.id: p for p in s.patches}
+                remote = {}
+                for q in old.solver.patches:
+                    n = ops.count(q.pops[i].domain)
+                    for pg in level.geom.patches:
+                        both = pg.box * q.geom.box
                         if both is None or n == 0:
                             continue
-                        while ops.capacity(p.pops[i].domain) < ops.count(p.pops[i].domain) + n:
-                            grow_store(ops, p, i, p.pops[i].domain)
-                        ops.export(q.layout, q.pops[i].domain, 0, n, abi.make_box(both.lo, both.hi), p.pops[i].domain)
+                        box = abi.make_box(both.lo, both.hi)
+                        if pg.owner == self.comm.rank:
+                            p = mine[pg.id]
+                            while ops.capacity(p.pops[i].domain) < ops.count(p.pops[i].domain) + n:
+                                grow_store(ops, p, i, p.pops[i].domain)
+                            ops.export(q.layout, q.pops[i].domain, 0, n, box, p.pops[i].domain)
+                        else:
+                            key = (pg.owner, pg.id)
+                            have = ops.count(remote[key]) if key in remote else 0
+                            if key not in remote:
+                                remote[key] = ops.staging_particles(q.layout, n)
+                            elif ops.capacity(remote[key]) < have + n:
+                                remote[key] = ops.grow_particles(q.layout, remote[key], have + n)
+                            ops.export(q.layout, q.pops[i].domain, 0, n, box, remote[key])
+                if self.comm.size > 1:
+                    def ensure(pid, needed, i=i):
+                        while ops.capacity(mine[pid].pops[i].domain) < needed:
+                            grow_store(ops, mine[pid], i, mine[pid].pops[i].domain)
+                        return mine[pid].pops[i].domain
+                    msg._exchange_particles({pid: p.layout for pid, p in mine.items()}, remote,
+                                            {pid: p.pops[i].domain for pid, p in mine.items()}, {pid: 0 for pid in mine}, ensure)
             # domainParticlesRefiners_ (interior; on a regrid: the part of the interior the old level did not cover) and
             # lvlGhostPartOldRefiners_ (coarseBoundaryOld)
             msg.split_from_coarser(i, self.nref, lambda pg: minus_all([pg.box], old_boxes), "domain")

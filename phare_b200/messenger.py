@@ -141,6 +141,9 @@ class LocalComm:
     def allreduce_max(self, v):
         return v
 
+    def allreduce_array_max(self, a):
+        return a
+
     def alltoall_counts(self, counts):
         return counts
 
@@ -179,6 +182,13 @@ class TorchComm:
         t = torch.tensor([int(v)], dtype=torch.int64, device=self.device)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return int(t.item())
+
+    def allreduce_array_max(self, a):
+        """element-wise max over the ranks of a small host integer array (tag masks)"""
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(a).astype(np.int32)).to(self.device if self.device is not None else "cpu")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.cpu().numpy().astype(a.dtype).reshape(a.shape)
 
     def alltoall_counts(self, counts):
         """counts[peer] = ints I send to peer (list of equal length per peer); returns what they send me"""

@@ -12,7 +12,7 @@ Mirrors (file:line relative to the PHARE tree):
 
 Scope: periodic boundaries, HybridModel; one level, or a STATIC hierarchy given by `refinement_boxes` (phare_b200.amr:
 ratio 2, sub-cycling, refluxing; patches of every level dealt to the ranks), or `refinement="tagging"` (the
-reference's tagging criterion, our own tile clustering, regridding after every root step; one rank).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
+reference's tagging criterion, our own tile clustering, regridding after every root step).  The compute back end is GpuOps (CUDA through the C ABI) — `ops_factory` is the seam the CPU parity
 tests replace.
 """
 import ctypes as C

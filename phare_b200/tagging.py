@@ -51,11 +51,12 @@ def default_tags(dim, interp, B, ncells, threshold=0.1):
     return tags
 
 
-def level_tag_mask(level, ops, threshold):
-    """(mask, origin): boolean mask of the tagged cells of `level` over the bounding box of its patches"""
+def level_tag_mask(level, ops, threshold, comm=None):
+    """(mask, origin): boolean mask of the tagged cells of `level` over the bounding box of its patches; every rank
+    tags the patches it owns, the masks are merged (element-wise max over the ranks)"""
     patches = level.solver.patches
-    lo = np.min([p.geom.box.lo for p in patches], axis=0)
-    hi = np.max([p.geom.box.hi for p in patches], axis=0)
+    lo = np.min([p.box.lo for p in level.geom.patches], axis=0)
+    hi = np.max([p.box.hi for p in level.geom.patches], axis=0)
     mask = np.zeros(tuple(int(x) for x in hi - lo + 1), dtype=bool)
     dim = len(lo)
     for p in patches:
@@ -63,6 +64,8 @@ def level_tag_mask(level, ops, threshold):
         t = default_tags(dim, p.layout.interp, B, [p.layout.ncells[d] for d in range(dim)], threshold)
         sl = tuple(slice(int(p.geom.box.lo[d] - lo[d]), int(p.geom.box.hi[d] - lo[d]) + 1) for d in range(dim))
         mask[sl] |= t.astype(bool)
+    if comm is not None and comm.size > 1:
+        mask = comm.allreduce_array_max(mask.astype(np.int32)).astype(bool)
     return mask, lo
 
 
@@ -163,10 +166,8 @@ class Tagger:
     def boxes(self, hierarchy, il):
         """cell boxes of level il (its own index space) to be covered by level il + 1"""
         level = hierarchy.levels[il]
-        if not level.solver.patches:
-            return []
         dim = level.geom.dim
-        mask, origin = level_tag_mask(level, hierarchy.ops, self.threshold)
+        mask, origin = level_tag_mask(level, hierarchy.ops, self.threshold, hierarchy.comm)
         if self.tag_buffer:
             mask = _dilate(mask, self.tag_buffer)
         # where level il+1 may live: anywhere on the root level; on a refined level inside its patches shrunk by the

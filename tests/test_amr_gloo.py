@@ -154,3 +154,73 @@ def test_simulator_with_refinement_on_two_ranks_equals_one(cpu_ref, tmp_path):
             ok = np.isfinite(w)
             assert np.array_equal(np.isnan(got[k]), np.isnan(w)), k
             assert np.max(np.abs(got[k][ok] - w[ok]), initial=0.0) <= 1e-11 * (np.max(np.abs(w[ok])) + 1e-30), k
+
+
+def _tagged_run():
+    """a double tangential discontinuity advected at vx = 2 with refinement="tagging" (three levels): the hierarchy is
+    built from tags and regridded after every root step (the finest level moves during the run)"""
+    import phare_b200.simulator as S
+    import pybindlibs.dictator as pp
+    from oracle.cpu_ops import CpuOps
+    from frontend_util import populate, const
+    S.ops_factory = lambda dim, interp: CpuOps(dim, interp)
+    cells, dl = 200, 1.0
+    Lx = cells * dl
+    Sx = lambda x, x0: 0.5 * (1 + np.tanh((x - x0) / 1.0))
+    by = lambda x: -1 + 2 * (Sx(x, 0.25 * Lx) - Sx(x, 0.75 * Lx))
+    T = lambda x: 1 - 0.5 * (by(x) ** 2 + 0.25)
+    pop = dict(name="protons", mass=1.0, charge=1.0, ppc=30, seed=11, density=const(1.0), vx=const(2.0), vy=const(0),
+               vz=const(0), vthx=T, vthy=T, vthz=T)
+    populate([cells], [dl], 1, [pop], [const(0.0), by, const(0.5)], time_step=0.04, steps=12, nu=0.01, largest=[50])
+    pp.add_int("simulation/AMR/max_nbr_levels", 3)
+    pp.add_string("simulation/AMR/refinement/tagging/method", "auto")
+    pp.add_double("simulation/AMR/refinement/tagging/threshold", 0.1)
+    pp.add_int("simulation/AMR/tag_buffer", 1)
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    boxes0 = [[(int(p.box.lo[0]), int(p.box.hi[0])) for p in lvl.geom.patches] for lvl in sim.amr.levels]
+    for _ in range(12):
+        sim.advance(sim.timeStep())
+    res = {"boxes0": np.array(sum(boxes0[1:], []))}
+    res["boxes"] = np.array(sum([[(int(p.box.lo[0]), int(p.box.hi[0])) for p in lvl.geom.patches] for lvl in sim.amr.levels[1:]], []))
+    for il, solver in enumerate(sim.level_solvers()):
+        for p in solver.patches:
+            for name, h in (("By", p.B[1]), ("Ez", p.E[2]), ("Ne", p.Ne)):
+                res[f"{il}_{p.geom.id}_{name}"] = solver.ops.get_field(h)
+            res[f"{il}_{p.geom.id}_n"] = np.array([solver.ops.count(pop.domain) for pop in p.pops])
+    S.dict_instance().stop()
+    return res
+
+
+def _tagged_worker(rank, world, port, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    np.savez(os.path.join(out_dir, f"tag_rank{rank}.npz"), **_tagged_run())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_tagging_and_regridding_on_two_ranks_equal_one(cpu_ref, tmp_path):
+    sys.path.insert(0, HERE)
+    import phare_b200.simulator as S
+    old = S.ops_factory
+    try:
+        mp.spawn(_tagged_worker, args=(2, 29500 + (os.getpid() % 2000) + 13, str(tmp_path)), nprocs=2, join=True)
+        want = _tagged_run()
+    finally:
+        S.ops_factory = old
+    got = {}
+    for r in range(2):
+        got.update(np.load(os.path.join(str(tmp_path), f"tag_rank{r}.npz")))
+    assert len(want["boxes"]) == 4 and not np.array_equal(want["boxes"], want["boxes0"])   # the hierarchy moved
+    assert set(got) == set(want)
+    for k, w in want.items():
+        if k.startswith("boxes") or k.endswith("_n"):
+            assert np.array_equal(got[k], w), k
+        else:
+            ok = np.isfinite(w)
+            assert np.array_equal(np.isnan(got[k]), np.isnan(w)), k
+            assert np.max(np.abs(got[k][ok] - w[ok]), initial=0.0) <= 1e-10 * (np.max(np.abs(w[ok])) + 1e-30), k
