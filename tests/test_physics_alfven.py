@@ -136,3 +136,39 @@ def test_alfven_wave_crosses_a_refined_level_unperturbed(cpu_backend, cpu_ref):
     # and no particle pile-up or depletion at the level boundary
     ne = ops.get_field(fine.Ne)[g:-g]
     assert abs(ne.mean() - 1.0) < 0.02 and np.max(np.abs(ne - 1.0)) < 0.25
+
+
+def test_alfven_wave_along_y_in_2d(cpu_backend):
+    """the same wave on a 2-D domain, propagating along y (fields and velocities cyclically permuted): the 2-D field
+    solvers, gather and deposit treat the second direction like the first one.  0 < t < 10 as in the refined-level test,
+    where the 1-D run gives 1.054."""
+    import importlib
+    cells, dl, ampl = [4, 100], [1.0, 1.0], 0.01
+    k = 2 * np.pi / (cells[1] * dl[1])
+    pop = dict(name="protons", mass=1.0, charge=1.0, ppc=50, seed=1337, density=const(1.0),
+               vx=lambda x, y: ampl * np.sin(k * y), vy=const(0.0), vz=lambda x, y: ampl * np.cos(k * y),
+               vthx=const(0.01), vthy=const(0.01), vthz=const(0.01))
+    bfn = [lambda x, y: ampl * np.sin(k * y), const(1.0), lambda x, y: ampl * np.cos(k * y)]
+    dt, nsteps, every = 0.02, 500, 50
+    populate(cells, dl, 1, [pop], bfn, time_step=dt, steps=nsteps, eta=0.0, nu=1e-3, Te=0.0, largest=[4, 50])
+    sim = S.make_simulator(S.make_hierarchy(), 2, 1, 4)
+    sim.initialize()
+    m = importlib.import_module("pybindlibs.cpp_2_1_4")
+    dw = m.DataWrangler(sim, sim.hier)
+
+    def mode1():
+        bz = dw.sync_merge(dw.getPatchLevel(0).getBz(), False)      # dual in x and y
+        return np.fft.fft(bz[:, :cells[1]].mean(axis=0))[1] / (cells[1] / 2)
+    times, bz = [0.0], [mode1()]
+    for step in range(1, nsteps + 1):
+        sim.advance(dt)
+        if step % every == 0:
+            times.append(step * dt)
+            bz.append(mode1())
+    times, bz = np.array(times), np.array(bz)
+    assert np.all(np.abs(np.abs(bz) - ampl) < 0.1 * ampl), np.abs(bz)
+    phase = np.unwrap(np.angle(bz))
+    fit = np.polyfit(times, phase, 1)
+    vphi = abs(fit[0]) / k
+    assert abs(vphi - 1.054) < 0.01, vphi
+    assert np.max(np.abs(phase - np.polyval(fit, times))) < 0.05
