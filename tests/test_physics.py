@@ -172,3 +172,40 @@ def test_alfven_wave_along_y_in_2d(cpu_backend):
     vphi = abs(fit[0]) / k
     assert abs(vphi - 1.054) < 0.01, vphi
     assert np.max(np.abs(phase - np.polyval(fit, times))) < 0.05
+
+
+def test_ion_ion_beam_right_hand_mode_grows_at_the_linear_rate(cpu_backend):
+    """config 4's physics (tests/functional/ionIonBeam/ion_ion_beam1d.py scaled down: dt = 0.01 instead of 0.001, 25
+    particles per cell and population, 0 < t < 40): a 1 % beam at 5 vA drives the right-hand resonant mode, whose first
+    Fourier mode By - i Bz grows at 0.09 Omega_ci in the linear phase (the reference accepts 0.09 +- 0.02).  Two
+    populations, so this also checks their coupling through the total moments."""
+    import importlib
+    cells, dl, dt, T = 165, 0.2, 0.01, 40.0
+    vth = np.sqrt(0.1)
+    common = dict(mass=1.0, charge=1.0, ppc=25, vy=const(0), vz=const(0), vthx=const(vth), vthy=const(vth), vthz=const(vth))
+    main = dict(name="main", seed=5, density=const(1.0), vx=const(0.0), **common)
+    beam = dict(name="beam", seed=6, density=const(0.01), vx=const(5.0), **common)
+    populate([cells], [dl], 1, [main, beam], [const(1.0), const(0.0), const(0.0)], time_step=dt, steps=int(T / dt),
+             eta=0.0, nu=0.01, Te=0.0)
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    dw = importlib.import_module("pybindlibs.cpp_1_1_2").DataWrangler(sim, sim.hier)
+
+    def mode1():
+        lvl = dw.getPatchLevel(0)
+        by, bz = dw.sync_merge(lvl.getBy(), False)[:cells], dw.sync_merge(lvl.getBz(), False)[:cells]
+        return abs(np.fft.fft(by - 1j * bz)[1])
+    times, ampl = [], []
+    for step in range(int(T / dt)):
+        sim.advance(dt)
+        if step % 100 == 0:
+            times.append((step + 1) * dt)
+            ampl.append(mode1())
+    times, ampl = np.array(times), np.array(ampl)
+    linear = (times > 10) & (times < 38)
+    gamma = np.polyfit(times[linear], np.log(ampl[linear]), 1)[0]
+    assert abs(gamma - 0.09) < 0.02, gamma                       # measured: 0.097
+    assert ampl[-1] > 50 * ampl[1]                               # two orders of magnitude above the noise
+    ops = sim.solver.ops
+    p = sim.solver.patches[0]
+    assert ops.count(p.pops[0].domain) == ops.count(p.pops[1].domain) == cells * 25
