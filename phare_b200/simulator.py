@@ -17,6 +17,7 @@ tests replace.
 """
 import ctypes as C
 import os
+import time
 
 import numpy as np
 
@@ -26,6 +27,11 @@ from .setup import node_coords
 from .solver import Patch, SolverPPC, make_level
 
 XYZ = "xyz"
+
+
+def restart_path_for_time(path, timestamp):
+    """Hierarchy::restartFilePathForTime (src/amr/wrappers/hierarchy.hpp): <path>/<time as %011.5f>"""
+    return os.path.join(path, "{:0>11.5f}".format(timestamp))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -293,6 +299,9 @@ class Simulator:
             self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)
             self.tagger = Tagger(smallest_patch_size=h.smallest, largest_patch_size=h.largest, **h.tagging)
             self.amr.regrid_tagged(self.tagger)  # the initial hierarchy: tag level 0, build level 1, tag it, ...
+        load = self.d.get("simulation/restarts/loadPath")
+        if load:  # Hierarchy::from_restart / initializeHierarchy from the restart database (simulator.hpp:332, 401)
+            self.load_restart(self.restart_file(load))
         self.is_initialized = True
 
     def level_solvers(self):
@@ -402,8 +411,115 @@ class Simulator:
                             f"{kind}/v": v}
         return {}
 
+    # ---- restarts.  The reference writes one SAMRAI restart database per rank under
+    # <filePath>/<time as %011.5f>/ plus the serialized simulation (restarts/detail/h5writer.hpp:41-61); here the directory
+    # and its name are the same (pyphare's own checks and its keep_last pruning see what they expect) and the per-rank file
+    # is a raw .npz of the device state
+    _PARTICLE_STORES = ("domain", "level_ghost", "level_ghost_old", "level_ghost_new")
+
+    def restart_file(self, directory):
+        return os.path.join(directory, f"restart_rank{self.solver.comm.rank:06d}.npz")
+
     def dump_restarts(self, timestamp, timestep):
-        return False  # restart files are out of scope (restarts)
+        """RestartsManager::dump (restarts/restarts_manager.hpp:62-100, 140-155): written when the next requested
+        simulation time is within one time step (compared in float) or the next requested wall-clock time has passed"""
+        r = self.d.get("simulation/restarts")
+        if not isinstance(r, dict) or self.solver is None or not ("write_timestamps" in r or "elapsed_timestamps" in r):
+            return False  # loading only, or restarts not active
+        if not hasattr(self, "_restart_next"):
+            self._restart_next = [0, 0]
+            self._restart_t0 = time.time()
+        ts = np.asarray(r.get("write_timestamps", ()), dtype=np.float64).reshape(-1)
+        el = np.asarray(r.get("elapsed_timestamps", ()), dtype=np.float64).reshape(-1)
+        i, j = self._restart_next
+        sim_unit = bool(i < ts.size and np.float32(abs(ts[i] - timestamp)) < np.float32(timestep))
+        elapsed = bool(j < el.size and time.time() > self._restart_t0 + el[j])
+        self._restart_next = [i + sim_unit, j + elapsed]
+        if not (sim_unit or elapsed):
+            return False
+        directory = restart_path_for_time(r.get("filePath", "phare_outputs"), timestamp)
+        self.save_restart(self.restart_file(directory), timestamp, r.get("serialized_simulation", ""))
+        self.solver.comm.allreduce_max(0)  # mpi::barrier()
+        return True
+
+    def save_restart(self, filename, timestamp=None, serialized_simulation=""):
+        """the whole state a step starts from: the boxes of every level, E, B, J and the ion moments, every particle store
+        in its current (cell-ordered) order with its cell offsets"""
+        ops = self.solver.ops
+        out = {"time": np.array(self.current_time if timestamp is None else float(timestamp)),
+               "serialized_simulation": np.array(serialized_simulation)}
+        solvers = self.level_solvers()
+        out["nlevels"] = np.array(len(solvers))
+        for il, solver in enumerate(solvers):
+            out[f"pl{il}/boxes"] = np.array([[g.box.lo, g.box.hi] for g in solver.geom.patches])
+            for p in solver.patches:
+                base = f"pl{il}/p{p.geom.id}/"
+                for name, vec in (("B", p.B), ("E", p.E), ("Vi", p.Vi), ("J", p.J)):
+                    for c in range(3):
+                        out[base + f"{name}{c}"] = ops.get_field(vec[c])
+                out[base + "Ne"], out[base + "rho_m"] = ops.get_field(p.Ne), ops.get_field(p.rho_m)
+                for i, pop in enumerate(p.pops):
+                    for k, m in enumerate(pop.moments()):
+                        out[base + f"pop{i}/moment{k}"] = ops.get_field(m)
+                    out[base + f"pop{i}/n_sorted"] = np.array(pop.n_sorted)
+                    out[base + f"pop{i}/cell_start"] = ops.get_field(pop.cell_start)
+                    for store in self._PARTICLE_STORES:
+                        st = getattr(pop, store)
+                        if st is None:
+                            continue
+                        ic, de, w, q, v = ops.get_particles(st)
+                        for key, a in (("iCell", ic), ("delta", de), ("weight", w), ("charge", q), ("v", v)):
+                            out[base + f"pop{i}/{store}/{key}"] = a
+        os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
+        np.savez(filename, **out)
+
+    def load_restart(self, filename):
+        """puts an initialised simulator (same input dict) into the state save_restart() wrote: levels are rebuilt on the
+        saved boxes when they differ (tagging), then every field and particle store is overwritten"""
+        from .amr import grow_store
+        from .boxes import Box
+        z = np.load(filename)
+        ops = self.solver.ops
+        nlevels = int(z["nlevels"])
+        if nlevels > 1:
+            amr = self.amr
+            for il in range(1, nlevels):
+                boxes = [Box(b[0], b[1]) for b in z[f"pl{il}/boxes"]]
+                have = il < len(amr.levels) and len(boxes) == len(amr.levels[il].geom.patches) and all(
+                    a == g.box for a, g in zip(boxes, amr.levels[il].geom.patches))
+                if not have:
+                    del amr.levels[il:]
+                    amr.add_level(boxes)
+            del amr.levels[nlevels:]
+        for il, solver in enumerate(self.level_solvers()):
+            for p in solver.patches:
+                base = f"pl{il}/p{p.geom.id}/"
+                for name, vec in (("B", p.B), ("E", p.E), ("Vi", p.Vi), ("J", p.J)):
+                    for c in range(3):
+                        ops.set_field(vec[c], z[base + f"{name}{c}"])
+                ops.set_field(p.Ne, z[base + "Ne"])
+                ops.set_field(p.rho_m, z[base + "rho_m"])
+                for i, pop in enumerate(p.pops):
+                    for k, m in enumerate(pop.moments()):
+                        ops.set_field(m, z[base + f"pop{i}/moment{k}"])
+                    pop.n_sorted = int(z[base + f"pop{i}/n_sorted"])
+                    pop.pending_bin = False
+                    ops.set_field(pop.cell_start, z[base + f"pop{i}/cell_start"])
+                    for store in self._PARTICLE_STORES:
+                        key = base + f"pop{i}/{store}/weight"
+                        if key not in z.files:
+                            continue
+                        n = len(z[key])
+                        while ops.capacity(getattr(pop, store)) < n:
+                            grow_store(ops, p, i, getattr(pop, store))
+                        cols = [z[base + f"pop{i}/{store}/{k}"] for k in ("iCell", "delta", "weight", "charge", "v")]
+                        ops.set_particles(getattr(pop, store), *cols)
+                        ops.set_count(getattr(pop, store), n)
+            solver.prepare_step()
+        self.current_time = float(z["time"])
+        self.elapsed = self.current_time - self.start_time
+        if getattr(self, "amr", None):
+            self.amr.time = self.current_time
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ add_int = _typed("add_int", _is_int, int)
 add_vector_int = _typed("add_vector_int", lambda v: all(_is_int(x) for x in v), lambda v: [int(x) for x in v])
 add_double = _typed("add_double", lambda v: isinstance(v, (float, int, np.floating, np.integer))
                     and not isinstance(v, bool), float)
-add_string = _typed("add_string", lambda v: isinstance(v, (str, bytes)), lambda v: v)  # std::string takes bytes too
+add_string = _typed("add_string", lambda v: isinstance(v, (str, bytes)), lambda v: v.decode() if isinstance(v, bytes) else v)  # std::string takes bytes too and comes back as str
 add_vector_string = _typed("add_vector_string", lambda v: all(isinstance(x, str) for x in v), list)
 addInitFunction1D = _typed("addInitFunction1D", callable, lambda f: f)
 addInitFunction2D = _typed("addInitFunction2D", callable, lambda f: f)

@@ -363,3 +363,130 @@ def test_npz_reader_names_population_quantities(cpu_backend, cpu_ref, tmp_path, 
     ops = sim.solver.ops
     want = ops.get_field(sim.level_solvers()[1].patches[0].pops[1].flux[0])
     assert np.array_equal(fx.dataset[:], want) and fx.ghosts_nbr[0] == 2 and abs(fx.x[2] - 40 * 0.1) < 1e-12
+
+
+def _state(sim):
+    """every field and particle store of every level, as numpy"""
+    ops = sim.solver.ops
+    out = {}
+    for il, solver in enumerate(sim.level_solvers()):
+        for p in solver.patches:
+            base = f"{il}/{p.geom.id}/"
+            for name, vec in (("B", p.B), ("E", p.E), ("Vi", p.Vi)):
+                for c in range(3):
+                    out[base + name + str(c)] = ops.get_field(vec[c])
+            out[base + "Ne"] = ops.get_field(p.Ne)
+            for i, pop in enumerate(p.pops):
+                for store in S.Simulator._PARTICLE_STORES:
+                    st = getattr(pop, store)
+                    if st is not None:
+                        for k, a in zip(("iCell", "delta", "w", "q", "v"), ops.get_particles(st)):
+                            out[base + f"pop{i}/{store}/{k}"] = a
+    return out
+
+
+@pytest.mark.parametrize("refined", [False, True])
+def test_restart_resumes_bit_for_bit(cpu_backend, cpu_ref, tmp_path, refined):
+    """restarts (simulator.hpp:123 dump_restarts, restarts_manager.hpp): a run stopped after the restart written at
+    t = 2 dt and resumed from it by a NEW simulator (dict with restarts/loadPath + restart_time, as pyphare's populateDict
+    adds them) ends in the same state, bit for bit, as the run that went straight through; one level and two levels"""
+    import pybindlibs.dictator as pp
+    etc = importlib.import_module("pybindlibs.cpp_etc")
+    dt = 0.005
+
+    def make(extra):
+        pops, bfn = two_pop_1d(64)
+        populate([64], [0.2], 1, pops, bfn, steps=4, largest=[16] if not refined else [32])
+        if refined:
+            pp.add_int("simulation/AMR/max_nbr_levels", 2)
+            pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+            pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 1)
+            pp.add_int("simulation/AMR/refinement/boxes/L0/B0/lower/x/", 20)
+            pp.add_int("simulation/AMR/refinement/boxes/L0/B0/upper/x/", 43)
+        pp.add_string("simulation/restarts/filePath", str(tmp_path))
+        pp.add_string("simulation/restarts/serialized_simulation", "the-serialized-simulation")
+        extra()
+        sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+        sim.initialize()
+        return sim
+
+    sim = make(lambda: pp.add_array_as_vector("simulation/restarts/write_timestamps", np.array([2 * dt])))
+    made = []
+    for k in range(4):
+        made.append(sim.dump_restarts(sim.currentTime(), dt))  # pyphare: restarts.dump before every advance
+        sim.advance(dt)
+    assert made == [False, False, True, False]
+    straight = _state(sim)
+    load = etc.restart_path_for_time(str(tmp_path), 2 * dt)
+    assert os.path.basename(load) == "00000.01000" and os.path.isdir(load)
+    assert etc.serialized_simulation_string(load) == "the-serialized-simulation" and etc.patch_data_ids(load) == []
+    assert os.path.exists(etc.samrai_restart_file(load))
+
+    def loading():
+        pp.add_string("simulation/restarts/loadPath", load)
+        pp.add_double("simulation/restarts/restart_time", 2 * dt)
+    S.dict_instance().stop()
+    sim2 = make(loading)
+    assert sim2.startTime() == pytest.approx(2 * dt) and sim2.currentTime() == pytest.approx(2 * dt)
+    assert not sim2.dump_restarts(sim2.currentTime(), dt)  # loading only: no writer properties
+    for k in range(2):
+        sim2.advance(dt)
+    assert sim2.currentTime() == pytest.approx(4 * dt)
+    resumed = _state(sim2)
+    assert straight.keys() == resumed.keys()
+    for k in straight:
+        assert np.array_equal(straight[k], resumed[k], equal_nan=straight[k].dtype.kind == "f"), k
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
+def test_pyphare_restart_options_write_and_resume(cpu_backend, cpu_ref, tmp_path, monkeypatch):
+    """pyphare's own restart flow, unchanged: restart_options={"dir", "mode", "timestamps"} writes <dir>/00000.01000/ during
+    the run; a second Simulation with restart_options["restart_time"] passes pyphare's checks (restart_path_for_time,
+    serialized_simulation_string -> is_restartable_compared_to, patch_data_ids), starts at that time and ends bit for bit
+    where the straight run did"""
+    pytest.importorskip("dill")
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections",
+                 "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1", "h5py"):
+        if name not in sys.modules:
+            monkeypatch.setitem(sys.modules, name, mock.MagicMock(name=name))
+    monkeypatch.syspath_prepend(os.path.join(REF, "pyphare"))
+    monkeypatch.chdir(tmp_path)
+    import pyphare.pharein as ph
+    from pyphare.simulator.simulator import Simulator
+    L = 64 * 0.2
+    zero = lambda x: 0. * x
+    vth = lambda x: 0.3 + 0. * x
+
+    def run(restart_options, nsteps):
+        ph.global_vars.sim = None
+        sim = ph.Simulation(time_step=0.005, time_step_nbr=nsteps, cells=64, dl=0.2, interp_order=1, largest_patch_size=16,
+                            restart_options=restart_options,
+                            diag_options={"format": "phareh5", "options": {"dir": "diags", "mode": "overwrite"}})
+        ph.MaxwellianFluidModel(
+            bx=lambda x: 1. + 0 * x, by=lambda x: 0.1 * np.cos(2 * np.pi * x / L), bz=zero,
+            protons={"charge": 1, "density": lambda x: 1. + 0.2 * np.sin(2 * np.pi * x / L), "vbulkx": zero, "vbulky": zero,
+                     "vbulkz": zero, "vthx": vth, "vthy": vth, "vthz": vth, "nbr_part_per_cell": 40, "init": {"seed": 12}})
+        ph.ElectronModel(closure="isothermal", Te=0.12)
+        s = Simulator(sim, log_to_file=False)
+        s.initialize()
+        t0 = s.currentTime()
+        for _ in range(nsteps):
+            s.advance()
+        c = s.cpp_sim
+        ops = c.solver.ops
+        out = [ops.get_field(f) for p in c.solver.patches for f in (*p.B, *p.E, p.Ne)]
+        out += [a for p in c.solver.patches for a in ops.get_particles(p.pops[0].domain)]
+        t1 = s.currentTime()
+        s.reset()
+        ph.global_vars.sim = None
+        return t0, t1, out
+
+    t0, t1, straight = run({"dir": "rst", "mode": "overwrite", "timestamps": [0.01]}, 4)
+    assert (t0, t1) == (0.0, pytest.approx(0.02)) and os.listdir(tmp_path / "rst") == ["00000.01000"]
+    t0, t1, resumed = run({"dir": "rst", "mode": "overwrite", "restart_time": 0.01}, 2)
+    assert (t0, t1) == (pytest.approx(0.01), pytest.approx(0.02))
+    assert len(straight) == len(resumed)
+    for a, b in zip(straight, resumed):
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    with pytest.raises(ValueError):  # no restart was written for that time
+        run({"dir": "rst", "mode": "overwrite", "restart_time": 0.015}, 1)

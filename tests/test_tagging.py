@@ -235,3 +235,49 @@ def test_pyphare_runs_the_reference_harris_script_with_its_tagging(cpu_backend, 
     ph.global_vars.sim = None
     for k in [k for k in sys.modules if k == "tests" or k.startswith("tests.")]:
         del sys.modules[k]
+
+
+def test_restart_rebuilds_a_tagged_hierarchy(cpu_backend, tmp_path):
+    """load_restart on a simulator whose hierarchy differs from the saved one (here: its refined levels removed) rebuilds
+    the levels on the saved boxes before it overwrites their data: the resumed run equals the straight one bit for bit"""
+    import pybindlibs.dictator as pp
+    cells, dl = 100, 0.5
+    Lx = cells * dl
+    Sx = lambda x, x0: 0.5 * (1 + np.tanh((x - x0) / 1.0))
+    by = lambda x: -1 + 2 * (Sx(x, 0.25 * Lx) - Sx(x, 0.75 * Lx))
+    pop = dict(name="protons", mass=1.0, charge=1.0, ppc=20, seed=7, density=const(1.0), vx=const(0), vy=const(0),
+               vz=const(0), vthx=const(0.4), vthy=const(0.4), vthz=const(0.4))
+
+    def make():
+        S.dict_instance().stop()
+        populate([cells], [dl], 1, [pop], [const(0.0), by, const(0.5)], time_step=0.005, steps=4, largest=[50])
+        pp.add_int("simulation/AMR/max_nbr_levels", 2)
+        pp.add_string("simulation/AMR/refinement/tagging/method", "auto")
+        pp.add_double("simulation/AMR/refinement/tagging/threshold", 0.1)
+        pp.add_vector_int("simulation/AMR/smallest_patch_size", [8])
+        sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+        sim.initialize()
+        return sim
+
+    def fields(sim):
+        ops = sim.solver.ops
+        return [ops.get_field(f) for s in sim.level_solvers() for p in s.patches for f in (*p.B, *p.E, p.Ne)] + \
+               [a for s in sim.level_solvers() for p in s.patches for a in ops.get_particles(p.pops[0].domain)]
+
+    sim = make()
+    sim.advance(0.005)
+    f = str(tmp_path / "r.npz")
+    sim.save_restart(f)
+    saved_boxes = [p.box for p in sim.amr.levels[1].geom.patches]
+    sim.advance(0.005)
+    straight = fields(sim)
+    sim2 = make()
+    del sim2.amr.levels[1:]
+    sim2.load_restart(f)
+    assert len(sim2.amr.levels) == 2 and sim2.currentTime() == pytest.approx(0.005)
+    assert [p.box for p in sim2.amr.levels[1].geom.patches] == saved_boxes
+    sim2.advance(0.005)
+    resumed = fields(sim2)
+    assert len(straight) == len(resumed)
+    for a, b in zip(straight, resumed):
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
