@@ -224,3 +224,73 @@ def test_tagging_and_regridding_on_two_ranks_equal_one(cpu_ref, tmp_path):
             ok = np.isfinite(w)
             assert np.array_equal(np.isnan(got[k]), np.isnan(w)), k
             assert np.max(np.abs(got[k][ok] - w[ok]), initial=0.0) <= 1e-10 * (np.max(np.abs(w[ok])) + 1e-30), k
+
+
+def _restart_worker(rank, world, port, out_dir):
+    """two ranks, refined level: 2 steps, restart written, 1 more step; then a new simulator resumed from the per-rank
+    restart files takes that step again and must land on the same state bit for bit"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import phare_b200.simulator as S
+    import pybindlibs.dictator as pp
+    from oracle.cpu_ops import CpuOps
+    from frontend_util import populate, two_pop_1d
+    S.ops_factory = lambda dim, interp: CpuOps(dim, interp)
+    dt = 0.005
+
+    def make(extra):
+        S.dict_instance().stop()
+        pops, bfn = two_pop_1d(64)
+        populate([64], [0.2], 1, pops, bfn, steps=3, largest=[16])
+        pp.add_int("simulation/AMR/max_nbr_levels", 2)
+        pp.add_int("simulation/AMR/refinement/boxes/nbr_levels/", 1)
+        pp.add_int("simulation/AMR/refinement/boxes/L0/nbr_boxes/", 2)
+        for ib, (lo, hi) in enumerate(((10, 25), (26, 45))):
+            pp.add_int(f"simulation/AMR/refinement/boxes/L0/B{ib}/lower/x/", lo)
+            pp.add_int(f"simulation/AMR/refinement/boxes/L0/B{ib}/upper/x/", hi)
+        pp.add_string("simulation/restarts/filePath", out_dir)
+        pp.add_string("simulation/restarts/serialized_simulation", "x")
+        extra()
+        sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+        sim.initialize()
+        return sim
+
+    def state(sim):
+        ops = sim.solver.ops
+        out = []
+        for solver in sim.level_solvers():
+            for p in solver.patches:
+                out += [ops.get_field(f) for f in (*p.B, *p.E, p.Ne, *p.Vi)]
+                for pop in p.pops:
+                    out += list(ops.get_particles(pop.domain))
+        return out
+
+    sim = make(lambda: pp.add_array_as_vector("simulation/restarts/write_timestamps", np.array([2 * dt])))
+    for _ in range(3):
+        sim.dump_restarts(sim.currentTime(), dt)
+        sim.advance(dt)
+    want = state(sim)
+    load = S.restart_path_for_time(out_dir, 2 * dt)
+    assert sorted(os.listdir(load)) == ["restart_rank000000.npz", "restart_rank000001.npz"]
+
+    def loading():
+        pp.add_string("simulation/restarts/loadPath", load)
+        pp.add_double("simulation/restarts/restart_time", 2 * dt)
+    sim2 = make(loading)
+    sim2.advance(dt)
+    got = state(sim2)
+    assert len(got) == len(want) and len(want) > 0
+    for a, b in zip(want, got):
+        assert np.array_equal(a, b, equal_nan=a.dtype.kind == "f")
+    with open(os.path.join(out_dir, f"ok{rank}"), "w") as f:
+        f.write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_restart_on_two_ranks_resumes_bit_for_bit(cpu_ref, tmp_path):
+    mp.spawn(_restart_worker, args=(2, 29500 + (os.getpid() % 2000) + 17, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
