@@ -468,18 +468,19 @@ def test_pyphare_restart_options_write_and_resume(cpu_backend, cpu_ref, tmp_path
                      "vbulkz": zero, "vthx": vth, "vthy": vth, "vthz": vth, "nbr_part_per_cell": 40, "init": {"seed": 12}})
         ph.ElectronModel(closure="isothermal", Te=0.12)
         s = Simulator(sim, log_to_file=False)
-        s.initialize()
-        t0 = s.currentTime()
-        for _ in range(nsteps):
-            s.advance()
-        c = s.cpp_sim
-        ops = c.solver.ops
-        out = [ops.get_field(f) for p in c.solver.patches for f in (*p.B, *p.E, p.Ne)]
-        out += [a for p in c.solver.patches for a in ops.get_particles(p.pops[0].domain)]
-        t1 = s.currentTime()
-        s.reset()
-        ph.global_vars.sim = None
-        return t0, t1, out
+        try:
+            s.initialize()
+            t0 = s.currentTime()
+            for _ in range(nsteps):
+                s.advance()
+            c = s.cpp_sim
+            ops = c.solver.ops
+            out = [ops.get_field(f) for p in c.solver.patches for f in (*p.B, *p.E, p.Ne)]
+            out += [a for p in c.solver.patches for a in ops.get_particles(p.pops[0].domain)]
+            return t0, s.currentTime(), out
+        finally:
+            s.reset()
+            ph.global_vars.sim = None
 
     t0, t1, straight = run({"dir": "rst", "mode": "overwrite", "timestamps": [0.01]}, 4)
     assert (t0, t1) == (0.0, pytest.approx(0.02)) and os.listdir(tmp_path / "rst") == ["00000.01000"]
