@@ -542,7 +542,8 @@ class Hierarchy:
     def advance(self, dt):
         """one step of the root level and the sub-cycles of every finer level (TimeRefinementIntegrator::advanceHierarchy
         driving MultiPhysicsIntegrator::advanceLevel / standardLevelSynchronization)"""
-        self._advance_level(0, self.time, self.time + dt, True, True)
+        self._root_end = self.time + dt
+        self._advance_level(0, self.time, self._root_end, True, True)
         self.time += dt
         return self.time
 
@@ -563,6 +564,8 @@ class Hierarchy:
         if last and il > 0:
             self._last_step(lvl)
         finest = il == len(self.levels) - 1
+        if finest:
+            self._fine_dump(il, t1)
         if il > 0 and finest:
             s.accumulate_flux_sum(1. / (RATIO * RATIO))
         if not finest:
@@ -574,6 +577,16 @@ class Hierarchy:
                 self._advance_level(il + 1, t, tn, k == 0, k == SUBSTEPS - 1)
                 t = tn
             self._synchronize(self.levels[il + 1], lvl, t1)
+            self._fine_dump(il, t1)
+
+    fine_dump = None  # callable(level number, time): the simulator's "fine_dump" functor (simulator.hpp:252-267)
+
+    def _fine_dump(self, il, time):
+        """MultiPhysicsIntegrator::dump_ (multiphysics_integrator.hpp:455-471): finer levels are dumped at the end of their
+        own sub-steps (the finest after its advance, the others after the synchronisation of the finer one), except at the
+        end time of the root step, which the regular dump covers"""
+        if self.fine_dump is not None and il > 0 and time != self._root_end:
+            self.fine_dump(il, time)
 
     def _first_step(self, lvl):
         """firstStep: levelGhostParticlesNew = split of the coarser level's particles, which are already at the end of its
@@ -614,28 +627,42 @@ class Hierarchy:
         # A fine patch coarsens onto the coarse patch directly when both live here, else into a staging array that is
         # shipped to the owner of the coarse patch (one packed message per pair of ranks, compiled once).
         staged, send_items, recv_items = [], {}, {}
+        # Destinations are found in the index space of each quantity (FieldGeometry overlaps; FieldVariable says
+        # dataLivesOnPatchBorder for anything primal, field_variable.hpp:44): a coarse patch that only TOUCHES the coarsened
+        # fine box still owns the shared border nodes and receives them, so that overlapped domain nodes of neighbouring
+        # coarse patches stay equal (the reference's test_overlaped_fields_are_equal); `t` runs over the periodic images.
+        zero = np.zeros(fine.geom.patches[0].box.dim, dtype=np.int64) if fine.geom.patches else None
+        shifts = list(coarse.geom.shifts) if coarse.geom.periodic else [zero]
         for pg in fine.geom.patches:
+            cbox = coarsen_box(pg.box)
             for qg in coarse.geom.patches:
-                cells = coarsen_box(pg.box) * qg.box
-                if cells is None or (pg.owner != me and qg.owner != me):
+                if pg.owner != me and qg.owner != me:
                     continue
-                for k, (fattr, c, cattr, qty0, op) in enumerate(self.SYNC_ITEMS):
-                    qty = qty0 + (c or 0)
-                    fb = field_box(cells, qty)
-                    if pg.owner == me and qg.owner == me:
-                        ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), pg.box.lo - gf,
-                                          arr(coarse_patch[qg.id], cattr, c), qg.box.lo - gc, fb.lo, fb.hi)
-                    elif pg.owner == me:
-                        if fine.sync_phase is None:
-                            stage = ops.array(fb.shape())
-                            send_items.setdefault(qg.owner, []).append((stage, [0] * fb.dim, fb.shape()))
-                        else:
-                            stage = fine.sync_phase["stages"][len(staged)]
-                        staged.append(stage)
-                        ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), pg.box.lo - gf, stage, fb.lo, fb.lo, fb.hi)
-                    elif fine.sync_phase is None:
-                        recv_items.setdefault(pg.owner, []).append(
-                            (arr(coarse_patch[qg.id], cattr, c), fb.lo - (qg.box.lo - gc), fb.shape()))
+                for t in shifts:
+                    t = np.asarray(t, dtype=np.int64)
+                    image = cbox.shift(t)
+                    if image.grow(1) * qg.box is None:
+                        continue
+                    flo = pg.box.lo - gf + RATIO * t  # the fine patch seen from the image
+                    for k, (fattr, c, cattr, qty0, op) in enumerate(self.SYNC_ITEMS):
+                        qty = qty0 + (c or 0)
+                        fb = field_box(image, qty) * field_box(qg.box, qty)
+                        if fb is None:
+                            continue
+                        if pg.owner == me and qg.owner == me:
+                            ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), flo,
+                                              arr(coarse_patch[qg.id], cattr, c), qg.box.lo - gc, fb.lo, fb.hi)
+                        elif pg.owner == me:
+                            if fine.sync_phase is None:
+                                stage = ops.array(fb.shape())
+                                send_items.setdefault(qg.owner, []).append((stage, [0] * fb.dim, fb.shape()))
+                            else:
+                                stage = fine.sync_phase["stages"][len(staged)]
+                            staged.append(stage)
+                            ops.field_coarsen(op, qty, arr(fine_patch[pg.id], fattr, c), flo, stage, fb.lo, fb.lo, fb.hi)
+                        elif fine.sync_phase is None:
+                            recv_items.setdefault(pg.owner, []).append(
+                                (arr(coarse_patch[qg.id], cattr, c), fb.lo - (qg.box.lo - gc), fb.shape()))
         if self.comm.size > 1:
             if fine.sync_phase is None:
                 fine.sync_phase = fs.messenger._finish([], send_items, recv_items, 0)

@@ -299,6 +299,9 @@ class Simulator:
             self.amr = PatchHierarchy(ops, self.solver, nref=self.refined_particle_nbr)
             self.tagger = Tagger(smallest_patch_size=h.smallest, largest_patch_size=h.largest, **h.tagging)
             self.amr.regrid_tagged(self.tagger)  # the initial hierarchy: tag level 0, build level 1, tag it, ...
+        fine_max = int(self.d.get("simulation/diagnostics/fine_dump_lvl_max", 0) or 0)
+        if self.amr is not None and fine_max > 0:  # diagnostics_init (simulator.hpp:252-267)
+            self.amr.fine_dump = lambda il, t: self.dump_level(il, t) if il <= fine_max else None
         load = self.d.get("simulation/restarts/loadPath")
         if load:  # Hierarchy::from_restart / initializeHierarchy from the restart database (simulator.hpp:332, 401)
             self.load_restart(self.restart_file(load))
@@ -350,17 +353,36 @@ class Simulator:
         ts = np.asarray(diag.get("write_timestamps", ()), dtype=np.float64)
         return ts.size > 0 and bool(np.any(np.abs(ts - timestamp) < 0.5 * timestep))
 
+    @staticmethod
+    def diag_format():
+        """'h5': the reference's per-quantity files (h5writer.hpp layout) through h5py, or through phare_b200.h5lite when
+        h5py is absent; 'npz': one raw .npz per quantity, time and rank.  PHARE_B200_DIAG_FORMAT picks one; the default is
+        'h5' when the real h5py is importable, else 'npz'"""
+        fmt = os.environ.get("PHARE_B200_DIAG_FORMAT")
+        if fmt:
+            return fmt
+        import importlib.util
+        try:
+            return "h5" if importlib.util.find_spec("h5py") is not None else "npz"
+        except (ValueError, ImportError):
+            return "npz"
+
     def dump_diagnostics(self, timestamp, timestep):
         diags = self.d.get("simulation/diagnostics")
         if not diags or self.solver is None:
             return False
         path = diags.get("filePath", "phare_output")
+        fmt = self.diag_format()
         written = False
         for dtype in ("electromag", "fluid", "particle"):
             for name, diag in (diags.get(dtype) or {}).items():
                 if not isinstance(diag, dict) or not self._due(diag, timestamp, timestep):
                     continue
                 os.makedirs(path, exist_ok=True)
+                if fmt == "h5":
+                    self._dump_h5(path, dtype, diag, timestamp, diags.get("mode", "overwrite"))
+                    written = True
+                    continue
                 # file attributes of the reference's h5 writer that pharesee needs to rebuild the hierarchy
                 # (diagnostic/detail/h5writer.hpp: interpOrder, domain_box, cell_width; per patch: origin, lower, upper)
                 arrays = {"_meta/interp_order": np.array(self.interp_order), "_meta/domain_cells": np.array(self.hier.cells),
@@ -381,6 +403,76 @@ class Simulator:
                 written = True
         self.ndumps += int(written)
         return written
+
+    def dump_level(self, level, timestamp):
+        """DiagnosticsManager::dump_level (diagnostic_manager.hpp:214-222): EVERY registered diagnostic, that level only"""
+        diags = self.d.get("simulation/diagnostics")
+        if not diags or self.solver is None or self.diag_format() != "h5":
+            return
+        path = diags.get("filePath", "phare_output")
+        os.makedirs(path, exist_ok=True)
+        for dtype in ("electromag", "fluid", "particle"):
+            for name, diag in (diags.get(dtype) or {}).items():
+                if isinstance(diag, dict):
+                    self._dump_h5(path, dtype, diag, timestamp, diags.get("mode", "overwrite"), levels=(level,))
+
+    def _dump_h5(self, path, dtype, diag, timestamp, mode, levels=None):
+        """one file per quantity holding every dump (H5Writer, diagnostic/detail/h5writer.hpp:105-127, 250-258):
+        <quantity with '/' -> '_'>.h5, groups /t/<time %.10f>/pl<level>/p<rank>#<patch>/<dataset>; file attributes dimension,
+        interpOrder, layoutType, domain_box, cell_width, origin, boundary_conditions (+ the diagnostic's own attributes under
+        /py_attrs, h5typewriter.hpp:108-111); patch attributes origin, nbrCells, lower, upper, mpi_rank
+        (diagnostic_model_view.hpp:93-97); a 'ghosts' attribute on every field dataset (h5typewriter.hpp:124-129); particle
+        datasets are the SoA arrays keyed as in particle_packer.hpp:66-67"""
+        try:
+            import h5py
+            if not hasattr(h5py, "File") or hasattr(h5py, "_mock_name"):
+                raise ImportError
+        except ImportError:
+            from . import h5lite as h5py
+        rank = self.solver.comm.rank
+        quantity = diag["quantity"]
+        fn = os.path.join(path, quantity.strip("/").replace("/", "_") + ".h5") + (f".rank{rank}" if rank else "")
+        opened = self.__dict__.setdefault("_h5_opened", set())
+        first = fn not in opened
+        opened.add(fn)
+        with h5py.File(fn, "w" if first and mode == "overwrite" or not os.path.exists(fn) else "a") as f:
+            if first:
+                dim = self.dims
+                for k, v in (("dimension", dim), ("interpOrder", self.interp_order), ("layoutType", "yee"),
+                             ("domain_box", np.array([c - 1 for c in self.hier.cells], dtype=np.int32)),
+                             ("cell_width", np.array(self.hier.dl, dtype=np.float64)), ("origin", np.zeros(dim)),
+                             ("boundary_conditions", "periodic")):
+                    f.attrs[k] = v
+                n_attr = int(diag.get("n_attributes", 0))
+                if n_attr:
+                    g = f.require_group("py_attrs")
+                    for i in range(n_attr):
+                        g.attrs[diag[f"attribute_{i}_key"]] = diag[f"attribute_{i}_value"]
+                q = quantity.strip("/").split("/")
+                if q[:2] == ["ions", "pop"]:
+                    mass = [pop.mass for pop in self.solver.patches[0].pops if pop.name == q[2]] if self.solver.patches else []
+                    if mass:
+                        f.attrs["pop_mass"] = float(mass[0])
+            tgrp = f.require_group(f"t/{timestamp:.10f}")
+            for il, solver in enumerate(self.level_solvers()):
+                if levels is not None and il not in levels:
+                    continue
+                lvl = tgrp.require_group(f"pl{il}")
+                for p in solver.patches:
+                    L = p.layout
+                    g = lvl.require_group(f"p{rank}#{p.geom.id}")
+                    g.attrs["origin"] = np.array([L.origin[k] for k in range(L.dim)])
+                    g.attrs["nbrCells"] = np.array([L.ncells[k] for k in range(L.dim)], dtype=np.uint32)
+                    g.attrs["lower"] = np.array([L.amr_lower[k] for k in range(L.dim)], dtype=np.int32)
+                    g.attrs["upper"] = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)], dtype=np.int32)
+                    g.attrs["mpi_rank"] = rank
+                    for key, a in self._diag_arrays(p, dtype, quantity).items():
+                        if dtype == "particle":
+                            # (n, dim) / (n, 3) / (n, 1): hdf5/writer/particle_writer.hpp:38-47
+                            ds = g.create_dataset(key.split("/", 1)[1], data=a if a.ndim == 2 else a.reshape(-1, 1))
+                        else:
+                            ds = g.create_dataset(key, data=a)
+                            ds.attrs["ghosts"] = (a.shape[0] - int(L.ncells[0])) // 2
 
     def _diag_arrays(self, p, dtype, quantity):
         get = self.solver.ops.get_field
