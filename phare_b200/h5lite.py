@@ -2,8 +2,10 @@
 h5py nor HighFive).  The reference writes its diagnostics with HighFive (src/diagnostic/detail/h5writer.hpp) and pyphare reads
 them with h5py (pyphare/pharesee/hierarchy/fromh5.py): `File(path, mode)`, groups addressed by '/'-separated paths, `.attrs`,
 `.keys() / .items() / .values()`, `.name`, datasets that behave like arrays.  This module offers exactly that surface over a
-container that is NOT HDF5: the whole tree is one pickled dict {path: (attrs, array-or-None)} next to which other ranks put
-`<file>.rank<r>` pieces that a reader merges (the reference writes one parallel-HDF5 file from all ranks).
+container that is NOT HDF5: a magic line followed by pickled records {path: (attrs, array-or-None)}; a file opened in append mode
+adds one record holding only the nodes it touched (a dump costs what it writes, whatever the file already holds), a reader merges
+the records in order.  Other ranks put `<file>.rank<r>` pieces next to the file, which a reader merges too (the reference writes one
+parallel-HDF5 file from all ranks).
 
 `phare_b200.simulator` writes through real h5py when it is importable and through this module otherwise; registering it as
 `sys.modules["h5py"]` (`h5lite.install()`) lets pyphare's own readers (`hierarchy_from(h5_filename=...)`, `Run`) open those files.
@@ -16,6 +18,7 @@ import sys
 import numpy as np
 
 MAGIC = b"PHB-H5LITE-1\n"
+_READ_CACHE = {}  # filename -> ((piece, mtime, size), ...), parsed tree
 
 
 def _norm(path):
@@ -42,6 +45,8 @@ class _Node:
 
     @property
     def attrs(self):
+        if self.file.mode != "r":
+            self.file._dirty.add(self.name)
         return self.file._tree[self.name][0]
 
     @property
@@ -67,6 +72,7 @@ class Dataset(_Node):
 
     def __setitem__(self, idx, value):
         self.file._check_writable()
+        self.file._dirty.add(self.name)
         self._a[idx] = value
 
     def __array__(self, dtype=None, copy=None):
@@ -85,8 +91,7 @@ class Group(_Node):
         return _norm(path) if path.startswith("/") else _norm(self.name + "/" + path)
 
     def _children(self):
-        prefix = self.name.rstrip("/") + "/"
-        return sorted({k[len(prefix):].split("/", 1)[0] for k in self.file._tree if k.startswith(prefix) and k != prefix})
+        return sorted(self.file._index().get(self.name, ()))
 
     def _wrap(self, path):
         node = self.file._tree[path]
@@ -122,7 +127,10 @@ class Group(_Node):
     def _make_parents(self, p):
         parts = [k for k in p.split("/") if k]
         for i in range(len(parts)):
-            self.file._tree.setdefault("/" + "/".join(parts[:i]), (AttributeManager(), None))
+            k = "/" + "/".join(parts[:i])
+            if k not in self.file._tree:
+                self.file._tree[k] = (AttributeManager(), None)
+                self.file._dirty.add(k)
 
     def create_group(self, path):
         self.file._check_writable()
@@ -131,6 +139,7 @@ class Group(_Node):
             raise ValueError(f"Unable to create group (name already exists): {p}")
         self._make_parents(p)
         self.file._tree[p] = (AttributeManager(), None)
+        self.file._dirty.add(p)
         return Group(self.file, p)
 
     def require_group(self, path):
@@ -144,6 +153,7 @@ class Group(_Node):
         a = np.zeros(shape, dtype or np.float64) if data is None else np.array(data, dtype=dtype)
         self._make_parents(p)
         self.file._tree[p] = (AttributeManager(), a)
+        self.file._dirty.add(p)
         return Dataset(self.file, p)
 
     def __setitem__(self, path, data):
@@ -154,6 +164,7 @@ class Group(_Node):
         p = self._abs(path)
         for k in [k for k in self.file._tree if k == p or k.startswith(p + "/")]:
             del self.file._tree[k]
+        self.file._rewrite, self.file._kids = True, None
 
     def visit(self, fn):
         prefix = self.name.rstrip("/") + "/"
@@ -173,6 +184,8 @@ class File(Group):
     def __init__(self, filename, mode="r", **kw):
         self.filename, self.mode = str(filename), mode
         self._tree, self._open = {"/": (AttributeManager(), None)}, True
+        self._dirty, self._rewrite = {"/"}, False
+        self._kids, self._kids_n = None, -1
         exists = os.path.exists(self.filename)
         if mode in ("r", "r+") and not exists:
             raise FileNotFoundError(f"Unable to open file (unable to open file: name = '{filename}')")
@@ -180,20 +193,47 @@ class File(Group):
             raise FileExistsError(f"Unable to create file (file exists): {filename}")
         if mode in ("r", "r+", "a") and exists:
             pieces = [self.filename] + (sorted(glob.glob(glob.escape(self.filename) + ".rank*")) if mode == "r" else [])
-            for piece in pieces:
-                self._merge(piece)
+            sig = tuple((q, os.stat(q).st_mtime_ns, os.stat(q).st_size) for q in pieces)
+            cached = _READ_CACHE.get(self.filename) if mode == "r" else None
+            if cached is not None and cached[0] == sig:
+                self._tree = cached[1]  # read-only handles of an unchanged file share the parsed tree
+            else:
+                for piece in pieces:
+                    self._merge(piece)
+                if mode == "r":
+                    if len(_READ_CACHE) >= 64:
+                        _READ_CACHE.pop(next(iter(_READ_CACHE)))
+                    _READ_CACHE[self.filename] = (sig, self._tree)
+            self._dirty = set()
+        else:
+            self._rewrite = True  # a new file: magic + first record
         super().__init__(self, "/")
+
+    def _index(self):
+        """parent path -> names of its children, rebuilt when the tree changed size"""
+        if self._kids is None or self._kids_n != len(self._tree):
+            kids = {}
+            for k in self._tree:
+                if k != "/":
+                    parent, _, name = k.rpartition("/")
+                    kids.setdefault(parent or "/", set()).add(name)
+            self._kids, self._kids_n = kids, len(self._tree)
+        return self._kids
 
     def _merge(self, piece):
         with open(piece, "rb") as f:
             if f.read(len(MAGIC)) != MAGIC:
                 raise OSError(f"Unable to open file (not an h5lite container): {piece}")
-            tree = pickle.load(f)
-        for k, (attrs, a) in tree.items():
-            if k in self._tree and a is None:
-                self._tree[k][0].update(attrs)
-            else:
-                self._tree[k] = (AttributeManager(attrs), a)
+            while True:
+                try:
+                    record = pickle.load(f)
+                except EOFError:
+                    break
+                for k, (attrs, a) in record.items():
+                    if k in self._tree and a is None and self._tree[k][1] is None:
+                        self._tree[k][0].update(attrs)
+                    else:
+                        self._tree[k] = (AttributeManager(attrs), a)
 
     def _check_writable(self):
         if not self._open or self.mode == "r":
@@ -202,11 +242,25 @@ class File(Group):
     def flush(self):
         if self.mode == "r" or not self._open:
             return
-        tmp = self.filename + ".tmp"
-        with open(tmp, "wb") as f:
-            f.write(MAGIC)
-            pickle.dump({k: (dict(v[0]), v[1]) for k, v in self._tree.items()}, f, protocol=pickle.HIGHEST_PROTOCOL)
-        os.replace(tmp, self.filename)
+        if self._rewrite:
+            tmp = self.filename + ".tmp"
+            with open(tmp, "wb") as f:
+                f.write(MAGIC)
+                pickle.dump({k: (dict(v[0]), v[1]) for k, v in self._tree.items()}, f, protocol=pickle.HIGHEST_PROTOCOL)
+            os.replace(tmp, self.filename)
+        elif self._dirty:
+            with open(self.filename, "ab") as f:
+                pickle.dump({k: (dict(self._tree[k][0]), self._tree[k][1]) for k in self._dirty if k in self._tree}, f,
+                            protocol=pickle.HIGHEST_PROTOCOL)
+        self._dirty, self._rewrite = set(), False
+
+    def release_datasets(self):
+        """writer-side helper for a file kept open across many dumps: flush, then forget the arrays already on disk (the
+        groups stay, so later dumps keep appending under them); the file must not be read through this handle afterwards"""
+        self.flush()
+        for k in [k for k, v in self._tree.items() if v[1] is not None]:
+            del self._tree[k]
+        self._kids = None
 
     def close(self):
         self.flush()

@@ -166,7 +166,9 @@ def _call_init_fn(fn, coords):
     out = np.asarray(out, dtype=np.float64)
     if out.ndim == 0:
         out = np.full(len(coords[0]), float(out))
-    return np.ascontiguousarray(out.reshape(-1))
+    # the pybind side reads len(coords[0]) values from the returned buffer (PyArrayWrapper over the array's data): an array
+    # that is larger (the reference's own tests return (N, N) constants for 2-D inputs) contributes its first N values
+    return np.ascontiguousarray(out.reshape(-1)[:len(coords[0])])
 
 
 class Simulator:
@@ -432,10 +434,14 @@ class Simulator:
         rank = self.solver.comm.rank
         quantity = diag["quantity"]
         fn = os.path.join(path, quantity.strip("/").replace("/", "_") + ".h5") + (f".rank{rank}" if rank else "")
-        opened = self.__dict__.setdefault("_h5_opened", set())
-        first = fn not in opened
-        opened.add(fn)
-        with h5py.File(fn, "w" if first and mode == "overwrite" or not os.path.exists(fn) else "a") as f:
+        # h5lite: the file stays open for the run and every dump appends one record; h5py: opened and closed per dump
+        handles = self.__dict__.setdefault("_h5_files", {})
+        first = fn not in handles
+        lite = hasattr(h5py, "MAGIC")
+        if first or not lite:
+            handles[fn] = h5py.File(fn, "w" if first and mode == "overwrite" or not os.path.exists(fn) else "a")
+        f = handles[fn]
+        if True:
             if first:
                 dim = self.dims
                 for k, v in (("dimension", dim), ("interpOrder", self.interp_order), ("layoutType", "yee"),
@@ -473,6 +479,18 @@ class Simulator:
                         else:
                             ds = g.create_dataset(key, data=a)
                             ds.attrs["ghosts"] = (a.shape[0] - int(L.ncells[0])) // 2
+        f.release_datasets() if lite else f.close()
+
+    def close_diagnostics(self):
+        for f in self.__dict__.pop("_h5_files", {}).values():
+            if f:  # h5py files are closed after every dump already
+                f.close()
+
+    def __del__(self):
+        try:
+            self.close_diagnostics()
+        except Exception:
+            pass
 
     def _diag_arrays(self, p, dtype, quantity):
         get = self.solver.ops.get_field

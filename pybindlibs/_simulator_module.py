@@ -29,21 +29,17 @@ def populate(module, dim, interp, nref):
         particles -> the same five arrays for their refined particles, on the fine index space (runs phb_split)"""
         import numpy as np
         from phare_b200 import abi
-        from phare_b200.device import Context, DeviceParticles
-        icell, delta, weight, charge, v = (np.asarray(a) for a in particles)
+        icell, delta, weight, charge, v = (np.asarray(a).reshape(-1) for a in particles)
         n = len(weight)
-        sp = Splitter()
-        ctx = Context(dim, interp)
-        try:
-            src = DeviceParticles(ctx, max(n, 1)).upload_soa(icell.reshape(n, dim), delta.reshape(n, dim), weight, charge,
-                                                             v.reshape(n, 3))
-            dst = DeviceParticles(ctx, max(n * nref, 1))
-            big = 2 ** 30
-            everywhere = abi.make_box([-big] * dim, [big] * dim)
-            ctx.split(src, 0, n, sp.deltas, sp.weights, sp.max_cell_distance, [everywhere], dst)
-            ic, de, w, q, vv = dst.download_soa()
-        finally:
-            ctx.close()
+        ops = _sim.ops_factory(dim, interp)  # the CUDA back end; the CPU parity tests swap in the oracle here
+        src, dst = ops.particles(max(n, 1)), ops.particles(max(n * nref, 1))
+        ops.set_particles(src, icell.reshape(n, dim), delta.reshape(n, dim), weight, charge, v.reshape(n, 3))
+        ops.set_count(dst, 0)
+        big = 2 ** 30
+        everywhere = abi.make_box([-big] * dim, [big] * dim)
+        if ops.split(nref, src, 0, n, [everywhere], dst) is None:
+            raise RuntimeError("split_pyarray_particles: destination store too small")
+        ic, de, w, q, vv = ops.get_particles(dst)
         return ic.reshape(-1), de.reshape(-1), w, q, vv.reshape(-1)
 
     module.Simulator = Simulator

@@ -38,8 +38,10 @@ def main(argv):
                 yield from flatten(t)
             else:
                 yield t
+    def label(t):  # test id + the ddt datum it was generated from
+        return t.id() + " " + repr(getattr(getattr(t, t._testMethodName, None), "ddt_value", ""))
     tests = [t for t in flatten(unittest.defaultTestLoader.loadTestsFromModule(m))
-             if all(k in t.id() for k in keep) and not any(x in t.id() for x in drop)]
+             if all(k in label(t) for k in keep) and not any(x in label(t) for x in drop)]
     r = unittest.TextTestRunner(verbosity=2).run(unittest.TestSuite(tests))
     print(f"RESULT {module} run={r.testsRun} fail={len(r.failures)} err={len(r.errors)} skip={len(r.skipped)}", flush=True)
     return 0 if r.wasSuccessful() else 1

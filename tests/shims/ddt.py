@@ -43,6 +43,7 @@ def ddt(cls):
                     return fn(self, v, *a, **k)
                 return test
             t = make()
+            t.ddt_value = v
             t.__name__ = _name(name, i, v)
             setattr(cls, t.__name__, t)
         delattr(cls, name)
