@@ -192,6 +192,7 @@ class Simulator:
         self.current_time = self.start_time
         self.elapsed = 0.0
         self.is_initialized = False
+        self._restart_next, self._restart_t0 = [0, 0], time.time()  # RestartsManager: next indices, start_time_
         self.solver = None
         self.ndumps = 0
         # SolverPPC(dict["simulation"]["algo"]): pusher name, OhmInfo::FROM (ohm.hpp:23-31)
@@ -316,12 +317,21 @@ class Simulator:
     def advance(self, dt):
         if self.solver is None:
             raise RuntimeError("Error - no valid integrator in the simulator")
-        if getattr(self, "amr", None):
-            self.amr.advance(dt)  # root step + sub-cycles of the finer levels + synchronisation
-            if getattr(self, "tagger", None):
-                self.amr.regrid_tagged(self.tagger)  # TimeRefinementIntegrator: regrid_interval = 1
-        else:
-            self.solver.advance_level(dt)
+        try:
+            if getattr(self, "amr", None):
+                self.amr.advance(dt)  # root step + sub-cycles of the finer levels + synchronisation
+                if getattr(self, "tagger", None):
+                    self.amr.regrid_tagged(self.tagger)  # TimeRefinementIntegrator: regrid_interval = 1
+            else:
+                self.solver.advance_level(dt)
+        except RuntimeError as e:
+            # handle_dictionary_exception (simulator.hpp:618-630): with allow_emergency_dumps, every diagnostic of every
+            # level is dumped at the current time when the particle pusher (or the level initialiser) gives up
+            if self.d.get("simulation/diagnostics/allow_emergency_dumps", False) and any(
+                    k in str(e) for k in ("Updater::updatePopulations", "HybridLevelInitializer::initialize")):
+                for il in range(len(self.level_solvers())):
+                    self.dump_level(il, self.current_time)
+            raise
         self.elapsed += dt  # ConstantTimeStamper (core/utilities/time_stamper.hpp)
         self.current_time = self.start_time + self.elapsed
         return dt
@@ -536,9 +546,6 @@ class Simulator:
         r = self.d.get("simulation/restarts")
         if not isinstance(r, dict) or self.solver is None or not ("write_timestamps" in r or "elapsed_timestamps" in r):
             return False  # loading only, or restarts not active
-        if not hasattr(self, "_restart_next"):
-            self._restart_next = [0, 0]
-            self._restart_t0 = time.time()
         ts = np.asarray(r.get("write_timestamps", ()), dtype=np.float64).reshape(-1)
         el = np.asarray(r.get("elapsed_timestamps", ()), dtype=np.float64).reshape(-1)
         i, j = self._restart_next

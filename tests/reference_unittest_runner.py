@@ -22,6 +22,10 @@ def main(argv):
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches", "matplotlib.collections", "matplotlib.gridspec",
                  "matplotlib.animation", "matplotlib.colors", "matplotlib.lines", "mpl_toolkits", "mpl_toolkits.axes_grid1"):
         sys.modules.setdefault(name, mock.MagicMock(name=name))
+    plt = sys.modules["matplotlib.pyplot"]
+    if isinstance(plt, mock.MagicMock):  # no matplotlib here: `fig, ax = plt.subplots()` still has to unpack
+        plt.subplots = lambda *a, **k: (mock.MagicMock(), mock.MagicMock())
+        sys.modules["matplotlib"].pyplot = plt
     sys.path[:0] = [os.path.dirname(HERE), os.path.join(REF, "pyphare"), REF, HERE, os.path.join(HERE, "shims")]
     os.environ["PHARE_B200_DIAG_FORMAT"] = "h5"
     from phare_b200 import h5lite
