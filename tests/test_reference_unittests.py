@@ -3,7 +3,8 @@ through tests/reference_unittest_runner.py: pyphare drives `pybindlibs`, diagnos
 and read back by pyphare's own fromh5 reader.  They check, among others: B, density and bulk velocity as provided by the
 user; particle number per cell; domain and level-ghost particles of refined levels equal to the split of the coarser
 particles; overlapped patch fields equal to 5.5e-15 (with and without refined levels); fine fields coarsened onto the coarser
-level through the sub-cycles; domain particles on refined levels after advancing.  MHD permutations are filtered out (another
+level through the sub-cycles; domain particles on refined levels after advancing; restarts (every diagnostic of a resumed run
+equal to the straight run's, time- and elapsed-triggered, modes, keep_last); the two-cell-jump exception and its emergency dump.  MHD permutations are filtered out (another
 solver).  CPU parity back end here; PHARE_B200_REFERENCE_TESTS_ON_GPU=1 runs the same modules on the CUDA back end."""
 import os
 import re
@@ -23,28 +24,49 @@ MODULES = {
     "tests.simulator.initialize.test_particles_init_1d": 23,
     "tests.simulator.advance.test_fields_advance_1d": 36,
     "tests.simulator.advance.test_particles_advance_1d": 6,
+    "tests.simulator.test_restarts": 16,          # the reference's restart tests: write, resume, compare the diagnostics
+    "tests.simulator.test_exceptions": 1,         # particle moved two cells -> exception + emergency dump
+    "tests.simulator.test_validation": 60,
+    "tests.simulator.test_simulation": 1,
+    "tests.simulator.test_init_periodicity": 1,
 }
 
 
-def run_module(module, tmp_path, backend):
+def start_module(module, cwd, backend):
     env = dict(os.environ, PHARE_B200_BACKEND=backend)
-    r = subprocess.run([sys.executable, os.path.join(HERE, "reference_unittest_runner.py"), module, "-x", "MHD"],
-                       cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=1500)
-    m = re.search(r"RESULT \S+ run=(\d+) fail=(\d+) err=(\d+) skip=(\d+)", r.stdout)
-    assert m, (r.stdout[-2000:], r.stderr[-4000:])
-    return tuple(int(x) for x in m.groups()), r
+    os.makedirs(cwd, exist_ok=True)
+    return subprocess.Popen([sys.executable, os.path.join(HERE, "reference_unittest_runner.py"), module, "-x", "MHD"],
+                            cwd=str(cwd), env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+
+
+def result_of(proc):
+    out, err = proc.communicate(timeout=1500)
+    m = re.search(r"RESULT \S+ run=(\d+) fail=(\d+) err=(\d+) skip=(\d+)", out)
+    assert m, (out[-2000:], err[-4000:])
+    return tuple(int(x) for x in m.groups()), proc.returncode, err
+
+
+@pytest.fixture(scope="module")
+def cpu_runs(tmp_path_factory, cpu_oracle, cpu_ref):
+    """every module in its own process and directory, all started together (they are independent)"""
+    base = tmp_path_factory.mktemp("reference_unittests")
+    procs = {m: start_module(m, base / m.rsplit(".", 1)[1], "cpu") for m in MODULES}
+    yield procs
+    for p in procs.values():
+        if p.poll() is None:
+            p.kill()
 
 
 @pytest.mark.parametrize("module", list(MODULES))
-def test_reference_unittest_module_passes(cpu_oracle, cpu_ref, tmp_path, module):
-    (run, fail, err, skip), r = run_module(module, tmp_path, "cpu")
-    assert (fail, err) == (0, 0), r.stderr[-6000:]
-    assert run == MODULES[module] and r.returncode == 0
+def test_reference_unittest_module_passes(cpu_runs, module):
+    (run, fail, err, skip), rc, stderr = result_of(cpu_runs[module])
+    assert (fail, err) == (0, 0), stderr[-6000:]
+    assert run == MODULES[module] and rc == 0
 
 
 @pytest.mark.gpu
 @pytest.mark.skipif(os.environ.get("PHARE_B200_REFERENCE_TESTS_ON_GPU") != "1", reason="opt-in")
 @pytest.mark.parametrize("module", list(MODULES))
 def test_reference_unittest_module_passes_on_the_gpu(tmp_path, module):
-    (run, fail, err, skip), r = run_module(module, tmp_path, "gpu")
-    assert (fail, err) == (0, 0), r.stderr[-6000:]
+    (run, fail, err, skip), rc, stderr = result_of(start_module(module, tmp_path, "gpu"))
+    assert (fail, err) == (0, 0), stderr[-6000:]
