@@ -362,8 +362,17 @@ class Simulator:
 
     # ---- diagnostics (raw writer; the reference writes HDF5 through HighFive)
     def _due(self, diag, timestamp, timestep):
+        """DiagnosticsManager::needsWrite_ (diagnostic_manager.hpp:124-157): a requested simulation time within the step, or
+        the next requested wall-clock time (seconds since the simulator was built) has passed"""
         ts = np.asarray(diag.get("write_timestamps", ()), dtype=np.float64)
-        return ts.size > 0 and bool(np.any(np.abs(ts - timestamp) < 0.5 * timestep))
+        now = ts.size > 0 and bool(np.any(np.abs(ts - timestamp) < 0.5 * timestep))
+        el = np.asarray(diag.get("elapsed_timestamps", ()), dtype=np.float64).reshape(-1)
+        nxt = self.__dict__.setdefault("_diag_next_elapsed", {})
+        key = str(diag.get("type", "")) + str(diag.get("quantity", ""))
+        elapsed = nxt.get(key, 0) < el.size and time.time() > self._restart_t0 + el[nxt.get(key, 0)]
+        if elapsed:
+            nxt[key] = nxt.get(key, 0) + 1
+        return now or bool(elapsed)
 
     @staticmethod
     def diag_format():
@@ -386,10 +395,12 @@ class Simulator:
         path = diags.get("filePath", "phare_output")
         fmt = self.diag_format()
         written = False
-        for dtype in ("electromag", "fluid", "particle"):
+        for dtype in ("electromag", "fluid", "particle", "info"):
             for name, diag in (diags.get(dtype) or {}).items():
                 if not isinstance(diag, dict) or not self._due(diag, timestamp, timestep):
                     continue
+                if fmt != "h5" and (dtype == "info" or diag["quantity"].endswith("momentum_tensor")):
+                    continue  # h5 layout only
                 os.makedirs(path, exist_ok=True)
                 if fmt == "h5":
                     self._dump_h5(path, dtype, diag, timestamp, diags.get("mode", "overwrite"))
@@ -423,10 +434,46 @@ class Simulator:
             return
         path = diags.get("filePath", "phare_output")
         os.makedirs(path, exist_ok=True)
-        for dtype in ("electromag", "fluid", "particle"):
+        for dtype in ("electromag", "fluid", "particle", "info"):
             for name, diag in (diags.get(dtype) or {}).items():
                 if isinstance(diag, dict):
                     self._dump_h5(path, dtype, diag, timestamp, diags.get("mode", "overwrite"), levels=(level,))
+
+    TENSOR = ("xx", "xy", "xz", "yy", "yz", "zz")
+
+    def _compute_momentum_tensor(self, quantity, levels=None):
+        """FluidDiagnosticWriter::compute (diagnostic/detail/types/fluid.hpp:80-135): M_ij = mass * sum w v_i v_j of the domain
+        and levelGhostOld particles of a population, border-summed like the other moments.  A diagnostic, off the hot path:
+        two passes of the moment deposit (K3) over a copy of the store whose velocity columns hold the products"""
+        q = quantity.strip("/").split("/")
+        for il, solver in enumerate(self.level_solvers()):
+            if levels is not None and il not in levels:
+                continue
+            ops = solver.ops
+            for i in range(solver.npop):
+                if q[:2] == ["ions", "pop"] and solver.patches and solver.patches[0].pops[i].name != q[2]:
+                    continue
+                for p in solver.patches:
+                    pop, L = p.pops[i], p.layout
+                    if not hasattr(pop, "mom"):
+                        pop.mom = [ops.vec(L, abi.VX), ops.vec(L, abi.VX)]
+                        pop.mom_scratch = [ops.field(L, abi.RHO) for _ in range(6)]
+                    for vec in pop.mom:
+                        for c in range(3):
+                            ops.zero(vec[c])
+                    for store in (pop.domain, pop.level_ghost_old):
+                        n = ops.count(store) if store is not None else 0
+                        if not n:
+                            continue
+                        ic, de, w, ch, v = ops.get_particles(store)
+                        tmp = ops.particles(n)
+                        for vec, cols in zip(pop.mom, ((v[:, 0] * v[:, 0], v[:, 0] * v[:, 1], v[:, 0] * v[:, 2]),
+                                                       (v[:, 1] * v[:, 1], v[:, 1] * v[:, 2], v[:, 2] * v[:, 2]))):
+                            ops.set_particles(tmp, ic, de, w, ch, np.stack(cols, 1))
+                            ops.deposit(L, tmp, pop.scratch[0], pop.scratch[1], vec, pop.mass, 0, n)
+                solver.messenger.sum_borders(f"mom{i}", {p.geom.id: [vec[c] for vec in p.pops[i].mom for c in range(3)]
+                                                         for p in solver.patches},
+                                             {p.geom.id: p.pops[i].mom_scratch for p in solver.patches})
 
     def _dump_h5(self, path, dtype, diag, timestamp, mode, levels=None):
         """one file per quantity holding every dump (H5Writer, diagnostic/detail/h5writer.hpp:105-127, 250-258):
@@ -443,6 +490,8 @@ class Simulator:
             from . import h5lite as h5py
         rank = self.solver.comm.rank
         quantity = diag["quantity"]
+        if quantity.endswith("momentum_tensor"):
+            self._compute_momentum_tensor(quantity, levels)
         fn = os.path.join(path, quantity.strip("/").replace("/", "_") + ".h5") + (f".rank{rank}" if rank else "")
         # h5lite: the file stays open for the run and every dump appends one record; h5py: opened and closed per dump
         handles = self.__dict__.setdefault("_h5_files", {})
@@ -482,6 +531,10 @@ class Simulator:
                     g.attrs["lower"] = np.array([L.amr_lower[k] for k in range(L.dim)], dtype=np.int32)
                     g.attrs["upper"] = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)], dtype=np.int32)
                     g.attrs["mpi_rank"] = rank
+                    if dtype == "info":  # InfoDiagnosticWriter (types/info.hpp): a patch attribute, no dataset
+                        if quantity == "/particle_count":
+                            g.attrs["particle_count"] = sum(solver.ops.count(pop.domain) for pop in p.pops)
+                        continue
                     for key, a in self._diag_arrays(p, dtype, quantity).items():
                         if dtype == "particle":
                             # (n, dim) / (n, 3) / (n, 1): hdf5/writer/particle_writer.hpp:38-47
@@ -512,6 +565,11 @@ class Simulator:
             return {"charge_density": get(p.Ne)}
         if q == "ions/mass_density":
             return {"mass_density": get(p.rho_m)}
+        if q == "ions/momentum_tensor":  # Ions::computeFullMomentumTensor: the sum over the populations
+            out = {}
+            for k, name in enumerate(self.TENSOR):
+                out[f"momentum_tensor_{name}"] = sum(get(pop.mom[k // 3][k % 3]) for pop in p.pops)
+            return out
         if q == "ions/bulkVelocity":
             return {f"bulkVelocity_{c}": get(p.Vi[i]) for i, c in enumerate(XYZ)}
         for pop in p.pops:
@@ -519,6 +577,8 @@ class Simulator:
                 return {"density": get(pop.rho_n)}
             if q == f"ions/pop/{pop.name}/charge_density":
                 return {"charge_density": get(pop.rho_q)}
+            if q == f"ions/pop/{pop.name}/momentum_tensor":
+                return {f"momentum_tensor_{name}": get(pop.mom[k // 3][k % 3]) for k, name in enumerate(self.TENSOR)}
             if q == f"ions/pop/{pop.name}/flux":
                 return {f"flux_{c}": get(pop.flux[i]) for i, c in enumerate(XYZ)}
             # ParticleDiagnostics (diagnostic/detail/types/particle.hpp): the SoA keys of particle_packer.hpp:66-67

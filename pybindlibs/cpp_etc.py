@@ -72,7 +72,9 @@ def phare_deps():
         backend = abi.load().phb_version().decode()
     except Exception:
         backend = "libphare_b200.so (not built)"
-    return {"phare_b200": backend}
+    # the reference reports samrai / highfive / pybind; they are not used here: the keys stay (pyphare writes
+    # "<dep>_version" attributes from them), the version says so
+    return {"phare_b200": backend, "samrai": "0.0.0", "highfive": "0.0.0", "pybind": "0.0.0"}
 
 
 AMRHierarchy = _sim.Hierarchy
