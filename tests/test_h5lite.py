@@ -84,3 +84,52 @@ def test_simulator_writes_the_reference_h5_layout(cpu_oracle, tmp_path, monkeypa
     n = parts["weight"].shape[0]
     assert parts["iCell"].shape == (n, 1) and parts["v"].shape == (n, 3) and parts["charge"].shape == (n, 1) and n > 0
     assert float(h5lite.File(str(tmp_path / "ions_pop_beam_flux.h5")).attrs["pop_mass"]) == 2.0
+
+
+def test_momentum_tensor_of_a_cold_beam(cpu_oracle, tmp_path, monkeypatch):
+    """ions/pop/<name>/momentum_tensor (fluid.hpp:97-102: mass * sum w v_i v_j, border-summed): for a population whose
+    particles all carry the same velocity, M_ij = mass * n * v_i v_j node by node with n the deposited density; the total
+    tensor is the sum over the populations"""
+    import pybindlibs.dictator as pp
+    import phare_b200.simulator as S
+    from oracle.cpu_ops import CpuOps
+    from frontend_util import populate, const
+    monkeypatch.setenv("PHARE_B200_DIAG_FORMAT", "h5")
+    monkeypatch.setattr(S, "ops_factory", lambda dim, interp: CpuOps(dim, interp))
+    v0 = (0.5, -0.25, 0.125)
+    beam = dict(name="beam", mass=2.0, charge=1.0, ppc=30, seed=5, density=lambda x: 1.0 + 0.3 * np.sin(2 * np.pi * x / 12.8),
+                vx=const(v0[0]), vy=const(v0[1]), vz=const(v0[2]), vthx=const(0), vthy=const(0), vthz=const(0))
+    core = dict(name="core", mass=1.0, charge=1.0, ppc=30, seed=6, density=const(1.0), vx=const(0), vy=const(0), vz=const(0),
+                vthx=const(0.2), vthy=const(0.2), vthz=const(0.2))
+    populate([64], [0.2], 2, [beam, core], [const(1.0), const(0.0), const(0.0)], steps=1, largest=[32], diag_dir=str(tmp_path),
+             diag_times=[0.0])
+    for name, q in (("mt_beam", "/ions/pop/beam/momentum_tensor"), ("mt_core", "/ions/pop/core/momentum_tensor"),
+                    ("mt_all", "/ions/momentum_tensor"), ("n_beam", "/ions/pop/beam/density"), ("count", "/particle_count")):
+        kind = "info" if name == "count" else "fluid"
+        pp.add_string(f"simulation/diagnostics/{kind}/{name}/type", kind)
+        pp.add_string(f"simulation/diagnostics/{kind}/{name}/quantity", q)
+        pp.add_array_as_vector(f"simulation/diagnostics/{kind}/{name}/write_timestamps", np.array([0.0]))
+    sim = S.make_simulator(S.make_hierarchy(), 1, 2, 2)
+    sim.initialize()
+    assert sim.dump_diagnostics(0.0, 0.005)
+    sim.close_diagnostics()
+    S.dict_instance().stop()
+    at = "t/0.0000000000/pl0"
+    Mb = h5lite.File(str(tmp_path / "ions_pop_beam_momentum_tensor.h5"))[at]
+    Mc = h5lite.File(str(tmp_path / "ions_pop_core_momentum_tensor.h5"))[at]
+    Ma = h5lite.File(str(tmp_path / "ions_momentum_tensor.h5"))[at]
+    n = h5lite.File(str(tmp_path / "ions_pop_beam_density.h5"))[at]
+    idx = {"x": 0, "y": 1, "z": 2}
+    for patch in ("p0#0", "p0#1"):
+        dens = np.asarray(n[patch]["density"])
+        assert dens[4:-4].min() > 0.5
+        for ij in ("xx", "xy", "xz", "yy", "yz", "zz"):
+            m = np.asarray(Mb[patch][f"momentum_tensor_{ij}"])
+            assert int(Mb[patch][f"momentum_tensor_{ij}"].attrs["ghosts"]) == 4
+            want = 2.0 * dens * v0[idx[ij[0]]] * v0[idx[ij[1]]]
+            assert np.allclose(m, want, rtol=1e-12, atol=1e-14), ij
+            assert np.allclose(np.asarray(Ma[patch][f"momentum_tensor_{ij}"]), m + np.asarray(Mc[patch][f"momentum_tensor_{ij}"]),
+                               rtol=1e-13, atol=1e-15)
+        assert np.asarray(Mc[patch]["momentum_tensor_xx"])[4:-4].min() > 0  # a warm population has pressure
+    cnt = h5lite.File(str(tmp_path / "particle_count.h5"))[at]
+    assert int(cnt["p0#0"].attrs["particle_count"]) == 32 * 60 and list(cnt["p0#0"].keys()) == []
