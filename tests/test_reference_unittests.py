@@ -33,6 +33,9 @@ MODULES = {
     # every diagnostic (incl. momentum tensors, particle_count, python attributes) present and readable at the dump times;
     # the 1-D permutations here, all 28 tests of the module (1/2/3-D, elapsed-time dumps) pass when run by hand (3 min)
     "tests.simulator.test_diagnostics": 9,
+    # 2-D Harris sheet with refinement="tagging": runs restarted at several times have the layout and the data of the
+    # continuous run
+    "tests.simulator.refinement.test_regridding": 1,
 }
 FILTERS = {"tests.simulator.test_diagnostic_timestamps": ["-k", "test_hierarchy_timestamp_cadence"],
            "tests.simulator.test_diagnostics": ["-k", "'ndim': 1"]}
