@@ -500,48 +500,47 @@ class Simulator:
         if first or not lite:
             handles[fn] = h5py.File(fn, "w" if first and mode == "overwrite" or not os.path.exists(fn) else "a")
         f = handles[fn]
-        if True:
-            if first:
-                dim = self.dims
-                for k, v in (("dimension", dim), ("interpOrder", self.interp_order), ("layoutType", "yee"),
-                             ("domain_box", np.array([c - 1 for c in self.hier.cells], dtype=np.int32)),
-                             ("cell_width", np.array(self.hier.dl, dtype=np.float64)), ("origin", np.zeros(dim)),
-                             ("boundary_conditions", "periodic")):
-                    f.attrs[k] = v
-                n_attr = int(diag.get("n_attributes", 0))
-                if n_attr:
-                    g = f.require_group("py_attrs")
-                    for i in range(n_attr):
-                        g.attrs[diag[f"attribute_{i}_key"]] = diag[f"attribute_{i}_value"]
-                q = quantity.strip("/").split("/")
-                if q[:2] == ["ions", "pop"]:
-                    mass = [pop.mass for pop in self.solver.patches[0].pops if pop.name == q[2]] if self.solver.patches else []
-                    if mass:
-                        f.attrs["pop_mass"] = float(mass[0])
-            tgrp = f.require_group(f"t/{timestamp:.10f}")
-            for il, solver in enumerate(self.level_solvers()):
-                if levels is not None and il not in levels:
+        if first:
+            dim = self.dims
+            for k, v in (("dimension", dim), ("interpOrder", self.interp_order), ("layoutType", "yee"),
+                         ("domain_box", np.array([c - 1 for c in self.hier.cells], dtype=np.int32)),
+                         ("cell_width", np.array(self.hier.dl, dtype=np.float64)), ("origin", np.zeros(dim)),
+                         ("boundary_conditions", "periodic")):
+                f.attrs[k] = v
+            n_attr = int(diag.get("n_attributes", 0))
+            if n_attr:
+                g = f.require_group("py_attrs")
+                for i in range(n_attr):
+                    g.attrs[diag[f"attribute_{i}_key"]] = diag[f"attribute_{i}_value"]
+            q = quantity.strip("/").split("/")
+            if q[:2] == ["ions", "pop"]:
+                mass = [pop.mass for pop in self.solver.patches[0].pops if pop.name == q[2]] if self.solver.patches else []
+                if mass:
+                    f.attrs["pop_mass"] = float(mass[0])
+        tgrp = f.require_group(f"t/{timestamp:.10f}")
+        for il, solver in enumerate(self.level_solvers()):
+            if levels is not None and il not in levels:
+                continue
+            lvl = tgrp.require_group(f"pl{il}")
+            for p in solver.patches:
+                L = p.layout
+                g = lvl.require_group(f"p{rank}#{p.geom.id}")
+                g.attrs["origin"] = np.array([L.origin[k] for k in range(L.dim)])
+                g.attrs["nbrCells"] = np.array([L.ncells[k] for k in range(L.dim)], dtype=np.uint32)
+                g.attrs["lower"] = np.array([L.amr_lower[k] for k in range(L.dim)], dtype=np.int32)
+                g.attrs["upper"] = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)], dtype=np.int32)
+                g.attrs["mpi_rank"] = rank
+                if dtype == "info":  # InfoDiagnosticWriter (types/info.hpp): a patch attribute, no dataset
+                    if quantity == "/particle_count":
+                        g.attrs["particle_count"] = sum(solver.ops.count(pop.domain) for pop in p.pops)
                     continue
-                lvl = tgrp.require_group(f"pl{il}")
-                for p in solver.patches:
-                    L = p.layout
-                    g = lvl.require_group(f"p{rank}#{p.geom.id}")
-                    g.attrs["origin"] = np.array([L.origin[k] for k in range(L.dim)])
-                    g.attrs["nbrCells"] = np.array([L.ncells[k] for k in range(L.dim)], dtype=np.uint32)
-                    g.attrs["lower"] = np.array([L.amr_lower[k] for k in range(L.dim)], dtype=np.int32)
-                    g.attrs["upper"] = np.array([L.amr_lower[k] + L.ncells[k] - 1 for k in range(L.dim)], dtype=np.int32)
-                    g.attrs["mpi_rank"] = rank
-                    if dtype == "info":  # InfoDiagnosticWriter (types/info.hpp): a patch attribute, no dataset
-                        if quantity == "/particle_count":
-                            g.attrs["particle_count"] = sum(solver.ops.count(pop.domain) for pop in p.pops)
-                        continue
-                    for key, a in self._diag_arrays(p, dtype, quantity).items():
-                        if dtype == "particle":
-                            # (n, dim) / (n, 3) / (n, 1): hdf5/writer/particle_writer.hpp:38-47
-                            ds = g.create_dataset(key.split("/", 1)[1], data=a if a.ndim == 2 else a.reshape(-1, 1))
-                        else:
-                            ds = g.create_dataset(key, data=a)
-                            ds.attrs["ghosts"] = (a.shape[0] - int(L.ncells[0])) // 2
+                for key, a in self._diag_arrays(p, dtype, quantity).items():
+                    if dtype == "particle":
+                        # (n, dim) / (n, 3) / (n, 1): hdf5/writer/particle_writer.hpp:38-47
+                        ds = g.create_dataset(key.split("/", 1)[1], data=a if a.ndim == 2 else a.reshape(-1, 1))
+                    else:
+                        ds = g.create_dataset(key, data=a)
+                        ds.attrs["ghosts"] = (a.shape[0] - int(L.ncells[0])) // 2
         f.release_datasets() if lite else f.close()
 
     def close_diagnostics(self):
