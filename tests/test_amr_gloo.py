@@ -294,3 +294,41 @@ def _restart_worker(rank, world, port, out_dir):
 def test_restart_on_two_ranks_resumes_bit_for_bit(cpu_ref, tmp_path):
     mp.spawn(_restart_worker, args=(2, 29500 + (os.getpid() % 2000) + 17, str(tmp_path)), nprocs=2, join=True)
     assert os.path.exists(tmp_path / "ok0") and os.path.exists(tmp_path / "ok1")
+
+
+def _h5_worker(rank, world, port, out_dir):
+    """two ranks write one quantity: rank 0 the file, rank 1 its `.rank1` piece; a reader sees the patches of both"""
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["PHARE_B200_DIAG_FORMAT"] = "h5"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import phare_b200.simulator as S
+    from phare_b200 import h5lite
+    from oracle.cpu_ops import CpuOps
+    from frontend_util import populate, two_pop_1d
+    S.ops_factory = lambda dim, interp: CpuOps(dim, interp)
+    pops, bfn = two_pop_1d(64)
+    populate([64], [0.2], 1, pops, bfn, steps=1, largest=[16], diag_dir=out_dir, diag_times=[0.0])
+    sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+    sim.initialize()
+    assert sim.dump_diagnostics(0.0, 0.005)
+    sim.close_diagnostics()
+    dist.barrier()
+    if rank == 0:
+        f = h5lite.File(os.path.join(out_dir, "EM_B.h5"))
+        patches = f["t/0.0000000000/pl0"]
+        assert len(patches.keys()) == 4 and {k[:2] for k in patches.keys()} == {"p0", "p1"}
+        lowers = sorted(int(p.attrs["lower"][0]) for p in patches.values())
+        assert lowers == [0, 16, 32, 48] and all(p["EM_B_y"].shape == (16 + 4,) for p in patches.values())
+        assert {int(p.attrs["mpi_rank"]) for p in patches.values()} == {0, 1}
+        with open(os.path.join(out_dir, "ok"), "w") as o:
+            o.write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_h5_diagnostics_from_two_ranks_merge(cpu_ref, tmp_path):
+    mp.spawn(_h5_worker, args=(2, 29500 + (os.getpid() % 2000) + 19, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok")
