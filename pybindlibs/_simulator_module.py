@@ -32,14 +32,19 @@ def populate(module, dim, interp, nref):
         icell, delta, weight, charge, v = (np.asarray(a).reshape(-1) for a in particles)
         n = len(weight)
         ops = _sim.ops_factory(dim, interp)  # the CUDA back end; the CPU parity tests swap in the oracle here
-        src, dst = ops.particles(max(n, 1)), ops.particles(max(n * nref, 1))
-        ops.set_particles(src, icell.reshape(n, dim), delta.reshape(n, dim), weight, charge, v.reshape(n, 3))
-        ops.set_count(dst, 0)
-        big = 2 ** 30
-        everywhere = abi.make_box([-big] * dim, [big] * dim)
-        if ops.split(nref, src, 0, n, [everywhere], dst) is None:
-            raise RuntimeError("split_pyarray_particles: destination store too small")
-        ic, de, w, q, vv = ops.get_particles(dst)
+        try:
+            src, dst = ops.particles(max(n, 1)), ops.particles(max(n * nref, 1))
+            ops.set_particles(src, icell.reshape(n, dim), delta.reshape(n, dim), weight, charge, v.reshape(n, 3))
+            ops.set_count(dst, 0)
+            big = 2 ** 30
+            everywhere = abi.make_box([-big] * dim, [big] * dim)
+            if ops.split(nref, src, 0, n, [everywhere], dst) is None:
+                raise RuntimeError("split_pyarray_particles: destination store too small")
+            ic, de, w, q, vv = ops.get_particles(dst)
+        finally:
+            ctx = getattr(ops, "ctx", None)  # the device context of this one call
+            if ctx is not None:
+                ctx.close()
         return ic.reshape(-1), de.reshape(-1), w, q, vv.reshape(-1)
 
     module.Simulator = Simulator
