@@ -24,7 +24,14 @@ def main(argv):
         sys.modules.setdefault(name, mock.MagicMock(name=name))
     plt = sys.modules["matplotlib.pyplot"]
     if isinstance(plt, mock.MagicMock):  # no matplotlib here: `fig, ax = plt.subplots()` still has to unpack
-        plt.subplots = lambda *a, **k: (mock.MagicMock(), mock.MagicMock())
+        def subplots(nrows=1, ncols=1, **kw):
+            ax = lambda: mock.MagicMock(name="Axes")
+            if nrows * ncols == 1:
+                return mock.MagicMock(name="Figure"), ax()
+            if min(nrows, ncols) == 1:
+                return mock.MagicMock(name="Figure"), tuple(ax() for _ in range(nrows * ncols))
+            return mock.MagicMock(name="Figure"), tuple(tuple(ax() for _ in range(ncols)) for _ in range(nrows))
+        plt.subplots = subplots
         sys.modules["matplotlib"].pyplot = plt
     sys.path[:0] = [os.path.dirname(HERE), os.path.join(REF, "pyphare"), REF, HERE, os.path.join(HERE, "shims")]
     os.environ["PHARE_B200_DIAG_FORMAT"] = "h5"
