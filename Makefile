@@ -6,16 +6,18 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 # the few deliberate fusions are explicit fma() calls.
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -fmad=false -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr $(EXTRA)
 SRC       := $(wildcard phare_b200/csrc/*.cu)
-OBJ       := $(patsubst phare_b200/csrc/%.cu,build/%.o,$(SRC))
-LIB       := phare_b200/lib/libphare_b200.so
+# tuning builds: make lib BUILD=build_v1 LIB=phare_b200/lib/libphare_b200_v1.so EXTRA=-DPHB_TILE_BS=256  (load with PHB_LIB=...)
+BUILD     ?= build
+OBJ       := $(patsubst phare_b200/csrc/%.cu,$(BUILD)/%.o,$(SRC))
+LIB       ?= phare_b200/lib/libphare_b200.so
 
 all: lib oracle
 
 lib: $(LIB)
 
-build/%.o: phare_b200/csrc/%.cu $(wildcard phare_b200/csrc/*.cuh) include/phare_b200.h
-	@mkdir -p build
-	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; false)
+$(BUILD)/%.o: phare_b200/csrc/%.cu $(wildcard phare_b200/csrc/*.cuh) include/phare_b200.h
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
 $(LIB): $(OBJ)
 	@mkdir -p phare_b200/lib
@@ -25,6 +27,6 @@ oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf build $(LIB)
+	rm -rf $(BUILD) $(LIB)
 	$(MAKE) -C oracle clean
 .PHONY: all lib oracle clean

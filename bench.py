@@ -5,6 +5,12 @@ interp order 1), weak scaling over the GPUs of one node.
 
     python bench.py --gpus N --steps K --warmup W              # our arm (CUDA kernels through the C ABI)
     python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU path on the host cores
+    python bench.py --config k ...                             # the other BASELINE configs (1-4, phare_b200/configs.py):
+                                                               # their patches are dealt to the N GPUs (strong scaling)
+
+At N > 1 a small global problem is first advanced 3 steps on the N ranks AND as one process holding every patch on
+rank 0; the two must agree (fields / moments <= 1e-10 per node, particle counts per patch equal, ghost nodes equal to
+the owner's values): "parity_check" in the JSON line, non-zero exit status on failure.
 
 A "step" = one SolverPPC::advanceLevel: 3 x (Faraday, Ampere, Ohm), 2 x average, the domain_only and the all
 particle sweeps (2 pushes per particle) and every same-level exchange phase.  For N > 1 the driver launches
@@ -28,6 +34,9 @@ INTERP = 1
 DX = (0.2, 0.2, 0.2)
 DT = 1e-3
 GPU_GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+# cells per patch of the multi-rank parity problem, by dimension
+PARITY_CELLS = {1: (256,), 2: (32, 32), 3: (16, 16, 16)}
+PARITY_PPC = 16
 BYTES_PUSH = {1: 80, 2: 104, 3: 128}      # K1 algorithmic bytes per particle
 BYTES_DEPOSIT = {1: 52, 2: 64, 3: 76}     # K3
 METRIC = "particle-pushes/sec (interp+push+deposit), whole job"
@@ -85,32 +94,139 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------
-def build_gpu_solver(n_gpus, rank, device):
-    """one 128^3 patch per GPU on a periodic Cartesian GPU grid; particles created on the device"""
-    import torch
-    from phare_b200 import abi
+def bench_config(k, n_gpus):
+    """config 5: one 128^3 patch per GPU on a periodic Cartesian GPU grid (weak scaling); configs 1-4: the config's own
+    domain and patches, dealt to the GPUs in order (strong scaling)"""
+    from phare_b200 import configs
+    if int(k) == 5:
+        return configs.config5(GPU_GRIDS[n_gpus]), "weak"
+    return configs.get(k), "strong"
+
+
+def build_gpu_solver(cfg, n_gpus, device, comm=None):
+    """the config on the CUDA back end, particles created on the device (phare_b200/configs.py)"""
+    from phare_b200 import configs
     from phare_b200.messenger import LocalComm, TorchComm
-    from phare_b200.solver import GpuOps, Patch, SolverPPC, make_level
-    from phare_b200.torch_interop import uniform_sorted_particles
-    grid = GPU_GRIDS[n_gpus]
-    domain = tuple(CELLS_PER_GPU[d] * grid[d] for d in range(3))
-    comm = TorchComm(device) if n_gpus > 1 else LocalComm()
-    ops = GpuOps(3, INTERP, device)
-    geom, layouts = make_level(domain, grid, INTERP, DX, nranks=n_gpus)
-    patches = []
-    for pg, L in zip(geom.patches, layouts):
-        if pg.owner != rank:
-            continue
-        n = int(L.ncells[0]) * int(L.ncells[1]) * int(L.ncells[2]) * PPC
-        patch = Patch(ops, pg, L, [dict(name="protons", mass=1.0, n=n)], capacity_factor=1.2)  # below the 85 % fill at which the stores would grow
-        pop = patch.pops[0]
-        # uniform Maxwellian: n = 1, V = 0, vth = 0.3, charge 1 (functional uniform bench, SURVEY §8(d) C5)
-        P = uniform_sorted_particles(ops.ctx, L, PPC, 0.3, device, seed=1337 + pg.id, store=pop.domain)
-        patch.B[0].t.fill_(1.0)  # B = (1, 0, 0)
-        patches.append(patch)
-    solver = SolverPPC(ops, patches, geom, comm, resistivity=0.0, hyper_resistivity=1e-4, Te=0.12)
-    solver.initialize()
+    from phare_b200.solver import GpuOps
+    comm = comm or (TorchComm(device) if n_gpus > 1 else LocalComm())
+    ops = GpuOps(cfg.dim, cfg.interp, device)
+    # capacity: below the 85 % fill at which the stores would grow
+    solver = configs.build_device_loaded(ops, comm, cfg, capacity_factor=1.2)
     return solver, ops
+
+
+def _node_err(got, want):
+    """largest per-node |got - want| / (|want| + 1e-3 max|want|)"""
+    import numpy as np
+    scale = float(np.max(np.abs(want)))
+    if scale == 0.0:
+        return float(np.max(np.abs(got)))
+    return float(np.max(np.abs(got - want) / (np.abs(want) + 1e-3 * scale)))
+
+
+def _snapshot(solver):
+    """every local patch: E, B (whole arrays, ghosts included), Ni, Vi, per-population moments and particle counts"""
+    ops, out = solver.ops, {}
+    for p in solver.patches:
+        rec = dict(lo=[int(p.layout.amr_lower[d]) for d in range(p.layout.dim)],
+                   n=[int(p.layout.ncells[d]) for d in range(p.layout.dim)])
+        for name in ("E", "B", "Vi"):
+            rec[name] = [ops.get_field(getattr(p, name)[c]) for c in range(3)]
+        rec["Ni"] = ops.get_field(p.Ne)
+        rec["pops"] = [dict(count=int(ops.count(pop.domain)), rho=ops.get_field(pop.rho_n),
+                            flux=[ops.get_field(pop.flux[c]) for c in range(3)]) for pop in p.pops]
+        out[p.geom.id] = rec
+    return out
+
+
+def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
+    """N-rank correctness, visible to the driver: a small global problem of the benchmarked config (same profiles, dl, dt;
+    PARITY_CELLS per patch, PARITY_PPC particles per cell, one patch per rank at least) advanced `steps` steps (a) on the
+    N ranks through the peer-memory halo / NCCL migration path that the timed region uses and (b) by rank 0 alone holding
+    every patch.  Compared on rank 0: every field and moment per node, particle counts per patch and population, and the
+    reference's own multi-rank criterion (tests/simulator/test_advance.py:180, overlap coherence): the ghost nodes of
+    every patch equal the values of the patch that owns them."""
+    import gc
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from phare_b200 import abi, configs
+    from phare_b200.messenger import LocalComm, centering
+    base, _ = bench_config(cfg_key, n_gpus)
+    grid = base.patch_grid
+    if int(np.prod(grid)) < n_gpus:
+        raise RuntimeError("fewer patches than GPUs")
+    per = PARITY_CELLS[base.dim]
+    small = base.with_cells(tuple(per[d] * grid[d] for d in range(base.dim)), grid)
+    small.pops = [dict(p, ppc=PARITY_PPC) for p in small.pops]
+    solver, ops = build_gpu_solver(small, n_gpus, device)
+    for _ in range(steps):
+        solver.advance_level(small.dt)
+    mine = _snapshot(solver)
+    everyone = [None] * n_gpus
+    dist.all_gather_object(everyone, mine)
+    del solver, ops
+    gc.collect()
+    verdict = None
+    if rank == 0:
+        multi = {}
+        for part in everyone:
+            multi.update(part)
+        one, ops1 = build_gpu_solver(small, 1, device, comm=LocalComm())
+        for _ in range(steps):
+            one.advance_level(small.dt)
+        single = _snapshot(one)
+        del one, ops1
+        worst, worst_name, counts_equal = 0.0, "", True
+        g = 2 if small.interp == 1 else 4
+        dim = small.dim
+        for pid, a in multi.items():
+            b = single[pid]
+            for name in ("E", "B", "Vi"):
+                for c in range(3):
+                    whole = name != "Vi"
+                    qty = dict(E=abi.EX, B=abi.BX, Vi=abi.VX)[name] + c
+                    sl = tuple(slice(None) if whole else slice(g, g + a["n"][d] + (1 if centering(qty, d) == 0 else 0))
+                               for d in range(dim))
+                    e = _node_err(a[name][c][sl], b[name][c][sl])
+                    if e > worst:
+                        worst, worst_name = e, f"{name}{'xyz'[c]}@patch{pid}"
+            phys = tuple(slice(g, g + a["n"][d] + 1) for d in range(dim))
+            e = _node_err(a["Ni"][phys], b["Ni"][phys])
+            if e > worst:
+                worst, worst_name = e, f"Ni@patch{pid}"
+            for i, (pa, pb) in enumerate(zip(a["pops"], b["pops"])):
+                counts_equal = counts_equal and pa["count"] == pb["count"]
+                for got, want in [(pa["rho"], pb["rho"])] + list(zip(pa["flux"], pb["flux"])):
+                    e = _node_err(got[phys], want[phys])
+                    if e > worst:
+                        worst, worst_name = e, f"pop{i} moment@patch{pid}"
+        # overlap coherence of the N-rank run: assemble the periodic global array of every E, B component from the
+        # patch interiors, then every node of every patch (ghosts included) must carry the global value
+        overlap = 0.0
+        for name, q0 in (("E", abi.EX), ("B", abi.BX)):
+            for c in range(3):
+                prim = [centering(q0 + c, d) == 0 for d in range(dim)]
+                G = np.full([small.cells[d] for d in range(dim)], np.nan)
+                for a in multi.values():  # dual: n nodes; primal: the first n of n + 1 (the last is the neighbour's first)
+                    src = tuple(slice(g, g + a["n"][d]) for d in range(dim))
+                    dst = tuple(slice(a["lo"][d], a["lo"][d] + a["n"][d]) for d in range(dim))
+                    G[dst] = a[name][c][src]
+                scale = float(np.nanmax(np.abs(G))) or 1.0
+                for a in multi.values():
+                    arr = a[name][c]
+                    idx = np.ix_(*[(np.arange(arr.shape[d]) - g + a["lo"][d]) % small.cells[d] for d in range(dim)])
+                    overlap = max(overlap, float(np.max(np.abs(arr - G[idx]))) / scale)
+        ok = bool(worst <= 1e-10 and counts_equal and overlap <= 1e-12)
+        verdict = dict(ok=ok, max_rel=worst, where=worst_name, counts_equal=bool(counts_equal), overlap_max_rel=overlap,
+                       steps=steps, problem=f"{small.name.split(':')[0]} profiles, {list(small.cells)} cells in "
+                                            f"{list(grid)} patches, {PARITY_PPC} ppc, N ranks vs one process",
+                       bar="fields and moments <= 1e-10 per node (|d| / (|ref| + 1e-3 max|ref|)), particle counts per patch "
+                           "equal, every ghost node of E and B within 1e-12 max|.| of its owner's value")
+    box = [verdict]
+    dist.broadcast_object_list(box, src=0)
+    torch.cuda.synchronize()
+    return box[0]
 
 
 def our_arm(args):
@@ -125,8 +241,11 @@ def our_arm(args):
     torch.cuda.set_device(device)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-    solver, ops = build_gpu_solver(n_gpus, rank, device)
-    n_local = sum(ops.count(p.pops[0].domain) for p in solver.patches)
+    parity = multi_rank_parity(args.config, n_gpus, rank, device) if world > 1 and not args.no_parity else None
+    cfg, scaling = bench_config(args.config, n_gpus)
+    DT, dim = cfg.dt, cfg.dim
+    solver, ops = build_gpu_solver(cfg, n_gpus, device)
+    n_local = sum(ops.count(pop.domain) for p in solver.patches for pop in p.pops)
 
     def barrier():
         if world > 1:
@@ -176,29 +295,42 @@ def our_arm(args):
     roofline = None
     extra = {}
     if push_ms:
-        alg = n_local * BYTES_PUSH[3]
+        # one K1 launch = one population of one patch: the average launch moves n_local / launches-per-sweep particles
+        n_launch = n_local / max(1, sum(len(p.pops) for p in solver.patches))
+        alg = n_launch * BYTES_PUSH[dim]
         ach = alg / (avg(push_ms) * 1e-3) / 1e9
-        # DRAM traffic per launch: dram__bytes_read+write of one `ncu --set full` capture of this kernel
-        # (profiles/traffic_c5s.json, taken on the same kernel at 16.8 M particles), scaled per particle
+        # DRAM traffic per launch: dram__bytes_read + dram__bytes_write of one `ncu --set full` capture of EXACTLY the
+        # kernel instantiation timed here (profiles/traffic_r2.json, keyed by config and kernel name), per particle
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "traffic_c5s.json")
+        prof = os.path.join(ROOT, "profiles", "traffic_r2.json")
         if os.path.exists(prof):
-            for k, v in json.load(open(prof)).items():
-                if k.startswith("push_tma_kernel<3, 1"):
-                    traffic = v["dram_bytes_per_particle"] * n_local
+            rec = json.load(open(prof)).get(f"c{cfg.key}", {}).get("push_in_place")
+            if rec:
+                traffic = rec["dram_bytes_per_particle"] * n_launch
         roofline = dict(bound="hbm", kernel="push (K1 fused interpolate+Boris)", achieved=round(ach, 1), peak=peak,
                         unit="GB/s", frac=round(ach / peak, 4), traffic=traffic, peak_source=peak_src,
                         algorithmic_bytes_per_launch=alg, avg_launch_ms=round(avg(push_ms), 4),
                         launches_timed=len(push_ms))
         if dep_ms:
-            a = n_local * BYTES_DEPOSIT[3] / (avg(dep_ms) * 1e-3) / 1e9
+            a = n_launch * BYTES_DEPOSIT[dim] / (avg(dep_ms) * 1e-3) / 1e9
             extra["deposit"] = dict(achieved=round(a, 1), frac=round(a / peak, 4), avg_launch_ms=round(avg(dep_ms), 4))
+        mv_ms = kernel_ms.get("move_domain_only", [])
+        if mv_ms:
+            # K1+K3 fused, nothing written back (the domain_only sweep): one read of the store; its algorithmic work is a
+            # whole particle-push (K1 + K3 bytes), so both fractions are given
+            a = n_launch * BYTES_DEPOSIT[dim] / (avg(mv_ms) * 1e-3) / 1e9
+            w = n_launch * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (avg(mv_ms) * 1e-3) / 1e9
+            extra["move_domain_only"] = dict(moved_gbs=round(a, 1), frac_of_bytes_moved=round(a / peak, 4),
+                                             frac_of_k1_plus_k3_bytes=round(w / peak, 4),
+                                             avg_launch_ms=round(avg(mv_ms), 4),
+                                             what="tile kernel (csrc/tile.cuh): interpolate + push + deposit in one pass, "
+                                                  "E,B block of each CTA staged in shared memory by bulk copies")
         if bin_ms:
             extra["bin"] = dict(avg_ms=round(avg(bin_ms), 4))
         ds_ms, plan_ms = kernel_ms.get("deposit_scatter", []), kernel_ms.get("bin_plan", [])
         if ds_ms:
             # K3+K2 fused (the `all` sweep): reads the store + 4 B slot, writes the re-binned store
-            a = n_local * (2 * BYTES_DEPOSIT[3] + 4) / (avg(ds_ms) * 1e-3) / 1e9
+            a = n_launch * (2 * BYTES_DEPOSIT[dim] + 4) / (avg(ds_ms) * 1e-3) / 1e9
             extra["deposit_scatter"] = dict(achieved=round(a, 1), frac=round(a / peak, 4),
                                             avg_launch_ms=round(avg(ds_ms), 4),
                                             what="deposit carried by the re-binning scatter pass (phb_deposit_scatter)")
@@ -207,38 +339,49 @@ def our_arm(args):
         extra["kernel_ms_per_step"] = {k: round(sum(v) / args.steps, 3) for k, v in sorted(kernel_ms.items())}
         # whole-step fraction: 2 sweeps x (K1 + K3 algorithmic bytes) / step time
         extra["whole_step_frac_of_hbm"] = round(
-            2 * n_local * (BYTES_PUSH[3] + BYTES_DEPOSIT[3]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)
+            2 * n_local * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)
+        # bytes the particle kernels of one step actually move per particle (their own column reads + writes)
+        moved = {"push": BYTES_PUSH[dim], "deposit": BYTES_DEPOSIT[dim], "move_domain_only": BYTES_DEPOSIT[dim],
+                 "move_all": BYTES_PUSH[dim] + 8,
+                 "bin_plan": 4 * dim + 4, "deposit_scatter": 2 * BYTES_DEPOSIT[dim] + 4, "bin": 4 * dim + 8 + 2 * BYTES_DEPOSIT[dim]}
+        sweeps = max(1, sum(len(p.pops) for p in solver.patches))
+        extra["bytes_moved_per_particle_per_step"] = round(
+            sum(moved.get(k, 0) * len(v) / (args.steps * sweeps) for k, v in kernel_ms.items()), 1)
+        extra["algorithmic_bytes_per_particle_per_step"] = 2 * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim])
 
     # ---- e2e: the same step driven with HOST buffers: the step's field inputs come from pinned host memory
     # and the step's results (moments and new fields) are read back, inside the timed region
     e2e = None
     if not args.no_e2e:
-        e2e = measure_e2e(solver, ops, args, world, device, n_total)
+        e2e = measure_e2e(solver, ops, args, world, device, n_total, DT)
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:
-        cpu_baseline = cpu_reference_rate(sample_seconds=12.0)
+        cpu_baseline = cpu_reference_rate(args.config)
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit="particle-pushes/s", n_gpus=n_gpus, steps=args.steps,
-                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak",
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling,
                     vs_baseline=None, dtype="f64", data="synthetic",
-                    config=dict(workload="config 5: 3-D uniform Maxwellian plasma, periodic, 128^3 cells and 64 ppc "
-                                         "per GPU, 1 population, interp order 1, dt=1e-3, dl=0.2",
-                                cells_per_gpu=list(CELLS_PER_GPU), ppc=PPC, interp_order=INTERP,
-                                particles_total=n_total, gpu_grid=list(GPU_GRIDS[n_gpus]),
-                                pushes_per_step=2 * n_total,
-                                l2="inputs (10.2 GB of particle columns per GPU) are far larger than the 126 MB L2",
-                                parallelism=f"one patch per GPU, {n_gpus} GPU(s)"),
+                    config=dict(workload=cfg.name, cells=list(cfg.cells), patch_grid=list(cfg.patch_grid),
+                                ppc=[p["ppc"] for p in cfg.pops], interp_order=cfg.interp,
+                                particles_total=n_total, pushes_per_step=2 * n_total,
+                                l2=f"inputs ({n_local * BYTES_DEPOSIT[dim] / 1e9:.1f} GB of particle columns per GPU) "
+                                   "against the 126 MB L2",
+                                parallelism=f"{len(solver.patches)} patch(es) per GPU, {n_gpus} GPU(s)"),
                     per_gpu=value / n_gpus, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
                     roofline_other=extra, cpu_baseline=cpu_baseline)
+        if parity is not None:
+            line["parity_check"] = parity
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
-def measure_e2e(solver, ops, args, world, device, n_total):
+def measure_e2e(solver, ops, args, world, device, n_total, DT):
     import torch
     import torch.distributed as dist
     from phare_b200.solver import HostStaging
@@ -273,14 +416,15 @@ def measure_e2e(solver, ops, args, world, device, n_total):
                     "stream as soon as each is final, overlapping the particle re-binning that ends the step); the "
                     "particle store stays device-resident (it is solver state, like the reference's ParticlesData)")
     # the naive drop-in for comparison: AoS Particle<3> records cross PCIe both ways around one sweep
-    try:
-        out["particles_roundtrip"] = particle_roundtrip(solver, ops)
-    except Exception as e:  # pragma: no cover
-        out["particles_roundtrip"] = dict(error=str(e))
+    if solver.patches[0].layout.dim == 3:
+        try:
+            out["particles_roundtrip"] = particle_roundtrip(solver, ops, DT)
+        except Exception as e:  # pragma: no cover
+            out["particles_roundtrip"] = dict(error=str(e))
     return out
 
 
-def particle_roundtrip(solver, ops):
+def particle_roundtrip(solver, ops, DT):
     """host AoS records -> device SoA, one `all` sweep kernels (push + deposit), -> host AoS, on a 16.8 M particle
     sub-sample (PCIe-bound, so the per-particle rate does not depend on the sample size)"""
     import ctypes as C
@@ -312,64 +456,80 @@ def particle_roundtrip(solver, ops):
 
 
 # ---------------------------------------------------------------------------------------------------------
+CPU_SLAB = {1: (20000,), 2: (128, 128), 3: (32, 32, 32)}  # cells of one reference worker (one MPI rank of the reference)
+
+
 def _cpu_worker(args):
-    """one reference worker = one MPI rank of the reference: a 3-D patch, domain_only + all + updateIons"""
-    seed, ncell, reps = args
+    """one reference worker = one MPI rank of the reference: one patch of the config's (dim, interp, populations, ppc) with
+    a uniform plasma, updatePopulations(domain_only) + (all) + updateIons"""
+    seed, cfg_key, reps = args
     import numpy as np
     sys.path.insert(0, ROOT)
     import oracle
-    from phare_b200 import abi
+    from phare_b200 import abi, configs
+    cfg = configs.get(cfg_key)
+    dim, interp = cfg.dim, cfg.interp
+    nc = CPU_SLAB[dim]
     impl = "ref" if oracle.have_ref() else "oracle"
     cpu = oracle.Cpu(impl)
-    L = abi.make_layout(3, INTERP, [ncell] * 3, DX)
+    L = abi.make_layout(dim, interp, list(nc), list(cfg.dl))
     rng = np.random.default_rng(seed)
-    n = ncell ** 3 * PPC
-    cells = np.stack(np.meshgrid(*[np.arange(ncell)] * 3, indexing="ij"), -1).reshape(-1, 3)
-    icell = np.repeat(cells, PPC, axis=0).astype(np.int32)
-    soa = (icell, rng.random((n, 3)), np.full(n, 1.0 / PPC), np.ones(n), rng.standard_normal((n, 3)) * 0.3)
+    cells = np.stack(np.meshgrid(*[np.arange(c) for c in nc], indexing="ij"), -1).reshape(-1, dim)
+    soas = []
+    for p in cfg.pops:
+        ppc = p["ppc"]
+        n = len(cells) * ppc
+        soas.append((np.repeat(cells, ppc, axis=0).astype(np.int32), rng.random((n, dim)), np.full(n, 1.0 / ppc),
+                     np.ones(n), rng.standard_normal((n, 3)) * 0.3))
+    ntot = sum(len(s[2]) for s in soas)
     shape = lambda q: cpu.field_shape(L, q)
     E = [np.zeros(shape(abi.EX + c)) for c in range(3)]
     B = [np.zeros(shape(abi.BX + c)) for c in range(3)]
     B[0][...] = 1.0
-    dom = abi.make_box([0] * 3, [ncell - 1] * 3)
-    ghost = abi.make_box([-1] * 3, [ncell] * 3)
+    pg = 1 if interp == 1 else 2
+    ghost = abi.make_box([-pg] * dim, [c - 1 + pg for c in nc])
+    masses = [p["mass"] for p in cfg.pops]
     best = None
     for _ in range(reps):
+        P = [oracle.HostParticles.from_soa(*s, capacity=int(len(s[2]) * 1.1)) for s in soas]
         if impl == "ref":
-            P = oracle.HostParticles.from_soa(*soa, capacity=int(n * 1.1))
-            pg, lg = oracle.HostParticles(3, n // 4 + 16), oracle.HostParticles(3, 16)
+            pgs = [oracle.HostParticles(dim, len(s[2]) // 4 + 16) for s in soas]
+            lgs = [oracle.HostParticles(dim, 16) for _ in soas]
             # time of the reference calls only (the wrapper's AoS staging is excluded)
-            r1 = cpu.ion_update(L, E, B, [1.0], [P], [pg], [lg], [ghost], DT, 1, update_ions=False)
-            r2 = cpu.ion_update(L, E, B, [1.0], [P], [pg], [lg], [ghost], DT, 2, update_ions=True)
+            r1 = cpu.ion_update(L, E, B, masses, P, pgs, lgs, [ghost], cfg.dt, 1, update_ions=False)
+            r2 = cpu.ion_update(L, E, B, masses, P, pgs, lgs, [ghost], cfg.dt, 2, update_ions=True)
             dt = r1["seconds"] + r2["seconds"]
         else:
-            P = oracle.HostParticles.from_soa(*soa, capacity=int(n * 1.1))
             t0 = time.perf_counter()
             for mode in (1, 2):
-                rc, Q = cpu.push(L, E, B, P, 1.0, DT)
-                cpu.deposit(L, Q, sel=[ghost])
+                for Pi, m in zip(P, masses):
+                    rc, Q = cpu.push(L, E, B, Pi, m, cfg.dt)
+                    cpu.deposit(L, Q, sel=[ghost])
             dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return 2 * n / best, impl
+    return 2 * ntot / best, impl, ntot
 
 
-def cpu_reference_rate(sample_seconds=12.0, workers=None):
+def cpu_reference_rate(cfg_key=5, workers=None):
     """The reference's own CPU implementation of the two particle sweeps of one PPC step
     (IonUpdater::updatePopulations(domain_only) + (all) + updateIons, compiled from the reference headers into
     oracle/_ref), one independent patch per host core (the reference is one MPI rank per core; no MPI in this
-    image, so no halo cost: an upper bound of the MPI path).  Bounded sample: 32^3 cells x 64 ppc per worker."""
+    image, so no halo cost: an upper bound of the MPI path).  Bounded sample: CPU_SLAB cells per worker."""
     import multiprocessing as mp
+    from phare_b200 import configs
+    cfg = configs.get(cfg_key)
     cores = workers or os.cpu_count() or 1
-    ncell = 32
     ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(100 + i, ncell, 2) for i in range(cores)])
+        res = pool.map(_cpu_worker, [(100 + i, cfg_key, 2) for i in range(cores)])
     wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     kind = "reference" if res[0][1] == "ref" else "port"
     return dict(value=total, unit="particle-pushes/s", cores=cores, kind=kind, per_core=total / cores,
-                sample=f"{cores} independent patches of {ncell}^3 cells x {PPC} ppc (3-D, interp 1), "
+                particles_per_worker=res[0][2],
+                sample=f"{cores} independent patches of {'x'.join(str(c) for c in CPU_SLAB[cfg.dim])} cells, "
+                       f"{len(cfg.pops)} population(s) x {cfg.pops[0]['ppc']} ppc ({cfg.dim}-D, interp {cfg.interp}), "
                        f"updatePopulations(domain_only)+(all)+updateIons, best of 2, {wall:.1f} s wall",
                 flags="g++ -O3 -DNDEBUG, x86-64 baseline ISA, -ffp-contract=off (the reference's default build)")
 
@@ -380,17 +540,20 @@ def reference_arm(args):
         return
     t0 = time.perf_counter()
     rates = []
+    from phare_b200 import configs
+    cfg = configs.get(args.config)
     for _ in range(max(args.warmup, 0) and 1):
-        cpu_reference_rate()
+        cpu_reference_rate(args.config)
     for _ in range(max(1, min(args.steps, 3))):
-        rates.append(cpu_reference_rate())
+        rates.append(cpu_reference_rate(args.config))
     best = max(rates, key=lambda r: r["value"])
-    n_sample = best["cores"] * 32 ** 3 * PPC
+    n_sample = best["cores"] * best["particles_per_worker"]
     line = dict(metric=METRIC, value=best["value"], unit="particle-pushes/s", n_gpus=args.gpus, steps=len(rates),
                 warmup=1 if args.warmup else 0, ms_per_step=2 * n_sample / best["value"] * 1e3, higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", impl="reference",
-                config=dict(workload="config 5 (3-D uniform plasma, 64 ppc, interp 1) per-core slabs of 32^3 cells; "
-                                     "CPU arm: rates are per particle, so they compare directly with 128^3 per GPU",
+                scaling="weak" if args.config == 5 else "strong", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference",
+                config=dict(workload=cfg.name + f"; CPU arm: per-core slabs of {list(CPU_SLAB[cfg.dim])} cells, uniform "
+                                                "plasma; rates are per particle, so they compare directly with the GPU arm",
                             parallelism=f"{best['cores']} host cores, one patch per core"),
                 cpu_baseline=best, e2e=dict(value=best["value"], unit="particle-pushes/s", h2d_bytes_per_step=0,
                                             d2h_bytes_per_step=0),
@@ -406,6 +569,8 @@ if __name__ == "__main__":
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank parity check that precedes the timed region")
+    ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)

@@ -244,6 +244,33 @@ int phb_push_deposit(phb_ctx*, const phb_layout*, const phb_vecfield* E, const p
                      const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
                      const phb_box* domain, const uint32_t* d_cell_start);
 
+/* ---- cell-ordered passes with the E,B nodes of a block of cells staged in shared memory (csrc/tile.cuh) -----------
+ * The kernels behind these entry points (and behind the cell-ordered path of phb_push_deposit) give one CTA a compact
+ * block of cells, stage the block's E,B nodes + stencil halo ONCE in shared memory with bulk asynchronous copies (TMA)
+ * and serve every gather from there.  `domain` / d_cell_start as in phb_deposit: parts[0, n_sorted) is ordered by the
+ * keys of phb_bin for `domain`; parts[n_sorted, n) (received since the last binning) may be in any order.
+ *
+ * phb_push_cells: BorisPusher::move (pusher/boris.hpp:93-138) exactly like phb_push with first_selector = NULL
+ * (same arithmetic, same bits).  `out` may be `in`, or a store whose weight/charge columns alias in's. */
+int phb_push_cells(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B, const phb_particles* in,
+                   phb_particles* out, size_t n_sorted, double mass, double dt, const phb_box* domain,
+                   const uint32_t* d_cell_start);
+/* phb_push_deposit_plan: IonUpdater::updateAndDepositAll_ for the domain array (ion_updater.hpp:228-295) in one pass
+ * over the store: pusher_->move in place, the deposit of the moved particles whose new cell lies in sel[nsel]
+ * (= phb_push_deposit with write_back = 1), and the bookkeeping of the partition / erase that follows (:245-273):
+ * per cell the number of particles that stay and, for the few that change cell, their rank among the arrivals of the
+ * new cell; then the scan -> d_cell_start_new (asynchronous; the same values phb_bin / phb_bin_plan produce).
+ * phb_scatter_planned then moves the data: `out` ends up exactly as phb_bin(parts, out, ...) leaves it (same
+ * d_cell_start, same per-cell multisets); phb_bin_counts returns the class counts.  The plan lives in the context
+ * until phb_scatter_planned consumes it. */
+int phb_push_deposit_plan(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,
+                          phb_particles* parts, size_t n_sorted, double mass, double dt, double* rho_n, double* rho_q,
+                          const phb_vecfield* flux, double coef, const phb_box* sel, int nsel, const phb_box* domain,
+                          const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, uint32_t* d_cell_start_new);
+int phb_scatter_planned(phb_ctx*, const phb_layout*, const phb_particles* in, size_t n_sorted, const phb_box* domain,
+                        const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, phb_particles* out,
+                        const uint32_t* d_cell_start_new);
+
 /* ---- particle splitting (level refinement) ---------------------------------------
  * ParticlesRefineOperator::refine_ (amr/data/particles/refine/particles_data_split.hpp:142-231) for one source
  * array: every coarse particle of coarse[first,last) is moved to the fine index space (toFineGrid, :32-46), and if

@@ -171,6 +171,10 @@ struct phb_ctx
     double* em_pack       = nullptr; // node-interleaved copy of E,B used by the push kernels
     size_t em_bytes       = 0;
     size_t plan_n         = size_t(-1); // particles covered by the pending phb_bin_plan (slots live in scratch)
+    int plan_kind         = 0;     // 0: none / phb_bin_plan (slots in scratch); 2: tile plan (stay / arrivals / slots in plan_buf)
+    void* plan_buf        = nullptr; // tile plan: [stay nk+1 | arrivals nk+1 | slot n | scan scratch]
+    size_t plan_bytes     = 0;
+    bool no_tile          = false; // PHB_NO_TILE=1: the cell-ordered passes use the round-1 kernels (E,B through L1)
 };
 
 namespace phb

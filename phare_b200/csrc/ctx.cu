@@ -19,6 +19,10 @@ int cuda_check(phb_ctx* ctx, cudaError_t e, const char* what)
 }
 int ensure_scratch(phb_ctx* ctx, size_t bytes)
 {
+    // whoever asks for the scratch is about to overwrite it: a pending phb_bin_plan (slots in the scratch) is void
+    // (phb_bin_plan sets plan_n after its own call; a tile plan keeps its slots in plan_buf)
+    if (ctx->plan_kind != 2)
+        ctx->plan_n = size_t(-1);
     if (bytes <= ctx->scratch_bytes)
         return 0;
     if (ctx->scratch)
@@ -75,6 +79,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
         ctx->no_tma = e[0] == '1';
     if (const char* e = getenv("PHB_NO_FUSED_CELLS"))
         ctx->no_fused_cells = e[0] == '1';
+    if (const char* e = getenv("PHB_NO_TILE"))
+        ctx->no_tile = e[0] == '1';
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return PHB_OK;
@@ -90,6 +96,8 @@ void phb_destroy(phb_ctx* ctx)
         cudaFree(ctx->scratch);
     if (ctx->em_pack)
         cudaFree(ctx->em_pack);
+    if (ctx->plan_buf)
+        cudaFree(ctx->plan_buf);
     if (ctx->d_err)
         cudaFree(ctx->d_err);
     if (ctx->h_err)

@@ -25,8 +25,7 @@
 //
 // Arithmetic of the move is the reference's (bit-identical positions, velocities, cells in exact mode); each
 // deposit contribution is ((q*weight)*coef)*wx*wy*wz as in the reference, only the summation order differs.
-#include "deposit_core.cuh"
-#include "push_core.cuh"
+#include "tile.cuh"
 
 #include <cstdlib>
 #include <type_traits>
@@ -428,7 +427,12 @@ int move_order(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>& A, bo
     if constexpr (cell_kernel_ok)
     {
         if (cells && A.nkeys > 0 && !has_first && !ctx->no_fused_cells)
+        {
+            // E,B block of each CTA staged in shared memory (tile.cuh) unless PHB_NO_TILE=1 (the round-1 kernel below)
+            if (!ctx->no_tile && A.last < 0xffffffffull)
+                return tile_push_deposit<DIM, ORDER>(ctx, P, A, WRITE);
             return move_cells<DIM, ORDER, EXACT, WRITE>(ctx, P, A);
+        }
     }
     constexpr int BS    = 256;
     unsigned const grid = unsigned((A.last - A.first + BS - 1) / BS);

@@ -312,7 +312,8 @@ int plan_dim(phb_ctx* ctx, const phb_layout* L, const phb_particles* in, const p
                                                                                  S.slot);
         PHB_LAUNCH_CHECK(ctx);
     }
-    ctx->plan_n = n;
+    ctx->plan_n    = n;
+    ctx->plan_kind = 0;
     return exclusive_scan(ctx, d_cell_start, d_cell_start, nk + 1, S.scan_tmp);
 }
 

@@ -273,6 +273,27 @@ class Context:
             rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel),
             C.byref(domain) if domain is not None else None, cell_start.ptr if cell_start is not None else None))
 
+    def push_cells(self, layout, E, B, pin, pout, n_sorted, mass, dt, domain, cell_start):
+        """phb_push_cells: K1 on the cell-ordered store, E,B block of each CTA staged in shared memory"""
+        self._check(self.lib.phb_push_cells(self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(pin.c),
+                                            C.byref(pout.c), int(n_sorted), mass, dt, C.byref(domain), cell_start.ptr))
+
+    def push_deposit_plan(self, layout, E, B, parts, n_sorted, mass, dt, rho_n, rho_q, flux, coef, sel, domain,
+                          cell_start_old, keep, cell_start_new):
+        """phb_push_deposit_plan: push in place + deposit + the plan of the re-binning (-> cell_start_new)"""
+        self._check(self.lib.phb_push_deposit_plan(
+            self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(parts.c), int(n_sorted), mass, dt, rho_n.ptr,
+            rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel), C.byref(domain),
+            cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep),
+            cell_start_new.ptr))
+
+    def scatter_planned(self, layout, pin, n_sorted, domain, cell_start_old, keep, pout, cell_start_new):
+        """phb_scatter_planned: the data movement of the re-binning planned by push_deposit_plan"""
+        self._check(self.lib.phb_scatter_planned(
+            self.h, C.byref(layout), C.byref(pin.c), int(n_sorted), C.byref(domain),
+            cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep), C.byref(pout.c),
+            cell_start_new.ptr))
+
     def maxwellian_load(self, layout, d_n, d_V, d_Vth, d_first, total, charge, ppc, seed, domain_cells, store):
         """phb_maxwellian_load: d_n / d_first device arrays, d_V / d_Vth objects with a .c VecField of per-cell arrays"""
         self._check(self.lib.phb_maxwellian_load(self.h, C.byref(layout), d_n.ptr, C.byref(d_V.c), C.byref(d_Vth.c),

@@ -384,8 +384,12 @@ class IonUpdater:
     """IonUpdater<Ions, Electromag, GridLayout> (ion_updater.hpp:24-83) on the device-resident store.
     The pusher is named in dict["pusher"]["name"]; only "modified_boris" exists (pusher_factory.hpp:20-30)."""
 
-    # (dim, interp) pairs where the one-pass kernel measured faster than push + deposit on B200 (tools/microbench.py)
+    # (dim, interp) pairs where the one-pass kernel measured faster than push + deposit on B200 (tools/microbench.py):
+    # in the `all` sweep (moved particles written back, re-binning as a separate pass) only in 1-D; in the domain_only
+    # sweep (nothing written back) wherever the tile kernel exists (csrc/tile.cuh: E,B block staged in shared memory;
+    # config 5: 5.0 ms against 3.8 + 2.3 ms for push + deposit, config 3: 2.3 against 3.6 ms)
     FUSED_AUTO = frozenset({(1, 1), (1, 2), (1, 3)})
+    FUSED_DOMAIN_AUTO = frozenset({(1, 1), (1, 2), (1, 3), (2, 1), (2, 2), (2, 3), (3, 1)})
 
     def __init__(self, ops, pusher_name="modified_boris", fused="auto", sort_with_deposit=True):
         if pusher_name != "modified_boris":
@@ -415,7 +419,8 @@ class IonUpdater:
                 ops.zero(m)
             n = ops.count(pop.domain)
             nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
-            fused = self.fused if isinstance(self.fused, bool) else (L.dim, L.interp) in self.FUSED_AUTO
+            fused = self.fused if isinstance(self.fused, bool) else (L.dim, L.interp) in (
+                self.FUSED_DOMAIN_AUTO if mode == DOMAIN_ONLY else self.FUSED_AUTO)
             if fused:
                 # both modes are the same pass; domain_only simply never stores the moved copy
                 wb = mode == ALL

@@ -79,6 +79,16 @@ def run(name, cfg):
         print(f"{name:4s} {label:22s} {ms:9.3f} ms  {n / ms / 1e6:8.2f} Gp/s  {gbs:8.1f} GB/s  {gbs / HBM:6.3f} of HBM peak",
               flush=True)
 
+    if os.environ.get('PHB_MB_ONLY') == 'tile':
+        if os.environ.get('PHB_MB_RANDOM', '1') != '0':
+            # cells drawn at random (Poisson counts per cell, like a store a few steps into a run) instead of exactly
+            # ppc per cell: kernels whose lanes own cells must not depend on every cell holding the same count
+            for d in range(dim):
+                P.icell[d][:n] = torch.randint(0, cfg["ncells"][d], (n,), generator=g, device=dev, dtype=torch.int32)
+        out = run_tile(name, cfg, ctx, L, P, Q, E, B, rn, rq, F, dom, keep, cs, dt, report)
+        ctx.poll_error()
+        ctx.close()
+        return out
     if os.environ.get('PHB_MB_ONLY') != 'fused':
         for exact in (True, False):
             ctx.set_exact(exact)
@@ -155,6 +165,74 @@ def run(name, cfg):
     ctx.poll_error()
     ctx.close()
     return out
+
+
+def run_tile(name, cfg, ctx, L, P, Q, E, B, rn, rq, F, dom, keep, cs, dt, report):
+    """the tile kernels (E,B block in shared memory) the way the step uses them: sweep 1 = push+deposit without
+    write-back, sweep 2 = push in place + deposit + plan, then the scatter; plus K1 alone (phb_push_cells)"""
+    dim = cfg["dim"]
+    dev = torch.device("cuda:0")
+    n = P.n
+    bpp_push = {1: 80, 2: 104, 3: 128}[dim]
+    bpp_dep = {1: 52, 2: 64, 3: 76}[dim]
+    state = {"P": P, "Q": Q}
+
+    def rebin():
+        c = ctx.bin(L, state["P"], state["Q"], dom, keep, cs)
+        state["P"], state["Q"] = state["Q"], state["P"]
+        state["n"] = c[0]
+    rebin()
+    gss = [int(g) for g in os.environ.get("PHB_MB_GS", "16").split(",")]
+    cs2 = TorchArray((ctx.bin_nkeys(L, dom) + 1,), dev, dtype=torch.int32)
+    for gs in gss:
+        os.environ["PHB_TILE_GS"] = str(gs)
+        S = state["P"]
+        ms, _ = timeit(lambda: ctx.push_deposit(L, E, B, S, 1.0, dt, rn, rq, F, 1.0, 0, state["n"], keep, dom, cs,
+                                                write_back=False))
+        report(f"tile sweep1 push+dep gs{gs}", ms, bpp_dep)
+        ms, _ = timeit(lambda: ctx.push_cells(L, E, B, S, S, state["n"], 1.0, 0.0, dom, cs))
+        report(f"tile K1 in place gs{gs}", ms, bpp_push)
+        T = state["Q"]
+        view = type("V", (), {})()
+        view.c = abi.Particles()
+        import ctypes as C
+        C.memmove(C.byref(view.c), C.byref(T.c), C.sizeof(abi.Particles))
+        view.c.weight, view.c.charge = S.c.weight, S.c.charge
+        ms, _ = timeit(lambda: ctx.push_cells(L, E, B, S, view, state["n"], 1.0, dt, dom, cs))
+        report(f"tile K1 out of place gs{gs}", ms, bpp_push)
+
+        def sweep2():
+            ctx.push_deposit_plan(L, E, B, state["P"], state["n"], 1.0, dt, rn, rq, F, 1.0, keep, dom, cs, keep, cs2)
+
+        def scatter():
+            ctx.scatter_planned(L, state["P"], state["n"], dom, cs, keep, state["Q"], cs2)
+        # time the two passes separately: plan on a fresh order each time (prep = the scatter of the previous one + swap)
+        sweep2()
+        ts_plan, ts_sc = [], []
+        for it in range(5):
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            a.record()
+            scatter()
+            b.record()
+            counts = ctx.bin_counts(L, dom, cs2, state["Q"])
+            state["P"], state["Q"] = state["Q"], state["P"]
+            state["n"] = counts[0]
+            cs.t.copy_(cs2.t)
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            sweep2()
+            b2.record()
+            torch.cuda.synchronize()
+            ts_sc.append(a.elapsed_time(b))
+            ts_plan.append(a2.elapsed_time(b2))
+        report(f"tile sweep2 push+dep+plan gs{gs}", min(ts_plan), bpp_dep + bpp_dep - 16)
+        report(f"scatter_planned gs{gs}", min(ts_sc), 2 * bpp_dep)
+        scatter()
+        counts = ctx.bin_counts(L, dom, cs2, state["Q"])
+        state["P"], state["Q"] = state["Q"], state["P"]
+        state["n"] = counts[0]
+        cs.t.copy_(cs2.t)
+    return {}
 
 
 if __name__ == "__main__":
