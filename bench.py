@@ -334,7 +334,10 @@ def our_arm(args):
             extra["deposit_scatter"] = dict(achieved=round(a, 1), frac=round(a / peak, 4),
                                             avg_launch_ms=round(avg(ds_ms), 4),
                                             what="deposit carried by the re-binning scatter pass (phb_deposit_scatter)")
-            extra["bin_plan"] = dict(avg_ms=round(avg(plan_ms), 4))
+            if plan_ms:
+                extra["bin_plan"] = dict(avg_ms=round(avg(plan_ms), 4))
+            else:
+                extra["bin_plan"] = "folded into the in-place push (phb_push_plan)"
         extra["particle_kernels_share_of_step"] = round(sum(sum(v) for v in kernel_ms.values()) / ms, 4)
         extra["kernel_ms_per_step"] = {k: round(sum(v) / args.steps, 3) for k, v in sorted(kernel_ms.items())}
         # whole-step fraction: 2 sweeps x (K1 + K3 algorithmic bytes) / step time
@@ -398,6 +401,7 @@ def measure_e2e(solver, ops, args, world, device, n_total, DT):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    staging.timing = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
@@ -405,12 +409,18 @@ def measure_e2e(solver, ops, args, world, device, n_total, DT):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
+    # per-rank diagnosis: this rank's step time and the duration of each host transfer (PCIe / host-memory contention
+    # between the ranks of a node shows up here, not in the kernels)
+    mine = dict(ms_per_step=round(ms / steps, 3), **{k: round(v, 3) for k, v in staging.timings_ms().items()})
+    per_rank = [mine]
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     out = dict(value=2 * n_total * steps / (ms * 1e-3), unit="particle-pushes/s", h2d_bytes_per_step=bi,
-               d2h_bytes_per_step=bo, steps=steps,
+               d2h_bytes_per_step=bo, steps=steps, staging_ms_per_rank=per_rank,
                what="SolverPPC.advance_level(dt, staging=HostStaging): per step E,B from pinned host memory -> device, "
                     "advanceLevel, per-population + total moments and the new E,B -> pinned host (read back on a copy "
                     "stream as soon as each is final, overlapping the particle re-binning that ends the step); the "

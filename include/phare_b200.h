@@ -244,6 +244,15 @@ int phb_push_deposit(phb_ctx*, const phb_layout*, const phb_vecfield* E, const p
                      const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
                      const phb_box* domain, const uint32_t* d_cell_start);
 
+/* phb_push_plan: the first half of IonUpdater::updateAndDepositAll_ for the domain array (ion_updater.hpp:228-245) in ONE
+ * pass over the store: pusher_->move in place (== phb_push(parts, parts, first = NULL), same bits) and, while the moved
+ * particle is still in registers, the count half of the re-binning (== phb_bin_plan(parts, domain, keep)): key of the new
+ * cell, slot inside it, histogram -> d_cell_start.  phb_deposit_scatter consumes the plan exactly as after phb_bin_plan.
+ * Saves the separate read of the iCell columns (0.69 ms of 16.5 ms per step at config 5). */
+int phb_push_plan(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B, phb_particles* parts,
+                  double mass, double dt, const phb_box* domain, const phb_box* keep, int nkeep,
+                  uint32_t* d_cell_start);
+
 /* ---- cell-ordered passes with the E,B nodes of a block of cells staged in shared memory (csrc/tile.cuh) -----------
  * The kernels behind these entry points (and behind the cell-ordered path of phb_push_deposit) give one CTA a compact
  * block of cells, stage the block's E,B nodes + stencil halo ONCE in shared memory with bulk asynchronous copies (TMA)
@@ -270,6 +279,17 @@ int phb_push_deposit_plan(phb_ctx*, const phb_layout*, const phb_vecfield* E, co
 int phb_scatter_planned(phb_ctx*, const phb_layout*, const phb_particles* in, size_t n_sorted, const phb_box* domain,
                         const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, phb_particles* out,
                         const uint32_t* d_cell_start_new);
+
+/* ---- GridLayout primitives on their own (test support for SURVEY 8 row a14) ---------------------------------------
+ * The device functions Faraday / Ampere / Ohm are built from, applied to one array of quantity `qty` (allocation shape
+ * of phb_field_shape):
+ *   op 0  GridLayout::deriv(field, index, direction = arg)   gridlayout.hpp:571-630.  d_out has the allocation of the
+ *         other centering along `arg` (allocSizeDerived, :866-880) and is written on that centering's physical range
+ *   op 1  GridLayout::laplacian(field, index)                gridlayout.hpp:640-700, written on the physical box of qty
+ *   op 2  the Yee linear combinations (momentsToEx, BzToEx, JxToMoments, ... gridlayout_hybrid_yee.hpp:350-749) by kind
+ *         per direction, arg = kx | ky << 2 | kz << 4 with 0 = same centering, 1 = primal -> dual {0,+1}, 2 = dual -> primal
+ *         {-1,0}; d_out has the shape of d_in and is written wherever the stencil stays inside the array. */
+int phb_gridlayout_probe(phb_ctx*, const phb_layout*, int op, int qty, int arg, const double* d_in, double* d_out);
 
 /* ---- particle splitting (level refinement) ---------------------------------------
  * ParticlesRefineOperator::refine_ (amr/data/particles/refine/particles_data_split.hpp:142-231) for one source

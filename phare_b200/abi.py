@@ -161,6 +161,9 @@ _PROTOS = {
                                    C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_double, C.c_double,
                                    C.POINTER(Box), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(VecField), C.c_double,
                                    C.POINTER(Box), C.c_int, C.POINTER(Box), C.c_void_p]),
+    "phb_push_plan": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                                C.POINTER(Particles), C.c_double, C.c_double, C.POINTER(Box), C.POINTER(Box), C.c_int,
+                                C.c_void_p]),
     "phb_push_cells": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
                                  C.POINTER(Particles), C.POINTER(Particles), C.c_size_t, C.c_double, C.c_double,
                                  C.POINTER(Box), C.c_void_p]),
@@ -170,6 +173,7 @@ _PROTOS = {
                                         C.c_void_p, C.POINTER(Box), C.c_int, C.c_void_p]),
     "phb_scatter_planned": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.POINTER(Box),
                                       C.c_void_p, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.c_void_p]),
+    "phb_gridlayout_probe": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "phb_split": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
                             C.c_int, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.POINTER(C.c_size_t)]),
     "phb_faraday": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),

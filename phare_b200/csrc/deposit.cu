@@ -304,7 +304,7 @@ int deposit_order(phb_ctx* ctx, DepositParams<DIM>& A, bool cells)
             else
                 launch_cells<DIM, ORDER, 2>(ctx, A);
             PHB_LAUNCH_CHECK(ctx);
-            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A);
+            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A);
             PHB_LAUNCH_CHECK(ctx);
             return PHB_OK;
         }

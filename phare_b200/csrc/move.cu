@@ -413,7 +413,7 @@ int move_cells(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>& A)
         rc = launch_move_cells<DIM, ORDER, 2, EXACT, WRITE>(ctx, P, A, R);
     if (rc)
         return rc;
-    deposit_records_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A, R);
+    deposit_records_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A, R);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }

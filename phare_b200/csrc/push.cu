@@ -10,10 +10,38 @@
 // with the cell-sorted store a warp sits in one or two cells, so every gather load is a one- or
 // two-address broadcast that hits L1/L2; field arrays are (o+1)^d-fold reused and never the
 // HBM bound.
+#include "bin_core.cuh"
+#include "deposit_core.cuh"
 #include "push_core.cuh"
 
 namespace phb
 {
+// the count half of the re-binning (bin_count_kernel of bin_core.cuh) done while the pushed particle is still in
+// registers: key of the new cell, one atomic per distinct key of the warp, the particle's slot inside its new cell
+template<int DIM>
+struct PlanCount
+{
+    KeySpace<DIM> K;
+    uint32_t* count; // histogram over the keys (zeroed by the caller, scanned afterwards)
+    uint32_t* slot;  // [n]
+};
+
+template<int DIM>
+__device__ __forceinline__ void plan_count(const PlanCount<DIM>& C, size_t i, const int (&icell)[DIM], bool live)
+{
+    unsigned const key    = live ? bin_key<DIM>(C.K, icell) : 0xffffffffu;
+    unsigned const peers  = __match_any_sync(0xffffffffu, key);
+    unsigned const lane   = threadIdx.x & 31;
+    int const leader      = __ffs(peers) - 1;
+    unsigned const before = __popc(peers & ((1u << lane) - 1));
+    unsigned base         = 0;
+    if (live && int(lane) == leader)
+        base = atomicAdd(C.count + key, unsigned(__popc(peers)));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live)
+        __stcs(C.slot + i, base + before);
+}
+
 // the per-particle work shared by both kernels: move_particle (push_core.cuh) + streaming stores
 template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
 __device__ __forceinline__ void push_particle(const PushParams<DIM>& P, size_t i, int (&icell)[DIM],
@@ -62,6 +90,36 @@ __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushP
     push_particle<DIM, ORDER, EXACT, HAS_FIRST>(P, i, icell, delta, v, charge);
 }
 
+// the same with the count of the re-binning folded in (in place, no first selector): whole warps stay alive for the
+// warp-aggregated atomics
+template<int DIM, int ORDER, bool EXACT>
+__global__ void __launch_bounds__(256)
+    push_plan_kernel(const __grid_constant__ PushParams<DIM> P, size_t first, const __grid_constant__ PlanCount<DIM> C)
+{
+    size_t const i  = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    bool const live = i < P.n;
+    int icell[DIM];
+    double delta[DIM], v[3];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+        icell[d] = 0;
+    if (live)
+    {
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+        {
+            icell[d] = __ldcs(P.in.icell[d] + i);
+            delta[d] = __ldcs(P.in.delta[d] + i);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            v[c] = __ldcs(P.in.v[c] + i);
+        double const charge = __ldcs(P.in.charge + i);
+        push_particle<DIM, ORDER, EXACT, false>(P, i, icell, delta, v, charge);
+    }
+    plan_count<DIM>(C, i, icell, live);
+}
+
 // TMA kernel: 256-particle tiles of every needed column are streamed into a ring of shared-memory
 // stages with cp.async.bulk (completion on an mbarrier).  The 8 warps of the CTA pick their
 // particle out of the stage, release it at once, and do gather + Boris + stores while the next
@@ -85,9 +143,10 @@ template<int DIM> __host__ __device__ constexpr int push_stage_bytes(bool copy_w
     return PUSH_TILE * (8 * push_ncol8<DIM>(copy_wq) + 4 * DIM);
 }
 
-template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool COPY_WQ>
+template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool COPY_WQ, bool PLAN = false>
 __global__ void __launch_bounds__(PUSH_TILE, PUSH_CTAS)
-    push_tma_kernel(const __grid_constant__ PushParams<DIM> P, unsigned ntiles)
+    push_tma_kernel(const __grid_constant__ PushParams<DIM> P, unsigned ntiles,
+                    const __grid_constant__ PlanCount<DIM> C)
 {
     constexpr int NC8   = push_ncol8<DIM>(COPY_WQ);
     constexpr int BYTES = push_stage_bytes<DIM>(COPY_WQ);
@@ -173,13 +232,15 @@ __global__ void __launch_bounds__(PUSH_TILE, PUSH_CTAS)
             __stcs(P.out.weight + i, weight);
         }
         push_particle<DIM, ORDER, EXACT, HAS_FIRST>(P, i, icell, delta, v, charge);
+        if constexpr (PLAN)
+            plan_count<DIM>(C, i, icell, true);
     }
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
-int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P)
+template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool PLAN = false>
+int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P, const PlanCount<DIM>& C = PlanCount<DIM>{})
 {
     // full tiles through the TMA kernel when every input column is 16-byte aligned
     bool tma_ok = aligned16(P.in.charge) && aligned16(P.in.weight);
@@ -195,23 +256,66 @@ int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P)
         unsigned const grid = unsigned(std::min<size_t>(ntiles, size_t(ctx->sm_count) * PUSH_CTAS));
         auto launch = [&](auto kernel) -> int {
             PHB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            kernel<<<grid, PUSH_TILE, smem, ctx->stream>>>(P, unsigned(ntiles));
+            kernel<<<grid, PUSH_TILE, smem, ctx->stream>>>(P, unsigned(ntiles), C);
             PHB_LAUNCH_CHECK(ctx);
             return PHB_OK;
         };
-        int const rc = wq ? launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, true>)
-                          : launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, false>);
+        int rc;
+        if constexpr (PLAN)
+            rc = launch(push_tma_kernel<DIM, ORDER, EXACT, false, false, true>);
+        else
+            rc = wq ? launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, true>)
+                    : launch(push_tma_kernel<DIM, ORDER, EXACT, HAS_FIRST, false>);
         if (rc)
             return rc;
     }
     size_t const first = ntiles * PUSH_TILE;
     if (first < P.n)
     {
-        constexpr int BS = 256;
-        push_kernel<DIM, ORDER, EXACT, HAS_FIRST><<<unsigned((P.n - first + BS - 1) / BS), BS, 0, ctx->stream>>>(P, first);
+        constexpr int BS    = 256;
+        unsigned const grid = unsigned((P.n - first + BS - 1) / BS);
+        if constexpr (PLAN)
+            push_plan_kernel<DIM, ORDER, EXACT><<<grid, BS, 0, ctx->stream>>>(P, first, C);
+        else
+            push_kernel<DIM, ORDER, EXACT, HAS_FIRST><<<grid, BS, 0, ctx->stream>>>(P, first);
         PHB_LAUNCH_CHECK(ctx);
     }
     return PHB_OK;
+}
+
+// phb_push_plan: push in place + the count half of phb_bin_plan in the same pass
+template<int DIM, int ORDER>
+int push_plan_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B, phb_particles* parts,
+                    double mass, double dt, const phb_box* domain, const phb_box* keep, int nkeep, uint32_t* d_cell_start)
+{
+    size_t const n = parts->n;
+    PlanCount<DIM> C;
+    C.K             = make_keyspace<DIM>(L, domain, keep, nkeep);
+    size_t const nk = size_t(C.K.Nd) + C.K.Ng + 1;
+    // same scratch layout as phb_bin_plan (sortdep.cu: [slot n][scan tmp][mover lists]); phb_deposit_scatter finds it there
+    size_t const scan_words = scan_scratch_words(nk + 1) + 8;
+    size_t const words      = n + scan_words + mover_scratch_words(n) + 8;
+    if (int rc = ensure_scratch(ctx, words * sizeof(uint32_t)))
+        return rc;
+    C.slot  = static_cast<uint32_t*>(ctx->scratch);
+    C.count = d_cell_start;
+    PHB_CUDA(ctx, cudaMemsetAsync(d_cell_start, 0, (nk + 1) * sizeof(uint32_t), ctx->stream));
+    if (n)
+    {
+        PushParams<DIM> P;
+        if (int rc = prepare_push<DIM>(ctx, L, E, B, mass, dt, nullptr, P))
+            return rc;
+        P.in = P.out         = make_part(*parts);
+        P.n                  = n;
+        P.copy_weight_charge = false;
+        int const rc = ctx->exact ? launch_push_variant<DIM, ORDER, true, false, true>(ctx, P, C)
+                                  : launch_push_variant<DIM, ORDER, false, false, true>(ctx, P, C);
+        if (rc)
+            return rc;
+    }
+    ctx->plan_n    = n;
+    ctx->plan_kind = 0;
+    return exclusive_scan(ctx, d_cell_start, d_cell_start, nk + 1, C.slot + n);
 }
 
 template<int DIM, int ORDER>
@@ -245,6 +349,31 @@ int push_dim(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb
     }
 }
 } // namespace phb
+
+extern "C" int phb_push_plan(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
+                             phb_particles* parts, double mass, double dt, const phb_box* domain, const phb_box* keep,
+                             int nkeep, uint32_t* d_cell_start)
+{
+    if (!phb::valid_layout(ctx, L) || !E || !B || !parts || !domain || !d_cell_start || nkeep < 0
+        || nkeep > phb::MAX_BOXES || (nkeep > 0 && !keep))
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_plan: invalid argument");
+    if (parts->n >= 0xffffffffull)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_plan: more than 2^32-1 particles in one store");
+#define PHB_PP(D, O) phb::push_plan_order<D, O>(ctx, L, E, B, parts, mass, dt, domain, keep, nkeep, d_cell_start)
+    switch (L->dim * 10 + L->interp)
+    {
+        case 11: return PHB_PP(1, 1);
+        case 12: return PHB_PP(1, 2);
+        case 13: return PHB_PP(1, 3);
+        case 21: return PHB_PP(2, 1);
+        case 22: return PHB_PP(2, 2);
+        case 23: return PHB_PP(2, 3);
+        case 31: return PHB_PP(3, 1);
+        case 32: return PHB_PP(3, 2);
+        default: return PHB_PP(3, 3);
+    }
+#undef PHB_PP
+}
 
 extern "C" int phb_push(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
                         const phb_particles* in, phb_particles* out, double mass, double dt,

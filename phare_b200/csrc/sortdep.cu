@@ -384,7 +384,7 @@ int ds_order(phb_ctx* ctx, const phb_layout* L, const phb_particles* in, size_t 
                 rc = launch_ds_cells<DIM, ORDER, 2>(ctx, A, K, o, new_start, S.slot);
             if (rc)
                 return rc;
-            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A);
+            deposit_list_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A);
             PHB_LAUNCH_CHECK(ctx);
         }
     }

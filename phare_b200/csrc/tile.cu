@@ -87,7 +87,7 @@ int tile_push_deposit(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>
     TileParams<DIM> T{};
     if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, write, false}, P, A, R, K, T))
         return rc;
-    tile_records_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A, R);
+    tile_records_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A, R);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }
@@ -280,7 +280,7 @@ int pdp_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const ph
             T.plan = S.a;
             if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, true, true}, P, A, R, K, T))
                 return rc;
-            tile_records_kernel<DIM, ORDER><<<MOVER_LISTS / 2, 256, 0, ctx->stream>>>(A, R);
+            tile_records_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A, R);
             PHB_LAUNCH_CHECK(ctx);
         }
         if (n_sorted < n)

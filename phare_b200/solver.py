@@ -162,6 +162,10 @@ class GpuOps:
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
 
+    def push_plan(self, layout, E, B, parts, mass, dt, domain, keep, cell_start_new):
+        """K1 in place with the count of the re-binning folded in (phb_push_plan)"""
+        self._timed("push", lambda: self.ctx.push_plan(layout, E, B, parts, mass, dt, domain, keep, cell_start_new))
+
     def bin_plan(self, layout, pin, domain, keep, cell_start_new):
         self._timed("bin_plan", lambda: self.ctx.bin_plan(layout, pin, domain, keep, cell_start_new))
 
@@ -449,9 +453,16 @@ class IonUpdater:
             else:
                 # updateAndDepositAll_ (:228-295): push in place; stayers + leavers inside the nonLevelGhostBox
                 # are deposited (= the domain + new patchGhost deposits of :290-293)
-                ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
-                if self.sort_with_deposit and not self.defer_sort and n:
-                    ops.bin_plan(L, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start_next)
+                planned = self.sort_with_deposit and not self.defer_sort and n
+                if planned and hasattr(ops, "push_plan"):
+                    # the keys of the re-binning are counted while the pushed particle is still in registers
+                    ops.push_plan(L, E, B, pop.domain, pop.mass, dt, patch.domain_box, patch.non_level_ghost,
+                                  pop.cell_start_next)
+                else:
+                    ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
+                    if planned:
+                        ops.bin_plan(L, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start_next)
+                if planned:
                     ops.deposit_scatter(L, pop.domain, pop.n_sorted, pop.rho_n, pop.rho_q, pop.flux, 1.0,
                                         patch.non_level_ghost, patch.domain_box, pop.cell_start, patch.non_level_ghost,
                                         pop.spare, pop.cell_start_next)
@@ -734,24 +745,44 @@ class HostStaging:
             h.copy_(a.t)
         self.h2d_bytes = sum(h.numel() * 8 for h in self.h_in)
         self.d2h_bytes = sum(h.numel() * 8 for h in self.h_moments + self.h_fields)
+        self.timing = False  # bench.py: CUDA-event pairs around each transfer (per-rank diagnosis of the staging cost)
+        self.timed = {}
+
+    def _mark(self, name):
+        if not self.timing:
+            return None
+        a, b = self.t.cuda.Event(enable_timing=True), self.t.cuda.Event(enable_timing=True)
+        self.timed.setdefault(name, []).append((a, b))
+        a.record()
+        return b
 
     def upload(self):
+        done = self._mark("upload")
         for h, a in zip(self.h_in, self.inputs):
             a.t.copy_(h, non_blocking=True)
+        if done is not None:
+            done.record()
 
-    def _download(self, hosts, arrs):
+    def _download(self, hosts, arrs, name):
         ready = self.t.cuda.Event()
         ready.record()
         with self.t.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(ready)
+            done = self._mark(name)
             for h, a in zip(hosts, arrs):
                 h.copy_(a.t, non_blocking=True)
+            if done is not None:
+                done.record()
 
     def download_moments(self):
-        self._download(self.h_moments, self.moments)
+        self._download(self.h_moments, self.moments, "download_moments")
 
     def download_fields(self):
-        self._download(self.h_fields, self.fields)
+        self._download(self.h_fields, self.fields, "download_fields")
+
+    def timings_ms(self):
+        """average milliseconds of each transfer since timing was switched on (call after a synchronize)"""
+        return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.timed.items() if v}
 
     def join(self):
         self.t.cuda.current_stream().wait_stream(self.copy_stream)

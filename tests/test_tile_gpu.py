@@ -228,3 +228,42 @@ def test_move_two_cells_is_reported_by_the_tile_kernels(ctxs, cpu_oracle):
     ctx.scatter_planned(L, parts, n_sorted, dom, cs_old, keep, out, cs_new)
     counts = ctx.bin_counts(L, dom, cs_new, out)
     assert sum(counts) == 5000
+
+
+@pytest.mark.parametrize("dim,interp", ALL_DIM_INTERP)
+def test_push_plan_equals_push_then_bin_plan(ctxs, cpu_oracle, dim, interp):
+    """phb_push_plan (K1 in place with the count of the re-binning folded in) == phb_push in place then phb_bin_plan:
+    particles bit-exact in place, the same cell_start, and phb_deposit_scatter consumes the plan to the same re-binned
+    store (per-cell multisets) and moments as the oracle's push -> deposit -> bin"""
+    ctx = ctxs(dim, interp)
+    rng = np.random.default_rng(5000 + 10 * dim + interp)
+    L = layout_for(dim, interp)
+    ncell = int(np.prod(SHAPES[dim]))
+    soa, n_sorted, cs = binned_store(cpu_oracle, rng, L, ncell * (12 if dim < 3 else 6) + 77, vth=1.0, tail=131)
+    n = len(soa[2])
+    dom = domain_box(L)
+    keep = [grown(dom, dim, particle_ghosts(interp))]
+    E = random_vec(rng, cpu_oracle.field_shape, L, abi.EX, 0.3)
+    B = random_vec(rng, cpu_oracle.field_shape, L, abi.BX, 0.3)
+    dt = 0.1
+    rc, pushed = cpu_oracle.push(L, E, B, HostParticles.from_soa(*soa), 1.0, dt)
+    assert rc == 0
+    want_m = cpu_oracle.deposit(L, pushed, coef=1.0, sel=keep)
+    want, want_cs, want_counts = cpu_oracle.bin(L, pushed, dom, keep)
+    pin, pout = DeviceParticles(ctx, n).upload_soa(*soa), DeviceParticles(ctx, n)
+    (rn, rq), F = moments(ctx, L, cpu_oracle)
+    cs_old = DeviceArray(ctx, cs.shape, np.uint32).upload(cs)
+    cs_new = DeviceArray(ctx, cs.shape, np.uint32)
+    dE, dB = DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B)
+    ctx.push_plan(L, dE, dB, pin, 1.0, dt, dom, keep, cs_new)
+    ctx.deposit_scatter(L, pin, n_sorted, rn, rq, F, 1.0, keep, dom, cs_old, keep, pout, cs_new)
+    counts = ctx.bin_counts(L, dom, cs_new, pout)
+    ctx.poll_error()
+    for g, w in zip(pin.download_soa(), pushed.soa()):  # pushed in place, order untouched
+        assert bit_equal(g, w)
+    assert np.array_equal(cs_new.download(), want_cs)
+    assert counts == want_counts
+    got = pout.download_soa()
+    assert np.array_equal(got[0], want.soa()[0])
+    assert np.array_equal(canonical_rows(*got), canonical_rows(*want.soa()))
+    close([rn.download(), rq.download()] + F.download(), want_m)
