@@ -244,6 +244,12 @@ int phb_push_deposit(phb_ctx*, const phb_layout*, const phb_vecfield* E, const p
                      const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
                      const phb_box* domain, const uint32_t* d_cell_start);
 
+/* Interpolator::operator()(Particle&, Electromag const&, GridLayout const&) (interpolator/interpolator.hpp:420-456) on its
+ * own: E and B interpolated at the position of parts[first,last), d_eb[6 * (i - first) + {0..5}] = {Ex,Ey,Ez,Bx,By,Bz}.
+ * The same device functions phb_push inlines (same bits). */
+int phb_gather(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B, const phb_particles* parts,
+               size_t first, size_t last, double* d_eb);
+
 /* phb_push_plan: the first half of IonUpdater::updateAndDepositAll_ for the domain array (ion_updater.hpp:228-245) in ONE
  * pass over the store: pusher_->move in place (== phb_push(parts, parts, first = NULL), same bits) and, while the moved
  * particle is still in registers, the count half of the re-binning (== phb_bin_plan(parts, domain, keep)): key of the new
@@ -318,6 +324,8 @@ int phb_electrons_update(phb_ctx*, const phb_layout*, const double* Ne, const ph
                          const phb_vecfield* J, double Te, phb_vecfield* Ve, double* Pe);
 /* Ions::computeChargeDensity / computeMassDensity / computeBulkVelocity (data/ions/ions.hpp:75-145)
  * h_* arrays of npop device pointers / masses live on the host */
+/* rho_q_tot, rho_m_tot and V may each be NULL (Ions::computeChargeDensity / computeMassDensity / computeBulkVelocity called
+ * separately, ions.hpp:75,92,111); at least one must be given */
 int phb_ions_totals(phb_ctx*, size_t nnodes, int npop, const double* const* h_rho_n,
                     const double* const* h_rho_q, const phb_vecfield* h_flux, const double* h_mass,
                     double* rho_q_tot, double* rho_m_tot, phb_vecfield* V);

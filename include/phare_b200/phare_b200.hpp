@@ -1,7 +1,17 @@
 // C++ host mirror of the reference's operator API for the hot path, forwarding to the C ABI
-// (include/phare_b200.h, libphare_b200.so).  Same class names, call signatures and error behaviour
-// as the PHARE functors they replace, so that SolverPPC's type bundle can be pointed at them
+// (include/phare_b200.h, libphare_b200.so).  Same class names and error behaviour as the PHARE functors they replace and
+// the same call signatures EXCEPT the two listed below, so that SolverPPC's type bundle can be pointed at them
 // (INTEGRATION.md).  Header-only; storage is device memory.
+//
+// Signatures that differ from the reference, and why:
+//   * Pusher::move(in, out, em, mass, interpolator, layout, ParticleSelector first, ParticleSelector second)
+//     (pusher.hpp:24-31): a ParticleSelector is a std::function over a host ParticleRange; it cannot run inside a kernel.
+//     BorisPusher::move takes the first selector as the BOX the reference's selectors test (UpdaterSelectionBoxing,
+//     ion_updater.hpp:119-163: inGhostBox) and leaves the second to the caller, which applies it as a key class of the
+//     re-binning (phb_bin / phb_push_plan) exactly where ion_updater.hpp applies it.
+//   * IonUpdater(PHAREDict const&) templated on <Ions, Electromag, GridLayout> (ion_updater.hpp:24-56): cppdict is not
+//     part of the PHARE tree (fetched by cmake), so the dictionary type is phare_b200::Dict (same operator[] / to<T>()
+//     surface), and the class is templated on <dim, interp_order>, which is all it reads from the three types.
 //
 //   reference (file:line, PHARE tree)                                     mirror
 //   core::GridLayout<Yee>          data/grid/gridlayout.hpp:95-1517         phare_b200::GridLayout<dim, interp>
@@ -27,6 +37,7 @@
 #include <utility>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <vector>
 
 namespace phare_b200
@@ -118,8 +129,22 @@ public:
         if (int rc = phb_create(device, dim, interp, &ctx_))
             throw std::runtime_error(std::string{"phare_b200: "} + phb_last_error(nullptr) + " (status "
                                      + std::to_string(rc) + ")");
+        current_() = this;
     }
-    ~Context() { phb_destroy(ctx_); }
+    ~Context()
+    {
+        if (current_() == this)
+            current_() = nullptr;
+        phb_destroy(ctx_);
+    }
+    // the context most recently created on this thread: used by the few reference signatures that carry no handle at all
+    // (Interpolator::operator()(Particle&, Electromag const&, GridLayout const&))
+    static Context const& current()
+    {
+        if (!current_())
+            throw std::runtime_error("phare_b200: no Context alive on this thread");
+        return *current_();
+    }
     Context(Context const&)            = delete;
     Context& operator=(Context const&) = delete;
     phb_ctx* get() const { return ctx_; }
@@ -136,6 +161,11 @@ public:
     void sync() const { check(phb_sync(ctx_)); }
 
 private:
+    static Context const*& current_()
+    {
+        thread_local Context const* c = nullptr;
+        return c;
+    }
     phb_ctx* ctx_ = nullptr;
 };
 
@@ -355,14 +385,57 @@ IndexRange<dim> makeIndexRange(ParticleArray<dim>& a)
     return {&a, 0, a.size()};
 }
 
-// Interpolator<dim, order>: the particle->mesh overload (interpolator.hpp:468-510). The mesh->particle overload is
-// fused into BorisPusher::move on the device (K1).
+enum class QtyCentering { primal = 0, dual = 1 }; // gridlayoutdefs.hpp:18
+
+// Interpolator<dim, order> (interpolator.hpp:410-566): particle -> mesh (:468-510), mesh -> particle for one particle
+// (:420-456; inside BorisPusher::move the same gather is fused into the push kernel, K1) and computeStartLeftShift (:519-549)
 template<std::size_t dim, std::size_t order>
 class Interpolator
 {
 public:
     static constexpr auto interp_order = order;
     static constexpr auto dimension    = dim;
+
+    // lower index of the stencil relative to the particle's cell, by centering (interpolator.hpp:519-549)
+    template<typename CenteringT, CenteringT Centering>
+    static int computeStartLeftShift([[maybe_unused]] double delta)
+    {
+        static_assert(order > 0 && order < 4);
+        constexpr bool isPrimal = Centering == CenteringT::primal;
+        if constexpr (order == 1)
+            return isPrimal ? 0 : (delta < .5 ? 1 : 0);
+        else if constexpr (order == 2)
+            return isPrimal ? (delta < .5 ? 1 : 0) : 1;
+        else
+            return isPrimal ? 1 : (delta < .5 ? 2 : 1);
+    }
+
+    // E and B at the particle (interpolator.hpp:420-456): one particle staged to the device, phb_gather, 6 doubles back.
+    // For whole arrays use gather(range, ...) below; the step itself never calls either (K1 gathers inline).
+    template<typename Particle_t, typename Electromag_t, typename GridLayout_t>
+    auto operator()(Particle_t const& particle, Electromag_t const& em, GridLayout_t const& layout)
+        -> std::tuple<std::array<double, 3>, std::array<double, 3>>
+    {
+        auto const& ctx = Context::current();
+        ParticleArray<dim> one{ctx, 1};
+        one.assign(std::vector<Particle_t>{particle});
+        std::vector<double> eb = gather(makeIndexRange(one), em, layout);
+        return {std::array<double, 3>{eb[0], eb[1], eb[2]}, std::array<double, 3>{eb[3], eb[4], eb[5]}};
+    }
+    // the same for every particle of a range: {Ex,Ey,Ez,Bx,By,Bz} per particle, on the host
+    template<typename Electromag_t, typename GridLayout_t>
+    std::vector<double> gather(IndexRange<dim> const& range, Electromag_t const& em, GridLayout_t const& layout)
+    {
+        auto const& ctx = range.array->context();
+        std::size_t const n = range.last - range.first;
+        DeviceBuffer out{ctx, 6 * n + 1};
+        auto E = em.E.c(), B = em.B.c();
+        ctx.check(phb_gather(ctx.get(), layout.c(), &E, &B, range.array->c(), range.first, range.last, out.data()));
+        std::vector<double> host(6 * n + 1);
+        out.download(host.data());
+        host.resize(6 * n);
+        return host;
+    }
     template<typename GridLayout_t>
     void operator()(IndexRange<dim> const& range, Field& particleDensity, Field& chargeDensity, VecField& flux,
                     GridLayout_t const& layout, double coef = 1.)
@@ -447,8 +520,15 @@ struct Ions // ions.hpp:26-261
     Field& chargeDensity() { return rho_q; }
     Field& massDensity() { return rho_m; }
     VecField& velocity() { return V; }
-    // computeChargeDensity + computeMassDensity + computeBulkVelocity (ions.hpp:75-145) in one kernel
-    void computeChargeDensityAndBulkVelocity()
+    // Ions::computeChargeDensity (ions.hpp:75-90), computeMassDensity (:92-108), computeBulkVelocity (:111-145, which
+    // computes the mass density first, like the reference)
+    void computeChargeDensity() { totals_(true, false, false); }
+    void computeMassDensity() { totals_(false, true, false); }
+    void computeBulkVelocity() { totals_(false, true, true); }
+    // the three in one kernel (what IonUpdater::updateIons needs)
+    void computeChargeDensityAndBulkVelocity() { totals_(true, true, true); }
+
+    void totals_(bool charge, bool massDensity, bool velocity)
     {
         std::vector<double const*> n, q;
         std::vector<phb_vecfield> f;
@@ -462,7 +542,8 @@ struct Ions // ions.hpp:26-261
         }
         auto v = V.c();
         ctx_.check(phb_ions_totals(ctx_.get(), rho_q.size(), int(m.size()), n.data(), q.data(), f.data(), m.data(),
-                                   rho_q.data(), rho_m.data(), &v));
+                                   charge ? rho_q.data() : nullptr, massDensity ? rho_m.data() : nullptr,
+                                   velocity ? &v : nullptr));
     }
     Context const& ctx_;
     Field rho_m, rho_q;

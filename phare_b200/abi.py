@@ -161,6 +161,8 @@ _PROTOS = {
                                    C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_double, C.c_double,
                                    C.POINTER(Box), C.c_int, C.c_void_p, C.c_void_p, C.POINTER(VecField), C.c_double,
                                    C.POINTER(Box), C.c_int, C.POINTER(Box), C.c_void_p]),
+    "phb_gather": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                             C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_void_p]),
     "phb_push_plan": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
                                 C.POINTER(Particles), C.c_double, C.c_double, C.POINTER(Box), C.POINTER(Box), C.c_int,
                                 C.c_void_p]),

@@ -246,11 +246,17 @@ __global__ void __launch_bounds__(256) totals_kernel(const __grid_constant__ Tot
         vy = vy + A.flux[s][1][p] * A.mass[s];
         vz = vz + A.flux[s][2][p] * A.mass[s];
     }
-    A.rho_q_tot[p] = q;
-    A.rho_m_tot[p] = m;
-    A.V[0][p]      = vx / m;
-    A.V[1][p]      = vy / m;
-    A.V[2][p]      = vz / m;
+    // outputs may be absent: Ions::computeChargeDensity / computeMassDensity / computeBulkVelocity called on their own
+    if (A.rho_q_tot)
+        A.rho_q_tot[p] = q;
+    if (A.rho_m_tot)
+        A.rho_m_tot[p] = m;
+    if (A.V[0])
+    {
+        A.V[0][p] = vx / m;
+        A.V[1][p] = vy / m;
+        A.V[2][p] = vz / m;
+    }
 }
 __global__ void __launch_bounds__(256)
     average_kernel(size_t n, const double* a, const double* b, double* avg)
@@ -391,8 +397,8 @@ int phb_ions_totals(phb_ctx* ctx, size_t nnodes, int npop, const double* const* 
                     const phb_vecfield* h_flux, const double* h_mass, double* rho_q_tot, double* rho_m_tot,
                     phb_vecfield* V)
 {
-    if (!ctx || npop < 1 || npop > phb::MAX_POP || !h_rho_n || !h_rho_q || !h_flux || !h_mass || !rho_q_tot
-        || !rho_m_tot || !V)
+    if (!ctx || npop < 1 || npop > phb::MAX_POP || !h_rho_n || !h_rho_q || !h_flux || !h_mass
+        || (!rho_q_tot && !rho_m_tot && !V))
         return phb::set_error(ctx, PHB_ERR_INVALID, "phb_ions_totals: invalid argument (npop <= 8)");
     phb::TotalsParams A;
     A.n    = nnodes;
@@ -408,7 +414,7 @@ int phb_ions_totals(phb_ctx* ctx, size_t nnodes, int npop, const double* const* 
     A.rho_q_tot = rho_q_tot;
     A.rho_m_tot = rho_m_tot;
     for (int c = 0; c < 3; ++c)
-        A.V[c] = V->comp[c];
+        A.V[c] = V ? V->comp[c] : nullptr;
     phb::totals_kernel<<<phb::blocks_for(nnodes), 256, 0, ctx->stream>>>(A);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;

@@ -68,10 +68,15 @@ int box_op(phb_ctx* ctx, int dim, double* dst, const uint32_t* ds, const uint32_
 // ---- batched variant: one launch runs a whole exchange phase (every face/edge/corner box of every
 // component of every patch pair).  Descriptors live in device memory and are built once per plan.
 __global__ void __launch_bounds__(256)
-    box_op_batch_kernel(const phb_box_desc* __restrict__ ops, int nops, unsigned long long total)
+    box_op_batch_kernel(const phb_box_desc* __restrict__ ops, int nops, unsigned long long total,
+                        const DevError* __restrict__ err)
 {
     unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total)
+        return;
+    // a neighbour GPU never delivered (phb_peer_wait timed out): its receive area holds the data of an older phase, so
+    // nothing is packed or unpacked any more; the host sees PHB_ERR_PEER_TIMEOUT at its next phb_poll_error
+    if (err->code == int(PHB_ERR_PEER_TIMEOUT))
         return;
     // binary search: last op whose first element index is <= t
     int lo = 0, hi = nops - 1;
@@ -154,7 +159,7 @@ int phb_box_op_batch(phb_ctx* ctx, const phb_box_desc* d_ops, int nops, uint64_t
     if (nops <= 0 || total_elements == 0)
         return PHB_OK;
     phb::box_op_batch_kernel<<<unsigned((total_elements + 255) / 256), 256, 0, ctx->stream>>>(d_ops, nops,
-                                                                                             total_elements);
+                                                                                             total_elements, ctx->d_err);
     PHB_LAUNCH_CHECK(ctx);
     return PHB_OK;
 }

@@ -237,6 +237,52 @@ __global__ void __launch_bounds__(PUSH_TILE, PUSH_CTAS)
     }
 }
 
+// Interpolator::operator()(particle, em, layout) on its own (interpolator.hpp:420-456): E and B at the position of each
+// particle, 6 doubles per particle {Ex,Ey,Ez,Bx,By,Bz}; the gather the push kernels inline, exposed for callers (and
+// tests) that want the interpolated fields themselves
+template<int DIM, int ORDER, bool EXACT>
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ PushParams<DIM> P, size_t first, double* eb)
+{
+    size_t const i = first + size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= P.n)
+        return;
+    int icell[DIM];
+    double delta[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+    {
+        icell[d] = P.in.icell[d][i];
+        delta[d] = P.in.delta[d][i];
+    }
+    IndexWeights<DIM, ORDER> iw;
+    both_centerings<DIM, ORDER>(P.L, icell, delta, iw);
+    double* o = eb + 6 * (i - first);
+    o[0] = gather_packed<DIM, ORDER, PHB_EX, 0, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+    o[1] = gather_packed<DIM, ORDER, PHB_EY, 1, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+    o[2] = gather_packed<DIM, ORDER, PHB_EZ, 2, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+    o[3] = gather_packed<DIM, ORDER, PHB_BX, 3, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+    o[4] = gather_packed<DIM, ORDER, PHB_BY, 4, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+    o[5] = gather_packed<DIM, ORDER, PHB_BZ, 5, EXACT>(iw, P.em, P.rs0, P.rs1, P.ps0, P.ps1);
+}
+
+template<int DIM, int ORDER>
+int gather_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B, const phb_particles* parts,
+                 size_t first, size_t last, double* d_eb)
+{
+    PushParams<DIM> P;
+    if (int rc = prepare_push<DIM>(ctx, L, E, B, 1.0, 0.0, nullptr, P))
+        return rc;
+    P.in = make_part(*parts);
+    P.n  = last;
+    unsigned const grid = unsigned((last - first + 255) / 256);
+    if (ctx->exact)
+        gather_kernel<DIM, ORDER, true><<<grid, 256, 0, ctx->stream>>>(P, first, d_eb);
+    else
+        gather_kernel<DIM, ORDER, false><<<grid, 256, 0, ctx->stream>>>(P, first, d_eb);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST, bool PLAN = false>
@@ -349,6 +395,29 @@ int push_dim(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb
     }
 }
 } // namespace phb
+
+extern "C" int phb_gather(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
+                          const phb_particles* parts, size_t first, size_t last, double* d_eb)
+{
+    if (!phb::valid_layout(ctx, L) || !E || !B || !parts || !d_eb || first > last || last > parts->n)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_gather: invalid argument");
+    if (first == last)
+        return PHB_OK;
+#define PHB_G(D, O) phb::gather_order<D, O>(ctx, L, E, B, parts, first, last, d_eb)
+    switch (L->dim * 10 + L->interp)
+    {
+        case 11: return PHB_G(1, 1);
+        case 12: return PHB_G(1, 2);
+        case 13: return PHB_G(1, 3);
+        case 21: return PHB_G(2, 1);
+        case 22: return PHB_G(2, 2);
+        case 23: return PHB_G(2, 3);
+        case 31: return PHB_G(3, 1);
+        case 32: return PHB_G(3, 2);
+        default: return PHB_G(3, 3);
+    }
+#undef PHB_G
+}
 
 extern "C" int phb_push_plan(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
                              phb_particles* parts, double mass, double dt, const phb_box* domain, const phb_box* keep,

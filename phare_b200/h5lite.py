@@ -12,6 +12,7 @@ parallel-HDF5 file from all ranks).
 """
 import glob
 import os
+import io
 import pickle
 import sys
 
@@ -226,7 +227,7 @@ class File(Group):
                 raise OSError(f"Unable to open file (not an h5lite container): {piece}")
             while True:
                 try:
-                    record = pickle.load(f)
+                    record = _SafeUnpickler(f).load()
                 except EOFError:
                     break
                 for k, (attrs, a) in record.items():
@@ -277,6 +278,22 @@ class File(Group):
 
     def __repr__(self):
         return f'<h5lite file "{os.path.basename(self.filename)}" (mode {self.mode})>'
+
+
+class _SafeUnpickler(pickle.Unpickler):
+    """records hold only dicts, strings, numbers and numpy arrays / scalars: anything else in a container (a file from
+    another user or machine may have been tampered with) is refused instead of being imported and called"""
+    ALLOWED = {("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+               ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+               ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy.core.numeric", "_frombuffer"),
+               ("numpy._core.numeric", "_frombuffer"), ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"),
+               ("builtins", "set"), ("builtins", "frozenset"), ("builtins", "bytes"), ("builtins", "bytearray"),
+               ("builtins", "complex"), ("builtins", "slice")}
+
+    def find_class(self, module, name):
+        if (module, name) in self.ALLOWED or (module.startswith("numpy.dtypes") and name.endswith("DType")):
+            return super().find_class(module, name)
+        raise pickle.UnpicklingError(f"h5lite: refusing to load {module}.{name} from a container")
 
 
 def is_h5lite(filename):

@@ -260,7 +260,10 @@ class PeerArena:
         self.cursor = self.FLAGS
         self.sent = [0] * self.size      # phases I delivered to each rank
         self.received = [0] * self.size  # phases each rank delivered to me
-        self.timeout_s = float(os.environ.get("PHB_PEER_TIMEOUT_S", 20.0))
+        # GPU-clock time a stream may wait for a neighbour's flag: it also covers the neighbour's HOST work between two
+        # phases (particle dumps, restarts), so it is generous; after a timeout no exchange phase applies anything any
+        # more (box_op_batch_kernel) and the next poll raises PHB_ERR_PEER_TIMEOUT
+        self.timeout_s = float(os.environ.get("PHB_PEER_TIMEOUT_S", 300.0))
         self._C = C
 
     def alloc(self, nbytes):
@@ -327,7 +330,6 @@ class HybridMessenger:
                 import warnings
                 warnings.warn("NVLink peer-memory halo unavailable (" + getattr(arena, "why", "another rank failed")
                               + "): field phases are staged through torch.distributed send/recv")
-        self._last_peer_key = None
 
     def _plan(self, kind, qty):
         key = (kind, qty)
@@ -354,18 +356,19 @@ class HybridMessenger:
 
     def _run(self, phase, key=None):
         ops = self.ops
-        ops.run_box_ops(phase["pre"])      # packs for every peer (+ the local copies when they are independent)
         if "peer_dsts" in phase:
-            # a receive area is reused every time its phase comes round: safe because some OTHER phase with the same
-            # neighbours always runs in between (the sender waits on it, and the receiver only signals it after
-            # having unpacked this one)
-            assert key is None or key != self._last_peer_key, f"phase {key} run twice in a row"
-            self._last_peer_key = key
+            # every receive area exists twice and a phase alternates between the two: a neighbour writes area (k & 1) of
+            # run k; before it can write that area again (run k + 2) it has waited for my signal of run k + 1, which my
+            # stream issues after the unpack of run k.  No assumption about which other phases run in between.
+            half = phase["halves"][phase["runs"] & 1]
+            phase["runs"] += 1
+            ops.run_box_ops(half["pre"])
             self.arena.signal(phase["peer_dsts"])
-            ops.run_box_ops(phase["local"])
+            ops.run_box_ops(half["local"])
             self.arena.wait(phase["peer_srcs"])
-            ops.run_box_ops(phase["post"])
+            ops.run_box_ops(half["post"])
             return
+        ops.run_box_ops(phase["pre"])      # packs for every peer (+ the local copies when they are independent)
         ops.run_box_ops(phase["local"])    # local operations that must follow the packs (in-place max)
         if phase["peers"]:
             if "p2p" not in phase:         # the grouped send/recv list is built once per phase
@@ -448,25 +451,29 @@ class HybridMessenger:
         """peer-memory variant: my receive areas live in my arena, the pack ops of my neighbours write into them
         (and mine into theirs); called collectively, in the same order, by every rank"""
         ops, arena = self.ops, self.arena
-        my_off = {src: arena.alloc(8 * sum(int(np.prod(e)) for _, _, e in items)) for src, items in sorted(recv_items.items())}
-        their_off = arena.exchange_offsets(my_off)
-        pack, unpack = [], []
-        for dst, items in sorted(send_items.items()):
-            at = arena.base[dst] + their_off[dst]
-            for (arr, lo, ext) in items:
-                pack.append((RawArray(at, ext), [0] * len(ext), arr, lo, ext, 0))
-                at += 8 * int(np.prod(ext))
-        for src, items in sorted(recv_items.items()):
-            at = arena.base[arena.me] + my_off[src]
-            for (arr, lo, ext) in items:
-                unpack.append((arr, lo, RawArray(at, ext), [0] * len(ext), ext, op))
-                at += 8 * int(np.prod(ext))
-        phase = dict(peers={}, peer_dsts=sorted(send_items), peer_srcs=sorted(recv_items))
-        if op == 2:
-            phase["pre"], phase["local"] = ops.compile_box_ops(pack), ops.compile_box_ops(local)
-        else:
-            phase["pre"], phase["local"] = ops.compile_box_ops(pack + local), None
-        phase["post"] = ops.compile_box_ops(unpack)
+        phase = dict(peers={}, peer_dsts=sorted(send_items), peer_srcs=sorted(recv_items), runs=0, halves=[])
+        for _ in range(2):
+            my_off = {src: arena.alloc(8 * sum(int(np.prod(e)) for _, _, e in items))
+                      for src, items in sorted(recv_items.items())}
+            their_off = arena.exchange_offsets(my_off)
+            pack, unpack = [], []
+            for dst, items in sorted(send_items.items()):
+                at = arena.base[dst] + their_off[dst]
+                for (arr, lo, ext) in items:
+                    pack.append((RawArray(at, ext), [0] * len(ext), arr, lo, ext, 0))
+                    at += 8 * int(np.prod(ext))
+            for src, items in sorted(recv_items.items()):
+                at = arena.base[arena.me] + my_off[src]
+                for (arr, lo, ext) in items:
+                    unpack.append((arr, lo, RawArray(at, ext), [0] * len(ext), ext, op))
+                    at += 8 * int(np.prod(ext))
+            half = {}
+            if op == 2:
+                half["pre"], half["local"] = ops.compile_box_ops(pack), ops.compile_box_ops(local)
+            else:
+                half["pre"], half["local"] = ops.compile_box_ops(pack + local), None
+            half["post"] = ops.compile_box_ops(unpack)
+            phase["halves"].append(half)
         return phase
 
     def migrate_particles(self, layouts, patch_ghost, domain, ensure=None):

@@ -65,7 +65,7 @@ class GpuOps:
         self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, dst.ptr, src.ptr, src.size * 8))
 
     def set_field(self, h, host):
-        h.t.copy_(self.torch.from_numpy(np.ascontiguousarray(host)).to(self.device))
+        h.t.copy_(self.torch.from_numpy(np.array(host, dtype=np.float64, order="C", copy=True)).to(self.device))
 
     def get_field(self, h):
         return h.t.cpu().numpy()

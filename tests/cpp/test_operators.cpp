@@ -260,6 +260,49 @@ void run()
                 scale = std::max(scale, std::fabs(wm[k][i])), err = std::max(err, std::fabs(gm[i] - wm[k][i]));
             CHECK(err <= 1e-10 * scale);
         }
+        // ---- the reference signatures that carry no device handle: the one-particle gather
+        // Interpolator::operator()(Particle&, Electromag const&, GridLayout const&) against the oracle, bit for bit, and
+        // against the range form; computeStartLeftShift; Ions::compute* called separately == the fused kernel
+        {
+            Interpolator<dim, interp> interpolator;
+            std::vector<double> web(6 * N0);
+            CHECK(pho_gather(layout.c(), &e, &b, &P, web.data()) == 0);
+            ParticleArray<dim> all{ctx, N0};
+            all.assign(host);
+            std::vector<double> geb = interpolator.gather(makeIndexRange(all), em, layout);
+            bool same_bits = geb.size() == web.size();
+            for (std::size_t i = 0; same_bits && i < web.size(); ++i)
+                same_bits = std::memcmp(&geb[i], &web[i], 8) == 0;
+            CHECK(same_bits);
+            for (std::size_t i : {std::size_t(0), N0 / 2, N0 - 1})
+            {
+                auto const [Ep, Bp] = interpolator(host[i], em, layout);
+                bool ok = true;
+                for (int c = 0; c < 3; ++c)
+                    ok = ok && std::memcmp(&Ep[c], &web[6 * i + c], 8) == 0 && std::memcmp(&Bp[c], &web[6 * i + 3 + c], 8) == 0;
+                CHECK(ok);
+            }
+            using I = Interpolator<dim, interp>;
+            int const want_p[3][2] = {{0, 0}, {1, 0}, {1, 1}}, want_d[3][2] = {{1, 0}, {1, 1}, {2, 1}}; // delta .25 / .75
+            CHECK((I::template computeStartLeftShift<QtyCentering, QtyCentering::primal>(.25)) == want_p[interp - 1][0]);
+            CHECK((I::template computeStartLeftShift<QtyCentering, QtyCentering::primal>(.75)) == want_p[interp - 1][1]);
+            CHECK((I::template computeStartLeftShift<QtyCentering, QtyCentering::dual>(.25)) == want_d[interp - 1][0]);
+            CHECK((I::template computeStartLeftShift<QtyCentering, QtyCentering::dual>(.75)) == want_d[interp - 1][1]);
+
+            std::vector<double> fused[5], sep[5];
+            DeviceBuffer* tot[5] = {&tq, &tm, &v0, &v1, &v2};
+            for (int k = 0; k < 5; ++k)
+                fused[k].resize(nn), sep[k].resize(nn), tot[k]->download(fused[k].data()), tot[k]->zero();
+            ions.computeChargeDensity();
+            ions.computeBulkVelocity();
+            bool totals_same = true;
+            for (int k = 0; k < 5; ++k)
+            {
+                tot[k]->download(sep[k].data());
+                totals_same = totals_same && std::memcmp(sep[k].data(), fused[k].data(), nn * 8) == 0;
+            }
+            CHECK(totals_same);
+        }
         // a bad pusher name throws like PusherFactory (pusher_factory.hpp:29)
         bool threw = false;
         try

@@ -71,3 +71,15 @@ def test_product_package_never_imports_the_oracle():
     for root, _, files in os.walk(os.path.join(abi.ROOT, "include")):
         for f in files:
             assert "import oracle" not in open(os.path.join(root, f)).read()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="needs the reference tree (dev container only)")
+def test_bridge_header_against_reference_types():
+    """include/phare_b200/bridge.hpp (the b200:: helpers of INTEGRATION.md) instantiated against the UNMODIFIED reference
+    GridLayout / Field / VecField headers: the member names it relies on exist (syntax check, nothing is linked or run)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["g++", "-std=c++20", "-fsyntax-only", "-w", "-I" + os.path.join(root, "oracle/ref"),
+                        "-I/root/reference/src", "-I/root/reference", os.path.join(root, "oracle/ref/ref_bridge_check.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

@@ -103,3 +103,55 @@ def test_cpp_solver_matches_python_driver_and_oracle(domain, interp, dx, ppc, np
             assert np.array_equal(np.isfinite(got[(attr, comp)]), ok), (name, attr, comp)
             scale = np.max(np.abs(want[ok])) + 1e-30
             assert np.max(np.abs(got[(attr, comp)][ok] - want[ok])) <= tol * scale + 1e-13, (name, attr, comp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("domain,interp,dx,ppc,npop,steps", [
+    ((64,), 1, (0.2,), 50, 2, 5),
+    ((24, 16), 1, (0.4, 0.4), 20, 2, 3),
+    ((16, 12), 3, (0.2, 0.2), 12, 1, 2),
+    ((12, 8, 8), 1, (0.2, 0.2, 0.2), 8, 1, 3),
+])
+def test_cpp_solver_matches_step_oracle(domain, interp, dx, ppc, npop, steps, tmp_path):
+    """the C++ SolverPPC (own box algebra in solver_ppc.hpp, CUDA through the C ABI) against the STEP ORACLE (the
+    reference's own functors under an independent level loop, oracle/ref/ref_step.cpp): <= 1e-10 per node"""
+    import oracle
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libphare_ref.so not built")
+    from oracle import ref_step as rs
+    from phare_b200.messenger import centering
+    from phare_b200.setup import node_coords
+    from step_oracle_util import node_errors, physical
+    build()
+    dim = len(domain)
+    masses = (1.0, 2.0)[:npop]
+    eta, nu, Te, dt = 1e-3, 1e-3, 0.12, 0.005
+    gparts = global_particles(domain, interp, dx, ppc, seed=3, pops=npop)
+    prob, res = str(tmp_path / "problem.bin"), str(tmp_path / "result.bin")
+    write_problem(prob, domain, interp, dx, gparts, masses, steps, dt, eta, nu, Te)
+    r = subprocess.run([EXE, prob, res], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ALL OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    got, counts = read_result(res, domain, interp, npop)
+    L = abi.make_layout(dim, interp, domain, dx)
+    ref = rs.RefStep(dim, interp, [([0] * dim, [c - 1 for c in domain])], dx, [0.0] * dim, domain, masses, Te=Te, eta=eta, nu=nu)
+    bfn = B_init(domain, dx)
+    B0 = []
+    for c in range(3):
+        mesh = np.meshgrid(*node_coords(L, abi.BX + c, centering, domain), indexing="ij")
+        B0.append(np.ascontiguousarray(np.broadcast_to(bfn(c, *mesh), mesh[0].shape)))
+    ref.set_vec(0, rs.B, B0)
+    for i, g in enumerate(gparts):
+        ref.set_particles(0, i, *g)
+    ref.initialize()
+    for _ in range(steps):
+        ref.advance(dt)
+    assert counts == [ref.count(0, i) for i in range(npop)]
+    want = {("B", c): ref.vec(0, rs.B)[c] for c in range(3)}
+    want.update({("E", c): ref.vec(0, rs.E)[c] for c in range(3)})
+    want.update({("Vi", c): ref.vec(0, rs.VI)[c] for c in range(3)})
+    want[("Ne", None)] = ref.scalar(0, rs.NI)
+    for attr, comp, qty in FIELDS:
+        a, b = got[(attr, comp)], want[(attr, comp)]
+        if attr in ("Ne", "Vi"):
+            a, b = physical(a, L, qty, centering), physical(b, L, qty, centering)
+        assert node_errors(a, b) <= 1e-10, (attr, comp, node_errors(a, b))

@@ -133,3 +133,21 @@ def test_momentum_tensor_of_a_cold_beam(cpu_oracle, tmp_path, monkeypatch):
         assert np.asarray(Mc[patch]["momentum_tensor_xx"])[4:-4].min() > 0  # a warm population has pressure
     cnt = h5lite.File(str(tmp_path / "particle_count.h5"))[at]
     assert int(cnt["p0#0"].attrs["particle_count"]) == 32 * 60 and list(cnt["p0#0"].keys()) == []
+
+
+def test_tampered_container_is_refused(tmp_path):
+    """a container is data, not code: a record that names anything but numpy arrays / plain values is refused"""
+    import pickle
+    import pytest
+    from phare_b200 import h5lite
+
+    class Evil:
+        def __reduce__(self):
+            import os
+            return (os.system, ("echo pwned",))
+    p = tmp_path / "evil.h5"
+    with open(p, "wb") as f:
+        f.write(h5lite.MAGIC)
+        pickle.dump({"/x": ({}, Evil())}, f)
+    with pytest.raises(pickle.UnpicklingError):
+        h5lite.File(str(p), "r")
