@@ -11,9 +11,17 @@ BUILD     ?= build
 OBJ       := $(patsubst phare_b200/csrc/%.cu,$(BUILD)/%.o,$(SRC))
 LIB       ?= phare_b200/lib/libphare_b200.so
 
-all: lib oracle
+HOSTLIB   := phare_b200/lib/libphare_b200_host.so
+
+all: lib host oracle
 
 lib: $(LIB)
+
+# the C++ level driver (include/phare_b200/solver_ppc.hpp) behind a small C ABI: plain g++, CUDA only through $(LIB)
+host: $(HOSTLIB)
+$(HOSTLIB): phare_b200/host/host_api.cpp $(wildcard include/phare_b200/*.hpp) include/phare_b200.h $(LIB)
+	g++ -std=c++20 -O2 -fPIC -shared -Iinclude -o $@ phare_b200/host/host_api.cpp -Lphare_b200/lib -lphare_b200 \
+	    -Wl,-rpath,'$$ORIGIN' -Wl,-rpath,/usr/local/cuda/lib64
 
 $(BUILD)/%.o: phare_b200/csrc/%.cu $(wildcard phare_b200/csrc/*.cuh) include/phare_b200.h
 	@mkdir -p $(BUILD)
@@ -29,4 +37,4 @@ oracle:
 clean:
 	rm -rf $(BUILD) $(LIB)
 	$(MAKE) -C oracle clean
-.PHONY: all lib oracle clean
+.PHONY: all lib host oracle clean

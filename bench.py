@@ -229,6 +229,49 @@ def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
     return box[0]
 
 
+def cpp_host_arm(args):
+    """the same step driven by the C++ level driver (include/phare_b200/solver_ppc.hpp through libphare_b200_host.so):
+    Python only builds the problem; the K timed steps are ONE call into C++.  One GPU (the C++ driver holds every patch of
+    the level in one process); kernel-level roofline figures come from the default (Python-driven) arm, whose launches are
+    bracketed one by one."""
+    import torch
+    from phare_b200.host_cpp import CppLevel
+    assert args.gpus == 1, "--host cpp drives one GPU"
+    cfg, scaling = bench_config(args.config, 1)
+    device = torch.device("cuda:0")
+    level = CppLevel(cfg, device)
+    level.initialize()
+    level.advance(cfg.dt, max(args.warmup, 3))
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = level.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    level.advance(cfg.dt, args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    n_total = sum(sum(c) for c in level.counts())
+    value = 2 * n_total * args.steps / (ms * 1e-3)
+    peak, _ = measured_peaks()
+    dim = cfg.dim
+    line = dict(metric=METRIC, value=value, unit="particle-pushes/s", n_gpus=1, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling,
+                vs_baseline=None, dtype="f64", data="synthetic", host="cpp",
+                config=dict(workload=cfg.name, cells=list(cfg.cells), patch_grid=list(cfg.patch_grid),
+                            ppc=[p["ppc"] for p in cfg.pops], interp_order=cfg.interp, particles_total=n_total,
+                            pushes_per_step=2 * n_total,
+                            parallelism=f"{len(level.layouts)} patch(es) on one GPU, C++ level driver"),
+                clocks=clocks, gpu_launches=level.ctx.launches - launches0, e2e=None, roofline=None,
+                roofline_other=dict(whole_step_frac_of_hbm=round(
+                    2 * n_total * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)),
+                cpu_baseline=None)
+    print(json.dumps(line))
+    level.close()
+
+
 def our_arm(args):
     import torch
     import torch.distributed as dist
@@ -581,8 +624,12 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank parity check that precedes the timed region")
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
+    ap.add_argument("--host", default="python", choices=["python", "cpp"],
+                    help="who enqueues the step: phare_b200/solver.py (default; every N) or the C++ SolverPPC (one GPU)")
     a = ap.parse_args()
     if a.impl == "reference":
         reference_arm(a)
+    elif a.host == "cpp":
+        cpp_host_arm(a)
     else:
         our_arm(a)

@@ -568,9 +568,19 @@ class IonUpdater
 public:
     explicit IonUpdater(Dict const& dict) : pusher_{PusherFactory::makePusher<dim, order>(dict["pusher"]["name"].to<std::string>())} {}
 
+    // updatePopulations (ion_updater.hpp:90-109) = launchPopulations (every kernel of the sweep, enqueued) +
+    // finishPopulations (the one host synchronisation: class counts of the re-binning, the error poll).  A level driver
+    // calls the first for every patch before the second for any, so the patches' kernels queue back to back.
     template<typename Boxing_t>
     void updatePopulations(Ions<dim>& ions, Electromag const& em, Boxing_t const& boxing, double dt,
                            UpdaterMode mode = UpdaterMode::all)
+    {
+        launchPopulations(ions, em, boxing, dt, mode);
+        finishPopulations(ions, boxing, mode);
+    }
+
+    template<typename Boxing_t>
+    void launchPopulations(Ions<dim>& ions, Electromag const& em, Boxing_t const& boxing, double dt, UpdaterMode mode)
     {
         auto const& ctx    = ions.ctx_;
         auto const& layout = boxing.layout;
@@ -580,46 +590,75 @@ public:
         phb_box const dom = boxing.domainBox.c();
         auto E = em.E.c(), B = em.B.c();
         pusher_->setMeshAndTimeStep(layout.meshSize(), dt);
+        // one-pass push + deposit exists where the cell's node sums fit the register accumulators (csrc/tile.cuh)
+        constexpr std::size_t support = order == 1 ? 2 : 4;
+        constexpr bool fusedDomainOnly = (dim == 1) || (dim == 2) || (dim == 3 && support == 2);
         for (auto& pp : ions)
         {
             auto& pop = *pp;
             // resetMoments (moments.hpp:15-23)
             for (Field* f : {&pop.rho_n, &pop.rho_q, &pop.F[0], &pop.F[1], &pop.F[2]})
                 ctx.check(phb_memset(ctx.get(), f->data(), 0, f->size() * sizeof(double)));
-            auto F               = pop.F.c();
-            std::size_t const n  = pop.domain.size();
-            auto deposit = [&](phb_particles const* store) {
-                uint32_t const* cs = pop.cell_start ? reinterpret_cast<uint32_t const*>(pop.cell_start->data()) : nullptr;
-                if (cs && pop.n_sorted)
-                    ctx.check(phb_deposit(ctx.get(), layout.c(), store, 0, pop.n_sorted, pop.rho_n.data(), pop.rho_q.data(),
-                                          &F, 1., keep.data(), int(keep.size()), &dom, cs));
-                if (n > pop.n_sorted || !cs)
-                    ctx.check(phb_deposit(ctx.get(), layout.c(), store, cs ? pop.n_sorted : 0, n, pop.rho_n.data(),
-                                          pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), nullptr, nullptr));
-            };
+            auto F              = pop.F.c();
+            std::size_t const n = pop.domain.size();
+            uint32_t const* cs  = pop.cell_start ? reinterpret_cast<uint32_t const*>(pop.cell_start->data()) : nullptr;
+            std::size_t const nsorted = cs ? pop.n_sorted : 0;
             if (mode == UpdaterMode::domain_only)
             {
                 // updateAndDepositDomain_ (:171-219): tmp_particles_ = domain; move; deposit the allowed ones
-                ctx.check(phb_push(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.spare.c(), pop.mass(), dt, nullptr));
-                deposit(pop.spare.c());
+                if (fusedDomainOnly && n)
+                {
+                    // the copy is never materialised: K1+K3 in one pass, nothing written back
+                    if (nsorted)
+                        ctx.check(phb_push_deposit(ctx.get(), layout.c(), &E, &B, pop.domain.c(), 0, nsorted, pop.mass(), dt,
+                                                   nullptr, 0, pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(),
+                                                   int(keep.size()), &dom, cs));
+                    if (n > nsorted)
+                        ctx.check(phb_push_deposit(ctx.get(), layout.c(), &E, &B, pop.domain.c(), nsorted, n, pop.mass(), dt,
+                                                   nullptr, 0, pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(),
+                                                   int(keep.size()), nullptr, nullptr));
+                }
+                else if (n)
+                {
+                    ctx.check(phb_push(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.spare.c(), pop.mass(), dt, nullptr));
+                    if (nsorted)
+                        ctx.check(phb_deposit(ctx.get(), layout.c(), pop.spare.c(), 0, nsorted, pop.rho_n.data(),
+                                              pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), &dom, cs));
+                    if (n > nsorted)
+                        ctx.check(phb_deposit(ctx.get(), layout.c(), pop.spare.c(), nsorted, n, pop.rho_n.data(),
+                                              pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), nullptr, nullptr));
+                }
             }
             else
             {
-                // updateAndDepositAll_ (:228-295)
-                ctx.check(phb_push(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.domain.c(), pop.mass(), dt, nullptr));
+                // updateAndDepositAll_ (:228-295): move in place with the keys of the partition counted in the same pass
+                // (phb_push_plan); then the deposit rides on the scatter pass of the re-binning (K3+K2 fused):
+                // partition + erase (:245-273) and both deposits (:290-293) in one walk over the pushed store
                 auto const words = (phb_bin_nkeys(layout.c(), &dom) + 2) / 2 + 1;
                 if (!pop.cell_start_next)
                     pop.cell_start_next = std::make_unique<DeviceBuffer>(ctx, words);
-                uint32_t const* old_start
-                    = pop.cell_start ? reinterpret_cast<uint32_t const*>(pop.cell_start->data()) : nullptr;
                 auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
+                ctx.check(phb_push_plan(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.mass(), dt, &dom, keep.data(),
+                                        int(keep.size()), new_start));
+                ctx.check(phb_deposit_scatter(ctx.get(), layout.c(), pop.domain.c(), nsorted, pop.rho_n.data(),
+                                              pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), &dom, cs, keep.data(),
+                                              int(keep.size()), pop.spare.c(), new_start));
+            }
+        }
+    }
+
+    template<typename Boxing_t>
+    void finishPopulations(Ions<dim>& ions, Boxing_t const& boxing, UpdaterMode mode)
+    {
+        auto const& ctx    = ions.ctx_;
+        auto const& layout = boxing.layout;
+        phb_box const dom  = boxing.domainBox.c();
+        if (mode == UpdaterMode::all)
+            for (auto& pp : ions)
+            {
+                auto& pop = *pp;
                 std::size_t counts[3];
-                // the deposit rides on the scatter pass of the re-binning (K3+K2 fused): partition + erase
-                // (:245-273) and both deposits (:290-293) in one walk over the pushed store
-                ctx.check(phb_bin_plan(ctx.get(), layout.c(), pop.domain.c(), &dom, keep.data(), int(keep.size()), new_start));
-                ctx.check(phb_deposit_scatter(ctx.get(), layout.c(), pop.domain.c(), old_start ? pop.n_sorted : 0,
-                                              pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), &dom,
-                                              old_start, keep.data(), int(keep.size()), pop.spare.c(), new_start));
+                auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
                 ctx.check(phb_bin_counts(ctx.get(), layout.c(), &dom, new_start, counts, pop.spare.c()));
                 std::swap(pop.cell_start, pop.cell_start_next);
                 // stayers -> domain, leavers inside nonLevelGhostBox -> patchGhost (:248-254), the rest erased (:273):
@@ -630,7 +669,6 @@ public:
                 pop.domain.c()->n = counts[0];
                 pop.n_sorted      = counts[0];
             }
-        }
         ctx.check(phb_poll_error(ctx.get())); // throws DictionaryException{"cause", ...} like boris.hpp:207-214
     }
 

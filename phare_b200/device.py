@@ -163,14 +163,27 @@ class Context:
         if stream is not None:
             self._check(self.lib.phb_set_stream(self.h, C.c_void_p(stream)))
 
+    @classmethod
+    def adopt(cls, handle, dim, interp, stream=None):
+        """a Python handle on a phb_ctx created (and destroyed) by someone else: the C++ level driver's
+        (phare_b200/host_cpp.py)"""
+        self = cls.__new__(cls)
+        self.lib = abi.load()
+        self.dim, self.interp = dim, interp
+        self.h = C.c_void_p(handle)
+        self._borrowed = True
+        if stream is not None:
+            self._check(self.lib.phb_set_stream(self.h, C.c_void_p(stream)))
+        return self
+
     def _check(self, rc):
         if rc != abi.PHB_OK:
             raise PhbError(rc, self.lib.phb_last_error(self.h).decode())
 
     def close(self):
-        if self.h:
+        if self.h and not getattr(self, "_borrowed", False):
             self.lib.phb_destroy(self.h)
-            self.h = None
+        self.h = None
 
     def sync(self):
         self._check(self.lib.phb_sync(self.h))

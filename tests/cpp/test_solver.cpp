@@ -3,6 +3,7 @@
 // the Python-driven step (same kernels) and with the CPU oracle step.
 #include "phare_b200/solver_ppc.hpp"
 
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -14,6 +15,7 @@ struct Header
 {
     int32_t dim, interp, nsteps, npop;
     uint32_t ncells[3];
+    uint32_t grid[3]; // patches per direction (cuts at round(i * n / k), like phare_b200.solver.make_level)
     double dx[3];
     double dt, eta, nu, Te;
 };
@@ -30,22 +32,46 @@ int run(Header const& h, std::ifstream& in, std::ofstream& out)
         dx[d] = h.dx[d], nc[d] = h.ncells[d];
         box.lower[d] = 0, box.upper[d] = int(h.ncells[d]) - 1;
     }
-    GridLayout<dim, interp> layout{dx, nc, origin, box};
+    // the level's patches: Cartesian grid, row-major patch order
+    std::vector<GridLayout<dim, interp>> layouts;
+    std::array<long, dim> domainCells;
+    std::size_t npatch = 1;
+    for (std::size_t d = 0; d < dim; ++d)
+        domainCells[d] = h.ncells[d], npatch *= h.grid[d];
+    for (std::size_t pid = 0; pid < npatch; ++pid)
+    {
+        std::size_t r = pid;
+        std::array<std::uint32_t, dim> pnc;
+        std::array<double, dim> porigin;
+        Box<dim> pbox;
+        for (int d = int(dim) - 1; d >= 0; --d)
+        {
+            std::size_t const i = r % h.grid[d];
+            r /= h.grid[d];
+            long const lo = std::lround(double(i) * h.ncells[d] / h.grid[d]);
+            long const hi = std::lround(double(i + 1) * h.ncells[d] / h.grid[d]) - 1;
+            pbox.lower[d] = int(lo), pbox.upper[d] = int(hi);
+            pnc[d]     = std::uint32_t(hi - lo + 1);
+            porigin[d] = lo * h.dx[d];
+        }
+        layouts.emplace_back(dx, pnc, porigin, pbox);
+    }
     Dict sim;
     sim["algo"]["ion_updater"]["pusher"]["name"] = "modified_boris";
     sim["algo"]["ohm"]["resistivity"]            = h.eta;
     sim["algo"]["ohm"]["hyper_resistivity"]      = h.nu;
     sim["algo"]["ohm"]["hyper_mode"]             = "constant";
     sim["electrons"]["pressure_closure"]["Te"]   = h.Te;
-    SolverPPC<dim, interp> solver{ctx, sim, layout};
+    SolverPPC<dim, interp> solver{ctx, sim, layouts, domainCells};
     std::vector<double> buf;
-    for (int c = 0; c < 3; ++c)
-    {
-        buf.resize(solver.EM.B[c].size());
-        in.read(reinterpret_cast<char*>(buf.data()), buf.size() * sizeof(double));
-        ctx.check(phb_h2d(ctx.get(), solver.EM.B[c].data(), buf.data(), buf.size() * sizeof(double)));
-        ctx.sync();
-    }
+    for (auto& pp : solver.patches) // per patch: Bx, By, Bz with their ghosts
+        for (int c = 0; c < 3; ++c)
+        {
+            buf.resize(pp->EM.B[c].size());
+            in.read(reinterpret_cast<char*>(buf.data()), buf.size() * sizeof(double));
+            ctx.check(phb_h2d(ctx.get(), pp->EM.B[c].data(), buf.data(), buf.size() * sizeof(double)));
+            ctx.sync();
+        }
     for (int p = 0; p < h.npop; ++p)
     {
         double mass;
@@ -67,17 +93,20 @@ int run(Header const& h, std::ifstream& in, std::ofstream& out)
         ctx.check(phb_d2h(ctx.get(), buf.data(), f.data(), buf.size() * sizeof(double)));
         out.write(reinterpret_cast<char const*>(buf.data()), buf.size() * sizeof(double));
     };
-    for (int c = 0; c < 3; ++c)
-        dump(solver.EM.B[c]);
-    for (int c = 0; c < 3; ++c)
-        dump(solver.EM.E[c]);
-    dump(solver.ions.chargeDensity());
-    for (int c = 0; c < 3; ++c)
-        dump(solver.ions.velocity()[c]);
-    for (auto& pop : solver.ions)
+    for (auto& pp : solver.patches)
     {
-        uint64_t n = pop->domain.size();
-        out.write(reinterpret_cast<char const*>(&n), 8);
+        for (int c = 0; c < 3; ++c)
+            dump(pp->EM.B[c]);
+        for (int c = 0; c < 3; ++c)
+            dump(pp->EM.E[c]);
+        dump(pp->ions.chargeDensity());
+        for (int c = 0; c < 3; ++c)
+            dump(pp->ions.velocity()[c]);
+        for (auto& pop : pp->ions)
+        {
+            uint64_t n = pop->domain.size();
+            out.write(reinterpret_cast<char const*>(&n), 8);
+        }
     }
     return 0;
 }
