@@ -337,37 +337,46 @@ def our_arm(args):
     avg = lambda v: sum(v) / len(v) if v else None
     roofline = None
     extra = {}
-    if push_ms:
+    if push_ms or kernel_ms.get("move_domain_only"):
         # one K1 launch = one population of one patch: the average launch moves n_local / launches-per-sweep particles
         n_launch = n_local / max(1, sum(len(p.pops) for p in solver.patches))
-        alg = n_launch * BYTES_PUSH[dim]
-        ach = alg / (avg(push_ms) * 1e-3) / 1e9
-        # DRAM traffic per launch: dram__bytes_read + dram__bytes_write of one `ncu --set full` capture of EXACTLY the
-        # kernel instantiation timed here (profiles/traffic_r2.json, keyed by config and kernel name), per particle
-        traffic = None
         prof = os.path.join(ROOT, "profiles", "traffic_r2.json")
-        if os.path.exists(prof):
-            rec = json.load(open(prof)).get(f"c{cfg.key}", {}).get("push_in_place")
-            if rec:
-                traffic = rec["dram_bytes_per_particle"] * n_launch
-        roofline = dict(bound="hbm", kernel="push (K1 fused interpolate+Boris)", achieved=round(ach, 1), peak=peak,
-                        unit="GB/s", frac=round(ach / peak, 4), traffic=traffic, peak_source=peak_src,
-                        algorithmic_bytes_per_launch=alg, avg_launch_ms=round(avg(push_ms), 4),
-                        launches_timed=len(push_ms))
+        prof = json.load(open(prof)).get(f"c{cfg.key}", {}) if os.path.exists(prof) else {}
+
+        def kernel_roofline(label, name, ms_list, alg_bpp, traffic_key, note):
+            """SURVEY 8(d) algorithmic bytes per particle x particles of one launch / the launch's CUDA-event time; traffic =
+            dram__bytes_read + dram__bytes_write per particle of one `ncu --set full` capture of EXACTLY this kernel
+            instantiation at this config (profiles/traffic_r2.json), or null when that capture does not exist"""
+            alg = n_launch * alg_bpp
+            ach = alg / (avg(ms_list) * 1e-3) / 1e9
+            rec = prof.get(traffic_key) if traffic_key else None
+            return dict(bound="hbm", kernel=label, kernel_name=name, achieved=round(ach, 1), peak=peak, unit="GB/s",
+                        frac=round(ach / peak, 4), traffic=(rec["dram_bytes_per_particle"] * n_launch) if rec else None,
+                        peak_source=peak_src, algorithmic_bytes_per_particle=alg_bpp, algorithmic_bytes_per_launch=alg,
+                        avg_launch_ms=round(avg(ms_list), 4), launches_timed=len(ms_list), note=note)
+
+        planned = not kernel_ms.get("bin_plan")  # phb_push_plan: the bin count rides on the in-place push
+        k1 = None if not push_ms else kernel_roofline("K1 fused interpolate + Boris push, in place" + (" + bin count (phb_push_plan)" if planned else ""),
+                             "push_tma_kernel", push_ms, BYTES_PUSH[dim] + (4 if planned else 0),
+                             None if planned else "push_in_place",
+                             "reads iCell, delta, v, charge; writes iCell, delta, v" + (" and the 4-byte slot" if planned else ""))
+        mv_all = kernel_ms.get("move_domain_only", [])
+        if mv_all and sum(mv_all) > sum(push_ms):  # (1-D configs run both sweeps fused: there is no separate K1 launch)
+            # the dominant kernel of the step: interpolate + push + deposit of a particle in ONE pass (the domain_only sweep).
+            # Its unit of work is SURVEY 8(d)'s whole "particle-push" (K1 + K3 = 80/104/128 + 52/64/76 B); it MOVES only the
+            # K3 bytes (the pushed copy is never written nor re-read), which is why traffic < algorithmic bytes
+            roofline = kernel_roofline("K1+K3 fused: interpolate + push + deposit in one pass (tile kernel, E,B block in shared memory)",
+                                       "tile_kernel", mv_all, BYTES_PUSH[dim] + BYTES_DEPOSIT[dim], "move_domain_only",
+                                       "algorithmic = one particle-push of SURVEY 8(d) (K1 + K3 bytes); the kernel moves only the "
+                                       "K3 bytes and is bound by the FP64 pipe (exact mode: no FMA contraction)")
+            roofline["frac_of_bytes_moved"] = round(n_launch * BYTES_DEPOSIT[dim] / (avg(mv_all) * 1e-3) / 1e9 / peak, 4)
+            if k1:
+                extra["push"] = k1
+        else:
+            roofline = k1
         if dep_ms:
             a = n_launch * BYTES_DEPOSIT[dim] / (avg(dep_ms) * 1e-3) / 1e9
             extra["deposit"] = dict(achieved=round(a, 1), frac=round(a / peak, 4), avg_launch_ms=round(avg(dep_ms), 4))
-        mv_ms = kernel_ms.get("move_domain_only", [])
-        if mv_ms:
-            # K1+K3 fused, nothing written back (the domain_only sweep): one read of the store; its algorithmic work is a
-            # whole particle-push (K1 + K3 bytes), so both fractions are given
-            a = n_launch * BYTES_DEPOSIT[dim] / (avg(mv_ms) * 1e-3) / 1e9
-            w = n_launch * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (avg(mv_ms) * 1e-3) / 1e9
-            extra["move_domain_only"] = dict(moved_gbs=round(a, 1), frac_of_bytes_moved=round(a / peak, 4),
-                                             frac_of_k1_plus_k3_bytes=round(w / peak, 4),
-                                             avg_launch_ms=round(avg(mv_ms), 4),
-                                             what="tile kernel (csrc/tile.cuh): interpolate + push + deposit in one pass, "
-                                                  "E,B block of each CTA staged in shared memory by bulk copies")
         if bin_ms:
             extra["bin"] = dict(avg_ms=round(avg(bin_ms), 4))
         ds_ms, plan_ms = kernel_ms.get("deposit_scatter", []), kernel_ms.get("bin_plan", [])
@@ -381,7 +390,9 @@ def our_arm(args):
                 extra["bin_plan"] = dict(avg_ms=round(avg(plan_ms), 4))
             else:
                 extra["bin_plan"] = "folded into the in-place push (phb_push_plan)"
-        extra["particle_kernels_share_of_step"] = round(sum(sum(v) for v in kernel_ms.values()) / ms, 4)
+        NOT_KERNELS = ("exchange_phases", "finish_particles", "fp_alltoall_counts", "fp_send_recv", "fp_maintain_arrays")  # brackets of the exchange / host-synchronising parts
+        extra["particle_kernels_share_of_step"] = round(
+            sum(sum(v) for k, v in kernel_ms.items() if k not in NOT_KERNELS) / ms, 4)
         extra["kernel_ms_per_step"] = {k: round(sum(v) / args.steps, 3) for k, v in sorted(kernel_ms.items())}
         # whole-step fraction: 2 sweeps x (K1 + K3 algorithmic bytes) / step time
         extra["whole_step_frac_of_hbm"] = round(

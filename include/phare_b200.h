@@ -254,10 +254,13 @@ int phb_gather(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vec
  * pass over the store: pusher_->move in place (== phb_push(parts, parts, first = NULL), same bits) and, while the moved
  * particle is still in registers, the count half of the re-binning (== phb_bin_plan(parts, domain, keep)): key of the new
  * cell, slot inside it, histogram -> d_cell_start.  phb_deposit_scatter consumes the plan exactly as after phb_bin_plan.
- * Saves the separate read of the iCell columns (0.69 ms of 16.5 ms per step at config 5). */
+ * d_cell_start_old / n_sorted (may be NULL / 0): the current ordering of parts[0, n_sorted) by the keys of phb_bin for
+ * `domain`; with it the ordered part goes through the strip kernel (csrc/strip.cuh: the E,B nodes of each strip of cells
+ * and their stencil halo staged in shared memory by bulk copies, gathers from shared memory), the rest and every store
+ * without an ordering through the streaming kernel (E,B through L1). */
 int phb_push_plan(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B, phb_particles* parts,
-                  double mass, double dt, const phb_box* domain, const phb_box* keep, int nkeep,
-                  uint32_t* d_cell_start);
+                  size_t n_sorted, double mass, double dt, const phb_box* domain, const uint32_t* d_cell_start_old,
+                  const phb_box* keep, int nkeep, uint32_t* d_cell_start);
 
 /* ---- cell-ordered passes with the E,B nodes of a block of cells staged in shared memory (csrc/tile.cuh) -----------
  * The kernels behind these entry points (and behind the cell-ordered path of phb_push_deposit) give one CTA a compact
@@ -266,7 +269,8 @@ int phb_push_plan(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_
  * keys of phb_bin for `domain`; parts[n_sorted, n) (received since the last binning) may be in any order.
  *
  * phb_push_cells: BorisPusher::move (pusher/boris.hpp:93-138) exactly like phb_push with first_selector = NULL
- * (same arithmetic, same bits).  `out` may be `in`, or a store whose weight/charge columns alias in's. */
+ * (same arithmetic, same bits) through the strip kernel (csrc/strip.cuh: E,B of each strip of cells staged in shared
+ * memory by bulk copies).  `out` may be `in`, or a store whose weight/charge columns alias in's. */
 int phb_push_cells(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B, const phb_particles* in,
                    phb_particles* out, size_t n_sorted, double mass, double dt, const phb_box* domain,
                    const uint32_t* d_cell_start);
@@ -414,6 +418,22 @@ int phb_ipc_open(phb_ctx*, const unsigned char h_handle[64], void** d_peer_ptr);
 int phb_ipc_close(phb_ctx*, void* d_peer_ptr);
 int phb_peer_signal(phb_ctx*, int n, uint64_t* const* h_flag_ptrs, const uint64_t* h_values);
 int phb_peer_wait(phb_ctx*, int n, uint64_t* const* h_flag_ptrs, const uint64_t* h_values, double timeout_s);
+
+/* One whole exchange phase in one call, with DEVICE-side phase counters: pack (K8 batch, remote stores into the neighbours'
+ * receive areas) -> signal -> local box ops -> wait -> unpack.  The value a signal publishes / a wait expects is
+ * *counter + 1, advanced by the kernel itself (counters are device words of the caller, one per peer and direction), so
+ * the descriptor of a phase is built once and never changes.  Replaces the SAMRAI RefineSchedule::fillData of one
+ * communicator (hybrid_hybrid_messenger_strategy.hpp:376-497). */
+typedef struct {
+    const phb_box_desc* pre;   int n_pre;   uint64_t total_pre;   /* device tables as for phb_box_op_batch (may be empty) */
+    const phb_box_desc* local; int n_local; uint64_t total_local;
+    const phb_box_desc* post;  int n_post;  uint64_t total_post;
+    int       n_signal;  uint64_t* signal_flag[32]; uint64_t* signal_counter[32]; /* flag: device word in the PEER's arena */
+    int       n_wait;    uint64_t* wait_flag[32];   uint64_t* wait_counter[32];   /* flag: device word in MY arena        */
+    double    timeout_s;
+} phb_peer_phase_desc;
+int phb_peer_phase(phb_ctx*, const phb_peer_phase_desc* h_phase);
+
 
 #ifdef __cplusplus
 }

@@ -638,8 +638,8 @@ public:
                 if (!pop.cell_start_next)
                     pop.cell_start_next = std::make_unique<DeviceBuffer>(ctx, words);
                 auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
-                ctx.check(phb_push_plan(ctx.get(), layout.c(), &E, &B, pop.domain.c(), pop.mass(), dt, &dom, keep.data(),
-                                        int(keep.size()), new_start));
+                ctx.check(phb_push_plan(ctx.get(), layout.c(), &E, &B, pop.domain.c(), nsorted, pop.mass(), dt, &dom, cs,
+                                        keep.data(), int(keep.size()), new_start));
                 ctx.check(phb_deposit_scatter(ctx.get(), layout.c(), pop.domain.c(), nsorted, pop.rho_n.data(),
                                               pop.rho_q.data(), &F, 1., keep.data(), int(keep.size()), &dom, cs, keep.data(),
                                               int(keep.size()), pop.spare.c(), new_start));

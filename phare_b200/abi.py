@@ -46,6 +46,16 @@ class BoxDesc(C.Structure):
                 ("op", C.c_int32), ("first", C.c_uint64)]
 
 
+class PeerPhaseDesc(C.Structure):
+    """phb_peer_phase_desc: one exchange phase (pack -> signal -> local -> wait -> unpack), built once"""
+    _fields_ = [("pre", C.c_void_p), ("n_pre", C.c_int), ("total_pre", C.c_uint64),
+                ("local", C.c_void_p), ("n_local", C.c_int), ("total_local", C.c_uint64),
+                ("post", C.c_void_p), ("n_post", C.c_int), ("total_post", C.c_uint64),
+                ("n_signal", C.c_int), ("signal_flag", C.c_void_p * 32), ("signal_counter", C.c_void_p * 32),
+                ("n_wait", C.c_int), ("wait_flag", C.c_void_p * 32), ("wait_counter", C.c_void_p * 32),
+                ("timeout_s", C.c_double)]
+
+
 class FieldView(C.Structure):
     """phb_field_view: array + AMR field index of its first element"""
     _fields_ = [("data", C.c_void_p), ("shape", C.c_uint32 * 3), ("lo", C.c_int32 * 3)]
@@ -164,8 +174,8 @@ _PROTOS = {
     "phb_gather": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
                              C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_void_p]),
     "phb_push_plan": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
-                                C.POINTER(Particles), C.c_double, C.c_double, C.POINTER(Box), C.POINTER(Box), C.c_int,
-                                C.c_void_p]),
+                                C.POINTER(Particles), C.c_size_t, C.c_double, C.c_double, C.POINTER(Box), C.c_void_p,
+                                C.POINTER(Box), C.c_int, C.c_void_p]),
     "phb_push_cells": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
                                  C.POINTER(Particles), C.POINTER(Particles), C.c_size_t, C.c_double, C.c_double,
                                  C.POINTER(Box), C.c_void_p]),
@@ -204,6 +214,7 @@ _PROTOS = {
     "phb_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "phb_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "phb_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "phb_peer_phase": (C.c_int, [C.c_void_p, C.POINTER(PeerPhaseDesc)]),
     "phb_peer_signal": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "phb_peer_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_double]),
     "phb_box_unpack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p,

@@ -174,6 +174,8 @@ struct phb_ctx
     int plan_kind         = 0;     // 0: none / phb_bin_plan (slots in scratch); 2: tile plan (stay / arrivals / slots in plan_buf)
     void* plan_buf        = nullptr; // tile plan: [stay nk+1 | arrivals nk+1 | slot n | scan scratch]
     size_t plan_bytes     = 0;
+    void* strip_counter   = nullptr; // work counter of the strip kernel (strip.cuh)
+    bool no_strip         = true;  // PHB_STRIP=1 routes K1 of a cell-ordered store through the strip kernel (strip.cuh)
     bool no_tile          = false; // PHB_NO_TILE=1: the cell-ordered passes use the round-1 kernels (E,B through L1)
 };
 

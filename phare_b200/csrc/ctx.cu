@@ -81,6 +81,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
         ctx->no_fused_cells = e[0] == '1';
     if (const char* e = getenv("PHB_NO_TILE"))
         ctx->no_tile = e[0] == '1';
+    if (const char* e = getenv("PHB_STRIP")) // the strip kernel is opt-in: measured no faster than the streaming K1
+        ctx->no_strip = e[0] != '1';
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = ctx;
     return PHB_OK;
@@ -98,6 +100,8 @@ void phb_destroy(phb_ctx* ctx)
         cudaFree(ctx->em_pack);
     if (ctx->plan_buf)
         cudaFree(ctx->plan_buf);
+    if (ctx->strip_counter)
+        cudaFree(ctx->strip_counter);
     if (ctx->d_err)
         cudaFree(ctx->d_err);
     if (ctx->h_err)

@@ -58,9 +58,93 @@ __global__ void peer_wait_kernel(const __grid_constant__ FlagList F, long long m
         __nanosleep(200);
     }
 }
+// ---- device-side phase counters: the value a signal publishes / a wait expects lives in device memory and is advanced by
+// the kernel itself (one thread per flag, stream order), so the launch arguments of a phase never change: one C call per
+// phase with precomputed arguments (and a phase that could be captured in a CUDA graph)
+struct AutoFlagList
+{
+    unsigned long long* flag[MAX_PEER_FLAGS];    // signal: word in the PEER's arena; wait: word in mine
+    unsigned long long* counter[MAX_PEER_FLAGS]; // my own count of phases delivered to / received from that peer
+    int n;
+};
+
+__global__ void peer_signal_auto_kernel(const __grid_constant__ AutoFlagList F)
+{
+    int const t = threadIdx.x;
+    if (t >= F.n)
+        return;
+    unsigned long long const v = *F.counter[t] + 1ull;
+    *F.counter[t]              = v;
+    __threadfence_system(); // the remote stores of the kernels before us are ordered before the flag
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(F.flag[t]), "l"(v) : "memory");
+}
+
+__global__ void peer_wait_auto_kernel(const __grid_constant__ AutoFlagList F, long long max_cycles, DevError* err)
+{
+    int const t = threadIdx.x;
+    if (t >= F.n)
+        return;
+    unsigned long long const value = *F.counter[t] + 1ull;
+    *F.counter[t]                  = value;
+    long long const t0             = clock64();
+    unsigned long long seen;
+    while (true)
+    {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(F.flag[t]) : "memory");
+        if (seen >= value)
+            break;
+        if (clock64() - t0 > max_cycles)
+        {
+            if (atomicCAS(&err->code, 0, int(PHB_ERR_PEER_TIMEOUT)) == 0)
+            {
+                err->index = (unsigned long long)t;
+                err->delta = double(seen);
+                err->vel   = double(value);
+            }
+            break;
+        }
+        __nanosleep(200);
+    }
+}
 } // namespace phb
 
 extern "C" {
+int phb_peer_phase(phb_ctx* ctx, const phb_peer_phase_desc* ph)
+{
+    if (!ctx || !ph || ph->n_signal < 0 || ph->n_signal > phb::MAX_PEER_FLAGS || ph->n_wait < 0
+        || ph->n_wait > phb::MAX_PEER_FLAGS)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_peer_phase: invalid argument");
+    if (int rc = phb_box_op_batch(ctx, ph->pre, ph->n_pre, ph->total_pre))
+        return rc;
+    if (ph->n_signal)
+    {
+        phb::AutoFlagList F;
+        F.n = ph->n_signal;
+        for (int i = 0; i < F.n; ++i)
+        {
+            F.flag[i]    = reinterpret_cast<unsigned long long*>(ph->signal_flag[i]);
+            F.counter[i] = reinterpret_cast<unsigned long long*>(ph->signal_counter[i]);
+        }
+        phb::peer_signal_auto_kernel<<<1, 32, 0, ctx->stream>>>(F);
+        PHB_LAUNCH_CHECK(ctx);
+    }
+    if (int rc = phb_box_op_batch(ctx, ph->local, ph->n_local, ph->total_local))
+        return rc;
+    if (ph->n_wait)
+    {
+        phb::AutoFlagList F;
+        F.n = ph->n_wait;
+        for (int i = 0; i < F.n; ++i)
+        {
+            F.flag[i]    = reinterpret_cast<unsigned long long*>(ph->wait_flag[i]);
+            F.counter[i] = reinterpret_cast<unsigned long long*>(ph->wait_counter[i]);
+        }
+        phb::peer_wait_auto_kernel<<<1, 32, 0, ctx->stream>>>(F, (long long)(ph->timeout_s * 2.0e9), ctx->d_err);
+        PHB_LAUNCH_CHECK(ctx);
+    }
+    return phb_box_op_batch(ctx, ph->post, ph->n_post, ph->total_post);
+}
+
 int phb_ipc_export(phb_ctx* ctx, void* d_ptr, unsigned char h_handle[64])
 {
     if (!ctx || !d_ptr || !h_handle)

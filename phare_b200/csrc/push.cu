@@ -10,38 +10,11 @@
 // with the cell-sorted store a warp sits in one or two cells, so every gather load is a one- or
 // two-address broadcast that hits L1/L2; field arrays are (o+1)^d-fold reused and never the
 // HBM bound.
-#include "bin_core.cuh"
 #include "deposit_core.cuh"
-#include "push_core.cuh"
+#include "strip.cuh"
 
 namespace phb
 {
-// the count half of the re-binning (bin_count_kernel of bin_core.cuh) done while the pushed particle is still in
-// registers: key of the new cell, one atomic per distinct key of the warp, the particle's slot inside its new cell
-template<int DIM>
-struct PlanCount
-{
-    KeySpace<DIM> K;
-    uint32_t* count; // histogram over the keys (zeroed by the caller, scanned afterwards)
-    uint32_t* slot;  // [n]
-};
-
-template<int DIM>
-__device__ __forceinline__ void plan_count(const PlanCount<DIM>& C, size_t i, const int (&icell)[DIM], bool live)
-{
-    unsigned const key    = live ? bin_key<DIM>(C.K, icell) : 0xffffffffu;
-    unsigned const peers  = __match_any_sync(0xffffffffu, key);
-    unsigned const lane   = threadIdx.x & 31;
-    int const leader      = __ffs(peers) - 1;
-    unsigned const before = __popc(peers & ((1u << lane) - 1));
-    unsigned base         = 0;
-    if (live && int(lane) == leader)
-        base = atomicAdd(C.count + key, unsigned(__popc(peers)));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (live)
-        __stcs(C.slot + i, base + before);
-}
-
 // the per-particle work shared by both kernels: move_particle (push_core.cuh) + streaming stores
 template<int DIM, int ORDER, bool EXACT, bool HAS_FIRST>
 __device__ __forceinline__ void push_particle(const PushParams<DIM>& P, size_t i, int (&icell)[DIM],
@@ -329,10 +302,107 @@ int launch_push_variant(phb_ctx* ctx, const PushParams<DIM>& P, const PlanCount<
     return PHB_OK;
 }
 
+// ---- strip kernel (strip.cuh): the cell-ordered part [0, n_sorted) of a store, E,B of each strip staged in shared memory
+template<int DIM, int ORDER, bool EXACT, bool PLAN>
+int launch_strips(phb_ctx* ctx, const PushParams<DIM>& P, const PlanCount<DIM>& C, const phb_box* domain,
+                  const uint32_t* cell_start, size_t n_sorted)
+{
+    using SG = StripGeom<DIM, ORDER>;
+    StripParams<DIM> S{};
+    S.cell_start = cell_start;
+    S.n_sorted   = n_sorted;
+    unsigned rows = 1;
+    for (int d = 0; d < DIM; ++d)
+    {
+        S.lo[d]  = domain->lower[d];
+        S.ext[d] = unsigned(domain->upper[d] - domain->lower[d] + 1);
+        if (d < DIM - 1)
+            rows *= S.ext[d];
+    }
+    S.strips_per_row = (S.ext[DIM - 1] + SG::R - 1) / SG::R;
+    S.nstrips        = rows * S.strips_per_row;
+    if (!ctx->strip_counter)
+        PHB_CUDA(ctx, cudaMalloc(&ctx->strip_counter, 256));
+    S.counter = static_cast<unsigned*>(ctx->strip_counter);
+    PHB_CUDA(ctx, cudaMemsetAsync(S.counter, 0, sizeof(unsigned), ctx->stream));
+    constexpr int smem = strip_smem_bytes<DIM, ORDER>();
+    auto kernel        = push_strip_kernel<DIM, ORDER, EXACT, PLAN>;
+    static bool configured = false; // per instantiation
+    if (!configured)
+    {
+        PHB_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    constexpr int ctas  = (smem + 1024) * PHB_STRIP_CTAS <= 227 * 1024 ? PHB_STRIP_CTAS : 2;
+    unsigned const grid = std::min<unsigned>(S.nstrips, unsigned(ctx->sm_count) * ctas);
+    kernel<<<grid, STRIP_BS, smem, ctx->stream>>>(P, S, C);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+
+// the strip kernel needs: the ordering of the store, the key box inside the patch's own cells (its E,B rows exist), 16-byte
+// aligned columns
+template<int DIM>
+bool strips_usable(phb_ctx* ctx, const phb_layout* L, const PushParams<DIM>& P, const phb_particles* parts, const phb_box* domain,
+                   const uint32_t* cell_start, size_t n_sorted)
+{
+    (void)parts;
+    if (ctx->no_tma || ctx->no_strip || !cell_start || n_sorted == 0)
+        return false;
+    for (int d = 0; d < DIM; ++d)
+        if (domain->lower[d] < L->amr_lower[d] || domain->upper[d] >= L->amr_lower[d] + int(L->ncells[d]))
+            return false;
+    bool ok = aligned16(P.in.charge);
+    for (int d = 0; d < DIM; ++d)
+        ok = ok && aligned16(P.in.icell[d]) && aligned16(P.in.delta[d]);
+    for (int c = 0; c < 3; ++c)
+        ok = ok && aligned16(P.in.v[c]);
+    return ok;
+}
+
+// push of parts[first, n) by the per-particle kernels (the particles appended since the last binning)
+template<int DIM, int ORDER, bool EXACT, bool PLAN>
+int launch_tail(phb_ctx* ctx, const PushParams<DIM>& P, const PlanCount<DIM>& C, size_t first)
+{
+    if (first >= P.n)
+        return PHB_OK;
+    unsigned const grid = unsigned((P.n - first + 255) / 256);
+    if constexpr (PLAN)
+        push_plan_kernel<DIM, ORDER, EXACT><<<grid, 256, 0, ctx->stream>>>(P, first, C);
+    else
+        push_kernel<DIM, ORDER, EXACT, false><<<grid, 256, 0, ctx->stream>>>(P, first);
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+
+// K1 (+ optional plan) over a whole store: strips for the ordered part when possible, the streaming kernels otherwise
+template<int DIM, int ORDER, bool PLAN>
+int push_store(phb_ctx* ctx, const phb_layout* L, const PushParams<DIM>& P, const PlanCount<DIM>& C, const phb_particles* parts,
+               const phb_box* domain, const uint32_t* cell_start, size_t n_sorted)
+{
+    if (n_sorted > P.n)
+        n_sorted = P.n;
+    // the bulk copies of a strip round its particle range up to a multiple of 4: keep them inside the columns (a store
+    // filled to a capacity that is not a multiple of 4 leaves its last particles to the per-particle kernel)
+    n_sorted = std::min(n_sorted, parts->capacity & ~size_t(3));
+    if (strips_usable<DIM>(ctx, L, P, parts, domain, cell_start, n_sorted))
+    {
+        int rc = ctx->exact ? launch_strips<DIM, ORDER, true, PLAN>(ctx, P, C, domain, cell_start, n_sorted)
+                            : launch_strips<DIM, ORDER, false, PLAN>(ctx, P, C, domain, cell_start, n_sorted);
+        if (rc)
+            return rc;
+        return ctx->exact ? launch_tail<DIM, ORDER, true, PLAN>(ctx, P, C, n_sorted)
+                          : launch_tail<DIM, ORDER, false, PLAN>(ctx, P, C, n_sorted);
+    }
+    return ctx->exact ? launch_push_variant<DIM, ORDER, true, false, PLAN>(ctx, P, C)
+                      : launch_push_variant<DIM, ORDER, false, false, PLAN>(ctx, P, C);
+}
+
 // phb_push_plan: push in place + the count half of phb_bin_plan in the same pass
 template<int DIM, int ORDER>
 int push_plan_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B, phb_particles* parts,
-                    double mass, double dt, const phb_box* domain, const phb_box* keep, int nkeep, uint32_t* d_cell_start)
+                    size_t n_sorted, double mass, double dt, const phb_box* domain, const uint32_t* cell_start_old,
+                    const phb_box* keep, int nkeep, uint32_t* d_cell_start)
 {
     size_t const n = parts->n;
     PlanCount<DIM> C;
@@ -354,14 +424,34 @@ int push_plan_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, co
         P.in = P.out         = make_part(*parts);
         P.n                  = n;
         P.copy_weight_charge = false;
-        int const rc = ctx->exact ? launch_push_variant<DIM, ORDER, true, false, true>(ctx, P, C)
-                                  : launch_push_variant<DIM, ORDER, false, false, true>(ctx, P, C);
-        if (rc)
+        if (int rc = push_store<DIM, ORDER, true>(ctx, L, P, C, parts, domain, cell_start_old, n_sorted))
             return rc;
     }
     ctx->plan_n    = n;
     ctx->plan_kind = 0;
     return exclusive_scan(ctx, d_cell_start, d_cell_start, nk + 1, C.slot + n);
+}
+
+// phb_push_cells: K1 of a cell-ordered store (in place, or into a store that shares the weight / charge columns)
+template<int DIM, int ORDER>
+int push_cells_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B, const phb_particles* in,
+                     phb_particles* out, size_t n_sorted, double mass, double dt, const phb_box* domain,
+                     const uint32_t* cell_start)
+{
+    if (in->weight != out->weight || in->n == 0)
+        return phb_push(ctx, L, E, B, in, out, mass, dt, nullptr);
+    PushParams<DIM> P;
+    if (int rc = prepare_push<DIM>(ctx, L, E, B, mass, dt, nullptr, P))
+        return rc;
+    P.in                 = make_part(*in);
+    P.out                = make_part(*out);
+    P.n                  = in->n;
+    P.copy_weight_charge = false;
+    PlanCount<DIM> C{};
+    if (int rc = push_store<DIM, ORDER, false>(ctx, L, P, C, in, domain, cell_start, n_sorted))
+        return rc;
+    out->n = in->n;
+    return PHB_OK;
 }
 
 template<int DIM, int ORDER>
@@ -420,15 +510,16 @@ extern "C" int phb_gather(phb_ctx* ctx, const phb_layout* L, const phb_vecfield*
 }
 
 extern "C" int phb_push_plan(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
-                             phb_particles* parts, double mass, double dt, const phb_box* domain, const phb_box* keep,
-                             int nkeep, uint32_t* d_cell_start)
+                             phb_particles* parts, size_t n_sorted, double mass, double dt, const phb_box* domain,
+                             const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, uint32_t* d_cell_start)
 {
     if (!phb::valid_layout(ctx, L) || !E || !B || !parts || !domain || !d_cell_start || nkeep < 0
         || nkeep > phb::MAX_BOXES || (nkeep > 0 && !keep))
         return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_plan: invalid argument");
     if (parts->n >= 0xffffffffull)
         return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_plan: more than 2^32-1 particles in one store");
-#define PHB_PP(D, O) phb::push_plan_order<D, O>(ctx, L, E, B, parts, mass, dt, domain, keep, nkeep, d_cell_start)
+#define PHB_PP(D, O)                                                                                                 \
+    phb::push_plan_order<D, O>(ctx, L, E, B, parts, n_sorted, mass, dt, domain, d_cell_start_old, keep, nkeep, d_cell_start)
     switch (L->dim * 10 + L->interp)
     {
         case 11: return PHB_PP(1, 1);
@@ -442,6 +533,30 @@ extern "C" int phb_push_plan(phb_ctx* ctx, const phb_layout* L, const phb_vecfie
         default: return PHB_PP(3, 3);
     }
 #undef PHB_PP
+}
+
+extern "C" int phb_push_cells(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
+                              const phb_particles* in, phb_particles* out, size_t n_sorted, double mass, double dt,
+                              const phb_box* domain, const uint32_t* d_cell_start)
+{
+    if (!phb::valid_layout(ctx, L) || !E || !B || !in || !out || !domain || !d_cell_start)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_cells: invalid argument");
+    if (out->capacity < in->n)
+        return phb::set_error(ctx, PHB_ERR_CAPACITY, "phb_push_cells: out.capacity < in.n");
+#define PHB_PC(D, O) phb::push_cells_order<D, O>(ctx, L, E, B, in, out, n_sorted, mass, dt, domain, d_cell_start)
+    switch (L->dim * 10 + L->interp)
+    {
+        case 11: return PHB_PC(1, 1);
+        case 12: return PHB_PC(1, 2);
+        case 13: return PHB_PC(1, 3);
+        case 21: return PHB_PC(2, 1);
+        case 22: return PHB_PC(2, 2);
+        case 23: return PHB_PC(2, 3);
+        case 31: return PHB_PC(3, 1);
+        case 32: return PHB_PC(3, 2);
+        default: return PHB_PC(3, 3);
+    }
+#undef PHB_PC
 }
 
 extern "C" int phb_push(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,

@@ -1,6 +1,5 @@
 // Entry points of the tile kernels (tile.cuh) and the scatter pass of the re-binning they plan.
 //
-//   phb_push_cells         K1 on the cell-ordered store, E,B block in shared memory (BorisPusher::move, boris.hpp:93-138)
 //   phb_push_deposit_plan  the whole of IonUpdater::updateAndDepositAll_ for the domain array (ion_updater.hpp:228-295)
 //                          except the data movement of its partition / erase: push in place + deposit + per-cell
 //                          stay / arrival counts + scan -> the new cell_start
@@ -360,66 +359,6 @@ int scatter_planned_dim(phb_ctx* ctx, const phb_layout* L, const phb_particles* 
     return PHB_OK;
 }
 
-// ---- phb_push_cells --------------------------------------------------------------------------------------------
-template<int DIM, int ORDER>
-int push_cells_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
-                     const phb_particles* in, phb_particles* out, size_t n_sorted, double mass, double dt,
-                     const phb_box* domain, const uint32_t* cell_start)
-{
-    bool const wq = in->weight != out->weight;
-    if constexpr (!tile_supported<DIM, ORDER>())
-        return phb_push(ctx, L, E, B, in, out, mass, dt, nullptr);
-    else
-    {
-        if (wq || ctx->no_tile || n_sorted == 0)
-            return phb_push(ctx, L, E, B, in, out, mass, dt, nullptr);
-        size_t const n = in->n;
-        if (n_sorted > n)
-            n_sorted = n;
-        PushParams<DIM> P;
-        if (int rc = prepare_push<DIM>(ctx, L, E, B, mass, dt, nullptr, P))
-            return rc;
-        P.in                 = make_part(*in);
-        P.out                = make_part(*out);
-        P.n                  = n;
-        P.copy_weight_charge = false;
-        DepositParams<DIM> A;
-        phb_vecfield none{};
-        prepare_deposit<DIM>(L, in, 0, n_sorted, nullptr, nullptr, &none, 1., nullptr, 0, domain, cell_start, A);
-        TileRecords R{};
-        KeySpace<DIM> K{};
-        TileParams<DIM> T{};
-        if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{false, true, false}, P, A, R, K, T))
-            return rc;
-        if (n_sorted < n)
-        {
-            // the particles appended since the last binning: the streaming K1 on a view of the tail
-            phb_particles tin = *in, tout = *out;
-            for (int d = 0; d < DIM; ++d)
-            {
-                tin.icell[d] += n_sorted;
-                tin.delta[d] += n_sorted;
-                tout.icell[d] += n_sorted;
-                tout.delta[d] += n_sorted;
-            }
-            for (int c = 0; c < 3; ++c)
-            {
-                tin.v[c] += n_sorted;
-                tout.v[c] += n_sorted;
-            }
-            tin.weight += n_sorted;
-            tin.charge += n_sorted;
-            tout.weight += n_sorted;
-            tout.charge += n_sorted;
-            tin.n         = n - n_sorted;
-            tout.capacity = out->capacity - n_sorted;
-            if (int rc = phb_push(ctx, L, E, B, &tin, &tout, mass, dt, nullptr))
-                return rc;
-        }
-        out->n = n;
-        return PHB_OK;
-    }
-}
 } // namespace phb
 
 #define PHB_BY_DIM_ORDER(L, CALL)                                                                                  \
@@ -479,17 +418,4 @@ extern "C" int phb_scatter_planned(phb_ctx* ctx, const phb_layout* L, const phb_
     ctx->plan_n    = size_t(-1);
     ctx->plan_kind = 0;
     return rc;
-}
-
-extern "C" int phb_push_cells(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const phb_vecfield* B,
-                              const phb_particles* in, phb_particles* out, size_t n_sorted, double mass, double dt,
-                              const phb_box* domain, const uint32_t* d_cell_start)
-{
-    if (!phb::valid_layout(ctx, L) || !E || !B || !in || !out || !domain || !d_cell_start)
-        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_push_cells: invalid argument");
-    if (out->capacity < in->n)
-        return phb::set_error(ctx, PHB_ERR_CAPACITY, "phb_push_cells: out.capacity < in.n");
-#define CALL(D, O) phb::push_cells_order<D, O>(ctx, L, E, B, in, out, n_sorted, mass, dt, domain, d_cell_start)
-    PHB_BY_DIM_ORDER(L, CALL)
-#undef CALL
 }

@@ -286,10 +286,13 @@ class Context:
             rho_n.ptr, rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel),
             C.byref(domain) if domain is not None else None, cell_start.ptr if cell_start is not None else None))
 
-    def push_plan(self, layout, E, B, parts, mass, dt, domain, keep, cell_start_new):
-        """phb_push_plan: push in place + the count half of the re-binning in one pass (-> cell_start_new)"""
-        self._check(self.lib.phb_push_plan(self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(parts.c), mass, dt,
-                                           C.byref(domain), abi.box_array(keep), len(keep), cell_start_new.ptr))
+    def push_plan(self, layout, E, B, parts, mass, dt, domain, keep, cell_start_new, n_sorted=0, cell_start_old=None):
+        """phb_push_plan: push in place + the count half of the re-binning in one pass (-> cell_start_new); with the
+        current ordering (cell_start_old, n_sorted) the ordered part goes through the strip kernel"""
+        self._check(self.lib.phb_push_plan(self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(parts.c),
+                                           int(n_sorted), mass, dt, C.byref(domain),
+                                           cell_start_old.ptr if cell_start_old is not None else None,
+                                           abi.box_array(keep), len(keep), cell_start_new.ptr))
 
     def push_cells(self, layout, E, B, pin, pout, n_sorted, mass, dt, domain, cell_start):
         """phb_push_cells: K1 on the cell-ordered store, E,B block of each CTA staged in shared memory"""

@@ -260,6 +260,11 @@ class PeerArena:
         self.cursor = self.FLAGS
         self.sent = [0] * self.size      # phases I delivered to each rank
         self.received = [0] * self.size  # phases each rank delivered to me
+        # device-side phase counters (phb_peer_phase): words of MY flag block that only my own kernels touch;
+        # flag words 8 * r for r < size <= 128 occupy [0, 1024)
+        assert self.size <= 128
+        self.sent_counter = lambda r: self.base[self.me] + 2048 + 8 * r
+        self.recv_counter = lambda r: self.base[self.me] + 3072 + 8 * r
         # GPU-clock time a stream may wait for a neighbour's flag: it also covers the neighbour's HOST work between two
         # phases (particle dumps, restarts), so it is generous; after a timeout no exchange phase applies anything any
         # more (box_op_batch_kernel) and the next poll raises PHB_ERR_PEER_TIMEOUT
@@ -355,6 +360,13 @@ class HybridMessenger:
         return self._compiled[key]
 
     def _run(self, phase, key=None):
+        # bench.py: one CUDA-event pair around every exchange phase (GPU-side duration, waits for the neighbours included)
+        timed = getattr(self.ops, "_timed", None)
+        if timed is not None and getattr(self.ops, "kernel_timing", False):
+            return timed("exchange_phases", lambda: self._run_phase(phase, key))
+        return self._run_phase(phase, key)
+
+    def _run_phase(self, phase, key=None):
         ops = self.ops
         if "peer_dsts" in phase:
             # every receive area exists twice and a phase alternates between the two: a neighbour writes area (k & 1) of
@@ -362,11 +374,9 @@ class HybridMessenger:
             # stream issues after the unpack of run k.  No assumption about which other phases run in between.
             half = phase["halves"][phase["runs"] & 1]
             phase["runs"] += 1
-            ops.run_box_ops(half["pre"])
-            self.arena.signal(phase["peer_dsts"])
-            ops.run_box_ops(half["local"])
-            self.arena.wait(phase["peer_srcs"])
-            ops.run_box_ops(half["post"])
+            # one C call: pack -> signal -> local -> wait -> unpack, with the phase counters kept on the device
+            ctx = self.arena.ctx
+            ctx._check(ctx.lib.phb_peer_phase(ctx.h, half["desc"]))
             return
         ops.run_box_ops(phase["pre"])      # packs for every peer (+ the local copies when they are independent)
         ops.run_box_ops(phase["local"])    # local operations that must follow the packs (in-place max)
@@ -473,14 +483,40 @@ class HybridMessenger:
             else:
                 half["pre"], half["local"] = ops.compile_box_ops(pack + local), None
             half["post"] = ops.compile_box_ops(unpack)
+            half["desc"] = self._phase_desc(half, phase["peer_dsts"], phase["peer_srcs"])
             phase["halves"].append(half)
         return phase
 
-    def migrate_particles(self, layouts, patch_ghost, domain, ensure=None):
+    def _phase_desc(self, half, dsts, srcs):
+        """the constant argument block of phb_peer_phase for one half of a phase"""
+        import ctypes as C
+        arena = self.arena
+        d = abi.PeerPhaseDesc()
+        for name in ("pre", "local", "post"):
+            comp = half[name]
+            if comp is not None:
+                table, n, total = comp
+                setattr(d, name, table.data_ptr())
+                setattr(d, "n_" + name, n)
+                setattr(d, "total_" + name, total)
+        d.n_signal, d.n_wait = len(dsts), len(srcs)
+        for i, r in enumerate(dsts):
+            d.signal_flag[i] = arena.base[r] + 8 * arena.me  # my word in rank r's flag block
+            d.signal_counter[i] = arena.sent_counter(r)
+        for i, r in enumerate(srcs):
+            d.wait_flag[i] = arena.base[arena.me] + 8 * r
+            d.wait_counter[i] = arena.recv_counter(r)
+        d.timeout_s = arena.timeout_s
+        return d
+
+    def migrate_particles(self, layouts, patch_ghost, domain, ensure=None, vote=None):
         """fillIonGhostParticles for one population.
         patch_ghost: {pid: (store, first, last)} the new patch-ghost particles of my patches;
-        domain: {pid: store} destination stores of my patches.  Returns the number received per patch."""
+        domain: {pid: store} destination stores of my patches.  Returns the number received per patch.
+        vote: an integer every rank contributes; its maximum over the ranks rides on the count exchange and is left in
+        self.last_vote (the error vote of mpi::any_errors() without a collective of its own)"""
         ops, me = self.ops, self.me
+        self.last_vote = vote
         received = {pid: 0 for pid in domain}
         remote = {}  # (dst owner, dst pid) -> staging store
         by_src = {}
@@ -510,19 +546,23 @@ class HybridMessenger:
                 if d.owner == me:
                     received[d.id] += c
         if self.comm.size > 1:
-            self._exchange_particles(layouts, remote, domain, received, ensure)
+            self._exchange_particles(layouts, remote, domain, received, ensure, vote)
         return received
 
-    def _exchange_particles(self, layouts, remote, domain, received, ensure=None):
+    def _exchange_particles(self, layouts, remote, domain, received, ensure=None, vote=None):
         """remote: {(owner rank, patch id): staging store} -> appended to domain[patch id] on the owner.
         ensure(pid, needed) -> store: lets the caller re-allocate a destination store that is too small"""
         ops, comm, geom = self.ops, self.comm, self.geom
         # every rank announces, per destination patch, how many particles it ships
         npatch = len(geom.patches)
-        counts = [[0] * npatch for _ in range(comm.size)]
+        counts = [[0] * npatch + [int(vote or 0)] for _ in range(comm.size)]
         for (owner, pid), st in remote.items():
             counts[owner][pid] = ops.count(st)
-        incoming = comm.alltoall_counts(counts)  # incoming[src rank][pid]
+        _t = getattr(ops, "_timed", None) if getattr(ops, "kernel_timing", False) else None
+        incoming = (_t("fp_alltoall_counts", lambda: comm.alltoall_counts(counts)) if _t
+                    else comm.alltoall_counts(counts))  # incoming[src rank][pid], last column: that rank's vote
+        if vote is not None:
+            self.last_vote = max(int(vote), max(int(row[npatch]) for row in incoming))
         any_layout = next(iter(layouts.values()), None)  # only carries dim / interp, which the back end knows
         sends, recvs, recv_meta = {}, {}, {}
         for peer in range(comm.size):
@@ -535,7 +575,9 @@ class HybridMessenger:
             if inc:
                 recvs[peer] = ops.new_particle_buffer(any_layout, sum(n for _, n in inc))
                 recv_meta[peer] = inc
-        comm.exchange({p: ops.as_tensor(b) for p, b in sends.items()}, {p: ops.as_tensor(b) for p, b in recvs.items()})
+        _x = lambda: comm.exchange({p: ops.as_tensor(b) for p, b in sends.items()},
+                                   {p: ops.as_tensor(b) for p, b in recvs.items()})
+        _t("fp_send_recv", _x) if _t else _x()
         for peer, inc in recv_meta.items():
             off = 0
             for pid, n in inc:

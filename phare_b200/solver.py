@@ -162,9 +162,10 @@ class GpuOps:
     def bin(self, layout, pin, pout, domain, keep, cell_start):
         return self._timed("bin", lambda: self.ctx.bin(layout, pin, pout, domain, keep, cell_start))
 
-    def push_plan(self, layout, E, B, parts, mass, dt, domain, keep, cell_start_new):
-        """K1 in place with the count of the re-binning folded in (phb_push_plan)"""
-        self._timed("push", lambda: self.ctx.push_plan(layout, E, B, parts, mass, dt, domain, keep, cell_start_new))
+    def push_plan(self, layout, E, B, parts, mass, dt, domain, keep, cell_start_new, n_sorted=0, cell_start_old=None):
+        """K1 in place with the count of the re-binning folded in (phb_push_plan); strip kernel on the ordered part"""
+        self._timed("push", lambda: self.ctx.push_plan(layout, E, B, parts, mass, dt, domain, keep, cell_start_new,
+                                                       n_sorted, cell_start_old))
 
     def bin_plan(self, layout, pin, domain, keep, cell_start_new):
         self._timed("bin_plan", lambda: self.ctx.bin_plan(layout, pin, domain, keep, cell_start_new))
@@ -457,7 +458,7 @@ class IonUpdater:
                 if planned and hasattr(ops, "push_plan"):
                     # the keys of the re-binning are counted while the pushed particle is still in registers
                     ops.push_plan(L, E, B, pop.domain, pop.mass, dt, patch.domain_box, patch.non_level_ghost,
-                                  pop.cell_start_next)
+                                  pop.cell_start_next, pop.n_sorted, pop.cell_start)
                 else:
                     ops.push(L, E, B, pop.domain, pop.domain, pop.mass, dt)
                     if planned:
@@ -601,21 +602,38 @@ class SolverPPC:
         """deferred half of moveIons_(all): re-binning, fillIonGhostParticles + patchGhostParticles.clear()
         (:581-585), and mpi::any_errors() (:549-563) for both sweeps of the step"""
         ops, msg = self.ops, self.messenger
-        for p in self.patches:
-            self.updater.maintain_arrays(p)
+        if getattr(ops, "kernel_timing", False) and not getattr(self, "_in_finish", False):
+            # bench.py: the host-synchronising tail of the step (counts, migration, error vote) as one bracket
+            self._in_finish = True
+            try:
+                return ops._timed("finish_particles", self._finish_particles)
+            finally:
+                self._in_finish = False
+        if getattr(ops, "kernel_timing", False):
+            ops._timed("fp_maintain_arrays", lambda: [self.updater.maintain_arrays(p) for p in self.patches])
+        else:
+            for p in self.patches:
+                self.updater.maintain_arrays(p)
         npop = self.npop
+        # mpi::any_errors(): every kernel that can raise (the pushes, the exchange phases) has run, and the stream is idle
+        # after the counts above.  With several ranks the vote rides on the count exchange of the first population.
+        err = ops.poll_error()
+        voted = None
         for i in range(npop):
             msg.migrate_particles(self.layouts,
                                   {p.geom.id: (p.pops[i].patch_ghost, 0, ops.count(p.pops[i].patch_ghost))
                                    for p in self.patches},
-                                  {p.geom.id: p.pops[i].domain for p in self.patches})
+                                  {p.geom.id: p.pops[i].domain for p in self.patches}, vote=err if i == 0 else None)
+            if i == 0 and self.comm.size > 1 and hasattr(msg, "last_vote"):
+                voted = msg.last_vote
             for p in self.patches:
                 ops.set_count(p.pops[i].patch_ghost, 0)
         for p in self.patches:
             for pop in p.pops:
                 self._ensure_headroom(pop)
-        err = ops.poll_error()
-        if self.comm.allreduce_max(err):
+        if voted is None:
+            voted = self.comm.allreduce_max(err)
+        if voted:
             raise RuntimeError("Updater::updatePopulations: " + (getattr(ops, "last_error", "") or "error on another rank"))
 
     GROW_AT, GROW_BY = 0.85, 1.5

@@ -22,18 +22,20 @@ SHAPES = {1: [300], 2: [21, 37], 3: [9, 6, 19]}
 def ctxs():
     cache = {}
 
-    def get(dim, interp, no_tile=False):
-        key = (dim, interp, no_tile)
+    def get(dim, interp, no_tile=False, strip=False):
+        key = (dim, interp, no_tile, strip)
         if key not in cache:
-            old = os.environ.get("PHB_NO_TILE")
+            old = {k: os.environ.get(k) for k in ("PHB_NO_TILE", "PHB_STRIP")}
             os.environ["PHB_NO_TILE"] = "1" if no_tile else "0"
+            os.environ["PHB_STRIP"] = "1" if strip else "0"
             try:
                 cache[key] = Context(dim, interp)
             finally:
-                if old is None:
-                    del os.environ["PHB_NO_TILE"]
-                else:
-                    os.environ["PHB_NO_TILE"] = old
+                for k, v in old.items():
+                    if v is None:
+                        del os.environ[k]
+                    else:
+                        os.environ[k] = v
         return cache[key]
 
     yield get
@@ -81,9 +83,9 @@ def close(got, want):
 @pytest.mark.parametrize("dim,interp", ALL_DIM_INTERP)
 @pytest.mark.parametrize("in_place", [True, False])
 def test_push_cells_bitexact(ctxs, cpu_oracle, dim, interp, in_place):
-    """K1 with the E,B block in shared memory == the oracle push, bit for bit; vth is large enough for a few per cent
-    of the particles to be pre-pushed two cells away (they gather from global memory instead of the tile)"""
-    ctx = ctxs(dim, interp)
+    """K1 with the E,B of each strip of cells in shared memory (csrc/strip.cuh) == the oracle push, bit for bit; vth is
+    large enough for many particles to be pre-pushed out of their strip's rows (they gather from global memory instead)"""
+    ctx = ctxs(dim, interp, strip=True)
     rng = np.random.default_rng(3000 + 10 * dim + interp)
     L = layout_for(dim, interp)
     ncell = int(np.prod(SHAPES[dim]))
@@ -230,12 +232,13 @@ def test_move_two_cells_is_reported_by_the_tile_kernels(ctxs, cpu_oracle):
     assert sum(counts) == 5000
 
 
+@pytest.mark.parametrize("strips", [True, False], ids=["strip_kernel", "streaming_kernel"])
 @pytest.mark.parametrize("dim,interp", ALL_DIM_INTERP)
-def test_push_plan_equals_push_then_bin_plan(ctxs, cpu_oracle, dim, interp):
+def test_push_plan_equals_push_then_bin_plan(ctxs, cpu_oracle, dim, interp, strips):
     """phb_push_plan (K1 in place with the count of the re-binning folded in) == phb_push in place then phb_bin_plan:
     particles bit-exact in place, the same cell_start, and phb_deposit_scatter consumes the plan to the same re-binned
     store (per-cell multisets) and moments as the oracle's push -> deposit -> bin"""
-    ctx = ctxs(dim, interp)
+    ctx = ctxs(dim, interp, strip=strips)
     rng = np.random.default_rng(5000 + 10 * dim + interp)
     L = layout_for(dim, interp)
     ncell = int(np.prod(SHAPES[dim]))
@@ -255,7 +258,10 @@ def test_push_plan_equals_push_then_bin_plan(ctxs, cpu_oracle, dim, interp):
     cs_old = DeviceArray(ctx, cs.shape, np.uint32).upload(cs)
     cs_new = DeviceArray(ctx, cs.shape, np.uint32)
     dE, dB = DeviceVec(ctx, L, abi.EX, E), DeviceVec(ctx, L, abi.BX, B)
-    ctx.push_plan(L, dE, dB, pin, 1.0, dt, dom, keep, cs_new)
+    if strips:
+        ctx.push_plan(L, dE, dB, pin, 1.0, dt, dom, keep, cs_new, n_sorted, cs_old)
+    else:
+        ctx.push_plan(L, dE, dB, pin, 1.0, dt, dom, keep, cs_new)
     ctx.deposit_scatter(L, pin, n_sorted, rn, rq, F, 1.0, keep, dom, cs_old, keep, pout, cs_new)
     counts = ctx.bin_counts(L, dom, cs_new, pout)
     ctx.poll_error()

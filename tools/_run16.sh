@@ -1,0 +1,8 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --steps 8 --warmup 3 --no-cpu --no-e2e --no-parity > gpurun_out/bench_r2i_n2.json 2> gpurun_out/bench_r2i_n2.err; echo rc=$?; tail -2 gpurun_out/bench_r2i_n2.err
+python -c "
+import json
+d=[json.loads(l) for l in open('gpurun_out/bench_r2i_n2.json') if l.startswith('{')][0]
+print(d['value']/1e9, d['ms_per_step']); print(d['roofline_other'].get('kernel_ms_per_step'))"
