@@ -324,6 +324,8 @@ class HybridMessenger:
         self._plans = {}
         self._compiled = {}
         self._migration = geom.migration_plan()
+        import os as _os
+        self.peer_migration = _os.environ.get("PHB_PEER_MIGRATION", "1") != "0"
         # fixed-size field phases go through NVLink peer memory when every rank drives a GPU of the same node
         self.arena = None
         import os
@@ -549,9 +551,104 @@ class HybridMessenger:
             self._exchange_particles(layouts, remote, domain, received, ensure, vote)
         return received
 
+    # ---- particle migration through NVLink peer memory -----------------------------------------------------------
+    def _peer_migration_state(self):
+        """receive areas for migrating particles in my arena, one per source rank and parity: a header (particles per
+        destination patch + the sender's error vote) and a flat message of fixed capacity (columns CAP apart, so neither
+        side needs the other's total).  Built collectively at the first exchange."""
+        if getattr(self, "_mig", None) is None:
+            import os
+            arena, me = self.arena, self.me
+            npatch = len(self.geom.patches)
+            dsts = sorted({d.owner for (s, d, _, _) in self._migration if s.owner == me and d.owner != me})
+            srcs = sorted({s.owner for (s, d, _, _) in self._migration if d.owner == me and s.owner != me})
+            cap = (int(os.environ.get("PHB_PEER_MIGRATION_CAP", 1 << 18)) + 63) & ~63
+            dim = self.geom.patches[0].box.dim
+            hdr_bytes = ((npatch + 1) * 8 + 255) & ~255
+            payload = arena.ctx.lib.phb_particles_flat_bytes(dim, cap)
+            my_off, their_off = [], []
+            for _ in range(2):
+                mine = {r: arena.alloc(hdr_bytes + payload) for r in srcs}
+                my_off.append(mine)
+                their_off.append(arena.exchange_offsets(mine))
+            desc = abi.PeerPhaseDesc()  # no box ops: only the signal / wait pair with the device-side counters
+            desc.n_signal, desc.n_wait = len(dsts), len(srcs)
+            for i, r in enumerate(dsts):
+                desc.signal_flag[i] = arena.base[r] + 8 * arena.me
+                desc.signal_counter[i] = arena.sent_counter(r)
+            for i, r in enumerate(srcs):
+                desc.wait_flag[i] = arena.base[arena.me] + 8 * r
+                desc.wait_counter[i] = arena.recv_counter(r)
+            desc.timeout_s = arena.timeout_s
+            # the vote reaches everybody only if every rank hears from every other rank
+            complete = len(srcs) == self.comm.size - 1 and len(dsts) == self.comm.size - 1
+            everyone = [None] * self.comm.size
+            self.comm.dist.all_gather_object(everyone, complete)
+            self._mig = dict(dsts=dsts, srcs=srcs, cap=cap, hdr_bytes=hdr_bytes, my_off=my_off, their_off=their_off, desc=desc,
+                             runs=0, npatch=npatch, vote_complete=all(everyone))
+        return self._mig
+
+    def _exchange_particles_peer(self, layouts, remote, domain, received, ensure=None, vote=None):
+        """the migrating particles of one population written straight into the neighbours' receive areas (remote stores
+        over NVLink by the pack kernel), one signal | wait pair, one read-back of the headers: no collective"""
+        import ctypes as C
+        ops, arena, M = self.ops, self.arena, self._peer_migration_state()
+        ctx, lib = arena.ctx, arena.ctx.lib
+        parity = M["runs"] & 1
+        M["runs"] += 1
+        npatch, cap = M["npatch"], M["cap"]
+        keep = []  # host headers stay alive until the copies have run
+        for peer in M["dsts"]:
+            hdr = np.zeros(npatch + 1, np.uint64)
+            base = arena.base[peer] + M["their_off"][parity][peer]
+            off = 0
+            for pid in range(npatch):
+                st = remote.get((peer, pid))
+                n = ops.count(st) if st is not None else 0
+                if not n:
+                    continue
+                if off + n > cap:
+                    raise RuntimeError(f"more than {cap} particles migrate to rank {peer} in one step: raise "
+                                       "PHB_PEER_MIGRATION_CAP (and PHB_PEER_ARENA_MB)")
+                ctx._check(lib.phb_particles_pack(ctx.h, C.byref(st.c), 0, n, C.c_void_p(base + M["hdr_bytes"]), cap, off))
+                hdr[pid] = n
+                off += n
+            hdr[npatch] = int(vote or 0)
+            keep.append(hdr)
+            ctx._check(lib.phb_h2d(ctx.h, C.c_void_p(base), hdr.ctypes.data, hdr.nbytes))
+        ctx._check(lib.phb_peer_phase(ctx.h, M["desc"]))
+        got = {}
+        for src in M["srcs"]:
+            h = np.zeros(npatch + 1, np.uint64)
+            ctx._check(lib.phb_d2h(ctx.h, h.ctypes.data, C.c_void_p(arena.base[arena.me] + M["my_off"][parity][src]), h.nbytes))
+            got[src] = h
+        ctx.sync()
+        del keep
+        votes = [int(vote or 0)]
+        for src in M["srcs"]:
+            h = got[src]
+            votes.append(int(h[npatch]))
+            buf = arena.base[arena.me] + M["my_off"][parity][src] + M["hdr_bytes"]
+            off = 0
+            for pid in range(npatch):
+                n = int(h[pid])
+                if not n:
+                    continue
+                if ensure is not None:
+                    domain[pid] = ensure(pid, ops.count(domain[pid]) + n)
+                dst = domain[pid]
+                if dst.n + n > dst.capacity:
+                    raise RuntimeError("particle store capacity exceeded while receiving migrating particles")
+                ctx._check(lib.phb_particles_unpack(ctx.h, C.c_void_p(buf), cap, off, n, C.byref(dst.c)))
+                received[pid] += n
+                off += n
+        self.last_vote = max(votes) if (vote is not None and M["vote_complete"]) else None
+
     def _exchange_particles(self, layouts, remote, domain, received, ensure=None, vote=None):
         """remote: {(owner rank, patch id): staging store} -> appended to domain[patch id] on the owner.
         ensure(pid, needed) -> store: lets the caller re-allocate a destination store that is too small"""
+        if self.arena is not None and getattr(self, "peer_migration", True):
+            return self._exchange_particles_peer(layouts, remote, domain, received, ensure, vote)
         ops, comm, geom = self.ops, self.comm, self.geom
         # every rank announces, per destination patch, how many particles it ships
         npatch = len(geom.patches)
