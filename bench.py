@@ -282,6 +282,9 @@ def our_arm(args):
     assert world == n_gpus or world == 1 and n_gpus == 1, "launch with torch.distributed.run --nproc-per-node N"
     device = torch.device(f"cuda:{local}")
     torch.cuda.set_device(device)
+    # host placement next to this rank's GPU, before any pinned buffer exists (phare_b200/numa.py; PHB_NUMA=0: leave it)
+    from phare_b200 import numa
+    placement = numa.bind_near_gpu(local) if os.environ.get("PHB_NUMA", "1") != "0" else dict(bound=False, why="PHB_NUMA=0")
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     parity = multi_rank_parity(args.config, n_gpus, rank, device) if world > 1 and not args.no_parity else None
@@ -379,6 +382,18 @@ def our_arm(args):
             extra["deposit"] = dict(achieved=round(a, 1), frac=round(a / peak, 4), avg_launch_ms=round(avg(dep_ms), 4))
         if bin_ms:
             extra["bin"] = dict(avg_ms=round(avg(bin_ms), 4))
+        rb_ms = kernel_ms.get("move_all_rebin", [])
+        if rb_ms:
+            # the all sweep in ONE pass (phb_push_deposit_rebin): interpolate + push + deposit + re-binning of a particle;
+            # unit of work = one particle-push of SURVEY 8(d) (K1 + K3 bytes); it moves 2 x K3 bytes + the 4-byte plan word
+            a = n_launch * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (avg(rb_ms) * 1e-3) / 1e9
+            extra["move_all_rebin"] = dict(
+                kernel_name="tile_kernel<.., PLAN_REBIN>", achieved=round(a, 1), frac=round(a / peak, 4),
+                avg_launch_ms=round(avg(rb_ms), 4), algorithmic_bytes_per_particle=BYTES_PUSH[dim] + BYTES_DEPOSIT[dim],
+                frac_of_bytes_moved=round(n_launch * (2 * BYTES_DEPOSIT[dim] + 4) / (avg(rb_ms) * 1e-3) / 1e9 / peak, 4),
+                what="K1+K3+K2 fused: move + deposit + write to the slot planned by the domain_only sweep "
+                     "(predicted re-binning, csrc/predict.cu)",
+                plans_that_did_not_hold=solver.updater.misfiled, rebin_fallbacks=solver.updater.rebin_fallbacks)
         ds_ms, plan_ms = kernel_ms.get("deposit_scatter", []), kernel_ms.get("bin_plan", [])
         if ds_ms:
             # K3+K2 fused (the `all` sweep): reads the store + 4 B slot, writes the re-binned store
@@ -399,8 +414,10 @@ def our_arm(args):
             2 * n_local * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)
         # bytes the particle kernels of one step actually move per particle (their own column reads + writes)
         moved = {"push": BYTES_PUSH[dim], "deposit": BYTES_DEPOSIT[dim], "move_domain_only": BYTES_DEPOSIT[dim],
-                 "move_all": BYTES_PUSH[dim] + 8,
+                 "move_all": BYTES_PUSH[dim] + 8, "move_all_rebin": 2 * BYTES_DEPOSIT[dim] + 4,
                  "bin_plan": 4 * dim + 4, "deposit_scatter": 2 * BYTES_DEPOSIT[dim] + 4, "bin": 4 * dim + 8 + 2 * BYTES_DEPOSIT[dim]}
+        if rb_ms:
+            moved["move_domain_only"] += 4  # the predicting sweep writes the 4-byte plan word
         sweeps = max(1, sum(len(p.pops) for p in solver.patches))
         extra["bytes_moved_per_particle_per_step"] = round(
             sum(moved.get(k, 0) * len(v) / (args.steps * sweeps) for k, v in kernel_ms.items()), 1)
@@ -411,6 +428,11 @@ def our_arm(args):
     e2e = None
     if not args.no_e2e:
         e2e = measure_e2e(solver, ops, args, world, device, n_total, DT)
+        places = [placement]
+        if world > 1:
+            places = [None] * world
+            dist.all_gather_object(places, placement)
+        e2e["host_placement"] = places
 
     cpu_baseline = None
     if rank == 0 and n_gpus == 1 and not args.no_cpu:

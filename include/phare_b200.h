@@ -290,6 +290,42 @@ int phb_scatter_planned(phb_ctx*, const phb_layout*, const phb_particles* in, si
                         const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, phb_particles* out,
                         const uint32_t* d_cell_start_new);
 
+/* ---- predicted re-binning (csrc/predict.cu): the `all` sweep of IonUpdater::updateAndDepositAll_
+ * (ion_updater.hpp:228-295) in ONE pass over the store -----------------------------------------------------------
+ * A PPC step pushes every particle twice from the same state (solver_ppc.hpp:325-333); the cell it ends in after the
+ * second push is the one the first push predicts, except for the few particles whose predicted position lies within
+ * eps (2^-12 of a cell; PHB_PREDICT_EPS) of a cell face.
+ *   phb_push_deposit_predict  == phb_push_deposit(parts[0,n), write_back = 0) for a store whose first n_sorted particles
+ *                             are ordered by d_cell_start (phb_bin keys of `domain`), and the plan of the re-binning into
+ *                             [domain | patch ghosts kept by keep[] | erased]: rank of every stayer in its cell, rank of
+ *                             every mover among the arrivals of its new cell, list of the face-near particles.  The plan
+ *                             lives in the caller's device buffer d_plan (phb_predict_plan_bytes(L, domain,
+ *                             parts->capacity) bytes) until phb_push_deposit_rebin consumes it; `parts` must not change
+ *                             in between.
+ *   phb_push_deposit_rebin    pusher_->move + deposit + partition/erase: the face-near particles are moved with THESE
+ *                             fields and join the plan, scan -> d_cell_start_new, then every particle of `in` is moved,
+ *                             deposited (sel[]) and written to the slot its plan reserved in `out`.  Every plan is checked
+ *                             against the particle's actual new cell.
+ *   phb_predict_counts        host-returning: h_counts[0..2] as phb_bin_counts, h_counts[3] = plans that did not hold
+ *                             ("misfiled": such a particle is pushed and deposited correctly but filed under the predicted
+ *                             cell).  0 -> `out` is exactly what phb_bin leaves; > 0 -> the caller restores the order with
+ *                             phb_bin(out -> ...) before using d_cell_start_new.
+ * Only for (dim, interp) whose cell support fits the tile kernel (phb_predict_supported). */
+int    phb_predict_supported(const phb_layout*);
+size_t phb_predict_plan_bytes(const phb_layout*, const phb_box* domain, size_t capacity);
+int phb_push_deposit_predict(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,
+                             const phb_particles* parts, size_t n_sorted, double mass, double dt, double* rho_n,
+                             double* rho_q, const phb_vecfield* flux, double coef, const phb_box* sel, int nsel,
+                             const phb_box* domain, const uint32_t* d_cell_start, const phb_box* keep, int nkeep,
+                             void* d_plan, size_t plan_bytes);
+int phb_push_deposit_rebin(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,
+                           const phb_particles* in, size_t n_sorted, double mass, double dt, double* rho_n, double* rho_q,
+                           const phb_vecfield* flux, double coef, const phb_box* sel, int nsel, const phb_box* domain,
+                           const uint32_t* d_cell_start_old, const phb_box* keep, int nkeep, phb_particles* out,
+                           uint32_t* d_cell_start_new, void* d_plan, size_t plan_bytes);
+int phb_predict_counts(phb_ctx*, const phb_layout*, const phb_box* domain, const uint32_t* d_cell_start,
+                       const void* d_plan, size_t h_counts[4], phb_particles* out);
+
 /* ---- GridLayout primitives on their own (test support for SURVEY 8 row a14) ---------------------------------------
  * The device functions Faraday / Ampere / Ohm are built from, applied to one array of quantity `qty` (allocation shape
  * of phb_field_shape):

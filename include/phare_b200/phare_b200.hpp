@@ -29,6 +29,7 @@
 
 #include "../phare_b200.h"
 
+#include <cstdlib>
 #include <array>
 #include <cstdint>
 #include <map>
@@ -508,6 +509,11 @@ struct IonPopulation // ion_population.hpp:19-140
     std::unique_ptr<DeviceBuffer> cell_start;      // ordering of `domain` (replaces the CellMap)
     std::unique_ptr<DeviceBuffer> cell_start_next; // written by phb_bin_plan while the old ordering is still read
     std::size_t n_sorted = 0;
+    // predicted re-binning (phb_push_deposit_predict / _rebin): the plan the domain_only sweep leaves for the all sweep
+    std::unique_ptr<DeviceBuffer> plan;
+    std::size_t plan_bytes = 0, plan_capacity = 0;
+    std::size_t planned_n = std::size_t(-1), planned_sorted = 0; // the store state the pending plan was made for
+    bool rebinned_by_plan = false;
 };
 
 template<std::size_t dim>
@@ -566,7 +572,11 @@ template<std::size_t dim, std::size_t order>
 class IonUpdater
 {
 public:
-    explicit IonUpdater(Dict const& dict) : pusher_{PusherFactory::makePusher<dim, order>(dict["pusher"]["name"].to<std::string>())} {}
+    explicit IonUpdater(Dict const& dict) : pusher_{PusherFactory::makePusher<dim, order>(dict["pusher"]["name"].to<std::string>())}
+    {
+        if (char const* e = std::getenv("PHB_PREDICT"))
+            usePrediction = std::string(e) != "0";
+    }
 
     // updatePopulations (ion_updater.hpp:90-109) = launchPopulations (every kernel of the sweep, enqueued) +
     // finishPopulations (the one host synchronisation: class counts of the re-binning, the error poll).  A level driver
@@ -606,7 +616,25 @@ public:
             if (mode == UpdaterMode::domain_only)
             {
                 // updateAndDepositDomain_ (:171-219): tmp_particles_ = domain; move; deposit the allowed ones
-                if (fusedDomainOnly && n)
+                if (fusedDomainOnly && n && usePrediction && phb_predict_supported(layout.c()))
+                {
+                    // the same pass + the plan of the re-binning the all sweep will carry out (csrc/predict.cu): the cell
+                    // a particle ends in after the second push of a PPC step is the one this push predicts
+                    auto const cap = pop.domain.c()->capacity;
+                    if (!pop.plan || pop.plan_capacity != cap)
+                    {
+                        pop.plan_bytes    = phb_predict_plan_bytes(layout.c(), &dom, cap);
+                        pop.plan          = std::make_unique<DeviceBuffer>(ctx, pop.plan_bytes / sizeof(double) + 1);
+                        pop.plan_capacity = cap;
+                    }
+                    ctx.check(phb_push_deposit_predict(ctx.get(), layout.c(), &E, &B, pop.domain.c(), nsorted, pop.mass(), dt,
+                                                       pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(),
+                                                       int(keep.size()), &dom, cs, keep.data(), int(keep.size()),
+                                                       pop.plan->data(), pop.plan_bytes));
+                    pop.planned_n      = n;
+                    pop.planned_sorted = nsorted;
+                }
+                else if (fusedDomainOnly && n)
                 {
                     // the copy is never materialised: K1+K3 in one pass, nothing written back
                     if (nsorted)
@@ -638,6 +666,18 @@ public:
                 if (!pop.cell_start_next)
                     pop.cell_start_next = std::make_unique<DeviceBuffer>(ctx, words);
                 auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
+                bool const planned = pop.plan && pop.planned_n == n && pop.planned_sorted == nsorted;
+                pop.planned_n      = std::size_t(-1);
+                if (planned)
+                {
+                    // move + deposit + partition / erase in ONE pass along the plan of the domain_only sweep
+                    ctx.check(phb_push_deposit_rebin(ctx.get(), layout.c(), &E, &B, pop.domain.c(), nsorted, pop.mass(), dt,
+                                                     pop.rho_n.data(), pop.rho_q.data(), &F, 1., keep.data(),
+                                                     int(keep.size()), &dom, cs, keep.data(), int(keep.size()),
+                                                     pop.spare.c(), new_start, pop.plan->data(), pop.plan_bytes));
+                    pop.rebinned_by_plan = true;
+                    continue;
+                }
                 ctx.check(phb_push_plan(ctx.get(), layout.c(), &E, &B, pop.domain.c(), nsorted, pop.mass(), dt, &dom, cs,
                                         keep.data(), int(keep.size()), new_start));
                 ctx.check(phb_deposit_scatter(ctx.get(), layout.c(), pop.domain.c(), nsorted, pop.rho_n.data(),
@@ -657,10 +697,30 @@ public:
             for (auto& pp : ions)
             {
                 auto& pop = *pp;
-                std::size_t counts[3];
+                std::size_t counts[4] = {0, 0, 0, 0};
                 auto* new_start = reinterpret_cast<uint32_t*>(pop.cell_start_next->data());
-                ctx.check(phb_bin_counts(ctx.get(), layout.c(), &dom, new_start, counts, pop.spare.c()));
+                if (pop.rebinned_by_plan)
+                {
+                    // class counts + the plans that did not hold (a particle filed under its predicted cell)
+                    ctx.check(phb_predict_counts(ctx.get(), layout.c(), &dom, new_start, pop.plan->data(), counts,
+                                                 pop.spare.c()));
+                    pop.rebinned_by_plan = false;
+                }
+                else
+                    ctx.check(phb_bin_counts(ctx.get(), layout.c(), &dom, new_start, counts, pop.spare.c()));
                 std::swap(pop.cell_start, pop.cell_start_next);
+                if (counts[3])
+                {
+                    // restore the exact order: phb_bin of the result (pushed and deposited correctly already)
+                    misfiled += counts[3];
+                    std::vector<phb_box> keep;
+                    for (auto const& b : boxing.nonLevelGhostBox)
+                        keep.push_back(b.c());
+                    pop.spare.c()->n = counts[0] + counts[1] + counts[2];
+                    ctx.check(phb_bin(ctx.get(), layout.c(), pop.spare.c(), pop.domain.c(), &dom, keep.data(), int(keep.size()),
+                                      reinterpret_cast<uint32_t*>(pop.cell_start->data()), counts));
+                    pop.domain.swap(pop.spare); // (swapped back below)
+                }
                 // stayers -> domain, leavers inside nonLevelGhostBox -> patchGhost (:248-254), the rest erased (:273):
                 // the re-binned store becomes the domain array (pointer swap), its patch-ghost range is copied out
                 pop.domain.swap(pop.spare);
@@ -672,6 +732,8 @@ public:
         ctx.check(phb_poll_error(ctx.get())); // throws DictionaryException{"cause", ...} like boris.hpp:207-214
     }
 
+    bool usePrediction   = true; // predicted re-binning where the tile kernel exists (PHB_PREDICT=0 in the environment: off)
+    std::size_t misfiled = 0;    // plans that did not hold so far
     void updateIons(Ions<dim>& ions) { ions.computeChargeDensityAndBulkVelocity(); } // ion_updater.hpp:112-116
     void reset() {}                                                                  // :66-70 (frees tmp_particles_)
 

@@ -185,6 +185,19 @@ _PROTOS = {
                                         C.c_void_p, C.POINTER(Box), C.c_int, C.c_void_p]),
     "phb_scatter_planned": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.POINTER(Box),
                                       C.c_void_p, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.c_void_p]),
+    "phb_predict_supported": (C.c_int, [C.POINTER(Layout)]),
+    "phb_predict_plan_bytes": (C.c_size_t, [C.POINTER(Layout), C.POINTER(Box), C.c_size_t]),
+    "phb_push_deposit_predict": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                                           C.POINTER(Particles), C.c_size_t, C.c_double, C.c_double, C.c_void_p,
+                                           C.c_void_p, C.POINTER(VecField), C.c_double, C.POINTER(Box), C.c_int,
+                                           C.POINTER(Box), C.c_void_p, C.POINTER(Box), C.c_int, C.c_void_p, C.c_size_t]),
+    "phb_push_deposit_rebin": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),
+                                         C.POINTER(Particles), C.c_size_t, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.POINTER(VecField), C.c_double, C.POINTER(Box), C.c_int, C.POINTER(Box),
+                                         C.c_void_p, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.c_void_p, C.c_void_p,
+                                         C.c_size_t]),
+    "phb_predict_counts": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Box), C.c_void_p, C.c_void_p,
+                                     C.POINTER(C.c_size_t), C.POINTER(Particles)]),
     "phb_gridlayout_probe": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "phb_split": (C.c_int, [C.c_void_p, C.POINTER(Particles), C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
                             C.c_int, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.POINTER(C.c_size_t)]),

@@ -84,7 +84,7 @@ int tile_push_deposit(phb_ctx* ctx, const PushParams<DIM>& P, DepositParams<DIM>
         return rc;
     KeySpace<DIM> K{};
     TileParams<DIM> T{};
-    if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, write, false}, P, A, R, K, T))
+    if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, write, PLAN_NONE}, P, A, R, K, T))
         return rc;
     tile_records_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A, R);
     PHB_LAUNCH_CHECK(ctx);
@@ -277,7 +277,7 @@ int pdp_order(phb_ctx* ctx, const phb_layout* L, const phb_vecfield* E, const ph
                 return rc;
             TileParams<DIM> T{};
             T.plan = S.a;
-            if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, true, true}, P, A, R, K, T))
+            if (int rc = tile_dispatch<DIM, ORDER>(ctx, TileMode{true, true, PLAN_INPLACE}, P, A, R, K, T))
                 return rc;
             tile_records_kernel<DIM, ORDER><<<MOVER_LISTS, 256, 0, ctx->stream>>>(A, R);
             PHB_LAUNCH_CHECK(ctx);

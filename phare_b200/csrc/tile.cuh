@@ -66,7 +66,48 @@ struct PlanArrays
     uint32_t* stay;      // [nk+1] particles that stay in cell k (written by the owner group)
     uint32_t* mover_cnt; // [nk+1] particles that arrive in cell k from elsewhere (atomic)
     uint32_t* slot;      // [n] rank of a mover among the arrivals of its new cell
+    // ---- predicted re-binning only (predict.cu): the plan is made one sweep ahead
+    uint32_t* key1;      // [n] key of the cell a planned mover goes to
+    uint32_t* risky;     // RISKY_LISTS x risky_cap entries {particle, key of its run}: left for predict_resolve_kernel
+    uint32_t* hdr;       // [0] misfiled, [32 + 32 l] fill of risky sub-list l
+    uint32_t risky_cap;
+    const uint32_t* new_start; // re-binning sweep: scan(stay + arrivals)
+    double eps;          // a predicted delta within eps of a cell face is "risky"
 };
+
+// tile_kernel's PLAN modes
+constexpr int PLAN_NONE    = 0;
+constexpr int PLAN_INPLACE = 1; // phb_push_deposit_plan: count stayers / rank movers of the particle just written back
+constexpr int PLAN_PREDICT = 2; // phb_push_deposit_predict: the same bookkeeping from the domain_only sweep's positions
+constexpr int PLAN_REBIN   = 3; // phb_push_deposit_rebin: every particle is written to the slot the plan reserved
+constexpr uint32_t PLAN_MOVER = 0x80000000u; // slot word: rank among the arrivals (else: rank among the stayers)
+constexpr uint32_t PLAN_RISKY = 0xffffffffu; // slot word between the predicting sweep and predict_resolve_kernel
+constexpr uint32_t PLAN_NOKEY = 0xffffffffu; // risky entry of a particle outside the cell-ordered part
+constexpr unsigned RISKY_LISTS = 256;
+
+template<int DIM>
+__device__ __forceinline__ bool near_face(const double (&delta)[DIM], double eps)
+{
+    bool r = false;
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+        r = r || !(delta[d] >= eps && delta[d] < 1. - eps);
+    return r;
+}
+
+// the predicted position is too close to a cell face to trust its cell: leave the particle to predict_resolve_kernel
+__device__ __forceinline__ bool list_risky(const PlanArrays& plan, uint32_t p, uint32_t run_key)
+{
+    unsigned const l = blockIdx.x % RISKY_LISTS;
+    uint32_t const k = atomicAdd(plan.hdr + 32 + 32 * l, 1u);
+    if (k >= plan.risky_cap)
+        return false; // list full: planned like any other particle; the re-binning sweep verifies every plan anyway
+    size_t const at    = (size_t(l) * plan.risky_cap + k) * 2;
+    plan.risky[at]     = p;
+    plan.risky[at + 1] = run_key;
+    plan.slot[p]       = PLAN_RISKY;
+    return true;
+}
 
 template<int DIM>
 struct TileParams
@@ -98,8 +139,8 @@ template<int DIM, int ORDER, bool LOADW>
 __host__ __device__ constexpr int tile_smem_bytes()
 {
     using TG = TileGeom<DIM, ORDER>;
-    int const ring = TILE_DEPTH * ((DIM + 4 + (LOADW ? 1 : 0)) * 8 + DIM * 4) * TILE_BS;
-    return TG::BYTES + ring + 2 * TG::NC * 4 + 16;
+    int const ring = TILE_DEPTH * ((DIM + 4 + (LOADW ? 1 : 0)) * 8 + (DIM + 1) * 4) * TILE_BS;
+    return TG::BYTES + ring + 3 * TG::NC * 4 + 16;
 }
 
 // MeshToParticle on the shared-memory tile: same nested z -> y -> x accumulation and operation order as
@@ -243,12 +284,16 @@ struct GroupReduceMasked
 template<int DIM, int ORDER, bool DEPOSIT>
 __host__ __device__ constexpr int tile_min_blocks()
 {
+#ifdef PHB_TILE_MINB // tuning builds
+    int const by_regs = PHB_TILE_MINB;
+#else
     int const by_regs = DEPOSIT ? (ipow(cell_support<ORDER>(), DIM) <= 8 ? 2 : 1) * (256 / TILE_BS) : 3 * (256 / TILE_BS);
+#endif
     int const by_smem = (227 * 1024) / (tile_smem_bytes<DIM, ORDER, DEPOSIT>() + 1024);
     return by_smem < 1 ? 1 : (by_regs < by_smem ? by_regs : by_smem);
 }
 
-template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, bool PLAN>
+template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN>
 __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>())
     tile_kernel(const __grid_constant__ PushParams<DIM> P, const __grid_constant__ DepositParams<DIM> A,
                 const __grid_constant__ TileRecords R, const __grid_constant__ KeySpace<DIM> K,
@@ -261,16 +306,20 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
     constexpr int G     = TILE_BS / GS;
     constexpr bool LOADW = DEPOSIT;
     constexpr int NC8   = DIM + 4 + (LOADW ? 1 : 0);
+    constexpr int NC4   = DIM + 1; // iCell + (PLAN_REBIN) the slot word of the plan
     static_assert(TILE_BS % GS == 0 && GS <= 32, "group size");
+    static_assert(PLAN != PLAN_REBIN || (DEPOSIT && WRITE), "the re-binning sweep deposits and writes");
+    static_assert(PLAN != PLAN_PREDICT || (DEPOSIT && !WRITE), "the predicting sweep is the domain_only sweep");
     static_assert(TG::NC % G == 0, "the groups of a warp must run out of cells together");
 
     extern __shared__ __align__(128) unsigned char smem[];
     double* const tile   = reinterpret_cast<double*>(smem);
     double* const ring8  = reinterpret_cast<double*>(smem + TG::BYTES);
     int* const ring4     = reinterpret_cast<int*>(smem + TG::BYTES + size_t(TILE_DEPTH) * NC8 * TILE_BS * 8);
-    uint32_t* const cbeg = reinterpret_cast<uint32_t*>(smem + TG::BYTES + size_t(TILE_DEPTH) * (NC8 * 8 + DIM * 4) * TILE_BS);
+    uint32_t* const cbeg = reinterpret_cast<uint32_t*>(smem + TG::BYTES + size_t(TILE_DEPTH) * (NC8 * 8 + NC4 * 4) * TILE_BS);
     uint32_t* const cend = cbeg + TG::NC;
-    uint64_t* const bar  = reinterpret_cast<uint64_t*>(cend + TG::NC);
+    uint32_t* const cstay = cend + TG::NC; // PLAN_PREDICT: stayers of every cell of the block, ranked as they come
+    uint64_t* const bar  = reinterpret_cast<uint64_t*>(cstay + TG::NC);
 
     int const tid = int(threadIdx.x);
     int const g = tid / GS, sub = tid % GS;
@@ -318,8 +367,9 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                 e = uint32_t(e2);
             }
         }
-        cbeg[c] = b;
-        cend[c] = e;
+        cbeg[c]  = b;
+        cend[c]  = e;
+        cstay[c] = 0;
     }
     if (tid == 0)
     {
@@ -410,7 +460,9 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                 cp_async8(ring8 + (slot * NC8 + c8++) * TILE_BS + tid, P.in.weight + p);
 #pragma unroll
             for (int d = 0; d < DIM; ++d)
-                cp_async4(ring4 + (slot * DIM + d) * TILE_BS + tid, P.in.icell[d] + p);
+                cp_async4(ring4 + (slot * NC4 + d) * TILE_BS + tid, P.in.icell[d] + p);
+            if constexpr (PLAN == PLAN_REBIN)
+                cp_async4(ring4 + (slot * NC4 + DIM) * TILE_BS + tid, T.plan.slot + p);
             ip += GS;
         }
         cp_async_commit();
@@ -448,6 +500,9 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                 key = key * unsigned(ext[d]) + unsigned(cell[d] - A.keybox.lo[d]);
         }
         bool const cell_selected = DEPOSIT ? selected<DIM>(A.sel, cell) : false;
+        size_t own = 0; // PLAN_REBIN: first slot of this cell in the re-binned store
+        if constexpr (PLAN == PLAN_REBIN)
+            own = nonempty ? __ldg(T.plan.new_start + key) : 0;
         double acc[NV];
 #pragma unroll
         for (int i = 0; i < NV; ++i)
@@ -472,8 +527,11 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                     weight = ring8[(rslot * NC8 + c8++) * TILE_BS + tid];
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
-                    icell[d] = ring4[(rslot * DIM + d) * TILE_BS + tid];
+                    icell[d] = ring4[(rslot * NC4 + d) * TILE_BS + tid];
             }
+            uint32_t word = 0;
+            if constexpr (PLAN == PLAN_REBIN)
+                word = uint32_t(ring4[(rslot * NC4 + DIM) * TILE_BS + tid]);
             issue_next(rslot);
             rslot = rslot + 1 == TILE_DEPTH ? 0 : rslot + 1;
 
@@ -487,12 +545,38 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                 if constexpr (DEPOSIT)
                 {
                     // fused passes: the offender stays as it was in the store (so it stays in its cell) and deposits nothing
-                    if constexpr (PLAN)
+                    if constexpr (PLAN == PLAN_INPLACE)
                         ++cnt_stay;
+                    if constexpr (PLAN == PLAN_PREDICT)
+                        T.plan.slot[p] = atomicAdd(cstay + ci, 1u);
+                    if constexpr (PLAN == PLAN_REBIN)
+                    {
+                        // copied as stored to the slot its plan reserved; a plan that expected it elsewhere is void
+                        size_t dst;
+                        if (word & PLAN_MOVER)
+                        {
+                            uint32_t const k1 = T.plan.key1[p];
+                            dst = size_t(__ldg(T.plan.new_start + k1)) + T.plan.stay[k1] + (word & ~PLAN_MOVER);
+                            atomicAdd(T.plan.hdr, 1u);
+                        }
+                        else
+                            dst = own + word;
+#pragma unroll
+                        for (int d = 0; d < DIM; ++d)
+                        {
+                            P.out.icell[d][dst] = P.in.icell[d][p];
+                            P.out.delta[d][dst] = P.in.delta[d][p];
+                        }
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+                            P.out.v[c][dst] = P.in.v[c][p];
+                        P.out.weight[dst] = weight;
+                        P.out.charge[dst] = charge;
+                    }
                     continue;
                 }
             }
-            if constexpr (WRITE)
+            if constexpr (WRITE && PLAN != PLAN_REBIN)
             {
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
@@ -510,12 +594,60 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
 #pragma unroll
                 for (int d = 0; d < DIM; ++d)
                     same = same && icell[d] == cell[d];
-                if constexpr (PLAN)
+                if constexpr (PLAN == PLAN_INPLACE)
                 {
                     if (same)
                         ++cnt_stay;
                     else
                         T.plan.slot[p] = atomicAdd(T.plan.mover_cnt + bin_key<DIM>(K, icell), 1u);
+                }
+                if constexpr (PLAN == PLAN_PREDICT)
+                {
+                    // the cell this particle will be filed under is decided HERE, one sweep early, unless its predicted
+                    // position is within eps of a cell face (then predict_resolve_kernel decides with the final fields)
+                    if (!(near_face<DIM>(delta, T.plan.eps) && list_risky(T.plan, p, key)))
+                    {
+                        if (same)
+#ifdef PHB_DIAG_NO_STAYRANK // timing diagnostic only (wrong ranks)
+                            T.plan.slot[p] = p - b;
+#else
+                            T.plan.slot[p] = atomicAdd(cstay + ci, 1u);
+#endif
+                        else
+                        {
+                            uint32_t const k1 = bin_key<DIM>(K, icell);
+                            T.plan.slot[p]    = atomicAdd(T.plan.mover_cnt + k1, 1u) | PLAN_MOVER;
+                            T.plan.key1[p]    = k1;
+                        }
+                    }
+                }
+                if constexpr (PLAN == PLAN_REBIN)
+                {
+                    size_t dst;
+                    if (word & PLAN_MOVER)
+                    {
+                        uint32_t const k1 = T.plan.key1[p];
+                        dst = size_t(__ldg(T.plan.new_start + k1)) + T.plan.stay[k1] + (word & ~PLAN_MOVER);
+                        if (k1 != bin_key<DIM>(K, icell))
+                            atomicAdd(T.plan.hdr, 1u); // filed under the predicted cell, not under its own
+                    }
+                    else
+                    {
+                        dst = own + word;
+                        if (!same)
+                            atomicAdd(T.plan.hdr, 1u);
+                    }
+#pragma unroll
+                    for (int d = 0; d < DIM; ++d)
+                    {
+                        __stcs(P.out.icell[d] + dst, icell[d]);
+                        __stcs(P.out.delta[d] + dst, delta[d]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        __stcs(P.out.v[c] + dst, v[c]);
+                    __stcs(P.out.weight + dst, weight);
+                    __stcs(P.out.charge + dst, charge);
                 }
                 if constexpr (DEPOSIT)
                 {
@@ -612,13 +744,18 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
         }
 
         __syncwarp();
-        if constexpr (PLAN)
+        if constexpr (PLAN == PLAN_INPLACE)
         {
 #pragma unroll
             for (int m = 1; m < GS; m <<= 1)
                 cnt_stay += __shfl_xor_sync(0xffffffffu, cnt_stay, m);
             if (sub == 0 && nonempty)
                 T.plan.stay[key] = cnt_stay;
+        }
+        if constexpr (PLAN == PLAN_PREDICT)
+        {
+            if (sub == 0 && nonempty)
+                T.plan.stay[key] = cstay[ci]; // every lane of the group is past its atomics (__syncwarp above)
         }
         if constexpr (DEPOSIT)
         {
@@ -736,10 +873,11 @@ __global__ void __launch_bounds__(256)
 // ---- host side -------------------------------------------------------------------------------------------------
 struct TileMode
 {
-    bool deposit, write, plan;
+    bool deposit, write;
+    int plan; // PLAN_*
 };
 
-template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, bool PLAN>
+template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN>
 int launch_tile(phb_ctx* ctx, const PushParams<DIM>& P, const DepositParams<DIM>& A, const TileRecords& R,
                 const KeySpace<DIM>& K, TileParams<DIM>& T)
 {
@@ -779,14 +917,18 @@ int run_tile(phb_ctx* ctx, TileMode m, int gs, const PushParams<DIM>& P, const D
 {
     auto go = [&](auto gsc) -> int {
         constexpr int GS = decltype(gsc)::value;
-        if (m.deposit && !m.write && !m.plan)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, false, false>(ctx, P, A, R, K, T);
-        if (m.deposit && m.write && !m.plan)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, true, false>(ctx, P, A, R, K, T);
-        if (m.deposit && m.write && m.plan)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, true, true>(ctx, P, A, R, K, T);
-        if (!m.deposit && m.write && !m.plan)
-            return launch_tile<DIM, ORDER, GS, EXACT, false, true, false>(ctx, P, A, R, K, T);
+        if (m.deposit && !m.write && m.plan == PLAN_NONE)
+            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_NONE>(ctx, P, A, R, K, T);
+        if (m.deposit && m.write && m.plan == PLAN_NONE)
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_NONE>(ctx, P, A, R, K, T);
+        if (m.deposit && m.write && m.plan == PLAN_INPLACE)
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_INPLACE>(ctx, P, A, R, K, T);
+        if (m.deposit && !m.write && m.plan == PLAN_PREDICT)
+            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_PREDICT>(ctx, P, A, R, K, T);
+        if (m.deposit && m.write && m.plan == PLAN_REBIN)
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_REBIN>(ctx, P, A, R, K, T);
+        if (!m.deposit && m.write && m.plan == PLAN_NONE)
+            return launch_tile<DIM, ORDER, GS, EXACT, false, true, PLAN_NONE>(ctx, P, A, R, K, T);
         return set_error(ctx, PHB_ERR_INVALID, "tile kernel: unsupported mode");
     };
     if (gs >= 32)

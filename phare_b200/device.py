@@ -315,6 +315,35 @@ class Context:
             cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep), C.byref(pout.c),
             cell_start_new.ptr))
 
+    def predict_supported(self, layout):
+        return bool(self.lib.phb_predict_supported(C.byref(layout)))
+
+    def predict_plan_bytes(self, layout, domain, capacity):
+        return int(self.lib.phb_predict_plan_bytes(C.byref(layout), C.byref(domain), int(capacity)))
+
+    def push_deposit_predict(self, layout, E, B, parts, n_sorted, mass, dt, rho_n, rho_q, flux, coef, sel, domain,
+                             cell_start, keep, plan_ptr, plan_bytes):
+        """phb_push_deposit_predict: the domain_only sweep + the plan of the re-binning the all sweep will carry out"""
+        self._check(self.lib.phb_push_deposit_predict(
+            self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(parts.c), int(n_sorted), mass, dt, rho_n.ptr,
+            rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel), C.byref(domain),
+            cell_start.ptr if cell_start is not None else None, abi.box_array(keep), len(keep), plan_ptr, plan_bytes))
+
+    def push_deposit_rebin(self, layout, E, B, pin, n_sorted, mass, dt, rho_n, rho_q, flux, coef, sel, domain,
+                           cell_start_old, keep, pout, cell_start_new, plan_ptr, plan_bytes):
+        """phb_push_deposit_rebin: move + deposit + re-binning in one pass, along the plan of push_deposit_predict"""
+        self._check(self.lib.phb_push_deposit_rebin(
+            self.h, C.byref(layout), C.byref(E.c), C.byref(B.c), C.byref(pin.c), int(n_sorted), mass, dt, rho_n.ptr,
+            rho_q.ptr, C.byref(flux.c), coef, abi.box_array(list(sel)), len(sel), C.byref(domain),
+            cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep), C.byref(pout.c),
+            cell_start_new.ptr, plan_ptr, plan_bytes))
+
+    def predict_counts(self, layout, domain, cell_start, plan_ptr, pout):
+        counts = (C.c_size_t * 4)()
+        self._check(self.lib.phb_predict_counts(self.h, C.byref(layout), C.byref(domain), cell_start.ptr, plan_ptr, counts,
+                                                C.byref(pout.c)))
+        return tuple(int(c) for c in counts)
+
     def maxwellian_load(self, layout, d_n, d_V, d_Vth, d_first, total, charge, ppc, seed, domain_cells, store):
         """phb_maxwellian_load: d_n / d_first device arrays, d_V / d_Vth objects with a .c VecField of per-cell arrays"""
         self._check(self.lib.phb_maxwellian_load(self.h, C.byref(layout), d_n.ptr, C.byref(d_V.c), C.byref(d_Vth.c),

@@ -16,6 +16,8 @@ orchestration.  There is no fallback: GpuOps raises if the CUDA library or a dev
 """
 import ctypes as C
 
+import os
+
 import numpy as np
 
 from . import abi
@@ -59,7 +61,7 @@ class GpuOps:
         return self.ti.TorchVec(self.ctx, layout, qty0, self.device)
 
     def zero(self, h):
-        h.t.zero_()
+        self.ctx._check(self.ctx.lib.phb_memset(self.ctx.h, h.ptr, 0, h.size * h.t.element_size()))
 
     def copy(self, dst, src):
         self.ctx._check(self.ctx.lib.phb_d2d(self.ctx.h, dst.ptr, src.ptr, src.size * 8))
@@ -178,6 +180,31 @@ class GpuOps:
 
     def bin_counts(self, layout, domain, cell_start, pout):
         return self.ctx.bin_counts(layout, domain, cell_start, pout)
+
+    # ---- predicted re-binning (csrc/predict.cu): the all sweep in one pass, planned by the domain_only sweep
+    def predict_supported(self, layout):
+        return self.ctx.predict_supported(layout)
+
+    def predict_plan(self, layout, domain, capacity):
+        """device buffer for the plan of one particle store"""
+        nbytes = self.ctx.predict_plan_bytes(layout, domain, capacity)
+        buf = self.torch.empty((nbytes + 3) // 4, dtype=self.torch.int32, device=self.device)
+        return buf, nbytes
+
+    def push_deposit_predict(self, layout, E, B, parts, n_sorted, mass, dt, rho_n, rho_q, F, coef, sel, domain, cell_start,
+                             keep, plan):
+        self._timed("move_domain_only", lambda: self.ctx.push_deposit_predict(
+            layout, E, B, parts, n_sorted, mass, dt, rho_n, rho_q, F, coef, sel, domain, cell_start, keep,
+            plan[0].data_ptr(), plan[1]))
+
+    def push_deposit_rebin(self, layout, E, B, pin, n_sorted, mass, dt, rho_n, rho_q, F, coef, sel, domain,
+                           cell_start_old, keep, pout, cell_start_new, plan):
+        self._timed("move_all_rebin", lambda: self.ctx.push_deposit_rebin(
+            layout, E, B, pin, n_sorted, mass, dt, rho_n, rho_q, F, coef, sel, domain, cell_start_old, keep, pout,
+            cell_start_new, plan[0].data_ptr(), plan[1]))
+
+    def predict_counts(self, layout, domain, cell_start, plan, pout):
+        return self.ctx.predict_counts(layout, domain, cell_start, plan[0].data_ptr(), pout)
 
     def export(self, layout, src, first, last, box, dst, minus=None, shift=None):
         return self.ctx.export(layout, src, first, last, box, dst, minus, shift)
@@ -345,6 +372,9 @@ class Population:
         self.cell_start = ops.cell_start(nkeys)
         self.cell_start_next = ops.cell_start(nkeys)  # written by bin_plan while the old order is still being read
         self.pending_bin = False                      # spare holds the re-binned store, counts not read back yet
+        self.plan = None                              # predicted re-binning: (device buffer, bytes) of this store's plan
+        self.predicted = None                         # (store, n, n_sorted) the pending plan was made for
+        self.pending_predicted = False                # the pending re-binning followed a prediction: verify it
         self.n_sorted = 0
         self.patch_ghost = ops.particles(capacity // 8 + 4096)  # patchGhostParticles (leavers of this step)
         # levelGhostParticles (+Old/New, particle_pack.hpp:20-36): only exist on refined levels
@@ -404,6 +434,12 @@ class IonUpdater:
         # (phb_bin_plan + phb_deposit_scatter, K3+K2) instead of phb_deposit followed by phb_bin
         self.sort_with_deposit = sort_with_deposit
         self.defer_sort = False  # set per step by SolverPPC.advance_level
+        # predict: the domain_only sweep plans the re-binning (the cell a particle ends in after the all sweep is the one
+        # the domain_only sweep predicts unless it sits on a cell face), the all sweep is then ONE pass: move + deposit +
+        # write to the planned slot (phb_push_deposit_predict / _rebin, csrc/predict.cu); PHB_PREDICT=0 switches it off
+        self.predict = os.environ.get("PHB_PREDICT", "1") != "0"
+        self.misfiled = 0        # plans that did not hold so far (each one costs a phb_bin of its store)
+        self.rebin_fallbacks = 0
         # fused: one pass per array and sweep (phb_push_deposit, K1+K3) instead of phb_push then phb_deposit
         self.fused = fused
 
@@ -426,6 +462,31 @@ class IonUpdater:
             nlg = ops.count(pop.level_ghost) if pop.level_ghost is not None else 0
             fused = self.fused if isinstance(self.fused, bool) else (L.dim, L.interp) in (
                 self.FUSED_DOMAIN_AUTO if mode == DOMAIN_ONLY else self.FUSED_AUTO)
+            if mode == ALL and pop.predicted is not None:
+                plan_for, pop.predicted = pop.predicted, None
+                if plan_for == (id(pop.domain), n, pop.n_sorted) and not self.defer_sort:
+                    # updateAndDepositAll_ (:228-295) in one pass along the plan of the domain_only sweep
+                    ops.push_deposit_rebin(L, E, B, pop.domain, pop.n_sorted, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux,
+                                           1.0, patch.non_level_ghost, patch.domain_box, pop.cell_start,
+                                           patch.non_level_ghost, pop.spare, pop.cell_start_next, pop.plan)
+                    pop.pending_bin = pop.pending_predicted = True
+                    if nlg:
+                        ops.push(L, E, B, pop.level_ghost, pop.level_ghost, pop.mass, dt, patch.ghost_box)
+                        ops.deposit(L, pop.level_ghost, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg, [patch.domain_box])
+                    continue
+            if (fused and mode == DOMAIN_ONLY and n and self.predict and self.sort_with_deposit and not self.defer_sort
+                    and hasattr(ops, "push_deposit_predict") and ops.predict_supported(L)):
+                need = ops.capacity(pop.domain)
+                if pop.plan is None or pop.plan[2] != need:
+                    pop.plan = ops.predict_plan(L, patch.domain_box, need) + (need,)
+                ops.push_deposit_predict(L, E, B, pop.domain, pop.n_sorted, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux,
+                                         1.0, patch.non_level_ghost, patch.domain_box, pop.cell_start,
+                                         patch.non_level_ghost, pop.plan)
+                pop.predicted = (id(pop.domain), n, pop.n_sorted)
+                if nlg:
+                    ops.push_deposit(L, E, B, pop.level_ghost, pop.mass, dt, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0,
+                                     nlg, [patch.domain_box], first_selector=patch.ghost_box, write_back=False)
+                continue
             if fused:
                 # both modes are the same pass; domain_only simply never stores the moved copy
                 wb = mode == ALL
@@ -482,7 +543,20 @@ class IonUpdater:
         still in the ghost layer remain level ghosts (:281-287)"""
         ops, L = self.ops, patch.layout
         for pop in patch.pops:
-            if pop.pending_bin:  # the scatter already happened with the deposit: only the counts are missing
+            if pop.pending_bin and pop.pending_predicted:
+                # the re-binning followed the plan of the domain_only sweep: class counts + the plans that did not hold
+                *counts, misfiled = ops.predict_counts(L, patch.domain_box, pop.cell_start_next, pop.plan, pop.spare)
+                pop.cell_start, pop.cell_start_next = pop.cell_start_next, pop.cell_start
+                pop.pending_bin = pop.pending_predicted = False
+                if misfiled:
+                    # a particle is filed under the cell it was predicted to reach, not under its own (it was pushed
+                    # and deposited correctly): restore the exact order before anything depends on it
+                    self.misfiled += misfiled
+                    self.rebin_fallbacks += 1
+                    ops.set_count(pop.spare, sum(counts))
+                    counts = ops.bin(L, pop.spare, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start)
+                    pop.domain, pop.spare = pop.spare, pop.domain  # (swapped back below)
+            elif pop.pending_bin:  # the scatter already happened with the deposit: only the counts are missing
                 counts = ops.bin_counts(L, patch.domain_box, pop.cell_start_next, pop.spare)
                 pop.cell_start, pop.cell_start_next = pop.cell_start_next, pop.cell_start
                 pop.pending_bin = False

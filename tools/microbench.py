@@ -79,6 +79,13 @@ def run(name, cfg):
         print(f"{name:4s} {label:22s} {ms:9.3f} ms  {n / ms / 1e6:8.2f} Gp/s  {gbs:8.1f} GB/s  {gbs / HBM:6.3f} of HBM peak",
               flush=True)
 
+    if os.environ.get('PHB_MB_ONLY') == 'predict':
+        for d in range(dim):
+            P.icell[d][:n] = torch.randint(0, cfg["ncells"][d], (n,), generator=g, device=dev, dtype=torch.int32)
+        out = run_predict(name, cfg, ctx, L, P, Q, E, B, rn, rq, F, dom, keep, cs, dt, report)
+        ctx.poll_error()
+        ctx.close()
+        return out
     if os.environ.get('PHB_MB_ONLY') == 'tile':
         if os.environ.get('PHB_MB_RANDOM', '1') != '0':
             # cells drawn at random (Poisson counts per cell, like a store a few steps into a run) instead of exactly
@@ -232,6 +239,40 @@ def run_tile(name, cfg, ctx, L, P, Q, E, B, rn, rq, F, dom, keep, cs, dt, report
         state["P"], state["Q"] = state["Q"], state["P"]
         state["n"] = counts[0]
         cs.t.copy_(cs2.t)
+    return {}
+
+
+def run_predict(name, cfg, ctx, L, P, Q, E, B, rn, rq, F, dom, keep, cs, dt, report):
+    """the two sweeps of a step as the predicted re-binning runs them (csrc/predict.cu), beside the plain sweep 1"""
+    dim = cfg["dim"]
+    dev = torch.device("cuda:0")
+    bpp_dep = {1: 52, 2: 64, 3: 76}[dim]
+    c = ctx.bin(L, P, Q, dom, keep, cs)
+    S, T, ns = Q, P, c[0]
+    S.n = ns
+    cs2 = TorchArray((ctx.bin_nkeys(L, dom) + 1,), dev, dtype=torch.int32)
+    nbytes = ctx.predict_plan_bytes(L, dom, S.capacity)
+    plan = torch.empty((nbytes + 3) // 4, dtype=torch.int32, device=dev)
+    ms, _ = timeit(lambda: ctx.push_deposit(L, E, B, S, 1.0, dt, rn, rq, F, 1.0, 0, ns, keep, dom, cs, write_back=False))
+    report("sweep1 plain (push+dep)", ms, bpp_dep)
+    predict = lambda: ctx.push_deposit_predict(L, E, B, S, ns, 1.0, dt, rn, rq, F, 1.0, keep, dom, cs, keep,
+                                               plan.data_ptr(), nbytes)
+    rebin = lambda: ctx.push_deposit_rebin(L, E, B, S, ns, 1.0, dt, rn, rq, F, 1.0, keep, dom, cs, keep, T, cs2,
+                                           plan.data_ptr(), nbytes)
+    t1, t2 = [], []
+    for it in range(6):
+        a, b, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a.record()
+        predict()
+        b.record()
+        rebin()
+        c2.record()
+        torch.cuda.synchronize()
+        t1.append(a.elapsed_time(b))
+        t2.append(b.elapsed_time(c2))
+    report("sweep1 predict (push+dep+plan)", min(t1[1:]), bpp_dep + 4)
+    report("sweep2 rebin (push+dep+scatter)", min(t2[1:]), 2 * bpp_dep + 4)
+    print("   counts+misfiled", ctx.predict_counts(L, dom, cs2, plan.data_ptr(), T), flush=True)
     return {}
 
 
