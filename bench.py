@@ -482,6 +482,7 @@ def measure_e2e(solver, ops, args, world, device, n_total, DT):
     e0.record()
     for _ in range(steps):
         one()
+    staging.copy_stream.synchronize()  # the last step's moments are still travelling: they belong to the timed region
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -498,9 +499,11 @@ def measure_e2e(solver, ops, args, world, device, n_total, DT):
     out = dict(value=2 * n_total * steps / (ms * 1e-3), unit="particle-pushes/s", h2d_bytes_per_step=bi,
                d2h_bytes_per_step=bo, steps=steps, staging_ms_per_rank=per_rank,
                what="SolverPPC.advance_level(dt, staging=HostStaging): per step E,B from pinned host memory -> device, "
-                    "advanceLevel, per-population + total moments and the new E,B -> pinned host (read back on a copy "
-                    "stream as soon as each is final, overlapping the particle re-binning that ends the step); the "
-                    "particle store stays device-resident (it is solver state, like the reference's ParticlesData)")
+                    "advanceLevel, the new E,B -> pinned host as soon as the corrector has produced them (the next step's "
+                    "inputs: on the critical path), per-population + total moments -> pinned host from a device-side "
+                    "snapshot taken when the all sweep has produced them, behind the fields and underneath the next step; "
+                    "the timed region ends when every result of every step is on the host; the particle store stays "
+                    "device-resident (it is solver state, like the reference's ParticlesData)")
     # the naive drop-in for comparison: AoS Particle<3> records cross PCIe both ways around one sweep
     if solver.patches[0].layout.dim == 3:
         try:

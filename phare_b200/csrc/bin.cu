@@ -147,12 +147,10 @@ int bin_dim(phb_ctx* ctx, const phb_layout* L, const phb_particles* in, phb_part
                                                               slot);
         PHB_LAUNCH_CHECK(ctx);
     }
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 0, d_cell_start + K.Nd, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 1, d_cell_start + K.Nd + K.Ng, sizeof(uint32_t),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 2, d_cell_start + K.Nd + K.Ng + 1, sizeof(uint32_t),
-                                  cudaMemcpyDeviceToHost, ctx->stream));
+    if (int rc = words_to_host(ctx, ctx->h_counts + 0, d_cell_start + K.Nd, sizeof(uint32_t)))
+        return rc;
+    if (int rc = words_to_host(ctx, ctx->h_counts + 1, d_cell_start + K.Nd + K.Ng, 2 * sizeof(uint32_t)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h_counts[0] = ctx->h_counts[0];
     h_counts[1] = ctx->h_counts[1] - ctx->h_counts[0];
@@ -243,8 +241,8 @@ int export_dim(phb_ctx* ctx, const phb_particles* src, size_t first, size_t last
     if (int rc = exclusive_scan(ctx, flag, flag, count + 1, flag + count + 1))
         return rc;
     // the total must be known before the copy to honour dst->capacity
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 4, flag + count, sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
+    if (int rc = words_to_host(ctx, ctx->h_counts + 4, flag + count, sizeof(uint32_t)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     size_t const total = ctx->h_counts[4];
     if (dst->n + total > dst->capacity)
@@ -361,9 +359,11 @@ int export_multi_dim(phb_ctx* ctx, const phb_particles* src, size_t first, size_
     unsigned const grid = unsigned((count + BS - 1) / BS);
     export_classify_kernel<DIM><<<grid, BS, 0, ctx->stream>>>(d_par, counts, tag, rank);
     PHB_LAUNCH_CHECK(ctx);
-    uint32_t h_counts[MAX_BOXES];
-    PHB_CUDA(ctx, cudaMemcpyAsync(h_counts, counts, nbox * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    static_assert(MAX_BOXES * sizeof(uint32_t) <= SMALL_D2H_BYTES, "box counts fit the bounce buffer");
+    if (int rc = words_to_host(ctx, ctx->h_bounce, counts, nbox * sizeof(uint32_t)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    uint32_t const* const h_counts = ctx->h_bounce;
     // destinations may repeat (several images of the same patch): hand out consecutive ranges
     size_t total = 0;
     for (int k = 0; k < nbox; ++k)

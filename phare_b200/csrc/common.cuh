@@ -168,6 +168,7 @@ struct phb_ctx
     void* scratch         = nullptr;
     size_t scratch_bytes  = 0;
     uint32_t* h_counts    = nullptr; // pinned, 8 entries
+    uint32_t* h_bounce    = nullptr; // pinned, SMALL_D2H_BYTES: small results on their way to pageable host memory
     double* em_pack       = nullptr; // node-interleaved copy of E,B used by the push kernels
     size_t em_bytes       = 0;
     size_t plan_n         = size_t(-1); // particles covered by the pending phb_bin_plan (slots live in scratch)
@@ -184,6 +185,12 @@ namespace phb
 int set_error(phb_ctx* ctx, int code, const std::string& msg);
 int cuda_check(phb_ctx* ctx, cudaError_t e, const char* what);
 int ensure_scratch(phb_ctx* ctx, size_t bytes);
+// Small results (class counts, totals of a scan, the error record) travel to the host through a store from a one-CTA kernel
+// into mapped pinned memory, NOT through a copy engine: an engine serves its queue in order, so a 4-byte count enqueued
+// behind another stream's field / moment read-back (solver.HostStaging: hundreds of MB) would hold the host for the whole
+// transfer.  `pinned_dst` is cudaMallocHost memory (h_counts, h_err, h_bounce); valid after the stream is synchronised.
+constexpr size_t SMALL_D2H_BYTES = 4096;
+int words_to_host(phb_ctx* ctx, void* pinned_dst, const void* d_src, size_t bytes);
 #define PHB_CUDA(ctx, call)                                                                              \
     do                                                                                                   \
     {                                                                                                    \

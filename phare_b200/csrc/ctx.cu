@@ -41,6 +41,25 @@ int ensure_scratch(phb_ctx* ctx, size_t bytes)
 
 static thread_local std::string g_create_error;
 
+namespace phb
+{
+__global__ void __launch_bounds__(128) words_to_host_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, unsigned n)
+{
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
+        dst[i] = src[i];
+    __threadfence_system();
+}
+int words_to_host(phb_ctx* ctx, void* pinned_dst, const void* d_src, size_t bytes)
+{
+    void* dev = nullptr;
+    PHB_CUDA(ctx, cudaHostGetDevicePointer(&dev, pinned_dst, 0));
+    words_to_host_kernel<<<1, 128, 0, ctx->stream>>>(static_cast<uint32_t*>(dev), static_cast<const uint32_t*>(d_src),
+                                                    unsigned(bytes / 4));
+    PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+} // namespace phb
+
 extern "C" {
 
 const char* phb_version(void) { return "phare_b200 0.1 (sm_100a)"; }
@@ -68,7 +87,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
         || (e = cudaMalloc(&ctx->d_err, sizeof(phb::DevError))) != cudaSuccess
         || (e = cudaMemset(ctx->d_err, 0, sizeof(phb::DevError))) != cudaSuccess
         || (e = cudaMallocHost(&ctx->h_err, sizeof(phb::DevError))) != cudaSuccess
-        || (e = cudaMallocHost(&ctx->h_counts, 8 * sizeof(uint32_t))) != cudaSuccess)
+        || (e = cudaMallocHost(&ctx->h_counts, 8 * sizeof(uint32_t))) != cudaSuccess
+        || (e = cudaMallocHost(&ctx->h_bounce, phb::SMALL_D2H_BYTES)) != cudaSuccess)
     {
         g_create_error = std::string("phb_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -108,6 +128,8 @@ void phb_destroy(phb_ctx* ctx)
         cudaFreeHost(ctx->h_err);
     if (ctx->h_counts)
         cudaFreeHost(ctx->h_counts);
+    if (ctx->h_bounce)
+        cudaFreeHost(ctx->h_bounce);
     if (ctx->own_stream)
         cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -150,8 +172,9 @@ int phb_poll_error(phb_ctx* ctx)
 {
     if (!ctx)
         return PHB_ERR_INVALID;
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, sizeof(phb::DevError), cudaMemcpyDeviceToHost,
-                                  ctx->stream));
+    static_assert(sizeof(phb::DevError) % 4 == 0, "DevError travels as words");
+    if (int rc = phb::words_to_host(ctx, ctx->h_err, ctx->d_err, sizeof(phb::DevError)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int const code = ctx->h_err->code;
     if (code == 0)
@@ -208,6 +231,15 @@ int phb_d2h(phb_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
 {
     if (!ctx)
         return PHB_ERR_INVALID;
+    if (bytes && bytes <= phb::SMALL_D2H_BYTES && bytes % 4 == 0 && reinterpret_cast<uintptr_t>(d_src) % 4 == 0)
+    {
+        // small: not through a copy engine (see words_to_host)
+        if (int rc = phb::words_to_host(ctx, ctx->h_bounce, d_src, bytes))
+            return rc;
+        PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        memcpy(h_dst, ctx->h_bounce, bytes);
+        return PHB_OK;
+    }
     PHB_CUDA(ctx, cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PHB_OK;

@@ -400,10 +400,13 @@ extern "C" int phb_predict_counts(phb_ctx* ctx, const phb_layout* L, const phb_b
         Ng *= e + 2 * pg;
     }
     size_t const at[3] = {Nd, Nd + Ng, Nd + Ng + 1};
-    for (int k = 0; k < 3; ++k)
-        PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + k, d_cell_start + at[k], sizeof(uint32_t), cudaMemcpyDeviceToHost,
-                                      ctx->stream));
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts + 3, d_plan, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    // (at[1] and at[2] are neighbours)
+    if (int rc = phb::words_to_host(ctx, ctx->h_counts + 0, d_cell_start + at[0], sizeof(uint32_t)))
+        return rc;
+    if (int rc = phb::words_to_host(ctx, ctx->h_counts + 1, d_cell_start + at[1], 2 * sizeof(uint32_t)))
+        return rc;
+    if (int rc = phb::words_to_host(ctx, ctx->h_counts + 3, d_plan, sizeof(uint32_t)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h_counts[0] = ctx->h_counts[0];
     h_counts[1] = ctx->h_counts[1] - ctx->h_counts[0];

@@ -143,7 +143,8 @@ int split_dim(phb_ctx* ctx, const phb_particles* src, size_t first, size_t last,
     PHB_LAUNCH_CHECK(ctx);
     if (int rc = exclusive_scan(ctx, cnt, cnt, n + 1, scan_tmp))
         return rc;
-    PHB_CUDA(ctx, cudaMemcpyAsync(ctx->h_counts, cnt + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (int rc = words_to_host(ctx, ctx->h_counts, cnt + n, sizeof(uint32_t)))
+        return rc;
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     size_t const total = ctx->h_counts[0];
     if (dst->n + total > dst->capacity)

@@ -752,12 +752,15 @@ class SolverPPC:
         self.messenger.fill_ghosts("B", abi.BX, self._by_id("B"))
 
     def advance_level(self, dt, staging=None):
-        """solver_ppc.hpp:315-341.  `staging` (HostStaging): the step takes E,B from pinned host buffers and
-        returns the moments and the new E,B to pinned host buffers; the read-back runs on a copy stream as soon
-        as each result is final, underneath the particle-array maintenance that ends the step."""
-        # with host staging the re-binning is kept as a separate, deferred pass: it is the GPU work the result
-        # read-back (PCIe) hides under; without it the deposit rides on the scatter pass (one read of the store less)
-        self.updater.defer_sort = staging is not None
+        """solver_ppc.hpp:315-341.  `staging` (HostStaging): the step takes E,B from pinned host buffers and returns the
+        moments and the new E,B to pinned host buffers.  The new E,B are on the critical path (the caller's next step
+        starts from them), so they are read back first, as soon as the corrector has produced them, under the
+        particle-array maintenance that ends the step; the moments are snapshotted on the device when the `all` sweep has
+        produced them and travel to the host behind the fields, under the NEXT step (nothing waits for them but
+        HostStaging.sync() / the next snapshot)."""
+        # staging.defer_sort (the round-1 arrangement): the re-binning kept as a separate, deferred pass that the moment
+        # read-back hides under; default: the one-pass `all` sweep (predicted re-binning), moments read back under the next step
+        self.updater.defer_sort = staging is not None and staging.defer_sort
         if staging is not None:
             staging.upload()
         self.prepare_step()
@@ -768,11 +771,16 @@ class SolverPPC:
         self._average()
         self._move_ions(dt, ALL)
         if staging is not None:
-            staging.download_moments()  # final after the `all` sweep (solver_ppc.hpp:333)
+            if staging.defer_sort:
+                staging.download_moments()  # final after the `all` sweep (solver_ppc.hpp:333)
+            else:
+                staging.snapshot_moments()
         self._field_solve("B", "Eavg", "B", "E", dt, "corrector")
         self.messenger.fill_ghosts("E", abi.EX, self._by_id("E"))
         if staging is not None:
             staging.download_fields()
+            if not staging.defer_sort:
+                staging.download_moments()
         self._finish_particles()
         if staging is not None:
             staging.join()
@@ -815,13 +823,17 @@ class HostStaging:
     """Host-buffer face of the step for callers whose fields live in host memory (the reference's FieldData
     buffers): pinned staging for the inputs (E, B of every local patch) and the results (per-population and
     total moments, new E and B), and a copy stream.  upload() is ordered before the step on the compute
-    stream; download_*() are ordered after the kernels that produce each result (event) and run on the copy
-    stream, so they overlap whatever the compute stream does next; join() makes the compute stream wait
-    for them (a step is complete when its results are on the host)."""
+    stream.  The new E,B go to the host as soon as the corrector has produced them (copy stream, underneath the
+    particle-array maintenance that ends the step) and join() makes the compute stream wait for them: the caller's
+    next step starts from them.  The moments are copied to a device-side snapshot when the `all` sweep has produced them
+    (snapshot_moments, 0.1 ms) and read back from the snapshot BEHIND the fields, underneath the next step;
+    they are on the host after sync() (or when the next step takes its own snapshot).
+    defer_sort=True is the round-1 arrangement (moments read back at once, hidden under a separate re-binning pass)."""
 
-    def __init__(self, ops, patches):
+    def __init__(self, ops, patches, defer_sort=False):
         t = ops.torch
-        self.t, self.patches = t, patches
+        self.t, self.patches, self.ops = t, patches, ops
+        self.defer_sort = defer_sort
         self.copy_stream = t.cuda.Stream(device=ops.device)
         self.inputs, self.moments, self.fields = [], [], []
         for p in patches:
@@ -833,6 +845,8 @@ class HostStaging:
                 self.moments += pop.moments()
         pin = lambda arrs: [t.empty(a.t.shape, dtype=t.float64).pin_memory() for a in arrs]
         self.h_in, self.h_moments, self.h_fields = pin(self.inputs), pin(self.moments), pin(self.fields)
+        self.snap = None if defer_sort else [t.empty_like(a.t) for a in self.moments]
+        self.moments_done = None
         for h, a in zip(self.h_in, self.inputs):
             h.copy_(a.t)
         self.h2d_bytes = sum(h.numel() * 8 for h in self.h_in)
@@ -855,29 +869,50 @@ class HostStaging:
         if done is not None:
             done.record()
 
-    def _download(self, hosts, arrs, name):
+    def _download(self, hosts, srcs, name):
         ready = self.t.cuda.Event()
         ready.record()
         with self.t.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(ready)
             done = self._mark(name)
-            for h, a in zip(hosts, arrs):
-                h.copy_(a.t, non_blocking=True)
+            for h, a in zip(hosts, srcs):
+                h.copy_(a, non_blocking=True)
             if done is not None:
                 done.record()
+            finished = self.t.cuda.Event()
+            finished.record()
+        return finished
+
+    def snapshot_moments(self):
+        """device-side copy of the moments the `all` sweep just produced (the next step zeroes the originals); the
+        previous snapshot must have left for the host first"""
+        if self.moments_done is not None:
+            self.t.cuda.current_stream().wait_event(self.moments_done)
+        for s, a in zip(self.snap, self.moments):
+            s.copy_(a.t, non_blocking=True)
 
     def download_moments(self):
-        self._download(self.h_moments, self.moments, "download_moments")
+        srcs = self.snap if self.snap is not None else [a.t for a in self.moments]
+        self.moments_done = self._download(self.h_moments, srcs, "download_moments")
 
     def download_fields(self):
-        self._download(self.h_fields, self.fields, "download_fields")
+        self.fields_done = self._download(self.h_fields, [a.t for a in self.fields], "download_fields")
 
     def timings_ms(self):
         """average milliseconds of each transfer since timing was switched on (call after a synchronize)"""
         return {k: sum(a.elapsed_time(b) for a, b in v) / len(v) for k, v in self.timed.items() if v}
 
     def join(self):
-        self.t.cuda.current_stream().wait_stream(self.copy_stream)
+        """the step is complete for the caller when the new E,B are on the host (and, with defer_sort, the moments)"""
+        if self.defer_sort:
+            self.t.cuda.current_stream().wait_stream(self.copy_stream)
+        else:
+            self.t.cuda.current_stream().wait_event(self.fields_done)
+
+    def sync(self):
+        """every result of every step issued so far is in the pinned host buffers"""
+        self.copy_stream.synchronize()
+        self.t.cuda.current_stream().synchronize()
 
     def results_become_inputs(self):
         """the host-side E,B of the next step are this step's results: swap the buffers (no transfer)"""
