@@ -50,8 +50,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons during the timed region.  nvidia-smi needs a second or more to come up (longer
+    on an 8-GPU box) and the timed region can be a fraction of a second, so the sampler is started BEFORE the warm-up,
+    samples every 50 ms with a timestamp, and window(t0, t1) keeps the samples that fall inside the timed region
+    (host clock taken right after the synchronisations that bracket it)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -61,36 +64,49 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        rows = []
+        for seen, ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                rows.append((seen, float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+        # a line is read a few ms after nvidia-smi took the sample: the window is widened by one sampling period
+        inside = [r for r in rows if t0 is None or (t0 <= r[0] <= t1 + 0.06)]
+        note = None
+        if not inside and rows:
+            mid = 0.5 * (t0 + t1)
+            inside = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            note = "timed region shorter than the sampling period: the 3 samples nearest to it"
+        sm, mx, reasons = [], [], set()
+        for _, a, b, flags in inside:
+            sm.append(a)
+            mx.append(b)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), flags):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        out = dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                   reasons=sorted(reasons), samples=len(sm))
+        if note:
+            out["note"] = note
+        return out
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -241,17 +257,19 @@ def cpp_host_arm(args):
     device = torch.device("cuda:0")
     level = CppLevel(cfg, device)
     level.initialize()
-    level.advance(cfg.dt, max(args.warmup, 3))
-    torch.cuda.synchronize()
     sampler = ClockSampler(0)
     sampler.start()
+    level.advance(cfg.dt, max(args.warmup, 3))
+    torch.cuda.synchronize()
     launches0 = level.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
     e0.record()
     level.advance(cfg.dt, args.steps)
     e1.record()
     torch.cuda.synchronize()
-    clocks = sampler.stop()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
     ms = e0.elapsed_time(e1)
     n_total = sum(sum(c) for c in level.counts())
     value = 2 * n_total * args.steps / (ms * 1e-3)
@@ -298,6 +316,8 @@ def our_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         solver.advance_level(DT)
     barrier()
@@ -305,17 +325,17 @@ def our_arm(args):
     # ---- timed region: EXACTLY K steps, CUDA events on the launching stream, max over ranks
     ops.kernel_timing = True
     ops.timed = {}
-    sampler = ClockSampler(local)
-    sampler.start()
     launches0 = ops.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t0 = time.time()
     e0.record()
     for _ in range(args.steps):
         solver.advance_level(DT)
     e1.record()
     barrier()
-    clocks = sampler.stop()
+    t1 = time.time()
+    clocks = sampler.stop(t0, t1)
     ops.kernel_timing = False
     ms = e0.elapsed_time(e1)
     launches = ops.ctx.launches - launches0
@@ -364,12 +384,35 @@ def our_arm(args):
                              None if planned else "push_in_place",
                              "reads iCell, delta, v, charge; writes iCell, delta, v" + (" and the 4-byte slot" if planned else ""))
         mv_all = kernel_ms.get("move_domain_only", [])
-        if mv_all and sum(mv_all) > sum(push_ms):  # (1-D configs run both sweeps fused: there is no separate K1 launch)
+        rb_ms = kernel_ms.get("move_all_rebin", [])
+        unit = BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]  # one particle-push = K1 + K3 bytes
+        if rb_ms:
+            # predicted re-binning (csrc/predict.cu): both sweeps are ONE pass each over the store.  The dominant kernel of the
+            # step is the all sweep: interpolate + push + deposit + re-binning of a particle (K1+K3+K2 fused).  Unit of work =
+            # one particle-push (K1 + K3 bytes; K2 is overhead, not algorithmic bytes); it MOVES 2 x K3 + 4 bytes.
+            roofline = kernel_roofline("K1+K3+K2 fused, the all sweep in one pass: interpolate + push + deposit + write to the slot "
+                                       "planned by the domain_only sweep (tile kernel, E,B block in shared memory, PLAN_REBIN)",
+                                       "tile_kernel", rb_ms, unit, "move_all_rebin",
+                                       "algorithmic = one particle-push of SURVEY 8(d) (K1 + K3 bytes); the kernel moves 2 x K3 + 4 "
+                                       "bytes (reads the store and the 4-byte plan word, writes the re-binned store) and is bound "
+                                       "by dependent FP64 issue (exact mode: no FMA contraction), ncu: profiles/r2p_kernels.md")
+            roofline["frac_of_bytes_moved"] = round(n_launch * (2 * BYTES_DEPOSIT[dim] + 4) / (avg(rb_ms) * 1e-3) / 1e9 / peak, 4)
+            roofline["plans_that_did_not_hold"] = solver.updater.misfiled
+            roofline["rebin_fallbacks"] = solver.updater.rebin_fallbacks
+            if mv_all:
+                extra["move_domain_only"] = kernel_roofline(
+                    "K1+K3 fused, the domain_only sweep + the plan of the re-binning (tile kernel, PLAN_PREDICT)", "tile_kernel",
+                    mv_all, unit, "move_domain_only", "moves K3 bytes + the 4-byte plan word; nothing written back")
+                extra["move_domain_only"]["frac_of_bytes_moved"] = round(
+                    n_launch * (BYTES_DEPOSIT[dim] + 4) / (avg(mv_all) * 1e-3) / 1e9 / peak, 4)
+            if k1:
+                extra["push"] = k1
+        elif mv_all and sum(mv_all) > sum(push_ms):  # (1-D configs run both sweeps fused: there is no separate K1 launch)
             # the dominant kernel of the step: interpolate + push + deposit of a particle in ONE pass (the domain_only sweep).
             # Its unit of work is SURVEY 8(d)'s whole "particle-push" (K1 + K3 = 80/104/128 + 52/64/76 B); it MOVES only the
             # K3 bytes (the pushed copy is never written nor re-read), which is why traffic < algorithmic bytes
             roofline = kernel_roofline("K1+K3 fused: interpolate + push + deposit in one pass (tile kernel, E,B block in shared memory)",
-                                       "tile_kernel", mv_all, BYTES_PUSH[dim] + BYTES_DEPOSIT[dim], "move_domain_only",
+                                       "tile_kernel", mv_all, unit, "move_domain_only_plain",
                                        "algorithmic = one particle-push of SURVEY 8(d) (K1 + K3 bytes); the kernel moves only the "
                                        "K3 bytes and is bound by the FP64 pipe (exact mode: no FMA contraction)")
             roofline["frac_of_bytes_moved"] = round(n_launch * BYTES_DEPOSIT[dim] / (avg(mv_all) * 1e-3) / 1e9 / peak, 4)
@@ -382,18 +425,6 @@ def our_arm(args):
             extra["deposit"] = dict(achieved=round(a, 1), frac=round(a / peak, 4), avg_launch_ms=round(avg(dep_ms), 4))
         if bin_ms:
             extra["bin"] = dict(avg_ms=round(avg(bin_ms), 4))
-        rb_ms = kernel_ms.get("move_all_rebin", [])
-        if rb_ms:
-            # the all sweep in ONE pass (phb_push_deposit_rebin): interpolate + push + deposit + re-binning of a particle;
-            # unit of work = one particle-push of SURVEY 8(d) (K1 + K3 bytes); it moves 2 x K3 bytes + the 4-byte plan word
-            a = n_launch * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (avg(rb_ms) * 1e-3) / 1e9
-            extra["move_all_rebin"] = dict(
-                kernel_name="tile_kernel<.., PLAN_REBIN>", achieved=round(a, 1), frac=round(a / peak, 4),
-                avg_launch_ms=round(avg(rb_ms), 4), algorithmic_bytes_per_particle=BYTES_PUSH[dim] + BYTES_DEPOSIT[dim],
-                frac_of_bytes_moved=round(n_launch * (2 * BYTES_DEPOSIT[dim] + 4) / (avg(rb_ms) * 1e-3) / 1e9 / peak, 4),
-                what="K1+K3+K2 fused: move + deposit + write to the slot planned by the domain_only sweep "
-                     "(predicted re-binning, csrc/predict.cu)",
-                plans_that_did_not_hold=solver.updater.misfiled, rebin_fallbacks=solver.updater.rebin_fallbacks)
         ds_ms, plan_ms = kernel_ms.get("deposit_scatter", []), kernel_ms.get("bin_plan", [])
         if ds_ms:
             # K3+K2 fused (the `all` sweep): reads the store + 4 B slot, writes the re-binned store

@@ -23,6 +23,9 @@ struct HostBase
     virtual phb_particles* particles(int patch, int pop)                          = 0;
     virtual void initialize()                                                     = 0;
     virtual void advance(double dt, int nsteps)                                   = 0;
+    virtual int patch_id(int local_patch)                                         = 0;
+    virtual void arena_export(unsigned char* handle)                              = 0;
+    virtual void arena_open(const unsigned char* handles)                         = 0;
 };
 thread_local std::string g_err;
 
@@ -33,8 +36,9 @@ struct Host : HostBase
     Context context;
     std::unique_ptr<Solver_t> solver;
 
+    // owners == nullptr: this process holds every patch; else patch p belongs to rank owners[p] of `world` (one per GPU)
     Host(int device, int npatch_, const phb_box* boxes, const double* dx, const int* domain_cells, double eta, double nu,
-         int hyper_mode, double Te)
+         int hyper_mode, double Te, const int* owners = nullptr, int rank = 0, int world = 1)
         : context{device, int(dim), int(interp)}
     {
         std::vector<GridLayout<dim, interp>> layouts;
@@ -62,8 +66,15 @@ struct Host : HostBase
         sim["algo"]["ohm"]["hyper_resistivity"]      = nu;
         sim["algo"]["ohm"]["hyper_mode"]             = hyper_mode == 0 ? "constant" : "spatial";
         sim["electrons"]["pressure_closure"]["Te"]   = Te;
-        solver = std::make_unique<Solver_t>(context, sim, layouts, cells);
+        if (owners)
+            solver = std::make_unique<Solver_t>(context, sim, layouts, cells, std::vector<int>(owners, owners + npatch_), rank,
+                                                world);
+        else
+            solver = std::make_unique<Solver_t>(context, sim, layouts, cells);
     }
+    int patch_id(int local_patch) override { return int(solver->messenger().globalIndex(std::size_t(local_patch))); }
+    void arena_export(unsigned char* handle) override { solver->messenger().exportArena(handle); }
+    void arena_open(const unsigned char* handles) override { solver->messenger().openArenas(handles); }
     phb_ctx* ctx() override { return context.get(); }
     int npatch() override { return int(solver->patches.size()); }
     const phb_layout* layout(int patch) override { return solver->patches.at(patch)->layout.c(); }
@@ -145,6 +156,42 @@ void* phh_create(int device, int dim, int interp, int npatch, const phb_box* box
             throw std::runtime_error("unsupported (dim, interp)");
     });
     return rc == 0 ? h : nullptr;
+}
+/* the level dealt to `world` ranks of one node (one process per GPU): boxes[npatch] names EVERY patch of the level,
+ * owners[p] the rank holding patch p; this process is `rank` and allocates its own patches only (phh_npatch, phh_patch_id).
+ * Before phh_initialize the ranks swap the CUDA IPC handles of their peer-memory arenas: phh_arena_export on every rank, an
+ * all-gather of the 64-byte handles by the launcher, phh_arena_open(handles[64 * world]).  Nothing else is ever exchanged
+ * outside the device: plans and arena offsets follow from the level's geometry on every rank alike. */
+void* phh_create_distributed(int device, int dim, int interp, int npatch, const phb_box* boxes, const int* owners, int rank,
+                             int world, const double* dx, const int* domain_cells, double eta, double nu, int hyper_mode,
+                             double Te)
+{
+    HostBase* h = nullptr;
+    int const rc = guarded([&] {
+#define PHH_CASE(D, I)                                                                                               \
+    if (dim == D && interp == I)                                                                                     \
+        h = new Host<D, I>(device, npatch, boxes, dx, domain_cells, eta, nu, hyper_mode, Te, owners, rank, world);
+        PHH_CASE(1, 1) PHH_CASE(1, 2) PHH_CASE(1, 3) PHH_CASE(2, 1) PHH_CASE(2, 2) PHH_CASE(2, 3) PHH_CASE(3, 1)
+        PHH_CASE(3, 2) PHH_CASE(3, 3)
+#undef PHH_CASE
+        if (!h)
+            throw std::runtime_error("unsupported (dim, interp)");
+    });
+    return rc == 0 ? h : nullptr;
+}
+int phh_patch_id(void* h, int local_patch)
+{
+    int id = -1;
+    guarded([&] { id = static_cast<HostBase*>(h)->patch_id(local_patch); });
+    return id;
+}
+int phh_arena_export(void* h, unsigned char* handle64)
+{
+    return guarded([&] { static_cast<HostBase*>(h)->arena_export(handle64); });
+}
+int phh_arena_open(void* h, const unsigned char* handles)
+{
+    return guarded([&] { static_cast<HostBase*>(h)->arena_open(handles); });
 }
 void phh_destroy(void* h) { delete static_cast<HostBase*>(h); }
 phb_ctx* phh_ctx(void* h) { return static_cast<HostBase*>(h)->ctx(); }

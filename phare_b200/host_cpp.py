@@ -33,7 +33,11 @@ class _Store:
 
 
 class CppLevel:
-    def __init__(self, cfg, device="cuda:0", capacity_factor=1.2):
+    """comm (messenger.TorchComm) with size > 1: the level is dealt to the ranks like make_level deals it (one process per
+    GPU); the C++ driver of every rank holds its own patches and reaches its neighbours' memory over NVLink.  torch.distributed
+    is used ONCE here, to all-gather the 64-byte CUDA IPC handles of the ranks' arenas."""
+
+    def __init__(self, cfg, device="cuda:0", capacity_factor=1.2, comm=None):
         import torch
         from . import torch_interop as ti
         from .solver import make_level
@@ -42,31 +46,50 @@ class CppLevel:
         abi.load()  # libphare_b200.so first (the host library resolves its symbols against it)
         lib = self.lib = C.CDLL(HOST_LIB)
         lib.phh_create.restype = C.c_void_p
+        lib.phh_create_distributed.restype = C.c_void_p
         lib.phh_ctx.restype = C.c_void_p
         lib.phh_layout.restype = C.POINTER(abi.Layout)
         lib.phh_field.restype = C.c_void_p
         lib.phh_particles.restype = C.c_void_p
         lib.phh_last_error.restype = C.c_char_p
         for fn in (lib.phh_ctx, lib.phh_npatch, lib.phh_layout, lib.phh_field, lib.phh_particles, lib.phh_initialize,
-                   lib.phh_advance, lib.phh_add_population, lib.phh_destroy):
+                   lib.phh_advance, lib.phh_add_population, lib.phh_destroy, lib.phh_patch_id, lib.phh_arena_export,
+                   lib.phh_arena_open):
             fn.argtypes = None
         self.cfg, self.torch = cfg, torch
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         dim = cfg.dim
-        geom, layouts = make_level(cfg.cells, cfg.patch_grid, cfg.interp, cfg.dl)
+        world = comm.size if comm is not None else 1
+        rank = comm.rank if comm is not None else 0
+        geom, layouts = make_level(cfg.cells, cfg.patch_grid, cfg.interp, cfg.dl, nranks=world)
         boxes = (abi.Box * len(layouts))()
         for i, L in enumerate(layouts):
             for d in range(dim):
                 boxes[i].lower[d] = L.amr_lower[d]
                 boxes[i].upper[d] = L.amr_lower[d] + L.ncells[d] - 1
         dbl = lambda xs: (C.c_double * len(xs))(*[float(x) for x in xs])
-        h = lib.phh_create(self.device.index or 0, dim, cfg.interp, len(layouts), boxes, dbl(cfg.dl),
-                           (C.c_int * dim)(*[int(c) for c in cfg.cells]), C.c_double(cfg.eta), C.c_double(cfg.nu), 0,
-                           C.c_double(cfg.Te))
+        cells = (C.c_int * dim)(*[int(c) for c in cfg.cells])
+        if world > 1:
+            owners = (C.c_int * len(layouts))(*[int(pg.owner) for pg in geom.patches])
+            h = lib.phh_create_distributed(self.device.index or 0, dim, cfg.interp, len(layouts), boxes, owners, rank, world,
+                                           dbl(cfg.dl), cells, C.c_double(cfg.eta), C.c_double(cfg.nu), 0, C.c_double(cfg.Te))
+        else:
+            h = lib.phh_create(self.device.index or 0, dim, cfg.interp, len(layouts), boxes, dbl(cfg.dl), cells,
+                               C.c_double(cfg.eta), C.c_double(cfg.nu), 0, C.c_double(cfg.Te))
         if not h:
             raise RuntimeError("phh_create: " + lib.phh_last_error().decode())
         self.h = C.c_void_p(h)
+        self.patch_ids = [pg.id for pg in geom.patches if pg.owner == rank]
+        if world > 1:
+            # the one exchange between the ranks that does not go through device memory: the handles of the arenas
+            mine = (C.c_ubyte * 64)()
+            self._check(lib.phh_arena_export(self.h, mine), "phh_arena_export")
+            everyone = [None] * world
+            comm.dist.all_gather_object(everyone, bytes(mine))
+            self._check(lib.phh_arena_open(self.h, (C.c_ubyte * (64 * world))(*b"".join(everyone))), "phh_arena_open")
+            assert [lib.phh_patch_id(self.h, C.c_int(i)) for i in range(len(self.patch_ids))] == self.patch_ids
+            layouts = [layouts[i] for i in self.patch_ids]
         # everything on torch's current stream, like GpuOps
         self.ctx = Context.adopt(lib.phh_ctx(self.h), dim, cfg.interp, stream=ti.current_stream_ptr())
         self.layouts = layouts
