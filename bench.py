@@ -245,49 +245,148 @@ def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
     return box[0]
 
 
+def _cpp_snapshot(level):
+    from phare_b200 import abi, host_cpp
+    out, counts = {}, level.counts()
+    for ip, pid in enumerate(level.patch_ids):
+        rec = dict(counts=list(counts[ip]))
+        for which, name, q0 in ((host_cpp.B, "B", abi.BX), (host_cpp.E, "E", abi.EX), (host_cpp.VI, "Vi", abi.VX)):
+            rec[name] = [level.get_field(ip, which, c, q0 + c) for c in range(3)]
+        rec["Ni"] = level.get_field(ip, host_cpp.NI, 0, abi.RHO)
+        out[pid] = rec
+    return out
+
+
+def cpp_multi_rank_parity(cfg_key, n_gpus, rank, device, comm, steps=3):
+    """multi_rank_parity for the C++ driver: the small problem of the benchmarked config advanced by the C++ level driver on the
+    N ranks (peer-memory exchange between the C++ messengers) and by ONE C++ driver holding every patch on rank 0"""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from phare_b200.host_cpp import CppLevel
+    base, _ = bench_config(cfg_key, n_gpus)
+    grid = base.patch_grid
+    per = PARITY_CELLS[base.dim]
+    small = base.with_cells(tuple(per[d] * grid[d] for d in range(base.dim)), grid)
+    small.pops = [dict(p, ppc=PARITY_PPC) for p in small.pops]
+    level = CppLevel(small, device, comm=comm)
+    level.initialize()
+    level.advance(small.dt, steps)
+    everyone = [None] * n_gpus
+    dist.all_gather_object(everyone, _cpp_snapshot(level))
+    level.close()
+    verdict = None
+    if rank == 0:
+        multi = {}
+        for part in everyone:
+            multi.update(part)
+        one = CppLevel(small, device)
+        one.initialize()
+        one.advance(small.dt, steps)
+        single = _cpp_snapshot(one)
+        one.close()
+        worst, where, counts_equal = 0.0, "", True
+        for pid, a in multi.items():
+            b = single[pid]
+            counts_equal = counts_equal and a["counts"] == b["counts"]
+            for name in ("B", "E", "Vi"):
+                for c in range(3):
+                    ok = np.isfinite(b[name][c])
+                    e = _node_err(a[name][c][ok], b[name][c][ok])
+                    if e > worst:
+                        worst, where = e, f"{name}{'xyz'[c]}@patch{pid}"
+            e = _node_err(a["Ni"], b["Ni"])
+            if e > worst:
+                worst, where = e, f"Ni@patch{pid}"
+        verdict = dict(ok=bool(worst <= 1e-10 and counts_equal), max_rel=worst, where=where, counts_equal=bool(counts_equal),
+                       steps=steps, problem=f"{small.name.split(':')[0]} profiles, {list(small.cells)} cells in {list(grid)} "
+                                            f"patches, {PARITY_PPC} ppc, C++ driver on N ranks vs one C++ driver",
+                       bar="fields and moments <= 1e-10 per node, particle counts per patch equal")
+    box = [verdict]
+    dist.broadcast_object_list(box, src=0)
+    torch.cuda.synchronize()
+    return box[0]
+
+
 def cpp_host_arm(args):
     """the same step driven by the C++ level driver (include/phare_b200/solver_ppc.hpp through libphare_b200_host.so):
-    Python only builds the problem; the K timed steps are ONE call into C++.  One GPU (the C++ driver holds every patch of
-    the level in one process); kernel-level roofline figures come from the default (Python-driven) arm, whose launches are
-    bracketed one by one."""
+    Python only builds the problem; the K timed steps are ONE call into C++ per rank.  At N > 1 the level is dealt to the
+    ranks (one process per GPU) and the C++ messengers exchange through NVLink peer memory; torch.distributed serves the
+    set-up (the IPC handles of the arenas) and this harness's own barrier / max-over-ranks.  Kernel-level roofline figures
+    come from the default (Python-driven) arm, whose launches are bracketed one by one."""
     import torch
+    import torch.distributed as dist
     from phare_b200.host_cpp import CppLevel
-    assert args.gpus == 1, "--host cpp drives one GPU"
-    cfg, scaling = bench_config(args.config, 1)
-    device = torch.device("cuda:0")
-    level = CppLevel(cfg, device)
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    assert world == args.gpus, "launch with torch.distributed.run --nproc-per-node N"
+    device = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(device)
+    comm, parity = None, None
+    if world > 1:
+        from phare_b200.messenger import TorchComm
+        dist.init_process_group("nccl", device_id=device)
+        comm = TorchComm(device)
+        if not args.no_parity:
+            parity = cpp_multi_rank_parity(args.config, world, rank, device, comm)
+    cfg, scaling = bench_config(args.config, world)
+    level = CppLevel(cfg, device, comm=comm)
     level.initialize()
-    sampler = ClockSampler(0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
     sampler.start()
     level.advance(cfg.dt, max(args.warmup, 3))
-    torch.cuda.synchronize()
+    barrier()
     launches0 = level.ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     t0 = time.time()
     e0.record()
     level.advance(cfg.dt, args.steps)
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     t1 = time.time()
     clocks = sampler.stop(t0, t1)
     ms = e0.elapsed_time(e1)
-    n_total = sum(sum(c) for c in level.counts())
+    n_local = sum(sum(c) for c in level.counts())
+    n_total = n_local
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        cnt = torch.tensor([n_local], device=device, dtype=torch.int64)
+        dist.all_reduce(cnt)
+        n_total = int(cnt.item())
     value = 2 * n_total * args.steps / (ms * 1e-3)
     peak, _ = measured_peaks()
     dim = cfg.dim
-    line = dict(metric=METRIC, value=value, unit="particle-pushes/s", n_gpus=1, steps=args.steps,
-                warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling,
-                vs_baseline=None, dtype="f64", data="synthetic", host="cpp",
-                config=dict(workload=cfg.name, cells=list(cfg.cells), patch_grid=list(cfg.patch_grid),
-                            ppc=[p["ppc"] for p in cfg.pops], interp_order=cfg.interp, particles_total=n_total,
-                            pushes_per_step=2 * n_total,
-                            parallelism=f"{len(level.layouts)} patch(es) on one GPU, C++ level driver"),
-                clocks=clocks, gpu_launches=level.ctx.launches - launches0, e2e=None, roofline=None,
-                roofline_other=dict(whole_step_frac_of_hbm=round(
-                    2 * n_total * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)),
-                cpu_baseline=None)
-    print(json.dumps(line))
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="particle-pushes/s", n_gpus=world, steps=args.steps,
+                    warmup=max(args.warmup, 3), ms_per_step=ms / args.steps, higher_is_better=True, scaling=scaling,
+                    vs_baseline=None, dtype="f64", data="synthetic", host="cpp",
+                    config=dict(workload=cfg.name, cells=list(cfg.cells), patch_grid=list(cfg.patch_grid),
+                                ppc=[p["ppc"] for p in cfg.pops], interp_order=cfg.interp, particles_total=n_total,
+                                pushes_per_step=2 * n_total,
+                                parallelism=f"{len(level.layouts)} patch(es) per GPU, {world} GPU(s), C++ level driver"),
+                    per_gpu=value / world, clocks=clocks, gpu_launches=level.ctx.launches - launches0, e2e=None, roofline=None,
+                    roofline_other=dict(whole_step_frac_of_hbm=round(
+                        2 * n_local * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)),
+                    cpu_baseline=None)
+        if parity is not None:
+            line["parity_check"] = parity
+        print(json.dumps(line))
     level.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 def our_arm(args):
