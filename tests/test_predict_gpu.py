@@ -187,3 +187,52 @@ def test_move_two_cells_is_reported_and_nobody_is_lost(ctxs, cpu_oracle):
         ctx.poll_error()
     assert e.value.code == abi.PHB_ERR_MOVE_TWO_CELL
     assert sum(counts[:3]) == n and counts[3] == 0
+
+
+@pytest.mark.parametrize("k,cells,grid", [(1, (512,), (2,)), (3, (64, 32), (2, 2)), (5, (16, 16, 16), (2, 1, 1))])
+def test_step_with_forced_repair_equals_step_without_prediction(k, cells, grid, monkeypatch):
+    """IonUpdater.maintain_arrays' remedy for failed plans (phb_bin of the re-binned store) driven from the solver: every second
+    step the count of failed plans is reported as 1 although every plan held; the repaired run must equal the run without
+    prediction (same particles in the same cells, fields to rounding) and the run that never repairs"""
+    from phare_b200 import configs
+    from phare_b200.messenger import LocalComm
+    from phare_b200.solver import GpuOps
+
+    def build(predict, force):
+        cfg = configs.get(k).with_cells(cells, grid)
+        cfg.pops = [dict(p, ppc=min(p["ppc"], 16)) for p in cfg.pops]
+        s = configs.build_device_loaded(GpuOps(cfg.dim, cfg.interp, "cuda:0"), LocalComm(), cfg)
+        s.updater.predict = predict
+        if force:
+            real, calls = s.ops.predict_counts, [0]
+
+            def lying(*a):
+                c = real(*a)
+                calls[0] += 1
+                return c[:3] + ((1,) if calls[0] % 2 == 0 else (c[3],))
+            monkeypatch.setattr(s.ops, "predict_counts", lying)
+        return cfg, s
+
+    runs = []
+    for predict, force in ((True, True), (True, False), (False, False)):
+        cfg, s = build(predict, force)
+        for _ in range(4):
+            s.advance_level(cfg.dt)
+        runs.append(s)
+    forced, plain, off = runs
+    assert forced.updater.rebin_fallbacks > 0 and plain.updater.rebin_fallbacks == 0 and plain.updater.misfiled == 0
+    for other in (plain, off):
+        for pa, pb in zip(forced.patches, other.patches):
+            for popa, popb in zip(pa.pops, pb.pops):
+                assert forced.ops.count(popa.domain) == other.ops.count(popb.domain)
+                a = forced.ops.get_particles(popa.domain)
+                b = other.ops.get_particles(popb.domain)
+                assert np.array_equal(np.sort(a[0], axis=0), np.sort(b[0], axis=0))  # the same cells are populated alike
+                csa, csb = popa.cell_start.t.cpu().numpy(), popb.cell_start.t.cpu().numpy()
+                assert np.array_equal(csa, csb)
+            for name in ("B", "E", "Vi"):
+                for c in range(3):
+                    x = forced.ops.get_field(getattr(pa, name)[c])
+                    y = other.ops.get_field(getattr(pb, name)[c])
+                    ok = np.isfinite(y)
+                    assert np.max(np.abs(x[ok] - y[ok])) <= 1e-11 * (np.max(np.abs(y[ok])) + 1e-300)

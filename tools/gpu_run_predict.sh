@@ -1,9 +1,5 @@
 cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu > gpurun_out/bench_r2n.json 2> gpurun_out/bench_r2n.err; echo rc=$?
-tail -3 gpurun_out/bench_r2n.err
-python -c "
-import json
-d=[json.loads(l) for l in open('gpurun_out/bench_r2n.json') if l.startswith('{')][0]
-print(d['value']/1e9, d['ms_per_step'], d['e2e']['value']/1e9, d['e2e']['staging_ms_per_rank']); print(d['roofline_other'].get('kernel_ms_per_step'))"
-timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
+timeout 900 python -m pytest tests/test_predict_gpu.py -q -x 2>&1 | tail -8
+timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 7 python -m pytest tests/test_predict_gpu.py -q -x -k "same_fields or failed_plans or move_two" > gpurun_out/san_predict.log 2>&1; echo san_rc=$?
+tail -5 gpurun_out/san_predict.log; grep -c "Invalid\|ERROR SUMMARY" gpurun_out/san_predict.log
