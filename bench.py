@@ -176,6 +176,7 @@ def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
     small = base.with_cells(tuple(per[d] * grid[d] for d in range(base.dim)), grid)
     small.pops = [dict(p, ppc=PARITY_PPC) for p in small.pops]
     solver, ops = build_gpu_solver(small, n_gpus, device)
+    solver.updater.predict_min_cells = 0  # the sweeps of the timed region (predicted re-binning), whatever the patch size
     for _ in range(steps):
         solver.advance_level(small.dt)
     mine = _snapshot(solver)
@@ -189,6 +190,7 @@ def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
         for part in everyone:
             multi.update(part)
         one, ops1 = build_gpu_solver(small, 1, device, comm=LocalComm())
+        one.updater.predict_min_cells = 0
         for _ in range(steps):
             one.advance_level(small.dt)
         single = _snapshot(one)
@@ -269,6 +271,7 @@ def cpp_multi_rank_parity(cfg_key, n_gpus, rank, device, comm, steps=3):
     per = PARITY_CELLS[base.dim]
     small = base.with_cells(tuple(per[d] * grid[d] for d in range(base.dim)), grid)
     small.pops = [dict(p, ppc=PARITY_PPC) for p in small.pops]
+    os.environ["PHB_PREDICT_MIN_CELLS"] = "0"  # the sweeps of the timed region (predicted re-binning), whatever the patch size
     level = CppLevel(small, device, comm=comm)
     level.initialize()
     level.advance(small.dt, steps)
@@ -302,6 +305,7 @@ def cpp_multi_rank_parity(cfg_key, n_gpus, rank, device, comm, steps=3):
                        steps=steps, problem=f"{small.name.split(':')[0]} profiles, {list(small.cells)} cells in {list(grid)} "
                                             f"patches, {PARITY_PPC} ppc, C++ driver on N ranks vs one C++ driver",
                        bar="fields and moments <= 1e-10 per node, particle counts per patch equal")
+    os.environ.pop("PHB_PREDICT_MIN_CELLS", None)
     box = [verdict]
     dist.broadcast_object_list(box, src=0)
     torch.cuda.synchronize()

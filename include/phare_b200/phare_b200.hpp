@@ -576,6 +576,8 @@ public:
     {
         if (char const* e = std::getenv("PHB_PREDICT"))
             usePrediction = std::string(e) != "0";
+        if (char const* e = std::getenv("PHB_PREDICT_MIN_CELLS"))
+            predictMinCells = std::size_t(std::atol(e));
     }
 
     // updatePopulations (ion_updater.hpp:90-109) = launchPopulations (every kernel of the sweep, enqueued) +
@@ -616,7 +618,8 @@ public:
             if (mode == UpdaterMode::domain_only)
             {
                 // updateAndDepositDomain_ (:171-219): tmp_particles_ = domain; move; deposit the allowed ones
-                if (fusedDomainOnly && n && usePrediction && phb_predict_supported(layout.c()))
+                if (fusedDomainOnly && n && usePrediction && phb_predict_supported(layout.c())
+                    && cellCount(layout) >= predictMinCells)
                 {
                     // the same pass + the plan of the re-binning the all sweep will carry out (csrc/predict.cu): the cell
                     // a particle ends in after the second push of a PPC step is the one this push predicts
@@ -732,7 +735,18 @@ public:
         ctx.check(phb_poll_error(ctx.get())); // throws DictionaryException{"cause", ...} like boris.hpp:207-214
     }
 
+    template<typename Layout>
+    static std::size_t cellCount(Layout const& layout)
+    {
+        std::size_t n = 1;
+        for (std::size_t d = 0; d < dim; ++d)
+            n *= std::size_t(layout.AMRBox().upper[d] - layout.AMRBox().lower[d] + 1);
+        return n;
+    }
     bool usePrediction   = true; // predicted re-binning where the tile kernel exists (PHB_PREDICT=0 in the environment: off)
+    // ... and fills the GPU: a CTA owns 128 cells, two are resident per SM; smaller patches keep the two-pass `all` sweep,
+    // whose streaming push and 16-lanes-per-cell scatter still spread over every SM (PHB_PREDICT_MIN_CELLS)
+    std::size_t predictMinCells = 128 * 2 * 148;
     std::size_t misfiled = 0;    // plans that did not hold so far
     void updateIons(Ions<dim>& ions) { ions.computeChargeDensityAndBulkVelocity(); } // ion_updater.hpp:112-116
     void reset() {}                                                                  // :66-70 (frees tmp_particles_)

@@ -438,6 +438,10 @@ class IonUpdater:
         # the domain_only sweep predicts unless it sits on a cell face), the all sweep is then ONE pass: move + deposit +
         # write to the planned slot (phb_push_deposit_predict / _rebin, csrc/predict.cu); PHB_PREDICT=0 switches it off
         self.predict = os.environ.get("PHB_PREDICT", "1") != "0"
+        # ... for patches whose tile-kernel grid fills the GPU: a CTA owns 128 cells and two CTAs are resident per SM, so below
+        # 2 x 148 CTAs the one-pass sweep runs on a fraction of the SMs while the streaming push / 16-lanes-per-cell scatter of
+        # the two-pass path still spread out (measured, config 3 with 128 x 128-cell patches: 10.1 against 9.0 ms per step)
+        self.predict_min_cells = int(os.environ.get("PHB_PREDICT_MIN_CELLS", 128 * 2 * 148))
         self.misfiled = 0        # plans that did not hold so far (each one costs a phb_bin of its store)
         self.rebin_fallbacks = 0
         # fused: one pass per array and sweep (phb_push_deposit, K1+K3) instead of phb_push then phb_deposit
@@ -475,7 +479,8 @@ class IonUpdater:
                         ops.deposit(L, pop.level_ghost, pop.rho_n, pop.rho_q, pop.flux, 1.0, 0, nlg, [patch.domain_box])
                     continue
             if (fused and mode == DOMAIN_ONLY and n and self.predict and self.sort_with_deposit and not self.defer_sort
-                    and hasattr(ops, "push_deposit_predict") and ops.predict_supported(L)):
+                    and hasattr(ops, "push_deposit_predict") and ops.predict_supported(L)
+                    and int(np.prod([L.ncells[d] for d in range(L.dim)])) >= self.predict_min_cells):
                 need = ops.capacity(pop.domain)
                 if pop.plan is None or pop.plan[2] != need:
                     pop.plan = ops.predict_plan(L, patch.domain_box, need) + (need,)

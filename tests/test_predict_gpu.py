@@ -236,3 +236,19 @@ def test_step_with_forced_repair_equals_step_without_prediction(k, cells, grid, 
                     y = other.ops.get_field(getattr(pb, name)[c])
                     ok = np.isfinite(y)
                     assert np.max(np.abs(x[ok] - y[ok])) <= 1e-11 * (np.max(np.abs(y[ok])) + 1e-300)
+
+
+def test_small_patches_keep_the_two_pass_sweep():
+    """below IonUpdater.predict_min_cells (a tile-kernel grid that would not fill the GPU) the all sweep stays two-pass"""
+    from phare_b200 import configs
+    from phare_b200.messenger import LocalComm
+    from phare_b200.solver import GpuOps
+    cfg = configs.get(3).with_cells((64, 32), (2, 2))
+    cfg.pops = [dict(p, ppc=8) for p in cfg.pops]
+    for min_cells, one_pass in ((128 * 2 * 148, False), (0, True)):
+        s = configs.build_device_loaded(GpuOps(cfg.dim, cfg.interp, "cuda:0"), LocalComm(), cfg)
+        s.updater.predict_min_cells = min_cells
+        s.ops.kernel_timing, s.ops.timed = True, {}
+        s.advance_level(cfg.dt)
+        assert ("move_all_rebin" in s.ops.timed) == one_pass
+        assert ("deposit_scatter" in s.ops.timed) == (not one_pass)
