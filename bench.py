@@ -15,7 +15,13 @@ the owner's values): "parity_check" in the JSON line, non-zero exit status on fa
 A "step" = one SolverPPC::advanceLevel: 3 x (Faraday, Ampere, Ohm), 2 x average, the domain_only and the all
 particle sweeps (2 pushes per particle) and every same-level exchange phase.  For N > 1 the driver launches
 this file under torch.distributed.run, one rank per GPU; patches are sharded one per GPU (Cartesian grid) and
-halos / migrating particles go through NCCL point-to-point.  Rank 0 prints ONE JSON line.
+halos / migrating particles go through NVLink peer memory (no collective on the data path).  Rank 0 prints ONE JSON line.
+
+Who enqueues the step (--host): by default (auto) `value` / `ms_per_step` are timed with the C++ level driver
+(include/phare_b200/solver_ppc.hpp: the host code in the reference's own language; W warm-up + K steps in one call per rank),
+then the same kernels are driven once more from Python (phare_b200/solver.py, same C ABI), which brackets every launch with
+CUDA events: `roofline`, `roofline_other`, `e2e` and `python_host` come from that pass.  If the C++ driver cannot run, the line
+carries the Python-driven figures and `cpp_host_error`.
 """
 import argparse
 import json
@@ -312,15 +318,59 @@ def cpp_multi_rank_parity(cfg_key, n_gpus, rank, device, comm, steps=3):
     return box[0]
 
 
+def cpp_timed_region(args, cfg, device, comm, world, local):
+    """W warm-up steps, then EXACTLY K steps of the C++ level driver (ONE call into C++ per rank), bracketed by barrier +
+    synchronize, CUDA events, max over ranks.  Returns dict(ms, n_local, n_total, launches, clocks, patches)."""
+    import torch
+    import torch.distributed as dist
+    from phare_b200.host_cpp import CppLevel
+    level = CppLevel(cfg, device, comm=comm)
+    try:
+        level.initialize()
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        sampler = ClockSampler(local)
+        sampler.start()
+        level.advance(cfg.dt, max(args.warmup, 3))
+        barrier()
+        launches0 = level.ctx.launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.time()
+        e0.record()
+        level.advance(cfg.dt, args.steps)
+        e1.record()
+        barrier()
+        t1 = time.time()
+        clocks = sampler.stop(t0, t1)
+        ms = e0.elapsed_time(e1)
+        n_local = sum(sum(c) for c in level.counts())
+        n_total = n_local
+        if world > 1:
+            t = torch.tensor([ms], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            cnt = torch.tensor([n_local], device=device, dtype=torch.int64)
+            dist.all_reduce(cnt)
+            n_total = int(cnt.item())
+        return dict(ms=ms, n_local=n_local, n_total=n_total, launches=level.ctx.launches - launches0, clocks=clocks,
+                    patches=len(level.layouts))
+    finally:
+        level.close()
+
+
 def cpp_host_arm(args):
     """the same step driven by the C++ level driver (include/phare_b200/solver_ppc.hpp through libphare_b200_host.so):
     Python only builds the problem; the K timed steps are ONE call into C++ per rank.  At N > 1 the level is dealt to the
     ranks (one process per GPU) and the C++ messengers exchange through NVLink peer memory; torch.distributed serves the
     set-up (the IPC handles of the arenas) and this harness's own barrier / max-over-ranks.  Kernel-level roofline figures
-    come from the default (Python-driven) arm, whose launches are bracketed one by one."""
+    come from the default arm, whose Python-driven pass brackets the launches one by one."""
     import torch
     import torch.distributed as dist
-    from phare_b200.host_cpp import CppLevel
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -335,38 +385,8 @@ def cpp_host_arm(args):
         if not args.no_parity:
             parity = cpp_multi_rank_parity(args.config, world, rank, device, comm)
     cfg, scaling = bench_config(args.config, world)
-    level = CppLevel(cfg, device, comm=comm)
-    level.initialize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    level.advance(cfg.dt, max(args.warmup, 3))
-    barrier()
-    launches0 = level.ctx.launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.time()
-    e0.record()
-    level.advance(cfg.dt, args.steps)
-    e1.record()
-    barrier()
-    t1 = time.time()
-    clocks = sampler.stop(t0, t1)
-    ms = e0.elapsed_time(e1)
-    n_local = sum(sum(c) for c in level.counts())
-    n_total = n_local
-    if world > 1:
-        t = torch.tensor([ms], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        cnt = torch.tensor([n_local], device=device, dtype=torch.int64)
-        dist.all_reduce(cnt)
-        n_total = int(cnt.item())
+    r = cpp_timed_region(args, cfg, device, comm, world, local)
+    ms, n_total, n_local = r["ms"], r["n_total"], r["n_local"]
     value = 2 * n_total * args.steps / (ms * 1e-3)
     peak, _ = measured_peaks()
     dim = cfg.dim
@@ -377,20 +397,43 @@ def cpp_host_arm(args):
                     config=dict(workload=cfg.name, cells=list(cfg.cells), patch_grid=list(cfg.patch_grid),
                                 ppc=[p["ppc"] for p in cfg.pops], interp_order=cfg.interp, particles_total=n_total,
                                 pushes_per_step=2 * n_total,
-                                parallelism=f"{len(level.layouts)} patch(es) per GPU, {world} GPU(s), C++ level driver"),
-                    per_gpu=value / world, clocks=clocks, gpu_launches=level.ctx.launches - launches0, e2e=None, roofline=None,
+                                parallelism=f"{r['patches']} patch(es) per GPU, {world} GPU(s), C++ level driver"),
+                    per_gpu=value / world, clocks=r["clocks"], gpu_launches=r["launches"], e2e=None, roofline=None,
                     roofline_other=dict(whole_step_frac_of_hbm=round(
                         2 * n_local * (BYTES_PUSH[dim] + BYTES_DEPOSIT[dim]) / (ms / args.steps * 1e-3) / 1e9 / peak, 4)),
                     cpu_baseline=None)
         if parity is not None:
             line["parity_check"] = parity
         print(json.dumps(line))
-    level.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if parity is not None and not parity["ok"]:
         sys.exit(3)
+
+
+def cpp_primary(args, cfg, device, world, local, rank):
+    """The default arm's PRIMARY timed region: the step as the product drives it, i.e. by the C++ level driver (one call into
+    C++ per rank for the K steps; at N > 1 its own parity check first).  Any failure, on any rank, makes every rank fall back
+    to the Python-driven region, and the JSON line says so."""
+    import torch
+    import torch.distributed as dist
+    ok, res, err = 1, None, None
+    try:
+        comm = None
+        if world > 1:
+            from phare_b200.messenger import TorchComm
+            comm = TorchComm(device)
+        par = cpp_multi_rank_parity(args.config, world, rank, device, comm) if world > 1 and not args.no_parity else None
+        res = cpp_timed_region(args, cfg, device, comm, world, local)
+        res["parity"] = par
+    except Exception as e:  # noqa: BLE001 - whatever it is, the Python-driven region is the fallback
+        ok, err = 0, f"{type(e).__name__}: {e}"
+    if world > 1:
+        t = torch.tensor([ok], device=device, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = int(t.item())
+    return res if ok else dict(error=err or "the C++ driver failed on another rank")
 
 
 def our_arm(args):
@@ -411,6 +454,10 @@ def our_arm(args):
     parity = multi_rank_parity(args.config, n_gpus, rank, device) if world > 1 and not args.no_parity else None
     cfg, scaling = bench_config(args.config, n_gpus)
     DT, dim = cfg.dt, cfg.dim
+    # --host auto (default): `value` is timed with the C++ level driver enqueueing the step (the product's host code, the
+    # reference's own language); the Python-driven pass that follows runs the same kernels through the same C ABI and brackets
+    # them one by one (roofline, per-kernel ms, e2e).  Both numbers are in the line.
+    cpp = cpp_primary(args, cfg, device, world, local, rank) if args.host == "auto" else None
     solver, ops = build_gpu_solver(cfg, n_gpus, device)
     n_local = sum(ops.count(pop.domain) for p in solver.patches for pop in p.pops)
 
@@ -454,6 +501,11 @@ def our_arm(args):
         n_total = n_local
     pushes = 2 * n_total * args.steps  # two particle sweeps per PPC step
     value = pushes / (ms * 1e-3)
+    python_host = dict(value=value, ms_per_step=ms / args.steps, gpu_launches=launches, clocks=clocks)
+    host = "python"
+    if cpp is not None and "error" not in cpp and cpp["n_total"] == n_total:
+        host, ms, launches, clocks = "cpp", cpp["ms"], cpp["launches"], cpp["clocks"]
+        value = pushes / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (K1 fused interpolate + push), measured live in the timed region
     peak, peak_src = measured_peaks()
@@ -541,7 +593,7 @@ def our_arm(args):
                 extra["bin_plan"] = "folded into the in-place push (phb_push_plan)"
         NOT_KERNELS = ("exchange_phases", "finish_particles", "fp_alltoall_counts", "fp_send_recv", "fp_maintain_arrays")  # brackets of the exchange / host-synchronising parts
         extra["particle_kernels_share_of_step"] = round(
-            sum(sum(v) for k, v in kernel_ms.items() if k not in NOT_KERNELS) / ms, 4)
+            sum(sum(v) for k, v in kernel_ms.items() if k not in NOT_KERNELS) / (python_host["ms_per_step"] * args.steps), 4)
         extra["kernel_ms_per_step"] = {k: round(sum(v) / args.steps, 3) for k, v in sorted(kernel_ms.items())}
         # whole-step fraction: 2 sweeps x (K1 + K3 algorithmic bytes) / step time
         extra["whole_step_frac_of_hbm"] = round(
@@ -583,14 +635,25 @@ def our_arm(args):
                                    "against the 126 MB L2",
                                 parallelism=f"{len(solver.patches)} patch(es) per GPU, {n_gpus} GPU(s)"),
                     per_gpu=value / n_gpus, clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline,
-                    roofline_other=extra, cpu_baseline=cpu_baseline)
+                    roofline_other=extra, cpu_baseline=cpu_baseline, host=host,
+                    host_note=("value / ms_per_step / gpu_launches / clocks: K steps enqueued by the C++ level driver "
+                               "(include/phare_b200/solver_ppc.hpp), one call per rank; roofline, per-kernel ms and e2e: the "
+                               "Python-driven pass of the same kernels (python_host), which brackets every launch"
+                               if host == "cpp" else "the step enqueued by phare_b200/solver.py"),
+                    python_host=python_host)
+        if cpp is not None and "error" in cpp:
+            line["cpp_host_error"] = cpp["error"]
         if parity is not None:
             line["parity_check"] = parity
+        if cpp is not None and cpp.get("parity") is not None:
+            line["parity_check_cpp_host"] = cpp["parity"]
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if parity is not None and not parity["ok"]:
+        sys.exit(3)
+    if cpp is not None and cpp.get("parity") is not None and not cpp["parity"]["ok"]:
         sys.exit(3)
 
 
@@ -794,9 +857,11 @@ if __name__ == "__main__":
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the N-rank parity check that precedes the timed region")
     ap.add_argument("--config", type=int, default=5, choices=[1, 2, 3, 4, 5])
-    ap.add_argument("--host", default="python", choices=["python", "cpp"],
-                    help="who enqueues the step: phare_b200/solver.py (default; every N) or the C++ SolverPPC (one GPU)")
+    ap.add_argument("--host", default="auto", choices=["auto", "python", "cpp"],
+                    help="who enqueues the timed steps: auto (default) = the C++ level driver for `value`, then the "
+                         "Python-driven pass of the same kernels for the per-kernel figures and e2e; python / cpp = only that one")
     a = ap.parse_args()
+    os.environ.setdefault("PHB_PEER_TIMEOUT_S", "60")  # a lost neighbour ends the bench instead of holding the box
     if a.impl == "reference":
         reference_arm(a)
     elif a.host == "cpp":
