@@ -632,13 +632,15 @@ class SolverPPC:
     def _by_id(self, attr):
         return {p.geom.id: getattr(p, attr) for p in self.patches}
 
-    def _field_solve(self, Bsrc, Esrc, Bdst, Edst, dt, tag):
+    def _field_solve(self, Bsrc, Esrc, Bdst, Edst, dt, tag, after_B=None):
         """Faraday -> fillMagneticGhosts -> Ampere -> fillCurrentGhosts -> electrons.update -> Ohm
-        (the common body of predictor1_/predictor2_/corrector_, solver_ppc.hpp:347-479)"""
+        (the common body of predictor1_/predictor2_/corrector_, solver_ppc.hpp:347-479).  after_B: called when Bdst is final"""
         ops, msg = self.ops, self.messenger
         for p in self.patches:
             ops.faraday(p.layout, getattr(p, Bsrc), getattr(p, Esrc), getattr(p, Bdst), dt)
         msg.fill_ghosts(Bdst, abi.BX, self._by_id(Bdst))
+        if after_B is not None:
+            after_B()
         for p in self.patches:
             ops.ampere(p.layout, getattr(p, Bdst), p.J)
         msg.fill_ghosts("J", abi.JX, self._by_id("J"))
@@ -780,10 +782,12 @@ class SolverPPC:
                 staging.download_moments()  # final after the `all` sweep (solver_ppc.hpp:333)
             else:
                 staging.snapshot_moments()
-        self._field_solve("B", "Eavg", "B", "E", dt, "corrector")
+        # the new B leaves for the host as soon as the corrector's Faraday has produced it, under Ampere / Ohm / the E ghost fill
+        early_B = staging is not None and not staging.defer_sort
+        self._field_solve("B", "Eavg", "B", "E", dt, "corrector", after_B=staging.download_B if early_B else None)
         self.messenger.fill_ghosts("E", abi.EX, self._by_id("E"))
         if staging is not None:
-            staging.download_fields()
+            staging.download_fields(skip_B=early_B)
             if not staging.defer_sort:
                 staging.download_moments()
         self._finish_particles()
@@ -851,7 +855,8 @@ class HostStaging:
         pin = lambda arrs: [t.empty(a.t.shape, dtype=t.float64).pin_memory() for a in arrs]
         self.h_in, self.h_moments, self.h_fields = pin(self.inputs), pin(self.moments), pin(self.fields)
         self.snap = None if defer_sort else [t.empty_like(a.t) for a in self.moments]
-        self.moments_done = None
+        self.moments_done = self.fields_done = None
+        self.array_done = {}  # index in fields / inputs -> event: that array's read-back has finished
         for h, a in zip(self.h_in, self.inputs):
             h.copy_(a.t)
         self.h2d_bytes = sum(h.numel() * 8 for h in self.h_in)
@@ -868,13 +873,23 @@ class HostStaging:
         return b
 
     def upload(self):
+        """E,B of this step from the pinned host buffers.  The buffers may still be receiving the previous step's results
+        (results_become_inputs): every array is uploaded as soon as ITS OWN read-back has finished, B first (it is read back
+        first), so the upload trails the read-back by one array, in the other direction of the link."""
         done = self._mark("upload")
-        for h, a in zip(self.h_in, self.inputs):
-            a.t.copy_(h, non_blocking=True)
+        cur = self.t.cuda.current_stream()
+        order = [i for i in range(len(self.inputs)) if i % 6 >= 3] + [i for i in range(len(self.inputs)) if i % 6 < 3]
+        for i in order:
+            ev = self.array_done.get(i)
+            if ev is not None:
+                cur.wait_event(ev)
+            self.inputs[i].t.copy_(self.h_in[i], non_blocking=True)
         if done is not None:
             done.record()
 
-    def _download(self, hosts, srcs, name):
+    def _download(self, hosts, srcs, name, each=None):
+        """srcs -> hosts on the copy stream, ordered after everything enqueued so far on the compute stream; each: list
+        receiving one event per array (recorded when that array has arrived)"""
         ready = self.t.cuda.Event()
         ready.record()
         with self.t.cuda.stream(self.copy_stream):
@@ -882,6 +897,10 @@ class HostStaging:
             done = self._mark(name)
             for h, a in zip(hosts, srcs):
                 h.copy_(a, non_blocking=True)
+                if each is not None:
+                    ev = self.t.cuda.Event()
+                    ev.record()
+                    each.append(ev)
             if done is not None:
                 done.record()
             finished = self.t.cuda.Event()
@@ -900,8 +919,19 @@ class HostStaging:
         srcs = self.snap if self.snap is not None else [a.t for a in self.moments]
         self.moments_done = self._download(self.h_moments, srcs, "download_moments")
 
-    def download_fields(self):
-        self.fields_done = self._download(self.h_fields, [a.t for a in self.fields], "download_fields")
+    def _download_fields(self, idx, name):
+        evs = []
+        fin = self._download([self.h_fields[i] for i in idx], [self.fields[i].t for i in idx], name, each=evs)
+        self.array_done.update(zip(idx, evs))
+        return fin
+
+    def download_B(self):
+        """fields = 3 E then 3 B components per patch"""
+        self._download_fields([i for i in range(len(self.fields)) if i % 6 >= 3], "download_B")
+
+    def download_fields(self, skip_B=False):
+        idx = [i for i in range(len(self.fields)) if not (skip_B and i % 6 >= 3)]
+        self.fields_done = self._download_fields(idx, "download_fields")
 
     def timings_ms(self):
         """average milliseconds of each transfer since timing was switched on (call after a synchronize)"""
@@ -911,8 +941,8 @@ class HostStaging:
         """the step is complete for the caller when the new E,B are on the host (and, with defer_sort, the moments)"""
         if self.defer_sort:
             self.t.cuda.current_stream().wait_stream(self.copy_stream)
-        else:
-            self.t.cuda.current_stream().wait_event(self.fields_done)
+        # otherwise nothing to do here: the next upload() waits for the read-back of each field it is about to re-send, and
+        # sync() for everything
 
     def sync(self):
         """every result of every step issued so far is in the pinned host buffers"""
