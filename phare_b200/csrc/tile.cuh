@@ -680,43 +680,47 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
                                     wf[d][s] = w[s];
                             }
                         }
-#pragma unroll
-                        for (int f = 0; f < 5; ++f)
+                        // node weight first, then the five quantities: S^d products shared by the quantities instead of five
+                        // chains ((dep wx) wy) wz — the sums are fma-accumulated and atomically ordered anyway (moments <= 1e-10)
+                        if constexpr (DIM == 1)
                         {
-                            if constexpr (DIM == 1)
-                            {
 #pragma unroll
-                                for (int ix = 0; ix < S; ++ix)
+                            for (int ix = 0; ix < S; ++ix)
+#pragma unroll
+                                for (int f = 0; f < 5; ++f)
                                     acc[ix * 5 + f] = fma(dep[f], wf[0][ix], acc[ix * 5 + f]);
-                            }
-                            else if constexpr (DIM == 2)
-                            {
+                        }
+                        else if constexpr (DIM == 2)
+                        {
 #pragma unroll
-                                for (int ix = 0; ix < S; ++ix)
+                            for (int ix = 0; ix < S; ++ix)
+#pragma unroll
+                                for (int iy = 0; iy < S; ++iy)
                                 {
-                                    double const tx = dep[f] * wf[0][ix];
+                                    double const w = wf[0][ix] * wf[1][iy];
 #pragma unroll
-                                    for (int iy = 0; iy < S; ++iy)
-                                        acc[(ix * S + iy) * 5 + f] = fma(tx, wf[1][iy], acc[(ix * S + iy) * 5 + f]);
+                                    for (int f = 0; f < 5; ++f)
+                                        acc[(ix * S + iy) * 5 + f] = fma(dep[f], w, acc[(ix * S + iy) * 5 + f]);
                                 }
-                            }
-                            else
-                            {
+                        }
+                        else
+                        {
 #pragma unroll
-                                for (int ix = 0; ix < S; ++ix)
+                            for (int ix = 0; ix < S; ++ix)
+#pragma unroll
+                                for (int iy = 0; iy < S; ++iy)
                                 {
-                                    double const tx = dep[f] * wf[0][ix];
+                                    double const wxy = wf[0][ix] * wf[1][iy];
 #pragma unroll
-                                    for (int iy = 0; iy < S; ++iy)
+                                    for (int iz = 0; iz < S; ++iz)
                                     {
-                                        double const txy = tx * wf[1][iy];
+                                        double const w = wxy * wf[2][iz];
 #pragma unroll
-                                        for (int iz = 0; iz < S; ++iz)
+                                        for (int f = 0; f < 5; ++f)
                                             acc[((ix * S + iy) * S + iz) * 5 + f]
-                                                = fma(txy, wf[2][iz], acc[((ix * S + iy) * S + iz) * 5 + f]);
+                                                = fma(dep[f], w, acc[((ix * S + iy) * S + iz) * 5 + f]);
                                     }
                                 }
-                            }
                         }
                     }
                     else if (selected<DIM>(A.sel, icell))
