@@ -217,11 +217,20 @@ public:
     }
     ~LevelMessenger()
     {
-        for (int r = 0; r < dist_.world; ++r)
-            if (r != dist_.rank && r < int(base_.size()) && base_[r])
-                phb_ipc_close(ctx_.get(), base_[r]);
+        releasePeers();
         if (arena_)
             phb_free(ctx_.get(), arena_);
+    }
+    // unmap the neighbours' arenas.  A tidy shutdown calls this on every rank, then synchronises the ranks, then destroys the
+    // messengers: no rank frees an arena that another one still has mapped
+    void releasePeers()
+    {
+        for (int r = 0; r < dist_.world; ++r)
+            if (r != dist_.rank && r < int(base_.size()) && base_[r])
+            {
+                phb_ipc_close(ctx_.get(), base_[r]);
+                base_[r] = nullptr;
+            }
     }
     bool distributed() const { return dist_.world > 1; }
     std::size_t globalIndex(std::size_t localPatch) const

@@ -26,6 +26,7 @@ struct HostBase
     virtual int patch_id(int local_patch)                                         = 0;
     virtual void arena_export(unsigned char* handle)                              = 0;
     virtual void arena_open(const unsigned char* handles)                         = 0;
+    virtual void release_peers()                                                  = 0;
 };
 thread_local std::string g_err;
 
@@ -75,6 +76,11 @@ struct Host : HostBase
     int patch_id(int local_patch) override { return int(solver->messenger().globalIndex(std::size_t(local_patch))); }
     void arena_export(unsigned char* handle) override { solver->messenger().exportArena(handle); }
     void arena_open(const unsigned char* handles) override { solver->messenger().openArenas(handles); }
+    void release_peers() override
+    {
+        phb_sync(context.get());
+        solver->messenger().releasePeers();
+    }
     phb_ctx* ctx() override { return context.get(); }
     int npatch() override { return int(solver->patches.size()); }
     const phb_layout* layout(int patch) override { return solver->patches.at(patch)->layout.c(); }
@@ -192,6 +198,11 @@ int phh_arena_export(void* h, unsigned char* handle64)
 int phh_arena_open(void* h, const unsigned char* handles)
 {
     return guarded([&] { static_cast<HostBase*>(h)->arena_open(handles); });
+}
+/* tidy shutdown of a distributed level: phh_release_peers on every rank, a barrier of the launcher, then phh_destroy */
+int phh_release_peers(void* h)
+{
+    return guarded([&] { static_cast<HostBase*>(h)->release_peers(); });
 }
 void phh_destroy(void* h) { delete static_cast<HostBase*>(h); }
 phb_ctx* phh_ctx(void* h) { return static_cast<HostBase*>(h)->ctx(); }

@@ -54,9 +54,9 @@ class CppLevel:
         lib.phh_last_error.restype = C.c_char_p
         for fn in (lib.phh_ctx, lib.phh_npatch, lib.phh_layout, lib.phh_field, lib.phh_particles, lib.phh_initialize,
                    lib.phh_advance, lib.phh_add_population, lib.phh_destroy, lib.phh_patch_id, lib.phh_arena_export,
-                   lib.phh_arena_open):
+                   lib.phh_arena_open, lib.phh_release_peers):
             fn.argtypes = None
-        self.cfg, self.torch = cfg, torch
+        self.cfg, self.torch, self.comm = cfg, torch, comm
         self.device = torch.device(device)
         torch.cuda.set_device(self.device)
         dim = cfg.dim
@@ -162,5 +162,9 @@ class CppLevel:
     def close(self):
         if self.h:
             self.torch.cuda.synchronize()
+            if self.comm is not None and self.comm.size > 1:
+                # nobody frees an arena that a neighbour still has mapped
+                self.lib.phh_release_peers(self.h)
+                self.comm.dist.barrier()
             self.lib.phh_destroy(self.h)
             self.h = None
