@@ -371,6 +371,9 @@ int phb_ions_totals(phb_ctx*, size_t nnodes, int npop, const double* const* h_rh
                     double* rho_q_tot, double* rho_m_tot, phb_vecfield* V);
 /* core::average (utilities/algorithm.hpp:68-77): avg = (a+b)*0.5 over n doubles */
 int phb_average(phb_ctx*, size_t n, const double* a, const double* b, double* avg);
+/* count <= 8 averages in one launch: avg[k][i] = (a[k][i] + b[k][i]) / 2 for i < n[k] (the six components of average_) */
+int phb_average_many(phb_ctx*, int count, const size_t* n, const double* const* a, const double* const* b,
+                     double* const* avg);
 
 /* ---- K8 same-level periodic halo on one device ----------------------------------------------
  * dst region = box `dst_box` (local array indices, inclusive) of array `dst` with shape

@@ -898,12 +898,20 @@ private:
     void average_() // :484-510
     {
         for (auto& pp : patches)
+        {
+            // core::average on the six components (algorithm.hpp:68-77), one launch
+            auto& P = *pp;
+            std::size_t n[6];
+            double const *a[6], *b[6];
+            double* avg[6];
             for (int c = 0; c < 3; ++c)
             {
-                auto& P = *pp;
-                ctx_.check(phb_average(ctx_.get(), P.EM.B[c].size(), P.EM.B[c].data(), P.EMpred.B[c].data(), P.EMavg.B[c].data()));
-                ctx_.check(phb_average(ctx_.get(), P.EM.E[c].size(), P.EM.E[c].data(), P.EMpred.E[c].data(), P.EMavg.E[c].data()));
+                n[c] = P.EM.B[c].size(), a[c] = P.EM.B[c].data(), b[c] = P.EMpred.B[c].data(), avg[c] = P.EMavg.B[c].data();
+                n[3 + c] = P.EM.E[c].size(), a[3 + c] = P.EM.E[c].data(), b[3 + c] = P.EMpred.E[c].data(),
+                      avg[3 + c] = P.EMavg.E[c].data();
             }
+            ctx_.check(phb_average_many(ctx_.get(), 6, n, a, b, avg));
+        }
         messenger_->fillGhosts(kEavg, [](Patch_t& P) -> VecField& { return P.EMavg.E; }, PHB_EX);
     }
     void finishMoments_()

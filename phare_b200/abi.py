@@ -212,6 +212,8 @@ _PROTOS = {
     "phb_ions_totals": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                   C.POINTER(VecField), c_double_p, C.c_void_p, C.c_void_p, C.POINTER(VecField)]),
     "phb_average": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "phb_average_many": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                   C.POINTER(C.c_void_p)]),
     "phb_box_op": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, C.c_void_p, c_u32_p, c_u32_p,
                              c_u32_p, C.c_int]),
     "phb_box_pack": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, c_u32_p, c_u32_p, c_u32_p, C.c_void_p]),

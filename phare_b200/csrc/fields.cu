@@ -266,6 +266,22 @@ __global__ void __launch_bounds__(256)
         avg[p] = (a[p] + b[p]) * .5;
 }
 
+// several averages in one launch (the six components of average_, solver_ppc.hpp:484-510): array in blockIdx.y
+struct AverageMany
+{
+    size_t n[8];
+    const double* a[8];
+    const double* b[8];
+    double* avg[8];
+};
+__global__ void __launch_bounds__(256) average_many_kernel(const __grid_constant__ AverageMany A)
+{
+    int const k    = blockIdx.y;
+    size_t const p = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (p < A.n[k])
+        A.avg[k][p] = (A.a[k][p] + A.b[k][p]) * .5;
+}
+
 inline unsigned blocks_for(size_t n) { return unsigned((n + 255) / 256); }
 
 template<int DIM>
@@ -417,6 +433,27 @@ int phb_ions_totals(phb_ctx* ctx, size_t nnodes, int npop, const double* const* 
         A.V[c] = V ? V->comp[c] : nullptr;
     phb::totals_kernel<<<phb::blocks_for(nnodes), 256, 0, ctx->stream>>>(A);
     PHB_LAUNCH_CHECK(ctx);
+    return PHB_OK;
+}
+int phb_average_many(phb_ctx* ctx, int count, const size_t* n, const double* const* a, const double* const* b,
+                     double* const* avg)
+{
+    if (!ctx || count < 1 || count > 8 || !n || !a || !b || !avg)
+        return phb::set_error(ctx, PHB_ERR_INVALID, "phb_average_many: invalid argument");
+    phb::AverageMany A{};
+    size_t most = 0;
+    for (int k = 0; k < count; ++k)
+    {
+        if (!a[k] || !b[k] || !avg[k])
+            return phb::set_error(ctx, PHB_ERR_INVALID, "phb_average_many: invalid argument");
+        A.n[k] = n[k], A.a[k] = a[k], A.b[k] = b[k], A.avg[k] = avg[k];
+        most = n[k] > most ? n[k] : most;
+    }
+    if (most)
+    {
+        phb::average_many_kernel<<<dim3(phb::blocks_for(most), unsigned(count)), 256, 0, ctx->stream>>>(A);
+        PHB_LAUNCH_CHECK(ctx);
+    }
     return PHB_OK;
 }
 int phb_average(phb_ctx* ctx, size_t n, const double* a, const double* b, double* avg)

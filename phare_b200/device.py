@@ -377,6 +377,13 @@ class Context:
     def average(self, a, b, avg):
         self._check(self.lib.phb_average(self.h, a.size, a.ptr, b.ptr, avg.ptr))
 
+    def average_many(self, triples):
+        """[(a, b, avg), ...] (at most 8) in one launch"""
+        k = len(triples)
+        n = (C.c_size_t * k)(*[t[0].size for t in triples])
+        col = lambda j: (C.c_void_p * k)(*[t[j].ptr for t in triples])
+        self._check(self.lib.phb_average_many(self.h, k, n, col(0), col(1), col(2)))
+
     def box_op(self, dim, dst, dst_shape, dst_lo, src, src_shape, src_lo, extent, op):
         u3 = lambda v: (C.c_uint32 * 3)(*([int(x) for x in v] + [1] * (3 - len(v))))
         dptr = dst.ptr if hasattr(dst, "ptr") else dst

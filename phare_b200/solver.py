@@ -240,6 +240,9 @@ class GpuOps:
     def average(self, a, b, avg):
         self.ctx.average(a, b, avg)
 
+    def average_many(self, triples):
+        self.ctx.average_many(triples)
+
     # ---- coarse <-> fine level operators (phare_b200.amr); *_lo = AMR field index of element 0 of the array
     def array(self, shape):
         return self.ti.TorchArray(tuple(int(s) for s in shape), self.device)
@@ -653,9 +656,12 @@ class SolverPPC:
         """average_ (solver_ppc.hpp:484-510)"""
         ops = self.ops
         for p in self.patches:
-            for c in range(3):
-                ops.average(p.B[c], p.Bpred[c], p.Bavg[c])
-                ops.average(p.E[c], p.Epred[c], p.Eavg[c])
+            triples = [(p.B[c], p.Bpred[c], p.Bavg[c]) for c in range(3)] + [(p.E[c], p.Epred[c], p.Eavg[c]) for c in range(3)]
+            if hasattr(ops, "average_many"):
+                ops.average_many(triples)  # the six components in one launch
+            else:
+                for t in triples:
+                    ops.average(*t)
         self.messenger.fill_ghosts("Eavg", abi.EX, self._by_id("Eavg"))
 
     def _move_ions(self, dt, mode):
