@@ -39,8 +39,19 @@ inline IterBox shrunk_ghost_box(const DevLayout& L, int qty)
 
 __device__ __forceinline__ bool unravel(const IterBox& b, size_t t, int& i, int& j, int& k)
 {
-    if (t >= b.volume())
+    size_t const vol = b.volume();
+    if (t >= vol)
         return false;
+    if (vol <= 0xffffffffull)
+    {
+        // (every patch in practice) 32-bit divisions: a pair of 64-bit div/mod per thread costs more than a stencil
+        unsigned const u = unsigned(t), n2 = unsigned(b.n[2]), n1 = unsigned(b.n[1]);
+        unsigned const q = u / n2, q1 = q / n1;
+        k = b.lo[2] + int(u - q * n2);
+        j = b.lo[1] + int(q - q1 * n1);
+        i = b.lo[0] + int(q1);
+        return true;
+    }
     k = b.lo[2] + int(t % b.n[2]);
     t /= b.n[2];
     j = b.lo[1] + int(t % b.n[1]);

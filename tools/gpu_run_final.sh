@@ -1,5 +1,8 @@
 cd /root/repo
 mkdir -p gpurun_out
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_r2f.csv python bench.py --host python --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/launches_r2f_bench.log 2>&1
-timeout 1200 ncu --set full --clock-control none --import-source on -k 'regex:tile_kernel' --launch-skip 6 --launch-count 2 -o gpurun_out/prof_r2_final -f python bench.py --host python --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/prof_r2_final.log 2>&1
-ls -la gpurun_out/prof_r2_final.ncu-rep gpurun_out/launches_r2f.csv
+timeout 1500 python -m pytest tests/test_gpu_parity.py tests/test_gridlayout_golden.py tests/test_configs_gpu.py tests/test_amr_gpu.py -q -x 2>&1 | tail -2
+timeout 900 python bench.py --no-cpu --no-e2e > gpurun_out/bench_r2ac.json 2> gpurun_out/bench_r2ac.err; echo rc=$?
+python -c "
+import json
+d=[json.loads(l) for l in open('gpurun_out/bench_r2ac.json') if l.startswith('{')][0]
+print(d['host'], round(d['value']/1e9,2), round(d['ms_per_step'],3), round(d['python_host']['ms_per_step'],3), d['roofline_other']['whole_step_frac_of_hbm'])"
