@@ -311,6 +311,10 @@ int phb_scatter_planned(phb_ctx*, const phb_layout*, const phb_particles* in, si
  *                             cell).  0 -> `out` is exactly what phb_bin leaves; > 0 -> the caller restores the order with
  *                             phb_bin(out -> ...) before using d_cell_start_new.
  * Only for (dim, interp) whose cell support fits the tile kernel (phb_predict_supported). */
+/* eps of the predicted re-binning (default 2^-12 of a cell; the environment variable PHB_PREDICT_EPS overrides both).  A host that
+ * sees failed plans (phb_predict_counts) raises it: the two sweeps of its steps differ by more than the default assumes. */
+int    phb_set_predict_eps(phb_ctx*, double eps);
+double phb_get_predict_eps(phb_ctx*);
 int    phb_predict_supported(const phb_layout*);
 size_t phb_predict_plan_bytes(const phb_layout*, const phb_box* domain, size_t capacity);
 int phb_push_deposit_predict(phb_ctx*, const phb_layout*, const phb_vecfield* E, const phb_vecfield* B,

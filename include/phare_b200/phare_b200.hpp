@@ -30,6 +30,7 @@
 #include "../phare_b200.h"
 
 #include <cstdlib>
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <map>
@@ -716,6 +717,12 @@ public:
                 {
                     // restore the exact order: phb_bin of the result (pushed and deposited correctly already)
                     misfiled += counts[3];
+                    // the two sweeps of this run differ by more than eps assumed: widen the band (4x per failure, <= 1/16 cell)
+                    if (!std::getenv("PHB_PREDICT_EPS"))
+                    {
+                        double const e = phb_get_predict_eps(ctx.get());
+                        phb_set_predict_eps(ctx.get(), std::min(4 * std::max(e, 1. / 16384), 1. / 16));
+                    }
                     std::vector<phb_box> keep;
                     for (auto const& b : boxing.nonLevelGhostBox)
                         keep.push_back(b.c());

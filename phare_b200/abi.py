@@ -185,6 +185,8 @@ _PROTOS = {
                                         C.c_void_p, C.POINTER(Box), C.c_int, C.c_void_p]),
     "phb_scatter_planned": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(Particles), C.c_size_t, C.POINTER(Box),
                                       C.c_void_p, C.POINTER(Box), C.c_int, C.POINTER(Particles), C.c_void_p]),
+    "phb_set_predict_eps": (C.c_int, [C.c_void_p, C.c_double]),
+    "phb_get_predict_eps": (C.c_double, [C.c_void_p]),
     "phb_predict_supported": (C.c_int, [C.POINTER(Layout)]),
     "phb_predict_plan_bytes": (C.c_size_t, [C.POINTER(Layout), C.POINTER(Box), C.c_size_t]),
     "phb_push_deposit_predict": (C.c_int, [C.c_void_p, C.POINTER(Layout), C.POINTER(VecField), C.POINTER(VecField),

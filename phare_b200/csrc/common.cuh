@@ -178,6 +178,7 @@ struct phb_ctx
     void* strip_counter   = nullptr; // work counter of the strip kernel (strip.cuh)
     bool no_strip         = true;  // PHB_STRIP=1 routes K1 of a cell-ordered store through the strip kernel (strip.cuh)
     bool no_tile          = false; // PHB_NO_TILE=1: the cell-ordered passes use the round-1 kernels (E,B through L1)
+    double predict_eps    = 1. / 4096.; // predicted re-binning: a predicted delta within eps of a cell face is left to the resolve kernel
 };
 
 namespace phb

@@ -95,6 +95,8 @@ int phb_create(int device, int dim, int interp, phb_ctx** out)
         return PHB_ERR_CUDA;
     }
     ctx->own_stream = true;
+    if (const char* e = getenv("PHB_PREDICT_EPS"))
+        ctx->predict_eps = atof(e);
     if (const char* e = getenv("PHB_NO_TMA"))
         ctx->no_tma = e[0] == '1';
     if (const char* e = getenv("PHB_NO_FUSED_CELLS"))
@@ -157,6 +159,15 @@ int phb_sync(phb_ctx* ctx)
     PHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PHB_OK;
 }
+
+int phb_set_predict_eps(phb_ctx* ctx, double eps)
+{
+    if (!ctx || !(eps >= 0.) || eps > 0.5)
+        return PHB_ERR_INVALID;
+    ctx->predict_eps = eps;
+    return PHB_OK;
+}
+double phb_get_predict_eps(phb_ctx* ctx) { return ctx ? ctx->predict_eps : 0.; }
 
 int phb_set_exact(phb_ctx* ctx, int exact)
 {

@@ -102,10 +102,9 @@ size_t plan_nk_any(const phb_layout* L, const phb_box* domain)
 
 double predict_eps(const phb_ctx* ctx)
 {
-    (void)ctx;
-    if (const char* e = getenv("PHB_PREDICT_EPS"))
+    if (const char* e = getenv("PHB_PREDICT_EPS")) // (tests switch it between calls)
         return atof(e);
-    return 1. / 4096.;
+    return ctx->predict_eps;
 }
 
 // ---- the part of a store that is not cell-ordered (received since the last binning): one thread per particle ----

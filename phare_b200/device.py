@@ -315,6 +315,12 @@ class Context:
             cell_start_old.ptr if cell_start_old is not None else None, abi.box_array(keep), len(keep), C.byref(pout.c),
             cell_start_new.ptr))
 
+    def set_predict_eps(self, eps):
+        self._check(self.lib.phb_set_predict_eps(self.h, float(eps)))
+
+    def predict_eps(self):
+        return float(self.lib.phb_get_predict_eps(self.h))
+
     def predict_supported(self, layout):
         return bool(self.lib.phb_predict_supported(C.byref(layout)))
 

@@ -561,6 +561,10 @@ class IonUpdater:
                     # and deposited correctly): restore the exact order before anything depends on it
                     self.misfiled += misfiled
                     self.rebin_fallbacks += 1
+                    # the two sweeps of this run differ by more than eps assumed: widen the band of particles that wait for
+                    # the final fields (4x per failure, at most a sixteenth of a cell)
+                    if hasattr(ops, "ctx") and not os.environ.get("PHB_PREDICT_EPS"):
+                        ops.ctx.set_predict_eps(min(4 * max(ops.ctx.predict_eps(), 2.0 ** -14), 1.0 / 16))
                     ops.set_count(pop.spare, sum(counts))
                     counts = ops.bin(L, pop.spare, pop.domain, patch.domain_box, patch.non_level_ghost, pop.cell_start)
                     pop.domain, pop.spare = pop.spare, pop.domain  # (swapped back below)
