@@ -35,7 +35,8 @@
 
 namespace phb
 {
-template<int DIM, int ORDER>
+// SMALL: half-size blocks (64 cells) for patches whose grid of 128-cell blocks would not fill one wave of the GPU
+template<int DIM, int ORDER, bool SMALL = false>
 struct TileGeom
 {
     // stencil reach of a gather around the local cell l (both centerings): order 1: l-1 .. l+1, order 2: l-1 .. l+2,
@@ -43,9 +44,9 @@ struct TileGeom
     static constexpr int LO = ORDER == 3 ? -3 : -2;
     static constexpr int HI = ORDER == 1 ? 2 : 3;
     static constexpr int W  = HI - LO + 1;
-    static constexpr int B0 = DIM == 1 ? 128 : DIM == 2 ? 8 : 4;
-    static constexpr int B1 = DIM == 1 ? 1 : DIM == 2 ? 16 : 4;
-    static constexpr int B2 = DIM == 3 ? 8 : 1;
+    static constexpr int B0 = DIM == 1 ? (SMALL ? 64 : 128) : DIM == 2 ? 8 : 4;
+    static constexpr int B1 = DIM == 1 ? 1 : DIM == 2 ? (SMALL ? 8 : 16) : 4;
+    static constexpr int B2 = DIM == 3 ? (SMALL ? 4 : 8) : 1;
     static constexpr int NC = B0 * B1 * B2; // cells per block
     static constexpr int N0 = B0 + W - 1;
     static constexpr int N1 = DIM >= 2 ? B1 + W - 1 : 1;
@@ -135,21 +136,21 @@ constexpr int TILE_DEPTH = PHB_TILE_DEPTH; // particles in flight per lane (cp.a
 #endif
 constexpr int TILE_BS = PHB_TILE_BS;
 
-template<int DIM, int ORDER, bool LOADW>
+template<int DIM, int ORDER, bool LOADW, bool SMALL = false>
 __host__ __device__ constexpr int tile_smem_bytes()
 {
-    using TG = TileGeom<DIM, ORDER>;
+    using TG = TileGeom<DIM, ORDER, SMALL>;
     int const ring = TILE_DEPTH * ((DIM + 4 + (LOADW ? 1 : 0)) * 8 + (DIM + 1) * 4) * TILE_BS;
     return TG::BYTES + ring + 3 * TG::NC * 4 + 16;
 }
 
 // MeshToParticle on the shared-memory tile: same nested z -> y -> x accumulation and operation order as
 // gather_packed(); strides are compile-time, so the (o+1)^d loads of a component are immediate offsets
-template<int DIM, int ORDER, int QTY, int COMP, bool EXACT>
+template<int DIM, int ORDER, int QTY, int COMP, bool EXACT, bool SMALL = false>
 __device__ __forceinline__ double gather_tile(const IndexWeights<DIM, ORDER>& iw, const int (&rel)[2][DIM],
                                               const double* __restrict__ tile)
 {
-    using TG = TileGeom<DIM, ORDER>;
+    using TG = TileGeom<DIM, ORDER, SMALL>;
     constexpr int cx = centering(QTY, 0), cy = centering(QTY, 1), cz = centering(QTY, 2);
     auto chain = [](double acc, double f, double w, bool first) { return first ? f * w : mad<EXACT>(f, w, acc); };
     double F = 0.;
@@ -197,13 +198,13 @@ __device__ __forceinline__ double gather_tile(const IndexWeights<DIM, ORDER>& iw
 
 // BorisPusher::move on the particle held in registers (move_particle of push_core.cuh) with the gather served from
 // the tile when the particle's stencil lies inside it, from the packed array in global memory otherwise
-template<int DIM, int ORDER, bool EXACT>
+template<int DIM, int ORDER, bool EXACT, bool SMALL = false>
 __device__ __forceinline__ void move_particle_tile(const PushParams<DIM>& P, const double* __restrict__ tile,
                                                    const int (&org)[DIM], int (&icell)[DIM], double (&delta)[DIM],
                                                    double (&v)[3], double charge, bool& ok, double& bad_delta,
                                                    double& bad_vel)
 {
-    using TG = TileGeom<DIM, ORDER>;
+    using TG = TileGeom<DIM, ORDER, SMALL>;
     advance_position<DIM>(P.h, icell, delta, v, ok, bad_delta, bad_vel);
     if (!ok)
         return;
@@ -223,12 +224,12 @@ __device__ __forceinline__ void move_particle_tile(const PushParams<DIM>& P, con
     double E[3], B[3];
     if (inside)
     {
-        E[0] = gather_tile<DIM, ORDER, PHB_EX, 0, EXACT>(iw, rel, tile);
-        E[1] = gather_tile<DIM, ORDER, PHB_EY, 1, EXACT>(iw, rel, tile);
-        E[2] = gather_tile<DIM, ORDER, PHB_EZ, 2, EXACT>(iw, rel, tile);
-        B[0] = gather_tile<DIM, ORDER, PHB_BX, 3, EXACT>(iw, rel, tile);
-        B[1] = gather_tile<DIM, ORDER, PHB_BY, 4, EXACT>(iw, rel, tile);
-        B[2] = gather_tile<DIM, ORDER, PHB_BZ, 5, EXACT>(iw, rel, tile);
+        E[0] = gather_tile<DIM, ORDER, PHB_EX, 0, EXACT, SMALL>(iw, rel, tile);
+        E[1] = gather_tile<DIM, ORDER, PHB_EY, 1, EXACT, SMALL>(iw, rel, tile);
+        E[2] = gather_tile<DIM, ORDER, PHB_EZ, 2, EXACT, SMALL>(iw, rel, tile);
+        B[0] = gather_tile<DIM, ORDER, PHB_BX, 3, EXACT, SMALL>(iw, rel, tile);
+        B[1] = gather_tile<DIM, ORDER, PHB_BY, 4, EXACT, SMALL>(iw, rel, tile);
+        B[2] = gather_tile<DIM, ORDER, PHB_BZ, 5, EXACT, SMALL>(iw, rel, tile);
     }
     else
     {
@@ -281,7 +282,7 @@ struct GroupReduceMasked
 
 // resident CTAs per SM the kernels are compiled for: what the register budget of the round-1 kernels allowed, capped by
 // what shared memory (tile + ring) allows anyway — a 3-D CTA holds 77 KB, so two fit and each thread may use 255 registers
-template<int DIM, int ORDER, bool DEPOSIT>
+template<int DIM, int ORDER, bool DEPOSIT, bool SMALL = false>
 __host__ __device__ constexpr int tile_min_blocks()
 {
 #ifdef PHB_TILE_MINB // tuning builds
@@ -289,17 +290,17 @@ __host__ __device__ constexpr int tile_min_blocks()
 #else
     int const by_regs = DEPOSIT ? (ipow(cell_support<ORDER>(), DIM) <= 8 ? 2 : 1) * (256 / TILE_BS) : 3 * (256 / TILE_BS);
 #endif
-    int const by_smem = (227 * 1024) / (tile_smem_bytes<DIM, ORDER, DEPOSIT>() + 1024);
+    int const by_smem = (227 * 1024) / (tile_smem_bytes<DIM, ORDER, DEPOSIT, SMALL>() + 1024);
     return by_smem < 1 ? 1 : (by_regs < by_smem ? by_regs : by_smem);
 }
 
-template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN>
-__global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>())
+template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN, bool SMALL = false>
+__global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT, SMALL>())
     tile_kernel(const __grid_constant__ PushParams<DIM> P, const __grid_constant__ DepositParams<DIM> A,
                 const __grid_constant__ TileRecords R, const __grid_constant__ KeySpace<DIM> K,
                 const __grid_constant__ TileParams<DIM> T)
 {
-    using TG            = TileGeom<DIM, ORDER>;
+    using TG            = TileGeom<DIM, ORDER, SMALL>;
     constexpr int S     = cell_support<ORDER>();
     constexpr int NODES = DEPOSIT ? ipow(S, DIM) : 1;
     constexpr int NV    = NODES * 5;
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(TILE_BS, tile_min_blocks<DIM, ORDER, DEPOSIT>(
             // ---- the move (BorisPusher::move on this one particle)
             bool ok = true;
             double bad_delta = 0, bad_vel = 0;
-            move_particle_tile<DIM, ORDER, EXACT>(P, tile, org, icell, delta, v, charge, ok, bad_delta, bad_vel);
+            move_particle_tile<DIM, ORDER, EXACT, SMALL>(P, tile, org, icell, delta, v, charge, ok, bad_delta, bad_vel);
             if (!ok)
             {
                 report_move_error(P.err, ok, bad_delta, bad_vel, p);
@@ -881,19 +882,30 @@ struct TileMode
     int plan; // PLAN_*
 };
 
-template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN>
+// number of CTAs of the big-block grid over the key box of A
+template<int DIM, int ORDER>
+unsigned tile_big_grid(const DepositParams<DIM>& A)
+{
+    using TG      = TileGeom<DIM, ORDER, false>;
+    unsigned grid = 1;
+    for (int d = 0; d < DIM; ++d)
+        grid *= unsigned((A.keybox.hi[d] - A.keybox.lo[d] + 1 + TG::B(d) - 1) / TG::B(d));
+    return grid;
+}
+
+template<int DIM, int ORDER, int GS, bool EXACT, bool DEPOSIT, bool WRITE, int PLAN, bool SMALL = false>
 int launch_tile(phb_ctx* ctx, const PushParams<DIM>& P, const DepositParams<DIM>& A, const TileRecords& R,
                 const KeySpace<DIM>& K, TileParams<DIM>& T)
 {
-    using TG = TileGeom<DIM, ORDER>;
+    using TG = TileGeom<DIM, ORDER, SMALL>;
     unsigned grid = 1;
     for (int d = 0; d < 3; ++d)
     {
         T.nblk[d] = d < DIM ? (A.keybox.hi[d] - A.keybox.lo[d] + 1 + TG::B(d) - 1) / TG::B(d) : 1;
         grid *= unsigned(T.nblk[d]);
     }
-    constexpr int smem = tile_smem_bytes<DIM, ORDER, DEPOSIT>();
-    auto kernel        = tile_kernel<DIM, ORDER, GS, EXACT, DEPOSIT, WRITE, PLAN>;
+    constexpr int smem = tile_smem_bytes<DIM, ORDER, DEPOSIT, SMALL>();
+    auto kernel        = tile_kernel<DIM, ORDER, GS, EXACT, DEPOSIT, WRITE, PLAN, SMALL>;
     static bool configured = false; // per instantiation
     if (!configured)
     {
@@ -919,27 +931,31 @@ int run_tile(phb_ctx* ctx, TileMode m, int gs, const PushParams<DIM>& P, const D
              const TileRecords& R, const KeySpace<DIM>& K, TileParams<DIM>& T)
 #ifdef PHB_TILE_INSTANTIATE
 {
-    auto go = [&](auto gsc) -> int {
-        constexpr int GS = decltype(gsc)::value;
+    auto go = [&](auto gsc, auto smallc) -> int {
+        constexpr int GS     = decltype(gsc)::value;
+        constexpr bool SMALL = decltype(smallc)::value;
         if (m.deposit && !m.write && m.plan == PLAN_NONE)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_NONE>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_NONE, SMALL>(ctx, P, A, R, K, T);
         if (m.deposit && m.write && m.plan == PLAN_NONE)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_NONE>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_NONE, SMALL>(ctx, P, A, R, K, T);
         if (m.deposit && m.write && m.plan == PLAN_INPLACE)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_INPLACE>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_INPLACE, SMALL>(ctx, P, A, R, K, T);
         if (m.deposit && !m.write && m.plan == PLAN_PREDICT)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_PREDICT>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, true, false, PLAN_PREDICT, SMALL>(ctx, P, A, R, K, T);
         if (m.deposit && m.write && m.plan == PLAN_REBIN)
-            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_REBIN>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, true, true, PLAN_REBIN, SMALL>(ctx, P, A, R, K, T);
         if (!m.deposit && m.write && m.plan == PLAN_NONE)
-            return launch_tile<DIM, ORDER, GS, EXACT, false, true, PLAN_NONE>(ctx, P, A, R, K, T);
+            return launch_tile<DIM, ORDER, GS, EXACT, false, true, PLAN_NONE, SMALL>(ctx, P, A, R, K, T);
         return set_error(ctx, PHB_ERR_INVALID, "tile kernel: unsupported mode");
     };
-    if (gs >= 32)
-        return go(std::integral_constant<int, 32>{});
+    // a patch whose grid of 128-cell blocks is less than one wave (two CTAs per SM) is cut into 64-cell blocks instead:
+    // twice the CTAs for the same work (config 3's 128 x 128-cell patches: 128 CTAs on 296 slots -> 256)
+    bool const small = tile_big_grid<DIM, ORDER>(A) < unsigned(2 * ctx->sm_count) && !getenv("PHB_TILE_BIG");
+    if (small)
+        return go(std::integral_constant<int, 8>{}, std::true_type{});
     if (gs >= 16)
-        return go(std::integral_constant<int, 16>{});
-    return go(std::integral_constant<int, 8>{});
+        return go(std::integral_constant<int, 16>{}, std::false_type{});
+    return go(std::integral_constant<int, 8>{}, std::false_type{});
 }
 #else
     ;

@@ -110,9 +110,25 @@ def check_exact(ctx, L, dom, got_cs, counts, pout, want, want_cs, want_counts):
     assert np.array_equal(canonical_rows(*got), canonical_rows(*want.soa()))
 
 
+@pytest.fixture(params=["blocks_64_cells", "blocks_128_cells"])
+def block_size(request):
+    """the test patches are smaller than one wave of 128-cell blocks, so the kernels cut them into 64-cell blocks;
+    PHB_TILE_BIG=1 (read at every call) keeps the 128-cell blocks the benchmark sizes run with"""
+    old = os.environ.get("PHB_TILE_BIG")
+    if request.param == "blocks_128_cells":
+        os.environ["PHB_TILE_BIG"] = "1"
+    else:
+        os.environ.pop("PHB_TILE_BIG", None)
+    yield request.param
+    if old is None:
+        os.environ.pop("PHB_TILE_BIG", None)
+    else:
+        os.environ["PHB_TILE_BIG"] = old
+
+
 @pytest.mark.parametrize("eps", [None, 0, 0.6], ids=["eps_default", "eps_0", "all_risky"])
 @pytest.mark.parametrize("dim,interp", TILED)
-def test_same_fields_every_plan_holds(ctxs, cpu_oracle, dim, interp, eps):
+def test_same_fields_every_plan_holds(ctxs, cpu_oracle, dim, interp, eps, block_size):
     ctx = ctxs(dim, interp)
     rng, L, soa, n_sorted, cs, dom, keep, E, B = problem(cpu_oracle, dim, interp, 7000)
     dt = 0.1
@@ -129,7 +145,7 @@ def test_same_fields_every_plan_holds(ctxs, cpu_oracle, dim, interp, eps):
 
 
 @pytest.mark.parametrize("dim,interp", TILED)
-def test_corrected_fields_plans_hold_through_the_risky_list(ctxs, cpu_oracle, dim, interp):
+def test_corrected_fields_plans_hold_through_the_risky_list(ctxs, cpu_oracle, dim, interp, block_size):
     """the second sweep sees fields that differ by 1e-5 (positions by ~1e-8 of a cell, as between the two sweeps of a PPC
     step): a few hundred of the 10^4..10^5 particles sit within 2^-12 of a face, and with eps = 0 some of them would be
     misfiled; with the default eps none is"""
