@@ -164,7 +164,7 @@ def _snapshot(solver):
 def multi_rank_parity(cfg_key, n_gpus, rank, device, steps=3):
     """N-rank correctness, visible to the driver: a small global problem of the benchmarked config (same profiles, dl, dt;
     PARITY_CELLS per patch, PARITY_PPC particles per cell, one patch per rank at least) advanced `steps` steps (a) on the
-    N ranks through the peer-memory halo / NCCL migration path that the timed region uses and (b) by rank 0 alone holding
+    N ranks through the peer-memory halo and migration path that the timed region uses and (b) by rank 0 alone holding
     every patch.  Compared on rank 0: every field and moment per node, particle counts per patch and population, and the
     reference's own multi-rank criterion (tests/simulator/test_advance.py:180, overlap coherence): the ghost nodes of
     every patch equal the values of the patch that owns them."""
