@@ -626,8 +626,15 @@ class Simulator:
                "serialized_simulation": np.array(serialized_simulation)}
         solvers = self.level_solvers()
         out["nlevels"] = np.array(len(solvers))
+        # what load_restart() checks before it touches anything: a restart file belongs to one rank of one decomposition
+        root = solvers[0]
+        lay = root.patches[0].layout if root.patches else None
+        out["meta/world"], out["meta/rank"] = np.array(root.comm.size), np.array(root.comm.rank)
+        out["meta/dim_interp"] = np.array([lay.dim, lay.interp] if lay is not None else [0, 0])
+        out["meta/populations"] = np.array([pop.name for pop in root.patches[0].pops] if root.patches else [], dtype=str)
         for il, solver in enumerate(solvers):
             out[f"pl{il}/boxes"] = np.array([[g.box.lo, g.box.hi] for g in solver.geom.patches])
+            out[f"pl{il}/local_patches"] = np.array([p.geom.id for p in solver.patches])
             for p in solver.patches:
                 base = f"pl{il}/p{p.geom.id}/"
                 for name, vec in (("B", p.B), ("E", p.E), ("Vi", p.Vi), ("J", p.J)):
@@ -657,6 +664,26 @@ class Simulator:
         z = np.load(filename)
         ops = self.solver.ops
         nlevels = int(z["nlevels"])
+        if "meta/world" in z.files:  # (files of earlier versions carry no header)
+            root = self.level_solvers()[0]
+            lay = root.patches[0].layout if root.patches else None
+            problems = []
+            if (int(z["meta/world"]), int(z["meta/rank"])) != (root.comm.size, root.comm.rank):
+                problems.append(f"written by rank {int(z['meta/rank'])} of {int(z['meta/world'])}, read by rank "
+                                f"{root.comm.rank} of {root.comm.size}")
+            if lay is not None and list(z["meta/dim_interp"]) != [lay.dim, lay.interp]:
+                problems.append(f"(dim, interp) = {tuple(int(x) for x in z['meta/dim_interp'])} in the file, "
+                                f"{(lay.dim, lay.interp)} in this simulation")
+            names = [pop.name for pop in root.patches[0].pops] if root.patches else []
+            if [str(n) for n in z["meta/populations"]] != names:
+                problems.append(f"populations {[str(n) for n in z['meta/populations']]} in the file, {names} in this simulation")
+            boxes0 = [[list(g.box.lo), list(g.box.hi)] for g in root.geom.patches]
+            if np.asarray(z["pl0/boxes"]).tolist() != boxes0:
+                problems.append("the root level is cut into different patches")
+            elif sorted(int(i) for i in z["pl0/local_patches"]) != sorted(p.geom.id for p in root.patches):
+                problems.append("this rank owns other root patches than the rank that wrote the file")
+            if problems:
+                raise RuntimeError(f"restart file {filename} does not fit this run: " + "; ".join(problems))
         if nlevels > 1:
             amr = self.amr
             for il in range(1, nlevels):
@@ -679,7 +706,8 @@ class Simulator:
                     for k, m in enumerate(pop.moments()):
                         ops.set_field(m, z[base + f"pop{i}/moment{k}"])
                     pop.n_sorted = int(z[base + f"pop{i}/n_sorted"])
-                    pop.pending_bin = False
+                    pop.pending_bin = pop.pending_predicted = False
+                    pop.predicted = None  # a plan made for the stores this load overwrites is void
                     ops.set_field(pop.cell_start, z[base + f"pop{i}/cell_start"])
                     for store in self._PARTICLE_STORES:
                         key = base + f"pop{i}/{store}/weight"

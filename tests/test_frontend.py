@@ -438,6 +438,30 @@ def test_restart_resumes_bit_for_bit(cpu_backend, cpu_ref, tmp_path, refined):
         assert np.array_equal(straight[k], resumed[k], equal_nan=straight[k].dtype.kind == "f"), k
 
 
+def test_restart_file_of_another_decomposition_is_refused(cpu_backend, cpu_ref, tmp_path):
+    """a restart file belongs to one rank of one decomposition: loading it into a run cut into other patches (or with other
+    populations) says so instead of failing on a missing key"""
+    import pybindlibs.dictator as pp
+
+    def make(largest):
+        pops, bfn = two_pop_1d(64)
+        populate([64], [0.2], 1, pops, bfn, steps=2, largest=largest)
+        sim = S.make_simulator(S.make_hierarchy(), 1, 1, 2)
+        sim.initialize()
+        return sim
+
+    sim = make([16])
+    path = str(tmp_path / "restart_rank0.npz")
+    sim.save_restart(path)
+    S.dict_instance().stop()
+    same = make([16])
+    same.load_restart(path)  # fits
+    S.dict_instance().stop()
+    other = make([32])
+    with pytest.raises(RuntimeError, match="does not fit this run.*different patches"):
+        other.load_restart(path)
+
+
 @pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pyphare")), reason="reference tree not mounted")
 def test_pyphare_restart_options_write_and_resume(cpu_backend, cpu_ref, tmp_path, monkeypatch):
     """pyphare's own restart flow, unchanged: restart_options={"dir", "mode", "timestamps"} writes <dir>/00000.01000/ during
