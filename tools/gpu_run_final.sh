@@ -1,5 +1,7 @@
+# what the driver runs at round end, on one B200 box: the GPU parity suite, the smoke test, both bench arms
 cd /root/repo
 mkdir -p gpurun_out
-PHB_MB_ONLY=predict timeout 900 ncu --set full --clock-control none -k regex:tile_kernel --launch-skip 3 --launch-count 3 -o gpurun_out/prof_r2_c4 -f python tools/microbench.py c4 > gpurun_out/prof_r2_c4.log 2>&1
-grep "c4 " gpurun_out/prof_r2_c4.log | cut -c1-90
-ls -la gpurun_out/prof_r2_c4.ncu-rep
+timeout 1500 python -m pytest tests -m gpu -q -x 2>&1 | tail -2
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo rc=$?
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
